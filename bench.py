@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Headline benchmark: VQ-VAE training step (forward + backward + Adam) on synthetic 160x224x160 volumes.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference ...                     # the reference algorithm on the host CPU cores
+
+Workload = BASELINE.json configs[1]: baseline_vqvae, 4 levels, 256 channels, codebook 2048x32, batch 8 per GPU,
+bf16 operands / fp32 accumulation (the reference trains this model with --amp=True fp16 autocast, README.md:52),
+loss = mse(recon, x) + commitment loss, Adam lr 1.65e-4 (README.md:57).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "VQ-VAE vols/sec @160x224x160 (fwd+bwd+Adam)"
+UNIT = "volumes/s"
+FLOP_PER_VOL_FWD = 4.991e12            # 58 convs, 2*MACs, per 160x224x160 volume
+KW = dict(n_levels=4, downsample_parameters=((4, 2, 1, 1),) * 4, upsample_parameters=((4, 2, 1, 0, 1),) * 4,
+          n_embed=2048, embed_dim=32, n_channels=256, n_res_channels=256, n_res_layers=3, vq_decay=0.5,
+          commitment_cost=0.25)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--vol", type=int, nargs=3, default=[160, 224, 160])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [v.strip() for v in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm (torch CPU fp32, all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_step_time(vol, batch, steps, warmup):
+    import torch
+    from oracle import vqvae_oracle as vo
+    cfg = vo.VQVAEConfig(**KW)
+    sd = vo.init_state_dict(cfg, seed=4)
+    x = torch.rand(batch, 1, *vol)
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sd.items() if not k.startswith("quantizer.")}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, grads, out = vo.train_step_grads(sd, cfg, x)
+        for k, g in grads.items():
+            m, v = state[k]
+            sd[k], m, v = vo.adam_step(sd[k], g, m, v, it + 1, 1.65e-4)
+            state[k] = (m, v)
+        for k, v in out["new_state"].items():
+            sd["quantizer.0.impl." + k] = v
+        sd["quantizer.0.impl.embedding.weight"] = sd["quantizer.0.impl.weight"]
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+CPU_CROPS = [(160, 224, 160), (128, 176, 128), (96, 128, 96), (80, 112, 80), (64, 96, 64), (48, 64, 48), (32, 48, 32)]
+
+
+def pick_cpu_sample(budget_s, n_steps):
+    """Largest crop of the 160x224x160 volume (every axis a multiple of 16 = the 4-level stride) whose predicted
+    time for n_steps fits the budget; the per-voxel cost is calibrated on two small crops."""
+    t = cpu_step_time((16, 16, 16), 1, 1, 1)                      # fixed overheads (Adam over 28 M params) dominate
+    t2 = cpu_step_time((32, 48, 32), 1, 1, 0)
+    per_voxel = max(t2 - t, 1e-3) / (32 * 48 * 32 - 16 ** 3)
+    for vol in CPU_CROPS:
+        if (t + per_voxel * vol[0] * vol[1] * vol[2]) * n_steps <= budget_s:
+            return vol
+    return CPU_CROPS[-1]
+
+
+def cpu_baseline(budget_s, steps=1, warmup=0):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    vol = pick_cpu_sample(budget_s, steps + warmup)
+    t = cpu_step_time(vol, 1, steps, warmup)
+    frac = (vol[0] * vol[1] * vol[2]) / (160 * 224 * 160)
+    return {"value": frac / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle port (torch CPU fp32) of the reference step, batch 1, crop {vol[0]}x{vol[1]}x{vol[2]} "
+                      f"= {frac:.4f} volume, {steps} timed step(s); value extrapolated by voxel count"}, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = args.steps + args.warmup
+    vol = pick_cpu_sample(150.0, n)
+    t = cpu_step_time(vol, 1, args.steps, args.warmup)
+    frac = (vol[0] * vol[1] * vol[2]) / (160 * 224 * 160)
+    val = frac / t
+    cb = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+          "sample": f"oracle port of the reference VQ-VAE step on CPU, batch 1, crop {vol[0]}x{vol[1]}x{vol[2]} "
+                    f"({frac:.4f} volume) per step; extrapolated by voxel count"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "baseline_vqvae 4-level 256ch 160x224x160 codebook 2048x32 (CPU sample, see cpu_baseline)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from synthanatomy_b200 import ops
+    from synthanatomy_b200.losses import MSELoss
+    from synthanatomy_b200.networks.vqvae import B200VQVAE
+    from synthanatomy_b200.optim import Adam
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.lib()   # fail loudly here if the CUDA library is missing
+
+    torch.manual_seed(4)                                   # README.md:55
+    net = B200VQVAE(**KW, compute_dtype=torch.bfloat16).to(dev).train()
+    model = net
+    if world > 1:
+        # every rank holds identical initial weights (same seed); DDP averages gradients over NCCL / NVLink
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=False,
+                                                          bucket_cap_mb=64, gradient_as_bucket_view=True)
+    opt = Adam(net.parameters(), lr=1.65e-4)
+    crit = MSELoss()
+    B, vol = args.batch, tuple(args.vol)
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = torch.rand(B, 1, *vol, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step(x):
+        out = model(x)
+        loss = crit(out, x)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            if e2e:
+                x = x_host.to(dev, non_blocking=True)       # H2D of this step's input from pinned memory
+                loss = step(x)
+                loss_host.copy_(loss.detach(), non_blocking=True)   # D2H of the step's result
+                torch.cuda.current_stream().synchronize()
+            else:
+                loss = step(x_dev)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, float(loss.detach().item())
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    # ---- device-resident timing, dominant kernel timed per launch with events on the launching stream
+    dom = lambda d: (d.c_in == 128 and d.c_out == 128 and d.ksize == 3 and d.stride == 1 and
+                     d.out_dhw[0] * 2 == vol[0] and d.out_dhw[2] * 2 == vol[2])
+    timer = ops.ConvTimer(dom)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ops.reset_launch_count()
+    ops.set_conv_timer(timer)
+    ms, loss = timed(args.steps, e2e=False)
+    ops.set_conv_timer(None)
+    launches = ops.launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    # ---- end-to-end through the public module API with host buffers
+    ms_e2e, _ = timed(args.steps, e2e=True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    vols = B * world * args.steps
+    value = vols / (ms / 1e3)
+    e2e_value = vols / (ms_e2e / 1e3)
+    full = vol == (160, 224, 160)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)     # kernel timed inside a long step -> sustained figure
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    dt = timer.elapsed_ms()
+    roof = None
+    if dt:
+        pos = B * (vol[0] // 2) * (vol[1] // 2) * (vol[2] // 2)
+        flop = 2.0 * pos * 27 * 128 * 128                    # algorithmic FLOPs of one 3x3x3 128->128 launch
+        avg_ms = sum(dt) / len(dt)
+        ach = flop / (avg_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "tc_conv_kernel (3x3x3 128->128 @ level 1, fwd + dgrad launches)",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "launches_timed": len(dt), "avg_ms": avg_ms, "flop_per_launch": flop, "peak_source": peak_src}
+    step_flop = 3 * FLOP_PER_VOL_FWD * B * (vol[0] * vol[1] * vol[2]) / (160 * 224 * 160)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"baseline_vqvae 4-level 256ch {vol[0]}x{vol[1]}x{vol[2]} codebook 2048x32 "
+                               f"batch {B}/GPU, fwd+bwd+Adam" + ("" if full else " (REDUCED volume: not the headline)"),
+                   "parallelism": f"dp{world}", "global_batch": B * world,
+                   "l2_policy": "inputs and activations (>= 1.4 GB per tensor) exceed the 126 MB L2; no flush needed"},
+        "step_tflops": step_flop / (ms / args.steps * 1e-3) / 1e12,
+        "loss": loss,
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(args.cpu_budget_s)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+/* synthanatomy_b200 -- C ABI of the B200 (sm_100a) hot path of AmigoLab/SynthAnatomy.
+ *
+ * Drop-in boundary: the reference has no FFI of its own (pure Python on top of torch / cuDNN /
+ * cuBLAS); what a maintainer binds is the set of torch operator calls on the hot path.  Every entry
+ * point below names the reference call site(s) it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless stated.
+ *  - activations are channels-last "NDHWC" (batch, depth, height, width, channel), fp32 or bf16.
+ *  - every function enqueues on `stream` (a cudaStream_t passed as void*) and never allocates,
+ *    never synchronises; workspace (if any) is supplied by the caller.
+ *  - returns SA_OK (0) or a negative sa_status; sa_last_error() gives the message of the last
+ *    failure on the calling thread.  Unsupported configurations return SA_ERR_UNSUPPORTED:
+ *    there is NO CPU fallback anywhere in this library.
+ */
+#ifndef SYNTHANATOMY_B200_H
+#define SYNTHANATOMY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sa_status {
+  SA_OK = 0,
+  SA_ERR_INVALID = -1,      /* bad argument (null pointer, negative size, ...) */
+  SA_ERR_UNSUPPORTED = -2,  /* configuration outside what the kernels implement */
+  SA_ERR_CUDA = -3,         /* a CUDA runtime / driver call failed */
+  SA_ERR_WORKSPACE = -4     /* workspace too small */
+} sa_status;
+
+typedef enum sa_dtype { SA_F32 = 0, SA_BF16 = 1 } sa_dtype;
+
+/* which implementation a dispatching entry point used last on this thread (for tests / gpu_launches) */
+typedef enum sa_path { SA_PATH_NONE = 0, SA_PATH_SIMT = 1, SA_PATH_TCGEN05 = 2 } sa_path;
+
+const char* sa_last_error(void);
+int sa_version(void);
+int sa_last_path(void);
+/* number of kernels launched by this library on the calling thread since the last reset */
+int64_t sa_launch_count(void);
+void sa_launch_count_reset(void);
+/* 0: dispatch normally; 1: force the CUDA-core (SIMT) kernels even where a tcgen05 kernel exists */
+void sa_set_force_simt(int on);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gather-GEMM convolution primitive.
+ *
+ *   transposed == 0 (FORM_CONV):
+ *     Y[b, o, n] = sum_{t, c}  X[b, o*stride - pad + t, c] * Wp[t][n][c]
+ *   transposed == 1 (FORM_TCONV):
+ *     Y[b, o, n] = sum_{t, c : (o + pad - t) % stride == 0}  X[b, (o + pad - t)/stride, c] * Wp[t][n][c]
+ *
+ * o, t are 3-vectors (depth, height, width), t ranges over ksize^3 taps (t = (td*ksize + th)*ksize + tw),
+ * out-of-range X reads are zero.  Wp is the PACKED weight [ksize^3][c_out][c_in] in the activation dtype
+ * (see sa_pack_weight).  Epilogue, in this order:  v = acc (+ bias[n]) (+ addend[b,o,n]);
+ * if relu: v = max(v, 0);  if mask: v = mask[b,o,n] > 0 ? v : 0.
+ *
+ * Replaces: nn.Conv3d / nn.ConvTranspose3d forward and their autograd data-gradients --
+ *   src/networks/vqvae/baseline.py:153,156 (ResidualLayer convs), :218-227 (strided down-convs),
+ *   :242-244, :258 (pre/post-quant convs), :283-293 (ConvTranspose3d), and the fused elementwise
+ *   nn.ReLU / F.relu(x + .) at :154,160,228,296-297.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sa_conv_desc {
+  int32_t batch;
+  int32_t in_dhw[3];   /* spatial extent of X (the gathered tensor) */
+  int32_t out_dhw[3];  /* spatial extent of Y */
+  int32_t c_in;        /* channels of X */
+  int32_t c_out;       /* channels of Y */
+  int32_t ksize, stride, pad;
+  int32_t transposed;
+  int32_t act_dtype;   /* sa_dtype of X, Y, addend, mask and Wp */
+} sa_conv_desc;
+
+int sa_conv3d_fwd(const sa_conv_desc* d, const void* x, const void* wp, const float* bias,
+                  const void* addend, const void* mask, int relu, void* y, void* stream);
+
+/* Weight gradient of the primitive above, always in FORM_CONV indexing:
+ *   dWp[t][n][c] (+)= sum_{b, o}  P[b, o, n] * Q[b, o*stride - pad + t, c]
+ * P has extent out_dhw with c_out channels, Q has extent in_dhw with c_in channels; dWp is fp32
+ * [ksize^3][c_out][c_in].  If accumulate == 0 dWp is overwritten (it is zeroed on `stream` first).
+ * Replaces: cuDNN wgrad reached through autograd of the convs listed above. */
+int sa_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void* q, float* dwp, int accumulate,
+                    void* stream);
+
+/* dst[t'][a][b] = src[a][b][t] (transpose == 0) or dst[t'][b][a] = src[a][b][t] (transpose == 1),
+ * t' = flip ? taps-1-t : t.  src is the torch layout (fp32, [A][B][taps]); dst is sa_dtype dst_dtype.
+ * sa_unpack_wgrad is the exact inverse on fp32 data (dst[a][b][t] (+)= src[...]), used to scatter dWp
+ * back into the torch-layout .grad. */
+int sa_pack_weight(const float* src, int A, int B, int taps, int transpose, int flip, void* dst,
+                   int dst_dtype, void* stream);
+int sa_unpack_wgrad(const float* src, int A, int B, int taps, int transpose, int flip, float* dst,
+                    int accumulate, void* stream);
+
+/* db[c] (+)= sum_rows dy[row][c]   (bias gradient of every conv above) */
+int sa_bias_grad(const void* dy, int64_t rows, int c, int dtype, float* db, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Vector quantiser (EMA codebook).  Replaces Quantizer_impl.forward, baseline.py:38-87, and
+ * Quantizer.forward's histogram, baseline.py:110-120.
+ *
+ * sa_vq_forward: z is [rows][dim] fp32 (NDHWC-flattened latents), codebook [n_embed][dim] fp32.
+ *   idx[row]   = argmin_k ( ||z||^2 - 2 z.w_k + ||w_k||^2 ), evaluated in fp32 in that association,
+ *                first (lowest) index on ties                                   (baseline.py:49-56)
+ *   q[row]     = codebook[idx[row]]                                             (baseline.py:63)
+ *                or, if straight_through != 0, (codebook[idx[row]] - z[row]) + z[row], the value of
+ *                (quantized - x).detach() + x with its two fp32 roundings          (baseline.py:85)
+ *   counts[k] += #rows with idx == k          (fp32; baseline.py:68)  -- may be NULL
+ *   dw[k][:]  += sum of z rows with idx == k  (fp32; baseline.py:69)  -- may be NULL
+ *   sse[0]    += sum (q - z)^2                (fp32; numerator of mse_loss, baseline.py:82) -- may be NULL
+ * counts, dw and sse must be zeroed by the caller (they are accumulated so that ranks/tiles can share them).
+ * idx is int64 (the reference returns LongTensor, baseline.py:56).
+ * ---------------------------------------------------------------------------------------------- */
+int sa_vq_forward(const float* z, const float* codebook, int64_t rows, int dim, int n_embed,
+                  int64_t* idx, float* q, int straight_through, float* counts, float* dw, float* sse,
+                  void* stream);
+
+/* Backward of the quantiser outputs w.r.t. the latents (any consistent layout, n elements):
+ *   dz = g_q + g_loss[0] * coef * (z - q)
+ * g_q: gradient of the straight-through output (identity, baseline.py:85); g_loss: DEVICE scalar gradient of
+ * the latent loss; coef = 2 * commitment_cost / numel (baseline.py:82).  g_q or g_loss may be NULL (= 0). */
+int sa_vq_backward(const float* g_q, const float* g_loss, const float* z, const float* q, float coef,
+                   int64_t n, float* dz, void* stream);
+
+/* EMA + Laplace smoothing + codebook refresh, baseline.py:75-80 (counts / dw already all-reduced):
+ *   N <- decay N + (1-decay) counts;  embed_avg <- decay embed_avg + (1-decay) dw;
+ *   n = sum N;  W = (N + eps)/(n + n_embed eps) n;  codebook <- embed_avg / W
+ * decay / eps are doubles because the reference forms `1 - decay` and `n_embed * eps` in Python doubles.
+ * workspace: >= 4 bytes (receives n), may be NULL. */
+int sa_vq_ema_update(float* N, float* embed_avg, float* codebook, const float* counts, const float* dw,
+                     int n_embed, int dim, double decay, double eps, float* workspace, void* stream);
+
+/* out[0] = exp(-sum_k p_k log(p_k + 1e-10)), p_k = counts[k] / total   (Quantizer.forward, baseline.py:110-120;
+ * counts are the per-rank histogram written by sa_vq_forward). */
+int sa_vq_perplexity(const float* counts, int n_embed, float total, float* out, void* stream);
+
+/* q[row] = codebook[idx[row]]   (Quantizer_impl.embed, baseline.py:89-91) */
+int sa_vq_embed(const int64_t* idx, const float* codebook, int64_t rows, int dim, int n_embed, float* q,
+                void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Elementwise / layout helpers
+ * ---------------------------------------------------------------------------------------------- */
+/* dst[b][s][c] = src[b][c][s]  (NCDHW -> NDHWC, `spatial` = D*H*W) and back; dtypes are sa_dtype */
+int sa_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t batch, int c,
+                    int64_t spatial, void* stream);
+int sa_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t batch, int c,
+                    int64_t spatial, void* stream);
+/* dst = (dst_dtype) src, n elements */
+int sa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* sse[0] += sum (a-b)^2 ; grad = scale * scale_dev[0] * (a - b)  (F.mse_loss fwd+bwd,
+ * src/losses/vqvae/vqvae.py:56).  a: prediction (a_dtype), b: target fp32; sse, grad (a_dtype) and the DEVICE
+ * scalar scale_dev (the incoming loss gradient) may each be NULL. */
+int sa_mse_fwd_bwd(const void* a, int a_dtype, const float* b, int64_t n, float scale, const float* scale_dev,
+                   float* sse, void* grad, void* stream);
+/* torch.optim.Adam step (run_vqvae.py:82, run_transformer.py:109): fp32 p, g, m, v; no weight decay.
+ * `step` is the 1-based step count AFTER increment. */
+int sa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNTHANATOMY_B200_H */

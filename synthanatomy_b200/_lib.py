@@ -1,0 +1,97 @@
+"""ctypes binding of libsynthanatomy_b200.so (the C ABI declared in include/synthanatomy_b200.h).
+
+There is NO fallback: if the shared library is missing and cannot be built, importing raises; if a call
+fails, a RuntimeError carrying ``sa_last_error()`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+c_void_p = C.c_void_p
+c_int = C.c_int
+c_int64 = C.c_int64
+c_float = C.c_float
+c_double = C.c_double
+
+SA_F32, SA_BF16 = 0, 1
+SA_PATH_NONE, SA_PATH_SIMT, SA_PATH_TCGEN05 = 0, 1, 2
+
+
+class ConvDesc(C.Structure):
+    """mirror of `sa_conv_desc`"""
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("in_dhw", C.c_int32 * 3),
+        ("out_dhw", C.c_int32 * 3),
+        ("c_in", C.c_int32),
+        ("c_out", C.c_int32),
+        ("ksize", C.c_int32),
+        ("stride", C.c_int32),
+        ("pad", C.c_int32),
+        ("transposed", C.c_int32),
+        ("act_dtype", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); the single source of truth for tests/test_abi.py as well
+SIGNATURES = {
+    "sa_last_error": (C.c_char_p, []),
+    "sa_version": (c_int, []),
+    "sa_last_path": (c_int, []),
+    "sa_launch_count": (c_int64, []),
+    "sa_launch_count_reset": (None, []),
+    "sa_set_force_simt": (None, [c_int]),
+    "sa_conv3d_fwd": (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                              c_void_p]),
+    "sa_conv3d_wgrad": (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "sa_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "sa_unpack_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "sa_bias_grad": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "sa_vq_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                              c_void_p, c_void_p]),
+    "sa_vq_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p]),
+    "sa_vq_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_double, c_double,
+                                 c_void_p, c_void_p]),
+    "sa_vq_perplexity": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "sa_vq_embed": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "sa_nchw_to_nhwc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
+    "sa_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
+    "sa_cast": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
+    "sa_mse_fwd_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sa_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int,
+                             c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load (building first if needed) the CUDA library.  Raises if that is impossible."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.library_path()
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise RuntimeError(f"{path} is missing: run `python -m synthanatomy_b200.build` (needs nvcc). "
+                                   "synthanatomy_b200 has no CPU / eager fallback.")
+            path = _build.build_library()
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError here == ABI drift; let it propagate
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().sa_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"synthanatomy_b200 {what} failed (status {rc}): {msg}")

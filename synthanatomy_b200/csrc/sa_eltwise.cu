@@ -1,0 +1,266 @@
+// Layout / elementwise / reduction helpers around the conv kernels (all HBM-bound, coalesced, grid-stride).
+#include "sa_common.cuh"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+inline unsigned ew_grid(int64_t n, int per_thread = 1) {
+  int64_t b = sa_cdiv(n, (int64_t)EW_THREADS * per_thread);
+  const int64_t cap = 148 * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+template <typename TO>
+__global__ void pack_weight_kernel(const float* __restrict__ src, int A, int B, int taps, int transpose, int flip,
+                                   TO* __restrict__ dst) {
+  const int64_t n = (int64_t)A * B * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes dst [t'][r][c]
+    const int R = transpose ? B : A, C = transpose ? A : B;
+    const int c = (int)(i % C);
+    const int r = (int)((i / C) % R);
+    const int tp = (int)(i / ((int64_t)C * R));
+    const int t = flip ? taps - 1 - tp : tp;
+    const int a = transpose ? c : r, b = transpose ? r : c;
+    sa_st(dst, i, src[((int64_t)a * B + b) * taps + t]);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, int A, int B, int taps, int transpose, int flip,
+                                    float* __restrict__ dst, int accumulate) {
+  const int64_t n = (int64_t)A * B * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes dst [a][b][t]
+    const int t = (int)(i % taps);
+    const int b = (int)((i / taps) % B);
+    const int a = (int)(i / ((int64_t)taps * B));
+    const int tp = flip ? taps - 1 - t : t;
+    const int R = transpose ? B : A, C = transpose ? A : B;
+    const int r = transpose ? b : a, c = transpose ? a : b;
+    const float v = src[((int64_t)tp * R + r) * C + c];
+    dst[i] = accumulate ? dst[i] + v : v;
+  }
+}
+
+// db[c] += sum over rows; block = (C-lane, row-lane) so that global reads stay coalesced along c
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restrict__ db, int64_t rows_per_block) {
+  __shared__ float s_acc[256];
+  const int cl = min(C, 256);          // threads along c
+  const int rl = 256 / cl;             // row lanes (>= 1)
+  const int tc = threadIdx.x % cl, tr = threadIdx.x / cl;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  for (int c0 = 0; c0 < C; c0 += cl) {
+    const int c = c0 + tc;
+    float acc = 0.f;
+    if (tr < rl && c < C)
+      for (int64_t r = r0 + tr; r < r1; r += rl) acc += sa_ld(dy, r * C + c);
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    if (tr == 0 && c < C) {
+      float s = 0.f;
+      for (int j = 0; j < rl; ++j) s += s_acc[j * cl + tc];
+      atomicAdd(db + c, s);
+    }
+    __syncthreads();
+  }
+}
+
+// [b][c][s] -> [b][s][c] through a 32x32 shared tile (both sides coalesced)
+template <typename TI, typename TO>
+__global__ void transpose_cs_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int C, int64_t S, bool to_nhwc) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int64_t s0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (to_nhwc) {
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j; const int64_t s = s0 + tx;
+      tile[j][tx] = (c < C && s < S) ? sa_ld(src, (b * C + c) * S + s) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int64_t s = s0 + j; const int c = c0 + tx;
+      if (c < C && s < S) sa_st(dst, (b * S + s) * C + c, tile[tx][j]);
+    }
+  } else {
+    for (int j = ty; j < 32; j += 8) {
+      const int64_t s = s0 + j; const int c = c0 + tx;
+      tile[j][tx] = (c < C && s < S) ? sa_ld(src, (b * S + s) * C + c) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j; const int64_t s = s0 + tx;
+      if (c < C && s < S) sa_st(dst, (b * C + c) * S + s, tile[tx][j]);
+    }
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    sa_st(dst, i, sa_ld(src, i));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS)
+mse_kernel(const T* __restrict__ a, const float* __restrict__ b, int64_t n, float scale,
+           const float* __restrict__ scale_dev, float* __restrict__ sse, T* __restrict__ grad) {
+  __shared__ float s_red[EW_THREADS / 32];
+  float acc = 0.f;
+  if (scale_dev) scale *= scale_dev[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = sa_ld(a, i) - b[i];
+    acc = fmaf(d, d, acc);
+    if (grad) sa_st(grad, i, scale * d);
+  }
+  acc = sa_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && sse) {
+    float s = 0.f;
+    for (int i = 0; i < EW_THREADS / 32; ++i) s += s_red[i];
+    atomicAdd(sse, s);
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float beta1, float beta2, float eps, float step_size,
+                            float inv_sqrt_bc2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);          // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);     // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;              // (sqrt(v) / sqrt(bc2)) + eps
+    p[i] = p[i] - step_size * (mi / denom);                          // p.addcdiv_(m, denom, value=-lr / bc1)
+  }
+}
+
+}  // namespace
+
+extern "C" int sa_pack_weight(const float* src, int A, int B, int taps, int transpose, int flip, void* dst,
+                              int dst_dtype, void* stream) {
+  SA_CHECK_ARG(src && dst, "null pointer");
+  SA_CHECK_ARG(A > 0 && B > 0 && taps > 0, "bad sizes");
+  const int64_t n = (int64_t)A * B * taps;
+  if (dst_dtype == SA_BF16)
+    pack_weight_kernel<__nv_bfloat16><<<ew_grid(n), EW_THREADS, 0, sa_stream(stream)>>>(src, A, B, taps, transpose, flip,
+                                                                                       (__nv_bfloat16*)dst);
+  else
+    pack_weight_kernel<float><<<ew_grid(n), EW_THREADS, 0, sa_stream(stream)>>>(src, A, B, taps, transpose, flip,
+                                                                               (float*)dst);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_unpack_wgrad(const float* src, int A, int B, int taps, int transpose, int flip, float* dst,
+                               int accumulate, void* stream) {
+  SA_CHECK_ARG(src && dst, "null pointer");
+  SA_CHECK_ARG(A > 0 && B > 0 && taps > 0, "bad sizes");
+  const int64_t n = (int64_t)A * B * taps;
+  unpack_wgrad_kernel<<<ew_grid(n), EW_THREADS, 0, sa_stream(stream)>>>(src, A, B, taps, transpose, flip, dst,
+                                                                        accumulate);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_bias_grad(const void* dy, int64_t rows, int c, int dtype, float* db, int accumulate, void* stream) {
+  SA_CHECK_ARG(dy && db, "null pointer");
+  SA_CHECK_ARG(rows >= 0 && c > 0, "bad sizes");
+  cudaStream_t st = sa_stream(stream);
+  if (!accumulate) SA_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * c, st));
+  if (rows == 0) return SA_OK;
+  int64_t blocks = sa_cdiv(rows, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int64_t rpb = sa_cdiv(rows, blocks);
+  blocks = sa_cdiv(rows, rpb);
+  if (dtype == SA_BF16)
+    bias_grad_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, c, db, rpb);
+  else
+    bias_grad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, rows, c, db, rpb);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+template <typename TI, typename TO>
+static int launch_transpose(const void* src, void* dst, int64_t batch, int c, int64_t spatial, bool to_nhwc,
+                            cudaStream_t st) {
+  if (c == 1) {  // the two layouts coincide
+    cast_kernel<TI, TO><<<ew_grid(batch * spatial, 4), EW_THREADS, 0, st>>>((const TI*)src, (TO*)dst, batch * spatial);
+  } else {
+    dim3 grid((unsigned)sa_cdiv(spatial, 32), (unsigned)sa_cdiv(c, 32), (unsigned)batch);
+    transpose_cs_kernel<TI, TO><<<grid, dim3(32, 8), 0, st>>>((const TI*)src, (TO*)dst, c, spatial, to_nhwc);
+  }
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+static int dispatch_transpose(const void* src, int sdt, void* dst, int ddt, int64_t batch, int c, int64_t spatial,
+                              bool to_nhwc, void* stream) {
+  SA_CHECK_ARG(src && dst, "null pointer");
+  SA_CHECK_ARG(batch >= 0 && c > 0 && spatial >= 0, "bad sizes");
+  SA_UNSUPPORTED(batch > 65535, "batch > 65535");
+  if (batch == 0 || spatial == 0) return SA_OK;
+  cudaStream_t st = sa_stream(stream);
+  if (sdt == SA_F32 && ddt == SA_F32) return launch_transpose<float, float>(src, dst, batch, c, spatial, to_nhwc, st);
+  if (sdt == SA_F32 && ddt == SA_BF16)
+    return launch_transpose<float, __nv_bfloat16>(src, dst, batch, c, spatial, to_nhwc, st);
+  if (sdt == SA_BF16 && ddt == SA_F32)
+    return launch_transpose<__nv_bfloat16, float>(src, dst, batch, c, spatial, to_nhwc, st);
+  return launch_transpose<__nv_bfloat16, __nv_bfloat16>(src, dst, batch, c, spatial, to_nhwc, st);
+}
+
+extern "C" int sa_nchw_to_nhwc(const void* src, int sdt, void* dst, int ddt, int64_t batch, int c, int64_t spatial,
+                               void* stream) {
+  return dispatch_transpose(src, sdt, dst, ddt, batch, c, spatial, true, stream);
+}
+extern "C" int sa_nhwc_to_nchw(const void* src, int sdt, void* dst, int ddt, int64_t batch, int c, int64_t spatial,
+                               void* stream) {
+  return dispatch_transpose(src, sdt, dst, ddt, batch, c, spatial, false, stream);
+}
+
+extern "C" int sa_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* stream) {
+  SA_CHECK_ARG(src && dst && n >= 0, "bad arguments");
+  if (n == 0) return SA_OK;
+  cudaStream_t st = sa_stream(stream);
+  const unsigned g = ew_grid(n, 4);
+  if (sdt == SA_F32 && ddt == SA_F32) cast_kernel<float, float><<<g, EW_THREADS, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (sdt == SA_F32) cast_kernel<float, __nv_bfloat16><<<g, EW_THREADS, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (ddt == SA_F32) cast_kernel<__nv_bfloat16, float><<<g, EW_THREADS, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, EW_THREADS, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_mse_fwd_bwd(const void* a, int a_dtype, const float* b, int64_t n, float scale,
+                              const float* scale_dev, float* sse, void* grad, void* stream) {
+  SA_CHECK_ARG(a && b && n >= 0, "bad arguments");
+  if (n == 0) return SA_OK;
+  cudaStream_t st = sa_stream(stream);
+  const unsigned g = ew_grid(n, 8);
+  if (a_dtype == SA_BF16)
+    mse_kernel<__nv_bfloat16><<<g, EW_THREADS, 0, st>>>((const __nv_bfloat16*)a, b, n, scale, scale_dev, sse,
+                                                        (__nv_bfloat16*)grad);
+  else
+    mse_kernel<float><<<g, EW_THREADS, 0, st>>>((const float*)a, b, n, scale, scale_dev, sse, (float*)grad);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                            float beta2, float eps, int step, void* stream) {
+  SA_CHECK_ARG(p && g && m && v && n >= 0 && step >= 1, "bad arguments");
+  if (n == 0) return SA_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<ew_grid(n, 4), EW_THREADS, 0, sa_stream(stream)>>>(p, g, m, v, n, beta1, beta2, eps,
+                                                                   (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)));
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}

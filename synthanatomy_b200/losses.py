@@ -1,0 +1,55 @@
+"""Losses on the hot path: mirror of the reference's ``MSELoss`` for the VQ-VAE
+(/root/reference/src/losses/vqvae/vqvae.py:14-71): ``mse(reconstruction, y) + sum(quantization_losses)``."""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+from torch.nn.modules.loss import _Loss
+
+from . import ops
+
+
+class _MSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        p = pred.detach().float().contiguous()
+        t = target.detach().float().contiguous()
+        sse = torch.zeros((), device=p.device, dtype=torch.float32)
+        ops.mse_fwd_bwd(p, t, sse, None, 1.0)
+        ctx.save_for_backward(p, t)
+        return sse / p.numel()
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t = ctx.saved_tensors
+        grad = torch.empty_like(p)
+        ops.mse_fwd_bwd(p, t, None, grad, 2.0 / p.numel(), g.float().contiguous())
+        return grad, None
+
+
+def mse_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """F.mse_loss(pred, target) (mean reduction) through the library's fused kernel."""
+    return _MSEFn.apply(pred, target)
+
+
+class MSELoss(_Loss):
+    def __init__(self, size_average: bool = None, reduce: bool = None, reduction: str = "mean"):
+        super().__init__(size_average, reduce, reduction)
+        if reduction not in ("sum", "mean"):
+            raise ValueError("Reduction must be either 'sum' or 'mean'")
+        self.summaries: Dict = {"scalar": dict()}
+
+    def forward(self, network_output: Dict[str, List[torch.Tensor]], y: torch.Tensor) -> torch.Tensor:
+        y_pred = network_output["reconstruction"][0]
+        q_losses = network_output["quantization_losses"]
+        loss = mse_loss(y_pred, y)     # the reference ignores `reduction` here as well (F.mse_loss default)
+        self.summaries["scalar"]["Loss-MSE-Reconstruction"] = loss
+        for idx, q_loss in enumerate(q_losses):
+            q_loss = q_loss.float()
+            self.summaries["scalar"][f"Loss-MSE-VQ{idx}_Commitment_Cost"] = q_loss
+            loss = loss + q_loss
+        return loss
+
+    def get_summaries(self) -> Dict[str, torch.Tensor]:
+        return self.summaries

@@ -1,0 +1,278 @@
+"""Tensor-level wrappers over the C ABI (include/synthanatomy_b200.h).
+
+PyTorch is used here only as plumbing: device memory (caching allocator), the current CUDA stream and
+dtype bookkeeping.  All arithmetic happens inside libsynthanatomy_b200.so.  Every function raises if the
+tensors are not CUDA tensors -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import SA_BF16, SA_F32, ConvDesc
+
+
+def lib():
+    return _lib.load()
+
+
+def _dt(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return SA_F32
+    if dtype == torch.bfloat16:
+        return SA_BF16
+    raise TypeError(f"synthanatomy_b200: unsupported dtype {dtype} (float32 / bfloat16 only)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
+    if not t.is_contiguous():
+        raise RuntimeError("synthanatomy_b200: tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(lib().sa_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().sa_launch_count_reset()
+
+
+def last_path() -> int:
+    return int(lib().sa_last_path())
+
+
+def set_force_simt(on: bool) -> None:
+    lib().sa_set_force_simt(1 if on else 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# conv geometry
+# ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ConvSpec:
+    """One nn.Conv3d (kind='conv') or nn.ConvTranspose3d (kind='deconv') of the reference
+    (src/networks/vqvae/baseline.py:153-156, 218-227, 242-244, 258, 283-293); cubic kernel, dilation 1."""
+    kind: str
+    cin: int
+    cout: int
+    k: int
+    s: int
+    p: int
+
+    def out_dhw(self, in_dhw: Sequence[int]) -> Tuple[int, int, int]:
+        if self.kind == "conv":
+            return tuple((i + 2 * self.p - self.k) // self.s + 1 for i in in_dhw)
+        return tuple((i - 1) * self.s - 2 * self.p + self.k for i in in_dhw)
+
+
+def _desc(batch, in_dhw, out_dhw, c_in, c_out, k, s, p, transposed, dtype) -> ConvDesc:
+    d = ConvDesc()
+    d.batch = batch
+    for i in range(3):
+        d.in_dhw[i] = in_dhw[i]
+        d.out_dhw[i] = out_dhw[i]
+    d.c_in, d.c_out, d.ksize, d.stride, d.pad = c_in, c_out, k, s, p
+    d.transposed = transposed
+    d.act_dtype = _dt(dtype)
+    return d
+
+
+def pack_weight(w: torch.Tensor, transpose: bool, dtype: torch.dtype, flip: bool = False) -> torch.Tensor:
+    """torch layout [A][B][k,k,k] fp32 -> packed [taps][A][B] (or [taps][B][A] if transpose) in `dtype`."""
+    A, B = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    R, Cc = (B, A) if transpose else (A, B)
+    out = torch.empty((taps, R, Cc), device=w.device, dtype=dtype)
+    _lib.check(lib().sa_pack_weight(_p(w), A, B, taps, int(transpose), int(flip), _p(out), _dt(dtype), _stream()),
+               "sa_pack_weight")
+    return out
+
+
+def unpack_wgrad(dwp: torch.Tensor, like: torch.Tensor, transpose: bool, flip: bool = False) -> torch.Tensor:
+    """packed fp32 [taps][..][..] -> torch layout gradient shaped like `like`."""
+    A, B = like.shape[0], like.shape[1]
+    taps = like[0, 0].numel()
+    out = torch.empty_like(like, dtype=torch.float32)
+    _lib.check(lib().sa_unpack_wgrad(_p(dwp), A, B, taps, int(transpose), int(flip), _p(out), 0, _stream()),
+               "sa_unpack_wgrad")
+    return out
+
+
+class ConvTimer:
+    """Optional per-launch CUDA-event timing of sa_conv3d_fwd calls whose descriptor matches `match`
+    (bench.py uses it to time the dominant kernel inside the timed region, on the launching stream)."""
+
+    def __init__(self, match):
+        self.match = match
+        self.events = []
+
+    def elapsed_ms(self):
+        return [a.elapsed_time(b) for a, b in self.events]
+
+
+_TIMER: Optional[ConvTimer] = None
+
+
+def set_conv_timer(timer: Optional[ConvTimer]) -> None:
+    global _TIMER
+    _TIMER = timer
+
+
+def _run_fwd(d: ConvDesc, x, wp, bias, addend, mask, relu, out_shape):
+    y = torch.empty(out_shape, device=x.device, dtype=x.dtype)
+    timed = _TIMER is not None and _TIMER.match(d)
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(lib().sa_conv3d_fwd(C.byref(d), _p(x), _p(wp), _p(bias), _p(addend), _p(mask), int(relu), _p(y),
+                                   _stream()), "sa_conv3d_fwd")
+    if timed:
+        e1.record()
+        _TIMER.events.append((e0, e1))
+    return y
+
+
+def conv_forward(spec: ConvSpec, x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor],
+                 addend: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """x: NDHWC [B, D, H, W, cin]; wp: pack_weight(weight, transpose=(kind == 'deconv')).
+    Returns act( conv(x) + bias (+ addend) ) as NDHWC [B, oD, oH, oW, cout]."""
+    B, in_dhw = x.shape[0], tuple(x.shape[1:4])
+    assert x.shape[4] == spec.cin, (x.shape, spec)
+    out_dhw = spec.out_dhw(in_dhw)
+    d = _desc(B, in_dhw, out_dhw, spec.cin, spec.cout, spec.k, spec.s, spec.p, int(spec.kind == "deconv"), x.dtype)
+    return _run_fwd(d, x, wp, bias, addend, None, relu, (B, *out_dhw, spec.cout))
+
+
+def conv_dgrad(spec: ConvSpec, dy: torch.Tensor, wp_t: torch.Tensor, in_dhw: Sequence[int],
+               addend: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Data gradient: dx = (dgrad(dy) (+ addend)) * (mask > 0).
+    wp_t: pack_weight(weight, transpose=(kind == 'conv'))  -- the opposite packing of the forward."""
+    B, out_dhw = dy.shape[0], tuple(dy.shape[1:4])
+    assert dy.shape[4] == spec.cout
+    # the dgrad of FORM_CONV is FORM_TCONV over dy and vice versa; X of the primitive is dy
+    d = _desc(B, out_dhw, tuple(in_dhw), spec.cout, spec.cin, spec.k, spec.s, spec.p, int(spec.kind == "conv"), dy.dtype)
+    return _run_fwd(d, dy, wp_t, None, addend, mask, False, (B, *in_dhw, spec.cin))
+
+
+def conv_wgrad(spec: ConvSpec, x: torch.Tensor, dy: torch.Tensor, weight_like: torch.Tensor) -> torch.Tensor:
+    """Weight gradient in the torch layout of `weight_like` (fp32)."""
+    B = x.shape[0]
+    in_dhw, out_dhw = tuple(x.shape[1:4]), tuple(dy.shape[1:4])
+    taps = spec.k ** 3
+    if spec.kind == "conv":
+        d = _desc(B, in_dhw, out_dhw, spec.cin, spec.cout, spec.k, spec.s, spec.p, 0, x.dtype)
+        pp, qq = dy, x
+    else:  # the strided gather runs over dy; P = x
+        d = _desc(B, out_dhw, in_dhw, spec.cout, spec.cin, spec.k, spec.s, spec.p, 0, x.dtype)
+        pp, qq = x, dy
+    dwp = torch.empty((taps, d.c_out, d.c_in), device=x.device, dtype=torch.float32)
+    _lib.check(lib().sa_conv3d_wgrad(C.byref(d), _p(pp), _p(qq), _p(dwp), 0, _stream()), "sa_conv3d_wgrad")
+    return unpack_wgrad(dwp, weight_like, transpose=False)
+
+
+def bias_grad(dy: torch.Tensor) -> torch.Tensor:
+    c = dy.shape[-1]
+    rows = dy.numel() // c
+    db = torch.empty((c,), device=dy.device, dtype=torch.float32)
+    _lib.check(lib().sa_bias_grad(_p(dy), rows, c, _dt(dy.dtype), _p(db), 0, _stream()), "sa_bias_grad")
+    return db
+
+
+# ------------------------------------------------------------------------------------------------
+# layout
+# ------------------------------------------------------------------------------------------------
+def ncdhw_to_ndhwc(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    B, Cc = x.shape[0], x.shape[1]
+    sp = tuple(x.shape[2:])
+    S = 1
+    for v in sp:
+        S *= v
+    out = torch.empty((B, *sp, Cc), device=x.device, dtype=dtype)
+    _lib.check(lib().sa_nchw_to_nhwc(_p(x), _dt(x.dtype), _p(out), _dt(dtype), B, Cc, S, _stream()), "sa_nchw_to_nhwc")
+    return out
+
+
+def ndhwc_to_ncdhw(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    B, Cc = x.shape[0], x.shape[-1]
+    sp = tuple(x.shape[1:-1])
+    S = 1
+    for v in sp:
+        S *= v
+    out = torch.empty((B, Cc, *sp), device=x.device, dtype=dtype)
+    _lib.check(lib().sa_nhwc_to_nchw(_p(x), _dt(x.dtype), _p(out), _dt(dtype), B, Cc, S, _stream()), "sa_nhwc_to_nchw")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# vector quantiser
+# ------------------------------------------------------------------------------------------------
+def vq_forward(z_flat: torch.Tensor, codebook: torch.Tensor, stats: Optional[torch.Tensor], straight_through: bool):
+    """z_flat [rows, dim] fp32, codebook [K, dim] fp32.  stats: zeroed fp32 [K + K*dim + 1] receiving
+    (counts | dw | sse), or None.  Returns (idx int64 [rows], q [rows, dim])."""
+    rows, dim = z_flat.shape
+    K = codebook.shape[0]
+    idx = torch.empty((rows,), device=z_flat.device, dtype=torch.int64)
+    q = torch.empty_like(z_flat)
+    counts = dw = sse = None
+    if stats is not None:
+        assert stats.numel() == K + K * dim + 1 and stats.dtype == torch.float32
+        base = stats.data_ptr()
+        counts, dw, sse = C.c_void_p(base), C.c_void_p(base + 4 * K), C.c_void_p(base + 4 * (K + K * dim))
+    _lib.check(lib().sa_vq_forward(_p(z_flat), _p(codebook), rows, dim, K, _p(idx), _p(q), int(straight_through), counts,
+                                   dw, sse, _stream()), "sa_vq_forward")
+    return idx, q
+
+
+def vq_ema_update(N, embed_avg, codebook, stats, decay: float, eps: float) -> None:
+    K, dim = codebook.shape
+    base = stats.data_ptr()
+    _lib.check(lib().sa_vq_ema_update(_p(N), _p(embed_avg), _p(codebook), C.c_void_p(base), C.c_void_p(base + 4 * K), K,
+                                      dim, float(decay), float(eps), None, _stream()), "sa_vq_ema_update")
+
+
+def vq_perplexity(counts: torch.Tensor, total: int) -> torch.Tensor:
+    out = torch.empty((), device=counts.device, dtype=torch.float32)
+    _lib.check(lib().sa_vq_perplexity(_p(counts), counts.numel(), float(total), _p(out), _stream()), "sa_vq_perplexity")
+    return out
+
+
+def vq_embed(idx: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
+    K, dim = codebook.shape
+    rows = idx.numel()
+    q = torch.empty((rows, dim), device=codebook.device, dtype=torch.float32)
+    _lib.check(lib().sa_vq_embed(_p(idx), _p(codebook), rows, dim, K, _p(q), _stream()), "sa_vq_embed")
+    return q
+
+
+def vq_backward(g_q, g_loss, z, q, coef: float) -> torch.Tensor:
+    dz = torch.empty_like(z)
+    _lib.check(lib().sa_vq_backward(_p(g_q), _p(g_loss), _p(z), _p(q), float(coef), z.numel(), _p(dz), _stream()),
+               "sa_vq_backward")
+    return dz
+
+
+# ------------------------------------------------------------------------------------------------
+# losses / optimiser
+# ------------------------------------------------------------------------------------------------
+def mse_fwd_bwd(pred: torch.Tensor, target: torch.Tensor, sse: Optional[torch.Tensor], grad: Optional[torch.Tensor],
+                scale: float, scale_dev: Optional[torch.Tensor] = None) -> None:
+    _lib.check(lib().sa_mse_fwd_bwd(_p(pred), _dt(pred.dtype), _p(target), pred.numel(), float(scale), _p(scale_dev),
+                                    _p(sse), _p(grad), _stream()), "sa_mse_fwd_bwd")
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step) -> None:
+    _lib.check(lib().sa_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
+                                  float(eps), int(step), _stream()), "sa_adam_step")
