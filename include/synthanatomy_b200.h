@@ -94,6 +94,17 @@ int sa_pack_weight(const float* src, int A, int B, int taps, int transpose, int 
 int sa_unpack_wgrad(const float* src, int A, int B, int taps, int transpose, int flip, float* dst,
                     int accumulate, void* stream);
 
+/* Single-channel helpers that turn the two 1-channel layers (first Conv3d 1->C, baseline.py:218-227, and the last
+ * ConvTranspose3d C->1, baseline.py:283-293) into 1x1x1 gather-GEMMs over a k^3-"channel" tensor:
+ *   sa_im2col_c1:  cols[b, o, t] = x[b, o*stride - pad + t]              (x: [B, in_dhw], cols: [B, out_dhw, k^3])
+ *   sa_col2im_c1:  y[b, o] = bias[0] + sum_{t: (o+pad-t) % stride == 0} cols[b, (o+pad-t)/stride, t]
+ *                                                                        (cols: [B, in_dhw, k^3], y: [B, out_dhw])
+ * dtype is the sa_dtype of x / cols / y. */
+int sa_im2col_c1(const void* x, int dtype, int batch, const int* in_dhw, const int* out_dhw, int ksize, int stride,
+                 int pad, void* cols, void* stream);
+int sa_col2im_c1(const void* cols, int dtype, int batch, const int* in_dhw, const int* out_dhw, int ksize, int stride,
+                 int pad, const float* bias, void* y, void* stream);
+
 /* db[c] (+)= sum_rows dy[row][c]   (bias gradient of every conv above) */
 int sa_bias_grad(const void* dy, int64_t rows, int c, int dtype, float* db, int accumulate, void* stream);
 

@@ -50,6 +50,10 @@ SIGNATURES = {
     "sa_conv3d_wgrad": (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sa_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "sa_unpack_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "sa_im2col_c1": (c_int, [c_void_p, c_int, c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), c_int, c_int, c_int, c_void_p,
+                             c_void_p]),
+    "sa_col2im_c1": (c_int, [c_void_p, c_int, c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), c_int, c_int, c_int, c_void_p,
+                             c_void_p, c_void_p]),
     "sa_bias_grad": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
     "sa_vq_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                               c_void_p, c_void_p]),

@@ -142,6 +142,65 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// cols[b, o, t] = x[b, o*s - p + t]  (single-channel x), t = (td*k + th)*k + tw.  One thread per (o, td, th):
+// the k taps along w are contiguous in x and in cols, a position's k^3 taps form one contiguous row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_c1_kernel(const T* __restrict__ x, int B, int iD, int iH, int iW, int oD, int oH, int oW, int k, int s, int p,
+                 T* __restrict__ cols) {
+  const int kk = k * k;
+  const int64_t total = (int64_t)B * oD * oH * oW * kk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int j = (int)(r % kk); r /= kk;
+    const int ow = (int)(r % oW); r /= oW;
+    const int oh = (int)(r % oH); r /= oH;
+    const int od = (int)(r % oD); r /= oD;
+    const int b = (int)r;
+    const int th = j % k, td = j / k;
+    const int id = od * s - p + td, ih = oh * s - p + th;
+    const bool row_ok = id >= 0 && id < iD && ih >= 0 && ih < iH;
+    const T* xr = x + (((int64_t)b * iD + id) * iH + ih) * iW;
+    T* cr = cols + i * k;
+    const T zero = T(0.f);
+    for (int tw = 0; tw < k; ++tw) {
+      const int iw = ow * s - p + tw;
+      cr[tw] = (row_ok && iw >= 0 && iw < iW) ? xr[iw] : zero;
+    }
+  }
+}
+
+// y[b, o] = bias + sum_{t : (o + p - t) % s == 0} cols[b, (o + p - t)/s, t]   (single-channel y)
+template <typename T>
+__global__ void __launch_bounds__(256)
+col2im_c1_kernel(const T* __restrict__ cols, int B, int iD, int iH, int iW, int oD, int oH, int oW, int k, int s, int p,
+                 const float* __restrict__ bias, T* __restrict__ y) {
+  // block = 32 (w) x 4 (h) x 2 (d) output brick so that neighbouring voxels re-use the cols rows through L1
+  const int ow = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int oh = blockIdx.y * 4 + ((threadIdx.x >> 5) & 3);
+  const int odb = blockIdx.z * 2 + (threadIdx.x >> 7);
+  const int nd = (oD + 1) / 2;
+  const int b = odb / (nd * 2), od = odb % (nd * 2);
+  if (b >= B || od >= oD || oh >= oH || ow >= oW) return;
+  const int taps = k * k * k;
+  float acc = bias ? bias[0] : 0.f;
+  for (int td = (od + p) % s; td < k; td += s) {
+    const int id = (od + p - td) / s;
+    if (od + p - td < 0 || id >= iD) continue;
+    for (int th = (oh + p) % s; th < k; th += s) {
+      const int ih = (oh + p - th) / s;
+      if (oh + p - th < 0 || ih >= iH) continue;
+      for (int tw = (ow + p) % s; tw < k; tw += s) {
+        const int iw = (ow + p - tw) / s;
+        if (ow + p - tw < 0 || iw >= iW) continue;
+        const int64_t ip = (((int64_t)b * iD + id) * iH + ih) * iW + iw;
+        acc += sa_ld(cols, ip * taps + (td * k + th) * k + tw);
+      }
+    }
+  }
+  sa_st(y, (((int64_t)b * oD + od) * oH + oh) * oW + ow, acc);
+}
+
 }  // namespace
 
 extern "C" int sa_pack_weight(const float* src, int A, int B, int taps, int transpose, int flip, void* dst,
@@ -261,6 +320,41 @@ extern "C" int sa_adam_step(float* p, const float* g, float* m, float* v, int64_
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<ew_grid(n, 4), EW_THREADS, 0, sa_stream(stream)>>>(p, g, m, v, n, beta1, beta2, eps,
                                                                    (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)));
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_im2col_c1(const void* x, int dtype, int batch, const int* in_dhw, const int* out_dhw, int k, int s,
+                            int p, void* cols, void* stream) {
+  SA_CHECK_ARG(x && cols && in_dhw && out_dhw && batch > 0 && k > 0 && s > 0 && p >= 0, "bad arguments");
+  const int64_t total = (int64_t)batch * out_dhw[0] * out_dhw[1] * out_dhw[2] * k * k;
+  cudaStream_t st = sa_stream(stream);
+  if (dtype == SA_BF16)
+    im2col_c1_kernel<__nv_bfloat16><<<ew_grid(total), EW_THREADS, 0, st>>>(
+        (const __nv_bfloat16*)x, batch, in_dhw[0], in_dhw[1], in_dhw[2], out_dhw[0], out_dhw[1], out_dhw[2], k, s, p,
+        (__nv_bfloat16*)cols);
+  else
+    im2col_c1_kernel<float><<<ew_grid(total), EW_THREADS, 0, st>>>((const float*)x, batch, in_dhw[0], in_dhw[1],
+                                                                   in_dhw[2], out_dhw[0], out_dhw[1], out_dhw[2], k, s,
+                                                                   p, (float*)cols);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_col2im_c1(const void* cols, int dtype, int batch, const int* in_dhw, const int* out_dhw, int k, int s,
+                            int p, const float* bias, void* y, void* stream) {
+  SA_CHECK_ARG(cols && y && in_dhw && out_dhw && batch > 0 && k > 0 && s > 0 && p >= 0, "bad arguments");
+  cudaStream_t st = sa_stream(stream);
+  const int nd = (out_dhw[0] + 1) / 2;
+  dim3 grid((unsigned)sa_cdiv(out_dhw[2], 32), (unsigned)sa_cdiv(out_dhw[1], 4), (unsigned)(nd * batch));
+  SA_UNSUPPORTED(grid.y > 65535 || grid.z > 65535, "volume too large for the col2im grid");
+  if (dtype == SA_BF16)
+    col2im_c1_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)cols, batch, in_dhw[0], in_dhw[1],
+                                                          in_dhw[2], out_dhw[0], out_dhw[1], out_dhw[2], k, s, p, bias,
+                                                          (__nv_bfloat16*)y);
+  else
+    col2im_c1_kernel<float><<<grid, 256, 0, st>>>((const float*)cols, batch, in_dhw[0], in_dhw[1], in_dhw[2], out_dhw[0],
+                                                  out_dhw[1], out_dhw[2], k, s, p, bias, (float*)y);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

@@ -19,6 +19,7 @@
 // Reference call sites replaced: cuDNN conv fprop / dgrad behind nn.Conv3d / nn.ConvTranspose3d,
 // src/networks/vqvae/baseline.py:153-160, 218-228, 242-244, 258, 283-297.
 #include <mutex>
+#include <stdlib.h>
 
 #include "sa_tc_common.cuh"
 
@@ -212,15 +213,18 @@ tc_conv_kernel(const __grid_constant__ TcConvParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------- host
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
 bool choose_tile(int gD, int gH, int gW, int* td, int* th, int* tw) {
-  // powers of two with td*th*tw == 128 and each t_i <= G_i; minimise padded volume, then prefer wide tw
+  // powers of two with td*th*tw == 128 and each t_i <= pow2_ceil(G_i) (a box may overhang the tensor: TMA zero-fills
+  // and the epilogue masks); minimise padded volume, then prefer wide tw
   int64_t best = -1; int bd = 0, bh = 0, bw = 0;
   for (int w = 1; w <= 128; w <<= 1) {
-    if (w > gW) break;
+    if (w > pow2_ceil(gW)) break;
     for (int h = 1; h * w <= 128; h <<= 1) {
-      if (h > gH) break;
+      if (h > pow2_ceil(gH)) break;
       const int d = 128 / (w * h);
-      if (d > gD) continue;
+      if (d > pow2_ceil(gD)) continue;
       const int64_t vol = sa_cdiv(gD, d) * d * sa_cdiv(gH, h) * h * sa_cdiv(gW, w) * w;
       if (best < 0 || vol < best || (vol == best && w > bw)) { best = vol; bd = d; bh = h; bw = w; }
     }
@@ -245,6 +249,10 @@ int launch(TcConvParams& P, int batch, cudaStream_t st) {
   const size_t budget = (size_t)g_max_smem - 1024 /*static*/ - 1024 /*align*/;
   int stages = (int)(budget / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (const char* e = getenv("SA_TC_MAX_STAGES")) {   // tuning knob: fewer stages => more co-resident CTAs per SM
+    const int v = atoi(e);
+    if (v >= 1 && v < stages) stages = v;
+  }
   const int iters = P.ntaps * P.cchunks;
   if (stages > iters) stages = iters;
   if (stages < 1) { sa_set_error("tc_conv: stage does not fit shared memory"); return SA_ERR_UNSUPPORTED; }

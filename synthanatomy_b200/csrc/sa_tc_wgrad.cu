@@ -37,7 +37,7 @@ struct WgParams {
   int ntaps, tpg, ngroups;     // taps, taps per group, groups
   int Cn, Cc;                  // channels of P (n) and Q (c)
   int nhalves, cblocks;        // Cn / 128, Cc / 64
-  int stages, variant;
+  int stages;
   int td, th, tw, ntd, nth, ntw;
   int64_t tiles_total, tiles_per_split;
   float* dwp;
@@ -113,8 +113,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams P) {
     if (lane == 0 && ntiles > 0) {
       const uint32_t idesc = make_idesc_bf16(128, P.Cc, 1, 1);   // both operands MN-major
       // MN-major SWIZZLE_128B: 64-channel blocks `lbo` apart, 8-position groups `sbo` apart
-      uint32_t lbo = WG_BLOCK_BYTES, sbo = 1024;
-      if (P.variant & 1) { const uint32_t x = lbo; lbo = sbo; sbo = x; }
+      const uint32_t lbo = WG_BLOCK_BYTES, sbo = 1024;
       int stage = 0; uint32_t phase = 0;
       for (int64_t tl = 0; tl < ntiles; ++tl) {
         mbar_wait(&full_bar[stage], phase);
@@ -156,14 +155,16 @@ tc_wgrad_kernel(const __grid_constant__ WgParams P) {
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
 bool choose_tile32(int gD, int gH, int gW, int* td, int* th, int* tw) {
   int64_t best = -1; int bd = 0, bh = 0, bw = 0;
   for (int w = 1; w <= WG_KP; w <<= 1) {
-    if (w > gW) break;
+    if (w > pow2_ceil(gW)) break;
     for (int h = 1; h * w <= WG_KP; h <<= 1) {
-      if (h > gH) break;
+      if (h > pow2_ceil(gH)) break;
       const int d = WG_KP / (w * h);
-      if (d > gD) continue;
+      if (d > pow2_ceil(gD)) continue;
       const int64_t vol = sa_cdiv(gD, d) * d * sa_cdiv(gH, h) * h * sa_cdiv(gW, w) * w;
       if (best < 0 || vol < best || (vol == best && w > bw)) { best = vol; bd = d; bh = h; bw = w; }
     }
@@ -175,7 +176,6 @@ bool choose_tile32(int gD, int gH, int gW, int* td, int* th, int* tw) {
 
 std::once_flag g_once;
 int g_max_smem = 0;
-int g_variant = 0;
 
 int make_map(CUtensorMap* m, const void* base, int C, int D, int H, int W, int B, int sub, int pd, int ph, int pw, int td,
              int th, int tw) {
@@ -215,8 +215,6 @@ int sa_tc_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void* q, floa
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 1024);
-    const char* v = getenv("SA_WGRAD_VARIANT");
-    g_variant = v ? atoi(v) : 0;
   });
   const int k = d->ksize, s = d->stride, pad = d->pad;
   const int iD = d->in_dhw[0], iH = d->in_dhw[1], iW = d->in_dhw[2];
@@ -229,7 +227,6 @@ int sa_tc_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void* q, floa
   P.tpg = 512 / d->c_in;
   if (P.tpg > P.ntaps) P.tpg = P.ntaps;
   P.ngroups = (int)sa_cdiv(P.ntaps, P.tpg);
-  P.variant = g_variant;
   P.dwp = dwp;
   choose_tile32(oD, oH, oW, &P.td, &P.th, &P.tw);
   P.ntd = (int)sa_cdiv(oD, P.td); P.nth = (int)sa_cdiv(oH, P.th); P.ntw = (int)sa_cdiv(oW, P.tw);
@@ -265,8 +262,9 @@ int sa_tc_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void* q, floa
   if (stages < 2) { sa_set_error("tc_wgrad: stage does not fit shared memory"); return SA_ERR_UNSUPPORTED; }
   P.stages = stages;
 
+  // one CTA per SM is resident (the stages fill shared memory): size the grid to at most 2 full waves of 148
   const int64_t base_ctas = (int64_t)P.ngroups * P.nhalves;
-  int64_t splits = sa_cdiv(148 * 2, base_ctas);
+  int64_t splits = (148 * 2) / base_ctas;
   const int64_t max_splits = sa_cdiv(P.tiles_total, 8);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -65,6 +65,16 @@ class _ConvOp:
     def params(self):
         return [self.module.weight, self.module.bias]
 
+    def single_channel_gemm(self, dt: torch.dtype) -> bool:
+        """bf16 path only: the 1-channel ends of the network (first Conv3d 1->C, last ConvTranspose3d C->1) run as
+        im2col / col2im + a 1x1x1 tensor-core GEMM over the k^3 = 64 taps."""
+        sp = self.spec
+        if dt != torch.bfloat16 or sp.k ** 3 != 64:
+            return False
+        if sp.kind == "conv":
+            return sp.cin == 1 and sp.cout % 16 == 0
+        return sp.cout == 1 and sp.cin % 64 == 0 and not self.relu
+
 
 class _ResOp:
     def __init__(self, layer: ResidualLayer):
@@ -85,9 +95,23 @@ def _stack_forward(ops_list, x: torch.Tensor, params: Sequence[torch.Tensor], sa
         if isinstance(op, _ConvOp):
             w, b = params[pi], params[pi + 1]
             pi += 2
-            wp = ops.pack_weight(w, transpose=(op.spec.kind == "deconv"), dtype=dt)
-            y = ops.conv_forward(op.spec, x, wp, b, None, op.relu)
-            saved.append((x,) if save else None)
+            sp = op.spec
+            if op.single_channel_gemm(dt):
+                taps = sp.k ** 3
+                if sp.kind == "conv":      # cols[pos][t] . w[n][t]
+                    cols = ops.im2col_c1(x, sp.k, sp.s, sp.p, sp.out_dhw(x.shape[1:4]))
+                    wp = ops.pack_weight(w.view(sp.cout, taps, 1), False, dt)
+                    y = ops.conv_forward(ConvSpec("conv", taps, sp.cout, 1, 1, 0), cols, wp, b, None, op.relu)
+                    saved.append((x, cols) if save else None)
+                else:                      # r[pos][t] = x[pos] . wt[:, t];  y = col2im(r) + b
+                    wp = ops.pack_weight(w.view(sp.cin, taps, 1), True, dt)
+                    r = ops.conv_forward(ConvSpec("conv", sp.cin, taps, 1, 1, 0), x, wp, None, None, False)
+                    y = ops.col2im_c1(r, sp.k, sp.s, sp.p, sp.out_dhw(x.shape[1:4]), b)
+                    saved.append((x,) if save else None)
+            else:
+                wp = ops.pack_weight(w, transpose=(sp.kind == "deconv"), dtype=dt)
+                y = ops.conv_forward(sp, x, wp, b, None, op.relu)
+                saved.append((x,) if save else None)
             x = y
         else:
             w3, b3, w1, b1 = params[pi:pi + 4]
@@ -125,7 +149,29 @@ def _stack_backward(ops_list, saved, params, g, in_is_relu: bool, need_dx: bool)
         o = offs[i]
         first = i == 0
         want_dx = need_dx or not first
-        if isinstance(op, _ConvOp):
+        if isinstance(op, _ConvOp) and op.single_channel_gemm(g.dtype):
+            sp = op.spec
+            taps = sp.k ** 3
+            w = params[o]
+            grads[o + 1] = ops.bias_grad(g)
+            if sp.kind == "conv":
+                x, cols = saved[i]
+                if want_dx:
+                    raise RuntimeError("synthanatomy_b200: data gradient of a 1-channel input conv is not implemented")
+                gemm = ConvSpec("conv", taps, sp.cout, 1, 1, 0)
+                grads[o] = ops.conv_wgrad(gemm, cols, g, w.view(sp.cout, taps, 1)).view_as(w)
+                g = None
+            else:
+                (x,) = saved[i]
+                cols = ops.im2col_c1(g, sp.k, sp.s, sp.p, x.shape[1:4])          # cols[i][t] = g[i*s - p + t]
+                gemm = ConvSpec("conv", taps, sp.cin, 1, 1, 0)                   # "input" cols, "output" x-shaped
+                grads[o] = ops.conv_wgrad(gemm, cols, x, w.view(sp.cin, taps, 1)).view_as(w)
+                if want_dx:
+                    wp = ops.pack_weight(w.view(sp.cin, taps, 1), False, g.dtype)
+                    g = ops.conv_forward(gemm, cols, wp, None, None, False, x if relu_in[i] else None)
+                else:
+                    g = None
+        elif isinstance(op, _ConvOp):
             (x,) = saved[i]
             w = params[o]
             grads[o] = ops.conv_wgrad(op.spec, x, g, w)

@@ -146,14 +146,15 @@ def _run_fwd(d: ConvDesc, x, wp, bias, addend, mask, relu, out_shape):
 
 
 def conv_forward(spec: ConvSpec, x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor],
-                 addend: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+                 addend: Optional[torch.Tensor] = None, relu: bool = False,
+                 mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: NDHWC [B, D, H, W, cin]; wp: pack_weight(weight, transpose=(kind == 'deconv')).
     Returns act( conv(x) + bias (+ addend) ) as NDHWC [B, oD, oH, oW, cout]."""
     B, in_dhw = x.shape[0], tuple(x.shape[1:4])
     assert x.shape[4] == spec.cin, (x.shape, spec)
     out_dhw = spec.out_dhw(in_dhw)
     d = _desc(B, in_dhw, out_dhw, spec.cin, spec.cout, spec.k, spec.s, spec.p, int(spec.kind == "deconv"), x.dtype)
-    return _run_fwd(d, x, wp, bias, addend, None, relu, (B, *out_dhw, spec.cout))
+    return _run_fwd(d, x, wp, bias, addend, mask, relu, (B, *out_dhw, spec.cout))
 
 
 def conv_dgrad(spec: ConvSpec, dy: torch.Tensor, wp_t: torch.Tensor, in_dhw: Sequence[int],
@@ -181,6 +182,31 @@ def conv_wgrad(spec: ConvSpec, x: torch.Tensor, dy: torch.Tensor, weight_like: t
     dwp = torch.empty((taps, d.c_out, d.c_in), device=x.device, dtype=torch.float32)
     _lib.check(lib().sa_conv3d_wgrad(C.byref(d), _p(pp), _p(qq), _p(dwp), 0, _stream()), "sa_conv3d_wgrad")
     return unpack_wgrad(dwp, weight_like, transpose=False)
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(a) for a in v])
+
+
+def im2col_c1(x: torch.Tensor, k: int, s: int, p: int, out_dhw: Sequence[int]) -> torch.Tensor:
+    """x: [B, D, H, W, 1] -> cols [B, oD, oH, oW, k^3] with cols[b, o, t] = x[b, o*s - p + t]."""
+    assert x.shape[-1] == 1
+    B, in_dhw = x.shape[0], tuple(x.shape[1:4])
+    cols = torch.empty((B, *out_dhw, k ** 3), device=x.device, dtype=x.dtype)
+    _lib.check(lib().sa_im2col_c1(_p(x), _dt(x.dtype), B, _i3(in_dhw), _i3(out_dhw), k, s, p, _p(cols), _stream()),
+               "sa_im2col_c1")
+    return cols
+
+
+def col2im_c1(cols: torch.Tensor, k: int, s: int, p: int, out_dhw: Sequence[int],
+              bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """cols: [B, iD, iH, iW, k^3] -> y [B, oD, oH, oW, 1] (transposed-conv scatter written as a gather)."""
+    assert cols.shape[-1] == k ** 3
+    B, in_dhw = cols.shape[0], tuple(cols.shape[1:4])
+    y = torch.empty((B, *out_dhw, 1), device=cols.device, dtype=cols.dtype)
+    _lib.check(lib().sa_col2im_c1(_p(cols), _dt(cols.dtype), B, _i3(in_dhw), _i3(out_dhw), k, s, p, _p(bias), _p(y),
+                                  _stream()), "sa_col2im_c1")
+    return y
 
 
 def bias_grad(dy: torch.Tensor) -> torch.Tensor:

@@ -111,3 +111,37 @@ def test_bf16_tensor_core_step_tracks_fp32_oracle():
         if p.requires_grad:
             assert p.grad is not None and torch.isfinite(p.grad).all(), k
     assert ops.launch_count() > 50
+
+
+def test_bf16_grads_close_to_oracle():
+    """1-level, 128 channels: exercises the single-channel im2col / col2im GEMM paths (first conv 1->128, last
+    transposed conv 128->1) and the tcgen05 conv / dgrad / wgrad kernels end to end; every parameter gradient must
+    point the same way as the fp32 oracle's (cosine > 0.99) and agree to a few bf16 ulps of its scale."""
+    from oracle import vqvae_oracle as vo
+    from synthanatomy_b200.networks.vqvae import B200VQVAE
+    kw = dict(n_levels=1, downsample_parameters=((4, 2, 1, 1),), upsample_parameters=((4, 2, 1, 0, 1),),
+              n_embed=64, embed_dim=16, n_channels=128, n_res_channels=128, n_res_layers=2, vq_decay=0.5,
+              commitment_cost=0.25)
+    torch.manual_seed(3)
+    net = B200VQVAE(**kw)
+    with torch.no_grad():
+        net.quantizer[0].impl.embedding.weight.mul_(0.05)
+        net.quantizer[0].impl.embed_avg.copy_(net.quantizer[0].impl.embedding.weight)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.rand(2, 1, 16, 24, 32)
+    loss_ref, grads_ref, out_ref = vo.train_step_grads(sd, vo.VQVAEConfig(**kw), x)
+    net = net.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = net(x.cuda())
+    loss = F.mse_loss(out["reconstruction"][0].float(), x.cuda()) + out["quantization_losses"][0]
+    loss.backward()
+    rerr = (out["reconstruction"][0].cpu() - out_ref["reconstruction"][0]).abs().max().item()
+    assert rerr < 5e-2, rerr
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    for k, p in net.named_parameters():
+        if not p.requires_grad:
+            continue
+        a, b = p.grad.cpu().flatten().double(), grads_ref[k].flatten().double()
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        assert cos > 0.99, f"{k}: cosine {cos:.4f}"
+        assert float((a - b).abs().max()) < 0.1 * float(b.abs().max()) + 1e-7, k

@@ -69,8 +69,8 @@ def wgrad_case(kind, cin, cout, k, s, p, shape):
     dws = ops.conv_wgrad(spec, x, gy, w)
     ops.set_force_simt(False)
     torch.cuda.synchronize()
-    bad = report(f"wgrad {kind} cin={cin} cout={cout} k={k} s={s} shape={shape} path={path} "
-                 f"variant={os.environ.get('SA_WGRAD_VARIANT', '0')}", dw, dws)
+    bad = report(f"wgrad {kind} cin={cin} cout={cout} k={k} s={s} shape={shape} path={path}"
+                 , dw, dws)
     if bad.any():
         structure(bad.reshape(wshape[0], wshape[1], -1), ["a", "b", "tap"])
 
