@@ -144,7 +144,8 @@ def test_tcgen05_fwd_dgrad_wgrad(kind, cin, cout, k, s, p, shape):
     gyd = _to_ndhwc(gy, torch.bfloat16)
     wp_t = ops.pack_weight(wd, transpose=(kind == "conv"), dtype=torch.bfloat16)
     dx = ops.conv_dgrad(spec, gyd, wp_t, (D, H, W))
-    assert ops.last_path() == 2
+    # the dgrad primitive gathers over dy (cout channels): it qualifies for tcgen05 only if cout % 64 == 0
+    assert ops.last_path() == (2 if cout % 64 == 0 else 1)
     sx = float(x.grad.abs().max())
     torch.testing.assert_close(_from_ndhwc(dx), x.grad, rtol=2 ** -7, atol=2e-3 * sx)
 
