@@ -37,6 +37,34 @@ class ConvDesc(C.Structure):
     ]
 
 
+class GemmEpilogue(C.Structure):
+    """mirror of `sa_gemm_epilogue` (include/synthanatomy_b200_performer.h)"""
+    _fields_ = [
+        ("bias", c_void_p),
+        ("dot_with", c_void_p),
+        ("dot_out", c_void_p),
+        ("scale_dev", c_void_p),
+        ("scale", C.c_float),
+        ("act", C.c_int32),
+        ("pre", c_void_p),
+        ("resid", c_void_p),
+        ("out_f32", c_void_p),
+        ("out_act", c_void_p),
+    ]
+
+
+class FavorDesc(C.Structure):
+    """mirror of `sa_favor_desc`"""
+    _fields_ = [(n, C.c_int32) for n in ("batch", "seq", "heads", "dim_head", "m", "mp", "ld", "act_dtype")]
+
+
+class LocalDesc(C.Structure):
+    """mirror of `sa_local_desc`"""
+    _fields_ = [(n, C.c_int32) for n in ("batch", "seq", "heads", "dim_head", "window", "ld", "out_ld", "act_dtype")]
+
+
+SA_ACT_NONE, SA_ACT_GELU_FWD, SA_ACT_GELU_BWD = 0, 1, 2
+
 # name -> (restype, argtypes); the single source of truth for tests/test_abi.py as well
 SIGNATURES = {
     "sa_last_error": (C.c_char_p, []),
@@ -68,6 +96,37 @@ SIGNATURES = {
     "sa_mse_fwd_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sa_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int,
                              c_void_p]),
+    # ---- Performer path (include/synthanatomy_b200_performer.h)
+    "sa_gemm_nt": (c_int, [c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, C.POINTER(GemmEpilogue),
+                           c_int64, c_void_p]),
+    "sa_gemm_tn": (c_int, [c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_float, c_void_p,
+                           c_int, c_void_p]),
+    "sa_embed_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, C.POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int,
+                             c_void_p, c_void_p, c_int, c_void_p]),
+    "sa_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, C.POINTER(c_void_p),
+                             c_void_p, c_void_p]),
+    "sa_favor_kmax": (c_int, [C.POINTER(FavorDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sa_favor_featmap_fwd": (c_int, [C.POINTER(FavorDesc), c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                     c_void_p]),
+    "sa_favor_featmap_bwd": (c_int, [C.POINTER(FavorDesc), c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    "sa_favor_kmax_fixup": (c_int, [C.POINTER(FavorDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sa_favor_scan_workspace": (C.c_size_t, [C.POINTER(FavorDesc), c_int]),
+    "sa_favor_scan_fwd": (c_int, [C.POINTER(FavorDesc), c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
+                                  c_void_p, C.c_size_t, c_void_p]),
+    "sa_favor_scan_bwd": (c_int, [C.POINTER(FavorDesc), c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_size_t, c_void_p]),
+    "sa_local_attn_fwd": (c_int, [C.POINTER(LocalDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "sa_local_attn_bwd": (c_int, [C.POINTER(LocalDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sa_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p]),
+    "sa_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
+    "sa_ce_fwd_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sa_cast2d": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p]),
+    "sa_rezero_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -1,0 +1,114 @@
+// C-ABI entry points of the Performer path (include/synthanatomy_b200_performer.h): argument checks and the
+// dispatch between the tcgen05 kernels (bf16 operands) and the CUDA-core kernels (fp32 parity path / fallback).
+#include "sa_pf_common.cuh"
+
+int sa_simt_gemm_nt(int64_t, int, int, int, const void*, int64_t, const void*, int64_t, const SaEpi&, cudaStream_t);
+int sa_simt_gemm_tn(int64_t, int, int, int, const void*, int64_t, const void*, int64_t, const float*, float, float*,
+                    cudaStream_t);
+bool sa_tc_gemm_nt_supported(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb);
+int sa_tc_gemm_nt(int64_t, int, int, const void*, int64_t, const void*, int64_t, const SaEpi&, cudaStream_t);
+bool sa_tc_gemm_tn_supported(int64_t m, int na, int nb, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb);
+int sa_tc_gemm_tn(int64_t, int, int, const void*, int64_t, const void*, int64_t, const float*, float, float*,
+                  cudaStream_t);
+
+int sa_simt_favor_kmax(const sa_favor_desc*, const void*, const float*, unsigned long long*, cudaStream_t);
+int sa_simt_favor_featmap_fwd(const sa_favor_desc*, const void*, const float*, int, const unsigned long long*, float,
+                              void*, int32_t*, cudaStream_t);
+int sa_simt_favor_featmap_bwd(const sa_favor_desc*, const void*, const float*, int, float, const void*, const void*,
+                              const int32_t*, void*, float*, cudaStream_t);
+int sa_simt_favor_kmax_fixup(const sa_favor_desc*, const float*, const unsigned long long*, const float*, void*,
+                             cudaStream_t);
+size_t sa_simt_favor_scan_workspace(const sa_favor_desc*, int);
+int sa_simt_favor_scan_fwd(const sa_favor_desc*, const void*, const void*, const void*, float, void*, int, float*, void*,
+                           size_t, cudaStream_t);
+int sa_simt_favor_scan_bwd(const sa_favor_desc*, const void*, const void*, const void*, float, const void*, const void*,
+                           int, const float*, void*, void*, void*, void*, size_t, cudaStream_t);
+int sa_simt_local_attn_fwd(const sa_local_desc*, const void*, const void*, const void*, const float*, void*, float*,
+                           cudaStream_t);
+int sa_simt_local_attn_bwd(const sa_local_desc*, const void*, const void*, const void*, const float*, const void*,
+                           const void*, const float*, void*, void*, void*, cudaStream_t);
+
+extern "C" int sa_gemm_nt(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
+                          const sa_gemm_epilogue* epi, int64_t ldo, void* stream) {
+  SA_CHECK_ARG(a && b && epi, "null pointer");
+  SA_CHECK_ARG(m > 0 && n > 0 && k > 0 && lda >= k && ldb >= k && ldo >= n, "bad sizes");
+  SA_CHECK_ARG(dtype == SA_F32 || dtype == SA_BF16, "bad dtype");
+  SA_CHECK_ARG(epi->out_f32 || epi->out_act || epi->dot_out, "no output");
+  SA_CHECK_ARG(epi->act == SA_ACT_NONE || epi->pre, "GELU epilogue needs `pre`");
+  SA_CHECK_ARG(!epi->dot_with == !epi->dot_out, "dot_with / dot_out must come together");
+  const SaEpi e = sa_make_epi(epi, ldo);
+  cudaStream_t st = sa_stream(stream);
+  if (!sa_force_simt() && sa_tc_gemm_nt_supported(m, n, k, dtype, a, lda, b, ldb)) return sa_tc_gemm_nt(m, n, k, a, lda, b, ldb, e, st);
+  return sa_simt_gemm_nt(m, n, k, dtype, a, lda, b, ldb, e, st);
+}
+
+extern "C" int sa_gemm_tn(int64_t m, int na, int nb, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
+                          const float* scale_dev, float scale, float* d, int accumulate, void* stream) {
+  SA_CHECK_ARG(a && b && d, "null pointer");
+  SA_CHECK_ARG(m > 0 && na > 0 && nb > 0 && lda >= na && ldb >= nb, "bad sizes");
+  SA_CHECK_ARG(dtype == SA_F32 || dtype == SA_BF16, "bad dtype");
+  cudaStream_t st = sa_stream(stream);
+  if (!accumulate) SA_CUDA(cudaMemsetAsync(d, 0, (size_t)na * nb * sizeof(float), st));
+  if (!sa_force_simt() && sa_tc_gemm_tn_supported(m, na, nb, dtype, a, lda, b, ldb))
+    return sa_tc_gemm_tn(m, na, nb, a, lda, b, ldb, scale_dev, scale, d, st);
+  return sa_simt_gemm_tn(m, na, nb, dtype, a, lda, b, ldb, scale_dev, scale, d, st);
+}
+
+extern "C" int sa_favor_kmax(const sa_favor_desc* d, const void* k, const float* proj, unsigned long long* kmax,
+                             void* stream) {
+  SA_CHECK_ARG(d && k && proj && kmax, "null pointer");
+  return sa_simt_favor_kmax(d, k, proj, kmax, sa_stream(stream));
+}
+
+extern "C" int sa_favor_featmap_fwd(const sa_favor_desc* d, const void* x, const float* proj, int is_query,
+                                    const unsigned long long* kmax, float eps, void* feat, int32_t* argmax, void* stream) {
+  SA_CHECK_ARG(d && x && proj && feat, "null pointer");
+  SA_CHECK_ARG(is_query ? argmax != nullptr : kmax != nullptr, "queries need argmax, keys need kmax");
+  return sa_simt_favor_featmap_fwd(d, x, proj, is_query, kmax, eps, feat, argmax, sa_stream(stream));
+}
+
+extern "C" int sa_favor_featmap_bwd(const sa_favor_desc* d, const void* x, const float* proj, int is_query, float eps,
+                                    const void* feat, const void* dfeat, const int32_t* argmax, void* dx, float* gsum,
+                                    void* stream) {
+  SA_CHECK_ARG(d && x && proj && feat && dfeat && dx, "null pointer");
+  SA_CHECK_ARG(is_query ? argmax != nullptr : gsum != nullptr, "queries need argmax, keys need gsum");
+  return sa_simt_favor_featmap_bwd(d, x, proj, is_query, eps, feat, dfeat, argmax, dx, gsum, sa_stream(stream));
+}
+
+extern "C" int sa_favor_kmax_fixup(const sa_favor_desc* d, const float* proj, const unsigned long long* kmax,
+                                   const float* gsum, void* dk, void* stream) {
+  SA_CHECK_ARG(d && proj && kmax && gsum && dk, "null pointer");
+  return sa_simt_favor_kmax_fixup(d, proj, kmax, gsum, dk, sa_stream(stream));
+}
+
+extern "C" size_t sa_favor_scan_workspace(const sa_favor_desc* d, int backward) {
+  if (!d) return 0;
+  return sa_simt_favor_scan_workspace(d, backward);
+}
+
+extern "C" int sa_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps_cumsum,
+                                 void* out, int out_ld, float* den, void* workspace, size_t ws_bytes, void* stream) {
+  SA_CHECK_ARG(d && qf && kf && v && out && den && workspace, "null pointer");
+  return sa_simt_favor_scan_fwd(d, qf, kf, v, eps_cumsum, out, out_ld, den, workspace, ws_bytes, sa_stream(stream));
+}
+
+extern "C" int sa_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps_cumsum,
+                                 const void* out, const void* dout, int out_ld, const float* den, void* dqf, void* dkf,
+                                 void* dv, void* workspace, size_t ws_bytes, void* stream) {
+  SA_CHECK_ARG(d && qf && kf && v && out && dout && den && dqf && dkf && dv && workspace, "null pointer");
+  return sa_simt_favor_scan_bwd(d, qf, kf, v, eps_cumsum, out, dout, out_ld, den, dqf, dkf, dv, workspace, ws_bytes,
+                                sa_stream(stream));
+}
+
+extern "C" int sa_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, const void* v,
+                                 const float* inv_freq, void* out, float* lse, void* stream) {
+  SA_CHECK_ARG(d && q && k && v && out && lse, "null pointer");
+  return sa_simt_local_attn_fwd(d, q, k, v, inv_freq, out, lse, sa_stream(stream));
+}
+
+extern "C" int sa_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, const void* v,
+                                 const float* inv_freq, const void* out, const void* dout, const float* lse, void* dq,
+                                 void* dk, void* dv, void* stream) {
+  SA_CHECK_ARG(d && q && k && v && out && dout && lse && dq && dk && dv, "null pointer");
+  return sa_simt_local_attn_bwd(d, q, k, v, inv_freq, out, dout, lse, dq, dk, dv, sa_stream(stream));
+}

@@ -1,5 +1,6 @@
-"""Losses on the hot path: mirror of the reference's ``MSELoss`` for the VQ-VAE
-(/root/reference/src/losses/vqvae/vqvae.py:14-71): ``mse(reconstruction, y) + sum(quantization_losses)``."""
+"""Losses on the hot path: mirrors of the reference's ``MSELoss`` for the VQ-VAE
+(/root/reference/src/losses/vqvae/vqvae.py:14-71): ``mse(reconstruction, y) + sum(quantization_losses)``, and of its
+``CELoss`` for the Performer (/root/reference/src/losses/transformer/transformer.py:10-36)."""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -7,7 +8,7 @@ from typing import Dict, List
 import torch
 from torch.nn.modules.loss import _Loss
 
-from . import ops
+from . import ops, pf_ops
 
 
 class _MSEFn(torch.autograd.Function):
@@ -49,6 +50,49 @@ class MSELoss(_Loss):
             q_loss = q_loss.float()
             self.summaries["scalar"][f"Loss-MSE-VQ{idx}_Commitment_Cost"] = q_loss
             loss = loss + q_loss
+        return loss
+
+    def get_summaries(self) -> Dict[str, torch.Tensor]:
+        return self.summaries
+
+
+class _CEFn(torch.autograd.Function):
+    """F.cross_entropy(input [B, V, N], target [B, N]) with one fused kernel per direction (no log-softmax tensor)."""
+
+    @staticmethod
+    def forward(ctx, y_pred, y, reduction):
+        if not y_pred.is_cuda:
+            raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
+        logits = y_pred.detach().float().transpose(1, 2).contiguous()      # [B, N, V]; a view for TransformerTrainingInferer output
+        B, N, V = logits.shape
+        target = y.detach().long().contiguous().view(-1)
+        loss_sum = torch.zeros((1,), device=logits.device, dtype=torch.float32)
+        pf_ops.ce_fwd_bwd(logits.view(B * N, V), target, 0.0, None, loss_sum, None)
+        ctx.save_for_backward(logits, target)
+        ctx.scale = 1.0 / (B * N) if reduction == "mean" else 1.0
+        return loss_sum[0] * ctx.scale
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target = ctx.saved_tensors
+        B, N, V = logits.shape
+        dl = torch.empty_like(logits)
+        pf_ops.ce_fwd_bwd(logits.view(B * N, V), target, ctx.scale, g.float().contiguous().view(1), None, dl.view(B * N, V))
+        return dl.transpose(1, 2), None, None
+
+
+class CELoss(_Loss):
+    def __init__(self, weight=None, size_average: bool = None, reduce: bool = None, reduction: str = "mean"):
+        super().__init__(size_average, reduce, reduction)
+        if reduction not in ("sum", "mean"):
+            raise ValueError("Reduction must be either 'sum' or 'mean'")
+        if weight is not None:
+            raise NotImplementedError("class weights are not implemented (the reference passes none); no fallback")
+        self.summaries: Dict = {"scalar": dict()}
+
+    def forward(self, y_pred: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        loss = _CEFn.apply(y_pred, y, self.reduction)
+        self.summaries["scalar"]["Loss-CE-Prediction"] = loss
         return loss
 
     def get_summaries(self) -> Dict[str, torch.Tensor]:

@@ -1,0 +1,626 @@
+"""B200-native Performer prior: drop-in for the reference's ``Performer``
+(/root/reference/src/networks/transformers/performer.py:70-288) and for the third-party stack it instantiates
+(performer-pytorch==1.0.11 ``Performer`` / ``SelfAttention`` / ``FastAttention`` / ``FeedForward`` / ``ReZero`` /
+``ProjectionUpdater``, local-attention ``LocalAttention``, fast-transformers ``CausalDotProduct``).
+
+Same keyword-only constructor, same module tree (=> same ``state_dict`` keys), same methods -- but no ``nn.Linear`` /
+``nn.Embedding`` forward is ever executed: the ``nn`` modules are parameter containers, the whole network runs as
+one hand-scheduled forward / backward programme over the C ABI in ``include/synthanatomy_b200_performer.h``.
+
+Precision: ``compute_dtype=None`` follows the caller like the reference (fp32 normally = CUDA-core fp32 "parity"
+path; bf16 operands + fp32 accumulation on tcgen05 under ``torch.autocast``).  The residual stream, LayerNorm
+statistics, softmax / feature-map statistics, logits and all gradients of parameters are fp32 in both modes.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from ... import ops, pf_ops
+from ...pf_ops import SA_ACT_GELU_BWD, SA_ACT_GELU_FWD
+from .transformer import TransformerBase
+
+_NONE = "none"   # TransformerConditioningType.NONE.value (src/utils/transformer.py)
+
+
+def _no_exec(*_a, **_k):
+    raise RuntimeError("synthanatomy_b200: parameter container, not executable (no eager fallback)")
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers: the reference's module tree
+# ------------------------------------------------------------------------------------------------
+class AbsolutePositionalEmbedding(nn.Module):
+    """performer-pytorch: emb(arange(n))"""
+
+    def __init__(self, dim, max_seq_len):
+        super().__init__()
+        self.emb = nn.Embedding(max_seq_len, dim)
+
+    forward = _no_exec
+
+
+class AbsoluteSpatialPositionalEmbedding(nn.Module):
+    """performer.py:23-40"""
+
+    def __init__(self, dim: int, spatial_indices_sequence: torch.Tensor):
+        super().__init__()
+        self.register_buffer("spatial_indices_sequence", spatial_indices_sequence)
+        self.spatial_indices_sequence = self.spatial_indices_sequence[:-1]     # the last element is the predicted one
+        self.emb = nn.Embedding(len(self.spatial_indices_sequence), dim)
+
+    forward = _no_exec
+
+
+class SinusoidalEmbeddings(nn.Module):
+    """local-attention rotary frequencies (buffer ``inv_freq``)"""
+
+    def __init__(self, dim):
+        super().__init__()
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim))
+        self.register_buffer("inv_freq", inv_freq)
+
+    forward = _no_exec
+
+
+class LocalAttention(nn.Module):
+    def __init__(self, window_size, dim_head, rel_pos: bool):
+        super().__init__()
+        self.window_size = window_size
+        self.rel_pos = SinusoidalEmbeddings(dim_head) if rel_pos else None
+
+    forward = _no_exec
+
+
+def orthogonal_matrix_chunk(cols, generator=None):
+    block = torch.randn((cols, cols), generator=generator)
+    q, _ = torch.linalg.qr(block, mode="reduced")
+    return q.t()
+
+
+def gaussian_orthogonal_random_matrix(nb_rows, nb_columns, scaling=0, generator=None):
+    """performer-pytorch 1.0.11 (QR on the host, as the reference does; off the GPU's critical path)."""
+    nb_full_blocks = int(nb_rows / nb_columns)
+    blocks = [orthogonal_matrix_chunk(nb_columns, generator) for _ in range(nb_full_blocks)]
+    remaining = nb_rows - nb_full_blocks * nb_columns
+    if remaining > 0:
+        blocks.append(orthogonal_matrix_chunk(nb_columns, generator)[:remaining])
+    final = torch.cat(blocks)
+    if scaling == 0:
+        multiplier = torch.randn((nb_rows, nb_columns), generator=generator).norm(dim=1)
+    elif scaling == 1:
+        multiplier = math.sqrt(float(nb_columns)) * torch.ones((nb_rows,))
+    else:
+        raise ValueError(f"Invalid scaling {scaling}")
+    return torch.diag(multiplier) @ final
+
+
+class FastAttention(nn.Module):
+    def __init__(self, dim_heads, nb_features=None, ortho_scaling=0):
+        super().__init__()
+        self.dim_heads = dim_heads
+        self.nb_features = nb_features if nb_features is not None else int(dim_heads * math.log(dim_heads))
+        self.ortho_scaling = ortho_scaling
+        self.register_buffer("projection_matrix", self._draw())
+
+    def _draw(self):
+        return gaussian_orthogonal_random_matrix(self.nb_features, self.dim_heads, self.ortho_scaling)
+
+    @torch.no_grad()
+    def redraw_projection_matrix(self, device=None):
+        self.projection_matrix.copy_(self._draw().to(self.projection_matrix.device, non_blocking=True))
+
+    forward = _no_exec
+
+
+class SelfAttention(nn.Module):
+    def __init__(self, dim, heads, dim_head, local_heads, local_window_size, nb_features, local_rel_pos: bool):
+        super().__init__()
+        inner = dim_head * heads
+        self.heads = heads
+        self.global_heads = heads - local_heads
+        if self.global_heads > 0:
+            self.fast_attention = FastAttention(dim_head, nb_features)
+        self.local_attn = LocalAttention(local_window_size, dim_head, local_rel_pos) if local_heads > 0 else None
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_k = nn.Linear(dim, inner, bias=False)
+        self.to_v = nn.Linear(dim, inner, bias=False)
+        self.to_out = nn.Linear(inner, dim, bias=False)
+
+    forward = _no_exec
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.w1 = nn.Linear(dim, dim * mult)
+        self.w2 = nn.Linear(dim * mult, dim)
+
+    forward = _no_exec
+
+
+class Chunk(nn.Module):
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    forward = _no_exec
+
+
+class ReZero(nn.Module):
+    def __init__(self, fn):
+        super().__init__()
+        self.g = nn.Parameter(torch.tensor(1e-3))
+        self.fn = fn
+
+    forward = _no_exec
+
+
+class SequentialSequence(nn.Module):
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = layers
+
+    forward = _no_exec
+
+
+class ProjectionUpdater(nn.Module):
+    """performer-pytorch 1.0.11 (the shared ``instance`` sub-module duplicates the keys in state_dict there too)."""
+
+    def __init__(self, instance, feature_redraw_interval):
+        super().__init__()
+        self.instance = instance
+        self.feature_redraw_interval = feature_redraw_interval
+        self.register_buffer("calls_since_last_redraw", torch.tensor(0))
+        self._calls = 0     # host mirror of the counter: no device -> host sync on the hot path
+
+    def fix_projections_(self):
+        self.feature_redraw_interval = None
+
+    def redraw_projections(self):
+        if not self.training:
+            return
+        if self.feature_redraw_interval is not None and self._calls >= self.feature_redraw_interval:
+            for mod in self.instance.modules():
+                if isinstance(mod, FastAttention):
+                    mod.redraw_projection_matrix()
+            self._calls = 0
+            self.calls_since_last_redraw.zero_()
+            return
+        self._calls += 1
+        self.calls_since_last_redraw += 1
+
+    forward = _no_exec
+
+
+class PerformerStack(nn.Module):
+    """container for performer_pytorch.Performer(dim, depth, heads, dim_head, ...) as built at performer.py:194-219"""
+
+    def __init__(self, dim, depth, heads, dim_head, local_attn_heads, local_window_size, ff_mult, nb_features,
+                 feature_redraw_interval, auto_check_redraw, local_rel_pos):
+        super().__init__()
+        layers = nn.ModuleList([])
+        for _ in range(depth):
+            layers.append(nn.ModuleList([
+                ReZero(SelfAttention(dim, heads, dim_head, local_attn_heads, local_window_size, nb_features,
+                                     local_rel_pos)),
+                ReZero(Chunk(FeedForward(dim, ff_mult))),
+            ]))
+        self.net = SequentialSequence(layers)
+        self.auto_check_redraw = auto_check_redraw
+        self.proj_updater = ProjectionUpdater(self.net, feature_redraw_interval)
+
+    def fix_projection_matrices_(self):
+        self.proj_updater.feature_redraw_interval = None
+
+    def check_redraw_projections(self):
+        self.proj_updater.redraw_projections()
+
+    forward = _no_exec
+
+
+# ------------------------------------------------------------------------------------------------
+# the programme
+# ------------------------------------------------------------------------------------------------
+class _Dims:
+    def __init__(self, net: "Performer", B: int, N: int, dt: torch.dtype):
+        self.B, self.N, self.M = B, N, B * N
+        self.dim, self.depth = net.dim, net.depth
+        self.heads, self.dh = net.heads, net.dim_head
+        self.lh = net.local_attn_heads
+        self.gh = net.heads - net.local_attn_heads
+        self.inner = net.heads * net.dim_head
+        self.ff = net.dim * net.ff_mult
+        self.W = net.local_window_size
+        self.m = net.nb_features
+        self.mp = ((self.m + 15) // 16) * 16
+        self.V = net.num_tokens
+        self.dt = dt
+        self.n_axes = len(net.spatial_position_emb)
+
+
+_WS = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index,)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def _as(t: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+    """dtype-converted contiguous copy made by the library's cast kernel (weights are tiny)."""
+    t = t.contiguous()
+    if t.dtype == dt:
+        return t
+    out = torch.empty_like(t, dtype=dt)
+    ops._lib.check(ops.lib().sa_cast(ops._p(t), ops._dt(t.dtype), ops._p(out), ops._dt(dt), t.numel(), ops._stream()),
+                   "sa_cast")
+    return out
+
+
+class _PerformerFn(torch.autograd.Function):
+    """params: token_emb, pos_emb, spatial tables..., then per layer (g_a, Wq, Wk, Wv, Wo, g_f, W1, b1, W2, b2),
+    then norm.weight, norm.bias, to_out.weight, to_out.bias."""
+
+    @staticmethod
+    def forward(ctx, tokens, net, dt, return_encodings, *params):
+        if not tokens.is_cuda:
+            raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
+        dev = tokens.device
+        B, N = tokens.shape
+        D = _Dims(net, B, N, dt)
+        need_grad = any(ctx.needs_input_grad)
+        f32 = torch.float32
+        is32 = dt == f32
+        p = [q.detach() for q in params]
+        tok_w, pos_w = p[0], p[1]
+        sp_ws = p[2:2 + D.n_axes]
+        base = 2 + D.n_axes
+        tokens = tokens.long().contiguous()
+        M = D.M
+
+        # ---- embeddings (performer.py:241-268)
+        x32 = torch.empty((M, D.dim), device=dev, dtype=f32)
+        xa = x32 if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
+        sp_idx = net._sp_idx(N, dev)
+        pf_ops.embed_fwd(tokens, sp_idx, tok_w, sp_ws, pos_w, x32, None if is32 else xa)
+
+        ws = None
+        if D.gh > 0:
+            fd = pf_ops.favor_desc(B, N, D.gh, D.dh, D.m, D.mp, 3 * D.inner, dt)
+            ws = _workspace(pf_ops.favor_scan_workspace(fd, need_grad), dev)
+        if D.lh > 0:
+            ld_ = pf_ops.local_desc(B, N, D.lh, D.dh, D.W, 3 * D.inner, D.inner, dt)
+        saved = []
+        weights = []
+        for li in range(D.depth):
+            g_a, Wq, Wk, Wv, Wo, g_f, W1, b1, W2, b2 = p[base + 10 * li: base + 10 * li + 10]
+            attn_mod = net.performer.net.layers[li][0].fn
+            Wqkv = _as(torch.cat((Wq, Wk, Wv), dim=0), dt)
+            Wo_, W1_, W2_ = _as(Wo, dt), _as(W1, dt), _as(W2, dt)
+            # ---- attention sub-layer
+            xa_attn = xa
+            qkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
+            pf_ops.gemm_nt(xa, Wqkv, out_act=qkv)
+            attn = torch.empty((M, D.inner), device=dev, dtype=dt)
+            qf = kf = argq = kmax = den = lse = proj = inv_freq = None
+            if D.gh > 0:
+                proj = attn_mod.fast_attention.projection_matrix
+                kmax = torch.zeros((1,), device=dev, dtype=torch.int64)
+                pf_ops.favor_kmax(fd, qkv, D.inner, proj, kmax)
+                qf = torch.empty((B, D.gh, N, D.mp), device=dev, dtype=dt)
+                kf = torch.empty((B, D.gh, N, D.mp), device=dev, dtype=dt)
+                argq = torch.empty((B, D.gh, N), device=dev, dtype=torch.int32)
+                pf_ops.favor_featmap_fwd(fd, qkv, 0, proj, True, None, net.eps_feature, qf, argq)
+                pf_ops.favor_featmap_fwd(fd, qkv, D.inner, proj, False, kmax, net.eps_feature, kf, None)
+                den = torch.empty((B, D.gh, N), device=dev, dtype=f32)
+                pf_ops.favor_scan_fwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, 0, den, ws)
+            if D.lh > 0:
+                inv_freq = attn_mod.local_attn.rel_pos.inv_freq if attn_mod.local_attn.rel_pos is not None else None
+                lse = torch.empty((B, D.lh, N), device=dev, dtype=f32)
+                c0 = D.gh * D.dh
+                pf_ops.local_attn_fwd(ld_, qkv, c0, D.inner + c0, 2 * D.inner + c0, inv_freq, attn, c0, lse)
+            if is32:
+                xn_ = torch.empty((M, D.dim), device=dev, dtype=f32)
+                pf_ops.gemm_nt(attn, Wo_, scale_dev=g_a, resid=x32, out_f32=xn_)
+                x32 = xa = xn_
+            else:
+                xa = torch.empty((M, D.dim), device=dev, dtype=dt)
+                pf_ops.gemm_nt(attn, Wo_, scale_dev=g_a, resid=x32, out_f32=x32, out_act=xa)
+            # ---- feed-forward sub-layer
+            xa_ffn = xa
+            u = torch.empty((M, D.ff), device=dev, dtype=dt)
+            h = torch.empty((M, D.ff), device=dev, dtype=dt)
+            pf_ops.gemm_nt(xa, W1_, bias=b1, act=SA_ACT_GELU_FWD, pre=u, out_act=h)
+            if is32:
+                xn_ = torch.empty((M, D.dim), device=dev, dtype=f32)
+                pf_ops.gemm_nt(h, W2_, bias=b2, scale_dev=g_f, resid=x32, out_f32=xn_)
+                x32 = xa = xn_
+            else:
+                xa = torch.empty((M, D.dim), device=dev, dtype=dt)
+                pf_ops.gemm_nt(h, W2_, bias=b2, scale_dev=g_f, resid=x32, out_f32=x32, out_act=xa)
+            if need_grad:
+                saved.append((xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq))
+                weights.append((Wqkv, Wo_, W1_, W2_))
+        # ---- final LayerNorm + logits (performer.py:273-286)
+        nw, nb, Wout, bout = p[base + 10 * D.depth: base + 10 * D.depth + 4]
+        mean = torch.empty((M,), device=dev, dtype=f32)
+        rstd = torch.empty((M,), device=dev, dtype=f32)
+        enc32 = torch.empty((M, D.dim), device=dev, dtype=f32) if (return_encodings or is32) else None
+        xn = enc32 if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
+        pf_ops.layernorm_fwd(x32, nw, nb, 1e-5, enc32, None if is32 else xn, mean, rstd)
+        if return_encodings:
+            out = enc32.view(B, N, D.dim)
+        else:
+            Wout_ = _as(Wout, dt)
+            logits = torch.empty((M, D.V), device=dev, dtype=f32)
+            pf_ops.gemm_nt(xn, Wout_, bias=bout, out_f32=logits)
+            out = logits.view(B, N, D.V)
+        if need_grad:
+            ctx.D, ctx.net = D, net
+            ctx.saved, ctx.weights = saved, weights
+            ctx.tail = (tokens, sp_idx, x32, xn, mean, rstd, return_encodings)
+            ctx.p = p
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        D, net, p = ctx.D, ctx.net, ctx.p
+        dt, M, B, N = D.dt, D.M, D.B, D.N
+        f32 = torch.float32
+        is32 = dt == f32
+        dev = gout.device
+        tokens, sp_idx, x32, xn, mean, rstd, return_encodings = ctx.tail
+        base = 2 + D.n_axes
+        nw, nb, Wout, bout = p[base + 10 * D.depth: base + 10 * D.depth + 4]
+        grads: List[Optional[torch.Tensor]] = [None] * len(p)
+        gi = base + 10 * D.depth
+
+        # ---- logits + LayerNorm
+        if return_encodings:
+            dxn = gout.float().contiguous().view(M, D.dim)
+        else:
+            dl = gout.float().contiguous().view(M, D.V)
+            grads[gi + 3] = ops.bias_grad(dl)
+            if is32:
+                dlb, Wout_t = dl, Wout.t().contiguous()
+            else:
+                Vp = ((D.V + 63) // 64) * 64
+                dlb = torch.empty((M, Vp), device=dev, dtype=dt)
+                pf_ops.cast2d(dl, dlb, D.V)
+                Wout_t = torch.empty((D.dim, Vp), device=dev, dtype=dt)
+                pf_ops.cast2d(Wout.t().contiguous(), Wout_t, D.V)
+            dxn = torch.empty((M, D.dim), device=dev, dtype=f32)
+            pf_ops.gemm_nt(dlb, Wout_t, out_f32=dxn)
+            dWout = torch.empty((D.V, D.dim), device=dev, dtype=f32)
+            pf_ops.gemm_tn(dlb[:, :D.V], xn, dWout)
+            grads[gi + 2] = dWout
+            del dl, dlb
+        dx32 = torch.empty((M, D.dim), device=dev, dtype=f32)
+        dnw = torch.zeros_like(nw)
+        dnb = torch.zeros_like(nb)
+        pf_ops.layernorm_bwd(dxn, x32, nw, mean, rstd, dx32, dnw, dnb)
+        grads[gi], grads[gi + 1] = dnw, dnb
+        del dxn
+        dxa = dx32 if is32 else _as(dx32, dt)
+
+        ws = None
+        if D.gh > 0:
+            fd = pf_ops.favor_desc(B, N, D.gh, D.dh, D.m, D.mp, 3 * D.inner, dt)
+            ws = _workspace(pf_ops.favor_scan_workspace(fd, True), dev)
+        if D.lh > 0:
+            ld_ = pf_ops.local_desc(B, N, D.lh, D.dh, D.W, 3 * D.inner, D.inner, dt)
+
+        for li in range(D.depth - 1, -1, -1):
+            o = base + 10 * li
+            g_a, _Wq, _Wk, _Wv, _Wo, g_f, _W1, b1, _W2, b2 = p[o:o + 10]
+            xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq = ctx.saved[li]
+            Wqkv, Wo_, W1_, W2_ = ctx.weights[li]
+            ctx.saved[li] = None
+            # ---- feed-forward sub-layer: x_out = x + g_f * (gelu(x W1^T + b1) W2^T + b2)
+            dot = torch.zeros((1,), device=dev, dtype=f32)
+            du = torch.empty((M, D.ff), device=dev, dtype=dt)
+            pf_ops.gemm_nt(dxa, W2_.t().contiguous(), dot_with=h, dot_out=dot, scale_dev=g_f, act=SA_ACT_GELU_BWD, pre=u,
+                           out_act=du)
+            colsum = ops.bias_grad(dxa)
+            db2 = torch.empty_like(b2)
+            dg_f = torch.empty((), device=dev, dtype=f32)
+            pf_ops.rezero_finish(colsum, b2, g_f, dot, db2, dg_f)
+            dW2 = torch.empty((D.dim, D.ff), device=dev, dtype=f32)
+            pf_ops.gemm_tn(dxa, h, dW2, scale_dev=g_f)
+            dW1 = torch.empty((D.ff, D.dim), device=dev, dtype=f32)
+            pf_ops.gemm_tn(du, xa_ffn, dW1)
+            db1 = ops.bias_grad(du)
+            pf_ops.gemm_nt(du, W1_.t().contiguous(), resid=dx32, out_f32=dx32, out_act=None if is32 else dxa)
+            grads[o + 5], grads[o + 6], grads[o + 7], grads[o + 8], grads[o + 9] = dg_f, dW1, db1, dW2, db2
+            del du, u, h
+            # ---- attention sub-layer: x_out = x + g_a * (attn Wo^T)
+            dot = torch.zeros((1,), device=dev, dtype=f32)
+            dattn = torch.empty((M, D.inner), device=dev, dtype=dt)
+            pf_ops.gemm_nt(dxa, Wo_.t().contiguous(), dot_with=attn, dot_out=dot, scale_dev=g_a, out_act=dattn)
+            dWo = torch.empty((D.dim, D.inner), device=dev, dtype=f32)
+            pf_ops.gemm_tn(dxa, attn, dWo, scale_dev=g_a)
+            dqkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
+            if D.lh > 0:
+                c0 = D.gh * D.dh
+                pf_ops.local_attn_bwd(ld_, qkv, c0, D.inner + c0, 2 * D.inner + c0, inv_freq, attn, dattn, c0, lse, dqkv)
+            if D.gh > 0:
+                dqf = torch.empty_like(qf)
+                dkf = torch.empty_like(kf)
+                pf_ops.favor_scan_bwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, dattn, 0, den, dqf, dkf, dqkv,
+                                      2 * D.inner, ws)
+                gsum = torch.zeros((1,), device=dev, dtype=f32)
+                pf_ops.favor_featmap_bwd(fd, qkv, 0, proj, True, net.eps_feature, qf, dqf, argq, dqkv, 0, None)
+                pf_ops.favor_featmap_bwd(fd, qkv, D.inner, proj, False, net.eps_feature, kf, dkf, None, dqkv, D.inner, gsum)
+                pf_ops.favor_kmax_fixup(fd, proj, kmax, gsum, dqkv, D.inner)
+                del dqf, dkf
+            dWqkv = torch.empty((3 * D.inner, D.dim), device=dev, dtype=f32)
+            pf_ops.gemm_tn(dqkv, xa_attn, dWqkv)
+            pf_ops.gemm_nt(dqkv, Wqkv.t().contiguous(), resid=dx32, out_f32=dx32, out_act=None if is32 else dxa)
+            grads[o] = dot.view(())
+            grads[o + 1], grads[o + 2], grads[o + 3] = dWqkv[:D.inner], dWqkv[D.inner:2 * D.inner], dWqkv[2 * D.inner:]
+            grads[o + 4] = dWo
+            del dqkv, dattn, attn, qkv, qf, kf
+
+        # ---- embeddings
+        d_tok = torch.zeros_like(p[0])
+        d_pos = torch.zeros_like(p[1])
+        d_sps = [torch.zeros_like(t) for t in p[2:2 + D.n_axes]]
+        pf_ops.embed_bwd(dx32, tokens, sp_idx, d_tok, d_sps, d_pos)
+        grads[0], grads[1] = d_tok, d_pos
+        for a, g in enumerate(d_sps):
+            grads[2 + a] = g
+        ctx.saved = ctx.weights = None
+        return (None, None, None, None, *grads)
+
+
+class Performer(TransformerBase):
+    """NOTE: All tensor logic assumes the following ordering [Batch, Length, Channel] (as the reference)."""
+
+    def __init__(
+        self,
+        *,
+        num_tokens: int,
+        max_seq_len: int,
+        dim: int,
+        depth: int,
+        heads: int,
+        ordering,
+        dim_head: int = 64,
+        local_attn_heads: int = 0,
+        local_window_size: int = 256,
+        causal: bool = True,
+        ff_mult: int = 4,
+        nb_features: Optional[int] = None,
+        feature_redraw_interval: int = 1000,
+        reversible: bool = False,
+        ff_chunks: int = 1,
+        ff_glu: bool = False,
+        emb_dropout: float = 0.0,
+        ff_dropout: float = 0.0,
+        attn_dropout: float = 0.0,
+        generalized_attention: bool = False,
+        kernel_fn: torch.nn.Module = nn.ReLU(),
+        use_scalenorm: bool = False,
+        use_rezero: bool = False,
+        cross_attend: bool = False,
+        no_projection: bool = False,
+        tie_embed: bool = False,
+        rotary_position_emb: bool = False,
+        fixed_position_emb: bool = False,
+        axial_position_emb: bool = False,
+        axial_position_shape: Tuple[int, int] = None,
+        auto_check_redraw: bool = True,
+        qkv_bias: bool = False,
+        attn_out_bias: bool = False,
+        spatial_position_emb: str = None,
+        spatial_shape: Union[Tuple[int, int], Tuple[int, int, int]] = None,
+        conditioning_num_tokens: Optional[Tuple[int, ...]] = None,
+        conditioning_type: str = _NONE,
+        # ---- extensions (not in the reference signature)
+        compute_dtype: Optional[torch.dtype] = None,
+        local_rel_pos: str = "rotary",
+    ):
+        super().__init__()
+        unsupported = {
+            "causal=False": not causal, "reversible": reversible, "ff_chunks != 1": ff_chunks != 1, "ff_glu": ff_glu,
+            "dropout > 0": (emb_dropout, ff_dropout, attn_dropout) != (0.0, 0.0, 0.0),
+            "generalized_attention": generalized_attention, "use_scalenorm": use_scalenorm,
+            "use_rezero=False": not use_rezero, "cross_attend": cross_attend, "no_projection": no_projection,
+            "tie_embed": tie_embed, "rotary/fixed/axial position_emb": rotary_position_emb or fixed_position_emb or
+            axial_position_emb, "qkv_bias / attn_out_bias": qkv_bias or attn_out_bias,
+            "spatial_position_emb='fixed'": spatial_position_emb == "fixed",
+            "conditioning": bool(conditioning_num_tokens) and conditioning_type != _NONE,
+        }
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError(f"synthanatomy_b200 Performer implements the README.md:124-141 configuration; "
+                                      f"not implemented: {bad} (no fallback)")
+        if isinstance(local_attn_heads, (tuple, list)):
+            assert len(local_attn_heads) == 1, "per-layer local head counts are not implemented"
+            local_attn_heads = local_attn_heads[0]
+        assert local_rel_pos in ("rotary", "none")
+        self.num_tokens, self.max_seq_len = num_tokens, max_seq_len
+        self.dim, self.depth, self.heads, self.dim_head = dim, depth, heads, dim_head
+        self.local_attn_heads, self.local_window_size, self.ff_mult = local_attn_heads, local_window_size, ff_mult
+        self.nb_features = nb_features if nb_features is not None else int(dim_head * math.log(dim_head))
+        self.eps_feature, self.eps_cumsum = 1e-4, 1e-6
+        self.compute_dtype = compute_dtype
+        self.conditioning_type = conditioning_type
+
+        self.token_emb = nn.Embedding(num_tokens, dim)
+        self.pos_emb = AbsolutePositionalEmbedding(dim, self.max_seq_len)
+        self.ordering = ordering
+        self.spatial_position_emb = nn.ModuleList()
+        if spatial_position_emb:
+            assert spatial_position_emb in ["fixed", "absolute"], \
+                f"spatial_position_emb must be either 'fixed' or  'absolute', but got {spatial_position_emb}"
+            axis = (0, 1, 2) if len(spatial_shape) == 3 else (0, 1)
+            coord_channels = np.array(np.meshgrid(*tuple(np.arange(0, s) for s in spatial_shape), indexing="ij"))
+            coord_channels = coord_channels[[s for s in axis]]
+            for i in axis:
+                seq = torch.from_numpy(coord_channels[i, ...].flatten())
+                seq = self.ordering(seq)
+                self.spatial_position_emb.append(AbsoluteSpatialPositionalEmbedding(dim=dim, spatial_indices_sequence=seq))
+        self.conditioning_emb = nn.ModuleList()
+        self.dropout = nn.Dropout(emb_dropout)
+        self.performer = PerformerStack(dim, depth, heads, dim_head, local_attn_heads, local_window_size, ff_mult,
+                                        nb_features, feature_redraw_interval, auto_check_redraw,
+                                        local_rel_pos == "rotary")
+        self.norm = nn.LayerNorm(dim)
+        self.to_out = nn.Linear(dim, num_tokens)
+        self._sp_cache = {}
+
+    # ---- reference API
+    def check_redraw_projections(self):
+        self.performer.check_redraw_projections()
+
+    def fix_projection_matrices_(self):
+        self.performer.fix_projection_matrices_()
+
+    def _sp_idx(self, n: int, device) -> Optional[torch.Tensor]:
+        """[n_axes, n] int32: coordinate of sequence position n - 1 along each axis, -1 at the BOS position."""
+        if len(self.spatial_position_emb) == 0:
+            return None
+        key = (n, str(device))
+        if key not in self._sp_cache:
+            rows = []
+            for mod in self.spatial_position_emb:
+                seq = mod.spatial_indices_sequence[: n - 1].to(torch.int32).cpu()
+                rows.append(torch.cat((torch.full((1,), -1, dtype=torch.int32), seq)))
+            self._sp_cache = {key: torch.stack(rows).contiguous().to(device)}
+        return self._sp_cache[key]
+
+    def _params(self) -> List[torch.Tensor]:
+        ps = [self.token_emb.weight, self.pos_emb.emb.weight]
+        ps += [m.emb.weight for m in self.spatial_position_emb]
+        for layer in self.performer.net.layers:
+            a, f = layer[0], layer[1]
+            ps += [a.g, a.fn.to_q.weight, a.fn.to_k.weight, a.fn.to_v.weight, a.fn.to_out.weight,
+                   f.g, f.fn.fn.w1.weight, f.fn.fn.w1.bias, f.fn.fn.w2.weight, f.fn.fn.w2.bias]
+        ps += [self.norm.weight, self.norm.bias, self.to_out.weight, self.to_out.bias]
+        return ps
+
+    def _dtype(self) -> torch.dtype:
+        if self.compute_dtype is not None:
+            return self.compute_dtype
+        return torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
+
+    def forward(self, x: torch.Tensor, conditionings: Sequence[torch.Tensor] = None, return_encodings: bool = False,
+                **kwargs):
+        b, n = x.shape
+        assert n <= self.max_seq_len, \
+            f"sequence length {n} must be less than the max sequence length {self.max_seq_len}"
+        if conditionings and self.conditioning_type != _NONE:
+            raise NotImplementedError("conditioning is not implemented (README configuration has none); no fallback")
+        if self.performer.auto_check_redraw:
+            self.performer.proj_updater.redraw_projections()
+        return _PerformerFn.apply(x, self, self._dtype(), return_encodings, *self._params())

@@ -1,0 +1,190 @@
+"""Tensor-level wrappers over the Performer C ABI (include/synthanatomy_b200_performer.h).
+
+PyTorch is plumbing only (device memory, current stream); every number is computed inside
+libsynthanatomy_b200.so.  CUDA tensors only -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import FavorDesc, GemmEpilogue, LocalDesc, SA_ACT_GELU_BWD, SA_ACT_GELU_FWD, SA_ACT_NONE  # noqa: F401
+from .ops import _dt, _p, _stream, lib
+
+
+def _ptr(t: Optional[torch.Tensor], offset_elems: int = 0):
+    """raw device pointer (+ element offset); the tensor need not be contiguous as a whole (column blocks)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
+    return C.c_void_p(t.data_ptr() + offset_elems * t.element_size())
+
+
+def _rowmajor(t: torch.Tensor) -> int:
+    """leading dimension of a 2-D row-major (possibly column-sliced) tensor"""
+    assert t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+    return t.stride(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# dense layers
+# ------------------------------------------------------------------------------------------------
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, bias=None, dot_with=None, dot_out=None, scale_dev=None,
+            scale: float = 1.0, act: int = SA_ACT_NONE, pre=None, resid=None, out_f32=None, out_act=None) -> None:
+    """v = a @ b.T with the fused epilogue of sa_gemm_nt.  a [m, k], b [n, k] (row-major, same dtype)."""
+    m, k = a.shape
+    n = b.shape[0]
+    assert b.shape[1] == k and a.dtype == b.dtype
+    ldo = None
+    for t in (dot_with, pre, resid, out_f32, out_act):
+        if t is not None:
+            assert t.shape[0] == m and t.shape[1] == n, (t.shape, m, n)
+            ld = _rowmajor(t)
+            assert ldo is None or ldo == ld, "epilogue tensors must share one leading dimension"
+            ldo = ld
+    if ldo is None:
+        ldo = n
+    for t in (dot_with, pre, out_act):
+        if t is not None:
+            assert t.dtype == a.dtype, "act-dtype epilogue tensors must match the operand dtype"
+    e = GemmEpilogue()
+    e.bias = _ptr(bias); e.dot_with = _ptr(dot_with); e.dot_out = _ptr(dot_out); e.scale_dev = _ptr(scale_dev)
+    e.scale = float(scale); e.act = int(act); e.pre = _ptr(pre); e.resid = _ptr(resid)
+    e.out_f32 = _ptr(out_f32); e.out_act = _ptr(out_act)
+    _lib.check(lib().sa_gemm_nt(m, n, k, _dt(a.dtype), _ptr(a), _rowmajor(a), _ptr(b), _rowmajor(b), C.byref(e), ldo,
+                                _stream()), "sa_gemm_nt")
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, scale_dev=None, scale: float = 1.0,
+            accumulate: bool = False) -> None:
+    """d[na, nb] (+)= scale * a.T @ b;  a [m, na], b [m, nb] row-major (column slices allowed), d fp32 dense."""
+    m, na = a.shape
+    nb = b.shape[1]
+    assert b.shape[0] == m and a.dtype == b.dtype
+    assert d.dtype == torch.float32 and d.is_contiguous() and tuple(d.shape) == (na, nb)
+    _lib.check(lib().sa_gemm_tn(m, na, nb, _dt(a.dtype), _ptr(a), _rowmajor(a), _ptr(b), _rowmajor(b), _ptr(scale_dev),
+                                float(scale), _p(d), int(accumulate), _stream()), "sa_gemm_tn")
+
+
+# ------------------------------------------------------------------------------------------------
+# embeddings / LayerNorm / cross-entropy
+# ------------------------------------------------------------------------------------------------
+def _ptr_array(ts: Sequence[torch.Tensor]):
+    arr = (C.c_void_p * max(1, len(ts)))()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def embed_fwd(tokens, sp_idx, tok_w, sp_ws, pos_w, x_f32, x_act) -> None:
+    B, N = tokens.shape
+    dim = tok_w.shape[1]
+    act = x_act if x_act is not None else x_f32
+    _lib.check(lib().sa_embed_fwd(_p(tokens), _p(sp_idx), len(sp_ws), _p(tok_w), _ptr_array(sp_ws), _p(pos_w), B, N, dim,
+                                  tok_w.shape[0], _p(x_f32), _p(x_act), _dt(act.dtype), _stream()), "sa_embed_fwd")
+
+
+def embed_bwd(dx, tokens, sp_idx, d_tok_w, d_sp_ws, d_pos_w) -> None:
+    B, N = tokens.shape
+    dim = d_tok_w.shape[1]
+    _lib.check(lib().sa_embed_bwd(_p(dx), _p(tokens), _p(sp_idx), len(d_sp_ws), B, N, dim, _p(d_tok_w),
+                                  _ptr_array(d_sp_ws), _p(d_pos_w), _stream()), "sa_embed_bwd")
+
+
+def layernorm_fwd(x, w, b, eps, y_f32, y_act, mean, rstd) -> None:
+    rows, dim = x.shape
+    act = y_act if y_act is not None else y_f32
+    _lib.check(lib().sa_layernorm_fwd(_p(x), _p(w), _p(b), rows, dim, float(eps), _p(y_f32), _p(y_act), _dt(act.dtype),
+                                      _p(mean), _p(rstd), _stream()), "sa_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, w, mean, rstd, dx, dw, db) -> None:
+    rows, dim = x.shape
+    _lib.check(lib().sa_layernorm_bwd(_p(dy), _p(x), _p(w), _p(mean), _p(rstd), rows, dim, _p(dx), _p(dw), _p(db),
+                                      _stream()), "sa_layernorm_bwd")
+
+
+def ce_fwd_bwd(logits2d, target, grad_scale, grad_scale_dev, loss_sum, dlogits2d) -> None:
+    rows, V = logits2d.shape
+    _lib.check(lib().sa_ce_fwd_bwd(_ptr(logits2d), _rowmajor(logits2d), _p(target), rows, V, float(grad_scale),
+                                   _p(grad_scale_dev), _p(loss_sum), _ptr(dlogits2d), _stream()), "sa_ce_fwd_bwd")
+
+
+def cast2d(src, dst, cols: int) -> None:
+    rows = src.shape[0]
+    _lib.check(lib().sa_cast2d(_ptr(src), _dt(src.dtype), _rowmajor(src), _ptr(dst), _dt(dst.dtype), _rowmajor(dst), rows,
+                               cols, _stream()), "sa_cast2d")
+
+
+def rezero_finish(colsum, bias, g, dot, dbias, dg) -> None:
+    n = 0 if colsum is None else colsum.numel()
+    _lib.check(lib().sa_rezero_finish(_p(colsum), _p(bias), _p(g), _p(dot), n, _p(dbias), _p(dg), _stream()),
+               "sa_rezero_finish")
+
+
+# ------------------------------------------------------------------------------------------------
+# FAVOR+ / local attention
+# ------------------------------------------------------------------------------------------------
+def favor_desc(batch, seq, heads, dim_head, m, mp, ld, dtype) -> FavorDesc:
+    d = FavorDesc()
+    d.batch, d.seq, d.heads, d.dim_head, d.m, d.mp, d.ld, d.act_dtype = batch, seq, heads, dim_head, m, mp, ld, _dt(dtype)
+    return d
+
+
+def local_desc(batch, seq, heads, dim_head, window, ld, out_ld, dtype) -> LocalDesc:
+    d = LocalDesc()
+    d.batch, d.seq, d.heads, d.dim_head, d.window, d.ld, d.out_ld, d.act_dtype = (batch, seq, heads, dim_head, window, ld,
+                                                                                  out_ld, _dt(dtype))
+    return d
+
+
+def favor_kmax(d, buf, col, proj, kmax) -> None:
+    _lib.check(lib().sa_favor_kmax(C.byref(d), _ptr(buf, col), _p(proj), _p(kmax), _stream()), "sa_favor_kmax")
+
+
+def favor_featmap_fwd(d, buf, col, proj, is_query, kmax, eps, feat, argmax) -> None:
+    _lib.check(lib().sa_favor_featmap_fwd(C.byref(d), _ptr(buf, col), _p(proj), int(is_query), _p(kmax), float(eps),
+                                          _p(feat), _p(argmax), _stream()), "sa_favor_featmap_fwd")
+
+
+def favor_featmap_bwd(d, buf, col, proj, is_query, eps, feat, dfeat, argmax, dbuf, dcol, gsum) -> None:
+    _lib.check(lib().sa_favor_featmap_bwd(C.byref(d), _ptr(buf, col), _p(proj), int(is_query), float(eps), _p(feat),
+                                          _p(dfeat), _p(argmax), _ptr(dbuf, dcol), _p(gsum), _stream()),
+               "sa_favor_featmap_bwd")
+
+
+def favor_kmax_fixup(d, proj, kmax, gsum, dbuf, dcol) -> None:
+    _lib.check(lib().sa_favor_kmax_fixup(C.byref(d), _p(proj), _p(kmax), _p(gsum), _ptr(dbuf, dcol), _stream()),
+               "sa_favor_kmax_fixup")
+
+
+def favor_scan_workspace(d, backward: bool) -> int:
+    return int(lib().sa_favor_scan_workspace(C.byref(d), int(backward)))
+
+
+def favor_scan_fwd(d, qf, kf, vbuf, vcol, eps, out, ocol, den, ws) -> None:
+    _lib.check(lib().sa_favor_scan_fwd(C.byref(d), _p(qf), _p(kf), _ptr(vbuf, vcol), float(eps), _ptr(out, ocol),
+                                       _rowmajor(out), _p(den), _p(ws), ws.numel() * ws.element_size(), _stream()),
+               "sa_favor_scan_fwd")
+
+
+def favor_scan_bwd(d, qf, kf, vbuf, vcol, eps, out, dout, ocol, den, dqf, dkf, dbuf, dvcol, ws) -> None:
+    assert _rowmajor(out) == _rowmajor(dout)
+    _lib.check(lib().sa_favor_scan_bwd(C.byref(d), _p(qf), _p(kf), _ptr(vbuf, vcol), float(eps), _ptr(out, ocol),
+                                       _ptr(dout, ocol), _rowmajor(out), _p(den), _p(dqf), _p(dkf), _ptr(dbuf, dvcol),
+                                       _p(ws), ws.numel() * ws.element_size(), _stream()), "sa_favor_scan_bwd")
+
+
+def local_attn_fwd(d, buf, qcol, kcol, vcol, inv_freq, out, ocol, lse) -> None:
+    _lib.check(lib().sa_local_attn_fwd(C.byref(d), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol), _p(inv_freq),
+                                       _ptr(out, ocol), _p(lse), _stream()), "sa_local_attn_fwd")
+
+
+def local_attn_bwd(d, buf, qcol, kcol, vcol, inv_freq, out, dout, ocol, lse, dbuf) -> None:
+    _lib.check(lib().sa_local_attn_bwd(C.byref(d), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol), _p(inv_freq),
+                                       _ptr(out, ocol), _ptr(dout, ocol), _p(lse), _ptr(dbuf, qcol), _ptr(dbuf, kcol),
+                                       _ptr(dbuf, vcol), _stream()), "sa_local_attn_bwd")

@@ -1,4 +1,4 @@
-"""CPU: the C-ABI shared library builds, loads, and exports every symbol include/synthanatomy_b200.h declares
+"""CPU: the C-ABI shared library builds, loads, and exports every symbol include/*.h declares
 (no compute calls here -- there is no GPU in the build container)."""
 import os
 import re
@@ -9,9 +9,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    src = open(os.path.join(ROOT, "include", "synthanatomy_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(sa_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for f in sorted(os.listdir(inc)):
+        if not f.endswith(".h"):
+            continue
+        src = open(os.path.join(inc, f)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(sa_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_symbols_are_exported_and_bound():
