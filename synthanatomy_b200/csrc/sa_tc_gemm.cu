@@ -1,6 +1,442 @@
-// placeholder until the tcgen05 GEMMs land (next commit): nothing is claimed supported
+// tcgen05 GEMMs of the Performer path (sm_100a): bf16 operands staged by TMA into 128B-swizzled shared memory,
+// fp32 accumulators in TMEM, fused epilogues out of TMEM.
+//
+//   NT  v[i][j] = sum_k A[i][k] B[j][k]          dense layers and their data gradients (both operands K-major)
+//       persistent, one CTA per SM; 128 x BN output tiles (BN <= 256), 64-wide k blocks, 4-stage TMA ring,
+//       TWO accumulator stages in TMEM (2 x BN columns) so the epilogue of tile t overlaps the MMAs of tile t+1.
+//       warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = epilogue (two warps per TMEM lane
+//       quadrant, each taking half of the tile's columns).
+//   TN  D[i][j] += s * sum_r A[r][i] B[r][j]    weight gradients (both operands MN-major: rows of the activation
+//       matrices are the contraction index).  128 x BN tiles, 64-row k blocks, split-K over the rows with fp32
+//       red.global.add into D.
+//
+// Reference call sites replaced: cuBLAS behind nn.Linear forward / backward of performer-pytorch SelfAttention
+// (to_q/to_k/to_v/to_out), FeedForward (w1, w2) and /root/reference/src/networks/transformers/performer.py:221,286.
+#include <mutex>
+
 #include "sa_pf_common.cuh"
-bool sa_tc_gemm_nt_supported(int64_t, int, int, int, const void*, int64_t, const void*, int64_t) { return false; }
-int sa_tc_gemm_nt(int64_t, int, int, const void*, int64_t, const void*, int64_t, const SaEpi&, cudaStream_t) { return SA_ERR_UNSUPPORTED; }
-bool sa_tc_gemm_tn_supported(int64_t, int, int, int, const void*, int64_t, const void*, int64_t) { return false; }
-int sa_tc_gemm_tn(int64_t, int, int, const void*, int64_t, const void*, int64_t, const float*, float, float*, cudaStream_t) { return SA_ERR_UNSUPPORTED; }
+#include "sa_tc_common.cuh"
+
+using namespace satc;
+
+namespace {
+
+constexpr int G_THREADS = 320;
+constexpr int G_BM = 128;
+constexpr int G_BK = 64;
+constexpr int G_STAGES = 4;
+
+struct NtParams {
+  CUtensorMap amap, bmap;
+  long long m;
+  int n, k;
+  int BN, m_tiles, n_tiles, kblocks;
+  int vec;          // epilogue pointers / leading dimension allow 16-byte accesses
+  SaEpi e;
+};
+
+__device__ __forceinline__ void ld32_bf16(const __nv_bfloat16* p, float (&f)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = q[i];
+    f[i * 8 + 0] = bf16lo(u.x); f[i * 8 + 1] = bf16hi(u.x); f[i * 8 + 2] = bf16lo(u.y); f[i * 8 + 3] = bf16hi(u.y);
+    f[i * 8 + 4] = bf16lo(u.z); f[i * 8 + 5] = bf16hi(u.z); f[i * 8 + 6] = bf16lo(u.w); f[i * 8 + 7] = bf16hi(u.w);
+  }
+}
+__device__ __forceinline__ void st32_bf16(__nv_bfloat16* p, const float (&f)[32]) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]); u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+    u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]); u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+    q[i] = u;
+  }
+}
+__device__ __forceinline__ void ld32_f32(const float* p, float (&f)[32]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 u = q[i];
+    f[i * 4 + 0] = u.x; f[i * 4 + 1] = u.y; f[i * 4 + 2] = u.z; f[i * 4 + 3] = u.w;
+  }
+}
+__device__ __forceinline__ void st32_f32(float* p, const float (&f)[32]) {
+  float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = make_float4(f[i * 4 + 0], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[G_STAGES];
+  __shared__ uint64_t empty_bar[G_STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t a_bytes = G_BM * 128;
+  const uint32_t b_bytes = (uint32_t)P.BN * 128;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int total_tiles = P.m_tiles * P.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < G_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&P.amap);
+      prefetch_tmap(&P.bmap);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        for (int kb = 0; kb < P.kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          tma_load_2d(sa, &P.amap, &full_bar[stage], kb * G_BK, mt * G_BM);
+          tma_load_2d(sa + a_bytes, &P.bmap, &full_bar[stage], kb * G_BK, nt * P.BN);
+          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(G_BM, P.BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
+        for (int kb = 0; kb < P.kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < G_BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, 2);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    using T = __nv_bfloat16;
+    const SaEpi& e = P.e;
+    const int ew = warp - 2;                  // 0..7
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;                 // which half of the tile's columns
+    const int half_cols = P.BN / 2;           // BN is a multiple of 16 -> halves are multiples of 8
+    const float st = e.scale * (e.scale_dev ? __ldg(e.scale_dev) : 1.0f);
+    float dot = 0.f;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+      const long long row = (long long)mt * G_BM + quad * 32 + lane;
+      const bool row_ok = row < P.m;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      for (int cc = 0; cc < half_cols; cc += 32) {
+        const int ct = half * half_cols + cc;             // column inside the tile
+        const int col = nt * P.BN + ct;                   // global column
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * P.BN + ct), v);
+        tmem_ld_wait();
+        const int nc = min(min(32, half_cols - cc), P.n - col);
+        if (!row_ok || nc <= 0) continue;
+        const long long o = row * e.ldo + col;
+        if (P.vec && nc == 32) {
+          float f[32], t[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (e.bias) {
+            ld32_f32(e.bias + col, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += t[j];
+          }
+          if (e.dot_with) {
+            ld32_bf16(reinterpret_cast<const T*>(e.dot_with) + o, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dot = fmaf(f[j], t[j], dot);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= st;
+          if (e.act == SA_ACT_GELU_FWD) {
+            st32_bf16(reinterpret_cast<T*>(e.pre) + o, f);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = sa_gelu(f[j]);
+          } else if (e.act == SA_ACT_GELU_BWD) {
+            ld32_bf16(reinterpret_cast<const T*>(e.pre) + o, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= sa_gelu_grad(t[j]);
+          }
+          if (e.resid) {
+            ld32_f32(e.resid + o, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += t[j];
+          }
+          if (e.out_f32) st32_f32(e.out_f32 + o, f);
+          if (e.out_act) st32_bf16(reinterpret_cast<T*>(e.out_act) + o, f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nc) dot += sa_epi_elem<T>(e, row, col + j, __uint_as_float(v[j]), st);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (e.dot_out) {
+      dot = sa_warp_sum(dot);
+      if (lane == 0) atomicAdd(e.dot_out, dot);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ TN (wgrad)
+constexpr int W_THREADS = 192;
+constexpr int W_KP = 64;                       // contraction rows per stage
+constexpr int W_BLOCK = W_KP * 128;            // one (64 columns x 64 rows) swizzled block
+constexpr int W_STAGES = 4;
+
+struct TnParams {
+  CUtensorMap amap, bmap;
+  long long m;
+  int na, nb;
+  int BN, bblocks;             // tile columns (multiple of 64, <= 256) and BN / 64
+  int a_tiles, b_tiles;
+  long long kblocks_total, kblocks_per_split;
+  int tmem_cols;
+  const float* scale_dev;
+  float scale;
+  float* d;
+};
+
+__global__ void __launch_bounds__(W_THREADS, 1)
+tc_gemm_tn_kernel(const __grid_constant__ TnParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[W_STAGES];
+  __shared__ uint64_t empty_bar[W_STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tile = blockIdx.x % (P.a_tiles * P.b_tiles);
+  const int split = blockIdx.x / (P.a_tiles * P.b_tiles);
+  const int bt = tile % P.b_tiles, at = tile / P.b_tiles;
+  const long long kb_beg = (long long)split * P.kblocks_per_split;
+  const long long kb_end = min(P.kblocks_total, kb_beg + P.kblocks_per_split);
+  const long long nkb = kb_end - kb_beg;
+  const uint32_t a_bytes = 2 * W_BLOCK;
+  const uint32_t b_bytes = (uint32_t)P.bblocks * W_BLOCK;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && nkb > 0) {
+      prefetch_tmap(&P.amap);
+      prefetch_tmap(&P.bmap);
+      int stage = 0; uint32_t phase = 0;
+      for (long long kb = kb_beg; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], stage_bytes);
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        const int r0 = (int)(kb * W_KP);
+        for (int h = 0; h < 2; ++h) tma_load_2d(sa + h * W_BLOCK, &P.amap, &full_bar[stage], at * 128 + h * 64, r0);
+        for (int c = 0; c < P.bblocks; ++c)
+          tma_load_2d(sa + a_bytes + c * W_BLOCK, &P.bmap, &full_bar[stage], bt * P.BN + c * 64, r0);
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {
+      const uint32_t idesc = make_idesc_bf16(128, P.BN, 1, 1);   // both operands MN-major
+      int stage = 0; uint32_t phase = 0;
+      for (long long kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+#pragma unroll
+        for (int j = 0; j < W_KP / 16; ++j) {
+          // MN-major SWIZZLE_128B: 64-column blocks W_BLOCK apart (LBO), 8-row groups 1024 B apart (SBO),
+          // a K step of 16 rows = 2048 B
+          const uint64_t da = make_smem_desc(sa + j * 2048, W_BLOCK, 1024, 2);
+          const uint64_t db = make_smem_desc(sb + j * 2048, W_BLOCK, 1024, 2);
+          umma_bf16(tmem_base, da, db, idesc, (kb | j) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else if (nkb > 0) {
+    const int quad = warp & 3;
+    const int i = at * 128 + quad * 32 + lane;
+    const float st = P.scale * (P.scale_dev ? __ldg(P.scale_dev) : 1.0f);
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < P.BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      const int col = bt * P.BN + c0;
+      if (i < P.na) {
+        float* dst = P.d + (long long)i * P.nb + col;
+        const int nc = min(32, P.nb - col);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nc) atomicAdd(dst + j, st * __uint_as_float(v[j]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+std::once_flag g_once;
+int g_max_smem = 0;
+int g_sms = 148;
+
+void init_once() {
+  std::call_once(g_once, [] {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 2048);
+    cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 2048);
+  });
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int make_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[2] = {2, ld * 2};
+  const uint32_t box[2] = {box_cols, box_rows};
+  return sa_make_tmap_bf16(m, base, 2, dims, strides, box);
+}
+
+}  // namespace
+
+bool sa_tc_gemm_nt_supported(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb) {
+  if (dtype != SA_BF16) return false;
+  if (m < 1 || n < 8 || k < 16) return false;
+  if ((lda & 7) || (ldb & 7) || !aligned16(a) || !aligned16(b)) return false;
+  if (m >= (1LL << 31) - 256) return false;
+  return sa_get_tmap_encode() != nullptr;
+}
+
+int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const void* b, int64_t ldb, const SaEpi& e,
+                  cudaStream_t st) {
+  init_once();
+  sa_note_path(SA_PATH_TCGEN05);
+  static thread_local NtParams P;
+  P.m = m; P.n = n; P.k = k;
+  P.BN = n >= 256 ? 256 : (int)sa_cdiv(n, 16) * 16;
+  P.m_tiles = (int)sa_cdiv(m, G_BM);
+  P.n_tiles = (int)sa_cdiv(n, P.BN);
+  P.kblocks = (int)sa_cdiv(k, G_BK);
+  P.e = e;
+  bool vec = (e.ldo & 7) == 0;
+  const void* ptrs[] = {e.bias, e.dot_with, e.pre, e.resid, e.out_f32, e.out_act};
+  for (const void* p : ptrs) vec = vec && aligned16(p);
+  P.vec = vec ? 1 : 0;
+  int rc = make_2d(&P.amap, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, G_BK, G_BM);
+  if (rc != SA_OK) return rc;
+  rc = make_2d(&P.bmap, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, G_BK, (uint32_t)P.BN);
+  if (rc != SA_OK) return rc;
+  const size_t smem = (size_t)G_STAGES * (G_BM * 128 + (size_t)P.BN * 128) + 1024;
+  const int total = P.m_tiles * P.n_tiles;
+  const unsigned grid = (unsigned)(total < g_sms ? total : g_sms);
+  tc_gemm_nt_kernel<<<grid, G_THREADS, smem, st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+bool sa_tc_gemm_tn_supported(int64_t m, int na, int nb, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb) {
+  if (dtype != SA_BF16) return false;
+  if (m < 64 || na < 8 || nb < 8) return false;
+  if ((lda & 7) || (ldb & 7) || !aligned16(a) || !aligned16(b)) return false;
+  if (m >= (1LL << 31) - 256) return false;
+  return sa_get_tmap_encode() != nullptr;
+}
+
+int sa_tc_gemm_tn(int64_t m, int na, int nb, const void* a, int64_t lda, const void* b, int64_t ldb,
+                  const float* scale_dev, float scale, float* d, cudaStream_t st) {
+  init_once();
+  sa_note_path(SA_PATH_TCGEN05);
+  static thread_local TnParams P;
+  P.m = m; P.na = na; P.nb = nb;
+  P.BN = nb >= 256 ? 256 : (int)sa_cdiv(nb, 64) * 64;
+  P.bblocks = P.BN / 64;
+  P.a_tiles = (int)sa_cdiv(na, 128);
+  P.b_tiles = (int)sa_cdiv(nb, P.BN);
+  P.kblocks_total = sa_cdiv(m, W_KP);
+  P.tmem_cols = P.BN <= 64 ? 64 : (P.BN <= 128 ? 128 : 256);
+  P.scale_dev = scale_dev; P.scale = scale; P.d = d;
+  const int64_t tiles = (int64_t)P.a_tiles * P.b_tiles;
+  int64_t splits = g_sms / tiles;
+  const int64_t max_splits = sa_cdiv(P.kblocks_total, 8);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  P.kblocks_per_split = sa_cdiv(P.kblocks_total, splits);
+  splits = sa_cdiv(P.kblocks_total, P.kblocks_per_split);
+  int rc = make_2d(&P.amap, a, (uint64_t)na, (uint64_t)m, (uint64_t)lda, 64, W_KP);
+  if (rc != SA_OK) return rc;
+  rc = make_2d(&P.bmap, b, (uint64_t)nb, (uint64_t)m, (uint64_t)ldb, 64, W_KP);
+  if (rc != SA_OK) return rc;
+  const size_t smem = (size_t)W_STAGES * (2 * W_BLOCK + (size_t)P.bblocks * W_BLOCK) + 1024;
+  tc_gemm_tn_kernel<<<(unsigned)(tiles * splits), W_THREADS, smem, st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}

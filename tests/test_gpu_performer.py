@@ -76,6 +76,74 @@ def test_gemm_tn_fp32_with_column_slices():
     _close(d, torch.zeros(70, 130), 1e-4, "tn accumulate")
 
 
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("m,n,k,ldo_pad", [(300, 512, 128, 0), (1000, 256, 512, 0), (257, 80, 64, 0), (130, 2049, 192, 0),
+                                           (128, 64, 1024, 64), (4099, 1024, 256, 0)])
+def test_tcgen05_gemm_nt_bf16(m, n, k, ldo_pad):
+    """bf16 operands / fp32 accumulation on tcgen05; reference = fp32 matmul of the same bf16-rounded operands.
+    Tolerance: bf16 output rounding (2^-8 relative) + fp32 accumulation-order slack."""
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(m * 7 + n)
+    a, b = _bf(torch.randn(m, k, generator=g)), _bf(torch.randn(n, k, generator=g) * 0.1)
+    bias, resid = torch.randn(n, generator=g), torch.randn(m, n, generator=g)
+    w = _bf(torch.randn(m, n, generator=g))
+    s = torch.tensor([0.37])
+    A, Bm = a.cuda().bfloat16(), b.cuda().bfloat16()
+    ldo = n + ldo_pad
+
+    def buf(dtype):
+        return torch.zeros(m, ldo, device="cuda", dtype=dtype)[:, :n]
+
+    v = a @ b.t()
+    sc = float(v.abs().max())
+    out32 = buf(torch.float32)
+    pf.gemm_nt(A, Bm, out_f32=out32)
+    assert ops.last_path() == 2, "tcgen05 GEMM was not selected"
+    _close(out32, v, 1e-5 * max(1.0, k / 64), "tc plain fp32 out")
+    # forward FFN-1 style epilogue
+    pre, h = buf(torch.bfloat16), buf(torch.bfloat16)
+    pf.gemm_nt(A, Bm, bias=bias.cuda(), act=pf.SA_ACT_GELU_FWD, pre=pre, out_act=h)
+    u = v + bias
+    torch.testing.assert_close(pre.float().cpu(), u, rtol=2 ** -7, atol=1e-3 * sc)
+    torch.testing.assert_close(h.float().cpu(), F.gelu(u), rtol=2 ** -6, atol=2e-3 * sc)
+    # ReZero residual epilogue, fp32 stream updated in place + bf16 copy
+    r = buf(torch.float32); r.copy_(resid.cuda())
+    xb = buf(torch.bfloat16)
+    pf.gemm_nt(A, Bm, bias=bias.cuda(), scale_dev=s.cuda(), resid=r, out_f32=r, out_act=xb)
+    _close(r, resid + 0.37 * u, 1e-5 * max(1.0, k / 64), "tc rezero")
+    torch.testing.assert_close(xb.float().cpu(), resid + 0.37 * u, rtol=2 ** -7, atol=1e-3 * sc)
+    # backward-style epilogue
+    dot = torch.zeros(1, device="cuda")
+    o3 = buf(torch.bfloat16)
+    wd = buf(torch.bfloat16); wd.copy_(w.cuda())
+    pf.gemm_nt(A, Bm, dot_with=wd, dot_out=dot, scale_dev=s.cuda(), scale=2.0, act=pf.SA_ACT_GELU_BWD, pre=pre, out_act=o3)
+    pu = pre.float().cpu().clone().requires_grad_(True)
+    F.gelu(pu).sum().backward()
+    assert abs(float(dot) - float((v * w).sum())) <= 1e-3 * float((v * w).abs().sum())
+    torch.testing.assert_close(o3.float().cpu(), v * 0.74 * pu.grad, rtol=2 ** -6, atol=2e-3 * sc)
+
+
+@pytest.mark.parametrize("m,na,nb", [(1000, 128, 256), (4096, 512, 1024), (777, 70, 130), (20000, 2049, 512), (64, 128, 64)])
+def test_tcgen05_gemm_tn_bf16(m, na, nb):
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(m + na)
+    lda, ldb = ((na + 7) // 8) * 8 + 8, ((nb + 7) // 8) * 8
+    a, b = _bf(torch.randn(m, na, generator=g)), _bf(torch.randn(m, nb, generator=g))
+    A = torch.zeros(m, lda, device="cuda", dtype=torch.bfloat16); A[:, 8:8 + na] = a.cuda()
+    Bm = torch.zeros(m, ldb, device="cuda", dtype=torch.bfloat16); Bm[:, :nb] = b.cuda()
+    d = torch.empty(na, nb, device="cuda")
+    s = torch.tensor([-0.5], device="cuda")
+    pf.gemm_tn(A[:, 8:8 + na], Bm[:, :nb], d, scale_dev=s, scale=2.0)
+    assert ops.last_path() == 2, "tcgen05 wgrad GEMM was not selected"
+    want = -(a.t() @ b)
+    _close(d, want, 2e-5 * max(1.0, m / 1000), "tc tn")
+    pf.gemm_tn(A[:, 8:8 + na], Bm[:, :nb], d, accumulate=True)
+    assert float(d.abs().max()) <= 1e-4 * float(want.abs().max()) * max(1.0, m / 1000)
+
+
 # ------------------------------------------------------------------------------------------------ FAVOR+
 def _heads_to_rows(t):          # [B, H, N, d] -> [B*N, H*d]
     B, H, N, d = t.shape
