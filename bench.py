@@ -1,12 +1,20 @@
 #!/usr/bin/env python
-"""Headline benchmark: VQ-VAE training step (forward + backward + Adam) on synthetic 160x224x160 volumes.
+"""Headline benchmark of the two hot paths BASELINE.json names, on synthetic data:
+
+  * VQ-VAE training step (forward + backward + Adam), 160x224x160 volumes  -> volumes/s   (top level of the JSON line)
+  * Performer prior training step (forward + CE + backward + Adam), seq 14 000 -> tokens/s (the "performer" object)
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference ...                     # the reference algorithm on the host CPU cores
+    python bench.py --workload vqvae|performer|both          # default: both
 
-Workload = BASELINE.json configs[1]: baseline_vqvae, 4 levels, 256 channels, codebook 2048x32, batch 8 per GPU,
+VQ-VAE workload = BASELINE.json configs[1]: baseline_vqvae, 4 levels, 256 channels, codebook 2048x32, batch 8 per GPU,
 bf16 operands / fp32 accumulation (the reference trains this model with --amp=True fp16 autocast, README.md:52),
-loss = mse(recon, x) + commitment loss, Adam lr 1.65e-4 (README.md:57).  Prints ONE JSON line on rank 0.
+loss = mse(recon, x) + commitment loss, Adam lr 1.65e-4 (README.md:57).
+Performer workload = BASELINE.json configs[3]: dim 512, 24 layers, 16 heads (8 local, window 420), 266 random features,
+vocab 2049, batch 6 per GPU, grid 20x28x25 => 14 000 tokens, feature_redraw_interval 1, CE loss, Adam lr 1e-3
+(README.md:119-141); bf16 operands / fp32 accumulation, fp32 residual stream.
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -41,6 +49,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    ap.add_argument("--workload", default="both", choices=["vqvae", "performer", "both"])
+    ap.add_argument("--pf-batch", type=int, default=6)
+    ap.add_argument("--pf-grid", type=int, nargs=3, default=[20, 28, 25])
+    ap.add_argument("--pf-depth", type=int, default=24)
+    ap.add_argument("--pf-breakdown", action="store_true", help="add a per-kernel time breakdown of one extra step")
     return ap.parse_args()
 
 
@@ -148,10 +161,7 @@ def cpu_baseline(budget_s, steps=1, warmup=0):
                       f"= {frac:.4f} volume, {steps} timed step(s); value extrapolated by voxel count"}, t
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def vqvae_reference(args):
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
     n = args.steps + args.warmup
@@ -162,7 +172,7 @@ def run_reference(args):
     cb = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
           "sample": f"oracle port of the reference VQ-VAE step on CPU, batch 1, crop {vol[0]}x{vol[1]}x{vol[2]} "
                     f"({frac:.4f} volume) per step; extrapolated by voxel count"}
-    print(json.dumps({
+    return ({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -170,28 +180,19 @@ def run_reference(args):
         "cpu_baseline": cb,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def run_b200(args):
+def vqvae_b200(args, world, rank, local, dev):
     import torch
     import torch.distributed as dist
     from synthanatomy_b200 import ops
     from synthanatomy_b200.losses import MSELoss
     from synthanatomy_b200.networks.vqvae import B200VQVAE
     from synthanatomy_b200.optim import Adam
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ops.lib()   # fail loudly here if the CUDA library is missing
 
     torch.manual_seed(4)                                   # README.md:55
     net = B200VQVAE(**KW, compute_dtype=torch.bfloat16).to(dev).train()
@@ -260,10 +261,10 @@ def run_b200(args):
     # ---- end-to-end through the public module API with host buffers
     ms_e2e, _ = (ms, None) if args.no_e2e else timed(args.steps, e2e=True)
 
+    del model, net, opt
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     vols = B * world * args.steps
     value = vols / (ms / 1e3)
     e2e_value = vols / (ms_e2e / 1e3)
@@ -305,17 +306,250 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(args.cpu_budget_s)
         out["cpu_baseline"] = cb
-    print(json.dumps(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Performer prior
+# ------------------------------------------------------------------------------------------------
+PF_METRIC = "Performer tokens/sec @seq14k (fwd+CE+bwd+Adam)"
+PF_UNIT = "tokens/s"
+PF_KW = dict(num_tokens=2049, dim=512, heads=16, dim_head=64, local_attn_heads=8, local_window_size=420)
+
+
+def pf_flop_per_token(depth, n, window=420):
+    """forward MFLOP per token per layer = QKV 3.146 + out 1.049 + FFN 4.194 + feature maps 0.545 +
+    causal scan 0.545 + local attention (causal-exact average of keys per query); + logits 2.098; x3 for fwd+bwd."""
+    nw = (n + window - 1) // window
+    keys = sum(min(window, n - w * window) * ((window if w else 0) + (min(window, n - w * window) + 1) / 2.0)
+               for w in range(nw)) / n
+    local = 8 * 2 * 2 * 64 * keys
+    per_layer = 3.146e6 + 1.049e6 + 4.194e6 + 0.545e6 + 0.545e6 + local
+    return 3.0 * (depth * per_layer + 2.098e6)
+
+
+def pf_cpu_step_time(grid, batch, depth, steps, warmup):
+    import numpy as np
+    import torch
+    from oracle import performer_oracle as po
+    n = int(np.prod(grid))
+    cfg = po.PerformerConfig(max_seq_len=n + 1, spatial_shape=tuple(grid), depth=depth, **PF_KW)
+    sd = po.init_state_dict(cfg, 4)
+    order = po.ordering_restated("raster_scan", (1, *grid), (False,) * 3, ((2, 0, 1),), ((0, 1),), ("rotate_90", "transpose"))
+    seqs = [torch.from_numpy(s.copy()) for s in po.spatial_index_sequences(grid, order)]
+    q = np.random.RandomState(2).randint(0, 2048, (batch, *grid))
+    x_in, y = po.prepare_batch(q, order, 2048)
+    x_in, y = torch.from_numpy(x_in), torch.from_numpy(y)
+    keys = po.trainable_keys(sd)
+    state = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in keys}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, grads, _ = po.train_step_grads(sd, cfg, x_in, y, seqs)
+        for k in keys:
+            m, v = state[k]
+            sd[k], m, v = po.adam_step(sd[k], grads[k], m, v, it + 1, 1e-3)
+            state[k] = (m, v)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), batch * n
+
+
+def pf_cpu_baseline(steps=1, warmup=0, depth=24):
+    """Bounded sample: the README-faithful latent grid 10x14x10 (N = 1400), batch 1, all `depth` layers (the per-token
+    cost of both attention kinds is independent of N, so tokens/s transfers to N = 14 000)."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    t, toks = pf_cpu_step_time((10, 14, 10), 1, depth, steps, warmup)
+    return {"value": toks / t, "unit": PF_UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle port (torch CPU fp32) of the reference Performer step, batch 1, grid 10x14x10 = 1400 tokens, "
+                      f"{depth} layers, {steps} timed step(s)"}, t
+
+
+def performer_reference(args):
+    cb, t = pf_cpu_baseline(steps=max(1, min(args.steps, 2)), warmup=min(args.warmup, 1), depth=args.pf_depth)
+    return {"impl": "reference", "metric": PF_METRIC, "value": cb["value"], "unit": PF_UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Performer dim512 L24 h16 (8 local, w420) m266 vocab2049 (CPU sample, see cpu_baseline)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": PF_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def performer_b200(args, world, rank, local, dev):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from synthanatomy_b200 import ops, pf_ops
+    from synthanatomy_b200.losses import CELoss
+    from synthanatomy_b200.networks.transformers import Ordering, Performer
+    from synthanatomy_b200.optim import Adam
+    from synthanatomy_b200.utils.transformer import prepare_batch
+
+    grid = tuple(args.pf_grid)
+    n = int(np.prod(grid))
+    B = args.pf_batch
+    torch.manual_seed(4)
+    order = Ordering("raster_scan", 3, (1, *grid), (False,) * 3, ((2, 0, 1),), ((0, 1),), ("rotate_90", "transpose"))
+    net = Performer(max_seq_len=n + 1, depth=args.pf_depth, ordering=order, causal=True, feature_redraw_interval=1,
+                    generalized_attention=False, use_rezero=True, spatial_position_emb="absolute", spatial_shape=grid,
+                    compute_dtype=torch.bfloat16, **PF_KW).to(dev).train()
+    model = net
     if world > 1:
-        dist.destroy_process_group()
+        # the reference wraps with broadcast_buffers=True so that every rank sees rank 0's projection matrices
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=True,
+                                                          bucket_cap_mb=128, gradient_as_bucket_view=True)
+    opt = Adam(net.parameters(), lr=1e-3)
+    crit = CELoss()
+    g = torch.Generator().manual_seed(200 + rank)
+    quant = torch.randint(0, 2048, (B, *grid), generator=g)
+    seq = order.get_sequence_ordering()
+    (x_host, _), y_host = prepare_batch({"quantization": quant}, seq, 2048)
+    x_host, y_host = x_host.contiguous().pin_memory(), y_host.contiguous().pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step(x, y):
+        logits = model(x)
+        loss = crit(logits.transpose(1, 2), y)          # TransformerTrainingInferer + CELoss
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            if e2e:
+                x = x_host.to(dev, non_blocking=True); y = y_host.to(dev, non_blocking=True)
+                loss = step(x, y)
+                loss_host.copy_(loss.detach(), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            else:
+                loss = step(x_dev, y_dev)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, float(loss.detach().item())
+
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    timer = pf_ops.KernelTimer(lambda name: name == "gemm_nt")
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ops.reset_launch_count()
+    pf_ops.set_timer(timer)
+    ms, loss = timed(args.steps, e2e=False)
+    pf_ops.set_timer(None)
+    launches = ops.launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e, _ = (ms, None) if args.no_e2e else timed(args.steps, e2e=True)
+    breakdown = None
+    if args.pf_breakdown and rank == 0:
+        t_all = pf_ops.KernelTimer()
+        pf_ops.set_timer(t_all)
+        step(x_dev, y_dev)
+        torch.cuda.synchronize()
+        pf_ops.set_timer(None)
+        breakdown = {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in
+                     sorted(t_all.summary().items(), key=lambda kv: -kv[1]["ms"])}
+    del model, net, opt
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    toks = B * n * world * args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    summ = timer.summary().get("gemm_nt")
+    roof = None
+    if summ:
+        ach = summ["flop"] / (summ["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "tc_gemm_nt_kernel (all dense-layer forward / data-gradient launches)",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "launches_timed": summ["launches"], "avg_ms": summ["ms"] / summ["launches"],
+                "flop_per_launch": summ["flop"] / summ["launches"], "share_of_step": summ["ms"] / ms,
+                "peak_source": peak_src}
+    full = grid == (20, 28, 25) and args.pf_depth == 24 and B == 6
+    step_flop = pf_flop_per_token(args.pf_depth, n) * B * n
+    out = {
+        "metric": PF_METRIC, "value": toks / (ms / 1e3), "unit": PF_UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"Performer dim512 L{args.pf_depth} h16 (8 local, w420) m266 vocab2049, grid "
+                               f"{grid[0]}x{grid[1]}x{grid[2]} = {n} tokens, batch {B}/GPU, fwd+CE+bwd+Adam, feature "
+                               f"redraw every 2nd step" + ("" if full else " (REDUCED: not the headline)"),
+                   "parallelism": f"dp{world}", "global_batch": B * world,
+                   "l2_policy": "per-layer activations (>= 86 MB each, 2.6 GB per layer) exceed the 126 MB L2; no flush needed"},
+        "step_tflops": step_flop / (ms / args.steps * 1e-3) / 1e12,
+        "loss": loss, "clocks": clk,
+        "e2e": {"value": toks / (ms_e2e / 1e3), "unit": PF_UNIT, "h2d_bytes_per_step": 2 * x_host.numel() * 8,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "roofline": roof,
+    }
+    if breakdown:
+        out["breakdown_ms"] = breakdown
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = pf_cpu_baseline(depth=args.pf_depth)
+        out["cpu_baseline"] = cb
+    return out
 
 
 def main():
     args = parse()
+    rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+        if rank != 0:
+            return
+        out = vqvae_reference(args) if args.workload in ("vqvae", "both") else None
+        if args.workload in ("performer", "both"):
+            pf = performer_reference(args)
+            if out is None:
+                out = pf
+            else:
+                out["performer"] = pf
+        print(json.dumps(out))
+        return
+    import torch
+    import torch.distributed as dist
+    from synthanatomy_b200 import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.lib()   # fail loudly here if the CUDA library is missing
+    out = vqvae_b200(args, world, rank, local, dev) if args.workload in ("vqvae", "both") else None
+    if args.workload in ("performer", "both"):
+        pf = performer_b200(args, world, rank, local, dev)
+        if rank == 0:
+            if out is None:
+                out = pf
+            else:
+                out["performer"] = pf
+                out["gpu_launches"] = int(out["gpu_launches"]) + int(pf["gpu_launches"])
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

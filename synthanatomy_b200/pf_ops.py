@@ -188,3 +188,63 @@ def local_attn_bwd(d, buf, qcol, kcol, vcol, inv_freq, out, dout, ocol, lse, dbu
     _lib.check(lib().sa_local_attn_bwd(C.byref(d), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol), _p(inv_freq),
                                        _ptr(out, ocol), _ptr(dout, ocol), _p(lse), _ptr(dbuf, qcol), _ptr(dbuf, kcol),
                                        _ptr(dbuf, vcol), _stream()), "sa_local_attn_bwd")
+
+
+# ------------------------------------------------------------------------------------------------
+# optional per-launch CUDA-event timing (bench.py: roofline of the dominant kernel, per-kernel breakdown)
+# ------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """Records (name, start event, end event) around every wrapper call whose name passes `match`.
+    Events are recorded on torch's current stream, the stream every kernel of this library is enqueued on."""
+
+    def __init__(self, match=None):
+        self.match = match
+        self.records = []
+
+    def summary(self):
+        out = {}
+        for name, e0, e1, meta in self.records:
+            ms = e0.elapsed_time(e1)
+            d = out.setdefault(name, {"ms": 0.0, "launches": 0, "flop": 0.0})
+            d["ms"] += ms; d["launches"] += 1; d["flop"] += meta
+        return out
+
+
+_TIMER: Optional[KernelTimer] = None
+
+
+def set_timer(timer: Optional[KernelTimer]) -> None:
+    global _TIMER
+    _TIMER = timer
+
+
+def _flops(name, args):
+    if name == "gemm_nt":
+        a, b = args[0], args[1]
+        return 2.0 * a.shape[0] * a.shape[1] * b.shape[0]
+    if name == "gemm_tn":
+        a, b = args[0], args[1]
+        return 2.0 * a.shape[0] * a.shape[1] * b.shape[1]
+    return 0.0
+
+
+def _instrument(name, fn):
+    def wrapper(*args, **kwargs):
+        t = _TIMER
+        if t is None or (t.match is not None and not t.match(name)):
+            return fn(*args, **kwargs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*args, **kwargs)
+        e1.record()
+        t.records.append((name, e0, e1, _flops(name, args)))
+        return r
+    wrapper.__name__ = fn.__name__
+    wrapper.__doc__ = fn.__doc__
+    return wrapper
+
+
+for _n in ("gemm_nt", "gemm_tn", "embed_fwd", "embed_bwd", "layernorm_fwd", "layernorm_bwd", "ce_fwd_bwd", "cast2d",
+           "favor_kmax", "favor_featmap_fwd", "favor_featmap_bwd", "favor_scan_fwd", "favor_scan_bwd", "local_attn_fwd",
+           "local_attn_bwd"):
+    globals()[_n] = _instrument(_n, globals()[_n])
