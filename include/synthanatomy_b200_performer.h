@@ -135,6 +135,14 @@ typedef struct sa_local_desc {
   int32_t act_dtype;
 } sa_local_desc;
 
+/* In-place rotary position term of the local heads (local_attention.apply_rotary_pos_emb with SinusoidalEmbeddings):
+ *   x <- x * cos(n * inv_freq) + rotate_half(x) * sin(n * inv_freq)    for the `heads` head blocks starting at `buf`
+ * inverse != 0 applies the transpose (the backward of the map).  buf: [batch * seq][ld], act dtype. */
+int sa_rotary(void* buf, int dtype, int64_t ld, int batch, int seq, int heads, int dim_head, const float* inv_freq,
+              int inverse, void* stream);
+
+/* inv_freq == NULL: q and k already carry the position term (sa_rotary) or none is wanted; the tcgen05 kernels take
+ * this form only. */
 int sa_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, const void* v, const float* inv_freq,
                       void* out, float* lse, void* stream);
 int sa_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, const void* v, const float* inv_freq,

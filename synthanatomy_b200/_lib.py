@@ -120,6 +120,7 @@ SIGNATURES = {
                                   c_void_p]),
     "sa_local_attn_bwd": (c_int, [C.POINTER(LocalDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sa_rotary": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "sa_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p]),
     "sa_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p,

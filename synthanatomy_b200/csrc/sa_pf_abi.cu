@@ -28,6 +28,12 @@ int sa_simt_local_attn_fwd(const sa_local_desc*, const void*, const void*, const
 int sa_simt_local_attn_bwd(const sa_local_desc*, const void*, const void*, const void*, const float*, const void*,
                            const void*, const float*, void*, void*, void*, cudaStream_t);
 
+bool sa_tc_local_supported(const sa_local_desc*, const void*, const void*, const void*, const float*);
+int sa_tc_local_attn_fwd(const sa_local_desc*, const void*, const void*, const void*, void*, float*, cudaStream_t);
+int sa_tc_local_attn_bwd(const sa_local_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
+                         void*, void*, void*, cudaStream_t);
+int sa_rotary_launch(void*, int, int64_t, int, int, int, int, const float*, int, cudaStream_t);
+
 extern "C" int sa_gemm_nt(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
                           const sa_gemm_epilogue* epi, int64_t ldo, void* stream) {
   SA_CHECK_ARG(a && b && epi, "null pointer");
@@ -103,6 +109,8 @@ extern "C" int sa_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const v
 extern "C" int sa_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, const void* v,
                                  const float* inv_freq, void* out, float* lse, void* stream) {
   SA_CHECK_ARG(d && q && k && v && out && lse, "null pointer");
+  if (!sa_force_simt() && sa_tc_local_supported(d, q, k, v, inv_freq))
+    return sa_tc_local_attn_fwd(d, q, k, v, out, lse, sa_stream(stream));
   return sa_simt_local_attn_fwd(d, q, k, v, inv_freq, out, lse, sa_stream(stream));
 }
 
@@ -110,5 +118,16 @@ extern "C" int sa_local_attn_bwd(const sa_local_desc* d, const void* q, const vo
                                  const float* inv_freq, const void* out, const void* dout, const float* lse, void* dq,
                                  void* dk, void* dv, void* stream) {
   SA_CHECK_ARG(d && q && k && v && out && dout && lse && dq && dk && dv, "null pointer");
+  if (!sa_force_simt() && sa_tc_local_supported(d, q, k, v, inv_freq))
+    return sa_tc_local_attn_bwd(d, q, k, v, out, dout, lse, dq, dk, dv, sa_stream(stream));
   return sa_simt_local_attn_bwd(d, q, k, v, inv_freq, out, dout, lse, dq, dk, dv, sa_stream(stream));
+}
+
+extern "C" int sa_rotary(void* buf, int dtype, int64_t ld, int batch, int seq, int heads, int dim_head,
+                         const float* inv_freq, int inverse, void* stream) {
+  SA_CHECK_ARG(buf && inv_freq, "null pointer");
+  SA_CHECK_ARG(batch > 0 && seq > 0 && heads > 0 && dim_head > 0 && (dim_head & 1) == 0 && ld >= (int64_t)heads * dim_head,
+               "bad sizes");
+  SA_CHECK_ARG(dtype == SA_F32 || dtype == SA_BF16, "bad dtype");
+  return sa_rotary_launch(buf, dtype, ld, batch, seq, heads, dim_head, inv_freq, inverse, sa_stream(stream));
 }

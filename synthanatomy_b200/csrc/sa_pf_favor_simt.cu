@@ -543,6 +543,7 @@ int sa_simt_favor_kmax(const sa_favor_desc* d, const void* k, const float* proj,
                        cudaStream_t st) {
   int rc = check_favor(d);
   if (rc != SA_OK) return rc;
+  sa_note_path(SA_PATH_SIMT);
   const FmArgs a = make_fm(d, 0.f);
   const size_t smem = fm_smem(a);
   dim3 grid((unsigned)sa_cdiv(d->seq, FT_CHUNK), (unsigned)(d->batch * d->heads));
@@ -562,6 +563,7 @@ int sa_simt_favor_featmap_fwd(const sa_favor_desc* d, const void* x, const float
                               const unsigned long long* kmax, float eps, void* feat, int32_t* argmax, cudaStream_t st) {
   int rc = check_favor(d);
   if (rc != SA_OK) return rc;
+  sa_note_path(SA_PATH_SIMT);
   const FmArgs a = make_fm(d, eps);
   const size_t smem = fm_smem(a);
   dim3 grid((unsigned)sa_cdiv(d->seq, FT_CHUNK), (unsigned)(d->batch * d->heads));
@@ -585,6 +587,7 @@ int sa_simt_favor_featmap_bwd(const sa_favor_desc* d, const void* x, const float
                               cudaStream_t st) {
   int rc = check_favor(d);
   if (rc != SA_OK) return rc;
+  sa_note_path(SA_PATH_SIMT);
   const FmArgs a = make_fm(d, eps);
   const size_t smem = fm_smem(a);
   dim3 grid((unsigned)sa_cdiv(d->seq, FT_CHUNK), (unsigned)(d->batch * d->heads));
@@ -606,6 +609,7 @@ int sa_simt_favor_kmax_fixup(const sa_favor_desc* d, const float* proj, const un
                              const float* gsum, void* dk, cudaStream_t st) {
   int rc = check_favor(d);
   if (rc != SA_OK) return rc;
+  sa_note_path(SA_PATH_SIMT);
   const FmArgs a = make_fm(d, 0.f);
   if (d->act_dtype == SA_F32) kmax_fixup_kernel<float><<<1, 64, 0, st>>>(a, proj, kmax, gsum, (float*)dk);
   else kmax_fixup_kernel<__nv_bfloat16><<<1, 64, 0, st>>>(a, proj, kmax, gsum, (__nv_bfloat16*)dk);
@@ -622,6 +626,7 @@ int sa_simt_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* k
                            int out_ld, float* den, void* ws, size_t ws_bytes, cudaStream_t st) {
   int rc = check_favor(d);
   if (rc != SA_OK) return rc;
+  sa_note_path(SA_PATH_SIMT);
   if (ws_bytes < sa_simt_favor_scan_workspace(d, 0)) { sa_set_error("favor_scan_fwd: workspace too small"); return SA_ERR_WORKSPACE; }
   const ScArgs a = make_sc(d, out_ld, eps);
   float* state = (float*)ws;
@@ -649,6 +654,7 @@ int sa_simt_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* k
                            void* dv, void* ws, size_t ws_bytes, cudaStream_t st) {
   int rc = check_favor(d);
   if (rc != SA_OK) return rc;
+  sa_note_path(SA_PATH_SIMT);
   if (ws_bytes < sa_simt_favor_scan_workspace(d, 1)) { sa_set_error("favor_scan_bwd: workspace too small"); return SA_ERR_WORKSPACE; }
   const ScArgs a = make_sc(d, out_ld, eps);
   float* stateS = (float*)ws;

@@ -309,6 +309,7 @@ int sa_simt_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k,
                            void* out, float* lse, cudaStream_t st) {
   int rc = check_local(d);
   if (rc != SA_OK) return rc;
+  sa_note_path(SA_PATH_SIMT);
   const LaArgs a = make_la(d);
   dim3 grid((unsigned)sa_cdiv(d->seq, LT), (unsigned)(d->batch * d->heads));
   const size_t smem = sizeof(float) * 4 * LT * LD;
@@ -330,6 +331,7 @@ int sa_simt_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k,
                            cudaStream_t st) {
   int rc = check_local(d);
   if (rc != SA_OK) return rc;
+  sa_note_path(SA_PATH_SIMT);
   const LaArgs a = make_la(d);
   dim3 grid((unsigned)sa_cdiv(d->seq, LT), (unsigned)(d->batch * d->heads));
   const size_t smem_q = sizeof(float) * (5 * LT * LD + 2 * LT);

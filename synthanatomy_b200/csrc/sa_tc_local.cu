@@ -1,0 +1,662 @@
+// tcgen05 local-window causal attention for sm_100a (bf16 operands, fp32 accumulation), flash style: the score tensor
+// never leaves the SM.
+//
+//   query p attends keys j with lo(p) <= j <= p,  lo(p) = max(0, floor(p / w) - 1) * w      (window w, look-back 1)
+//   S = q k^T * d^-1/2   P = softmax(S)   O = P v          (q, k already carry the rotary position term: sa_rotary)
+//
+// forward   one CTA per (batch, head, 128-query tile); key tiles of 64.  S = Q K^T and O_part = P V on tcgen05
+//           (accumulators in TMEM), online softmax out of TMEM by 4 warps (thread = query row), P re-staged as bf16
+//           into 128B-swizzled shared memory (the K-major A operand of the second MMA), O accumulated in registers.
+// backward  dq kernel: per 128-query tile, loop key tiles:  S, dP = dO V^T  ->  dS = P (dP - delta) / sqrt(d)  ->  dQ += dS K
+//           dkv kernel: per 128-key tile, loop 64-query tiles, transposed roles (TMEM lane = key):
+//                       S^T = K Q^T, dP^T = V dO^T  ->  P^T, dS^T  ->  dV += P^T dO,  dK += dS^T Q
+// Warp roles: warps 0-3 softmax / epilogue (TMEM lane quadrants 0-3), warp 4 MMA issuer, warp 5 TMA producer.
+//
+// Replaces local_attention.LocalAttention.forward (+ autograd) called by performer-pytorch SelfAttention for the local
+// heads, reached from /root/reference/src/networks/transformers/performer.py:270 (ctor args :199-200).
+#include <mutex>
+
+#include "sa_pf_common.cuh"
+#include "sa_tc_common.cuh"
+
+using namespace satc;
+
+namespace {
+
+constexpr int L_THREADS = 192;
+constexpr int L_STAGES_FWD = 3;
+constexpr int L_STAGES_BWD = 2;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct LcParams {
+  CUtensorMap qmap, kmap, vmap, domap;   // 2-D maps over the [rows][ld] buffers, based at head 0 of each block
+  int B, N, H, W;
+  int ld, out_ld;
+  float scale;
+  const __nv_bfloat16* out;
+  const __nv_bfloat16* dout;
+  __nv_bfloat16* o_out;      // forward output
+  float* lse;
+  __nv_bfloat16* dq;
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+};
+
+__device__ __forceinline__ int lc_lo(int p, int W) { const int w = p / W - 1; return (w > 0 ? w : 0) * W; }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// write 32 consecutive columns [c0, c0+32) of row r of a K-major SWIZZLE_128B bf16 block ([rows][64 cols], 128 B rows)
+__device__ __forceinline__ void st_sw128_32(uint8_t* block, int r, int c0, const float (&f)[32]) {
+  uint8_t* row = block + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = (c0 >> 3) + i;
+    uint4 u;
+    u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]); u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+    u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]); u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+    *reinterpret_cast<uint4*>(row + ((ch ^ (r & 7)) << 4)) = u;
+  }
+}
+
+// D[tmem] (+)= A[128 x 64, K-major block] * B^T, B a K-major [n x 64] block  (contraction over the 64 columns)
+__device__ __forceinline__ void mma_kk(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 32, 16, 1024, 2), idesc,
+              (accumulate || k != 0) ? 1u : 0u);
+}
+// D[tmem] (+)= A[128 x 64, K-major block] * B, B an MN-major [64 rows (contraction) x 64 cols] block
+__device__ __forceinline__ void mma_km(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, 1024, 2), make_smem_desc(b_addr + k * 2048, 8192, 1024, 2), idesc,
+              (accumulate || k != 0) ? 1u : 0u);
+}
+
+__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const float (&f)[64]) {
+  uint4* q = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]); u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+    u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]); u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+    q[i] = u;
+  }
+}
+
+// delta = sum_e dO[e] * O[e] of one row (global reads, 2 x 128 B)
+__device__ __forceinline__ float row_delta(const __nv_bfloat16* o, const __nv_bfloat16* d_o) {
+  const uint4* a = reinterpret_cast<const uint4*>(o);
+  const uint4* b = reinterpret_cast<const uint4*>(d_o);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 x = __ldg(a + i), y = __ldg(b + i);
+    acc = fmaf(bf16lo(x.x), bf16lo(y.x), acc); acc = fmaf(bf16hi(x.x), bf16hi(y.x), acc);
+    acc = fmaf(bf16lo(x.y), bf16lo(y.y), acc); acc = fmaf(bf16hi(x.y), bf16hi(y.y), acc);
+    acc = fmaf(bf16lo(x.z), bf16lo(y.z), acc); acc = fmaf(bf16hi(x.z), bf16hi(y.z), acc);
+    acc = fmaf(bf16lo(x.w), bf16lo(y.w), acc); acc = fmaf(bf16hi(x.w), bf16hi(y.w), acc);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(L_THREADS, 2)
+tc_local_fwd_kernel(const __grid_constant__ LcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, s_full[2], p_full, o_full;
+  __shared__ uint64_t kv_full[L_STAGES_FWD], kv_empty[L_STAGES_FWD];
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Qs = smem;                       // 16 KB
+  uint8_t* Ps = Qs + 16384;                 // 8 KB used as [128 x 64] -> 16 KB
+  uint8_t* KV = Ps + 16384;                 // stages x (K 8 KB | V 8 KB)
+  const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
+  const int i0 = blockIdx.x * 128;
+  const int j_beg = (lc_lo(i0, P.W) / 64) * 64;
+  const int j_last = min(P.N - 1, i0 + 127);
+  const int ntiles = (j_last - j_beg) / 64 + 1;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1); mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
+    for (int i = 0; i < L_STAGES_FWD; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 4) { tmem_alloc(&tmem_base_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 128;     // S buffers at columns 0 / 64, O_part at 128
+
+  if (warp == 5) {
+    if (lane == 0) {
+      prefetch_tmap(&P.qmap); prefetch_tmap(&P.kmap); prefetch_tmap(&P.vmap);
+      mbar_expect_tx(&q_full, 16384);
+      tma_load_2d(Qs, &P.qmap, &q_full, h * 64, b * P.N + i0);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&kv_full[stage], 16384);
+        uint8_t* ks = KV + stage * 16384;
+        tma_load_2d(ks, &P.kmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
+        tma_load_2d(ks + 8192, &P.vmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
+        if (++stage == L_STAGES_FWD) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t qa = smem_u32(Qs), pa = smem_u32(Ps), kva = smem_u32(KV);
+      mbar_wait(&q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      mma_kk(tS0, qa, kva, idesc_s, false);
+      umma_commit(&s_full[0]);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        int nstage = stage + 1; uint32_t nphase = phase;
+        if (nstage == L_STAGES_FWD) { nstage = 0; nphase ^= 1; }
+        if (t + 1 < ntiles) {                                   // S of the next tile, while the softmax warps work on this one
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          mma_kk(tS0 + (uint32_t)(((t + 1) & 1) * 64), qa, kva + nstage * 16384, idesc_s, false);
+          umma_commit(&s_full[(t + 1) & 1]);
+        }
+        mbar_wait(&p_full, (uint32_t)(t & 1));                  // P_t is in shared memory (and S_t, O_{t-1} were read)
+        tc_fence_after();
+        mma_km(tO, pa, kva + stage * 16384 + 8192, idesc_o, false);
+        umma_commit(&o_full);
+        umma_commit(&kv_empty[stage]);
+        stage = nstage; phase = nphase;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warps: thread = query row
+    const int r = warp * 32 + lane;
+    const int p = i0 + r;
+    const int lo = lc_lo(p, P.W);
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float c2 = P.scale * LOG2E;
+    float o[64];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) o[e] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+      const int j0 = j_beg + t * 64;
+      mbar_wait(&s_full[t & 1], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const uint32_t ts = tS0 + lane_addr + (uint32_t)((t & 1) * 64);
+      // pass 1 over the S row: running maximum (TMEM reads are cheap; keeps the register footprint at 2 CTAs / SM)
+      float mt = -INFINITY;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld_32x32(ts + (uint32_t)(hh * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int j = j0 + hh * 32 + c;
+          const bool ok = (j <= p) && (j >= lo) && (p < P.N);
+          mt = fmaxf(mt, ok ? __uint_as_float(v[c]) * c2 : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m, mt);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = ex2(m - m_safe);
+      if (t > 0) {                                              // fold in O_part of the previous tile (scale m_old)
+        mbar_wait(&o_full, (uint32_t)((t - 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld_32x32(tO + lane_addr + (uint32_t)(hh * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[hh * 32 + e] += __uint_as_float(v[e]);
+        }
+      }
+      // pass 2: probabilities -> bf16 -> swizzled shared memory (A operand of P V)
+      float ps = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld_32x32(ts + (uint32_t)(hh * 32), v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int j = j0 + hh * 32 + c;
+          const bool ok = (j <= p) && (j >= lo) && (p < P.N);
+          f[c] = ok ? ex2(__uint_as_float(v[c]) * c2 - m_safe) : 0.f;
+          ps += f[c];
+        }
+        st_sw128_32(Ps, r, hh * 32, f);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&p_full);
+#pragma unroll
+      for (int e = 0; e < 64; ++e) o[e] *= alpha;
+      l = l * alpha + ps;
+      m = m_new;
+    }
+    mbar_wait(&o_full, (uint32_t)((ntiles - 1) & 1));
+    tc_fence_after();
+    {
+      uint32_t v[32];
+      tmem_ld_32x32(tO + lane_addr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[e] += __uint_as_float(v[e]);
+      tmem_ld_32x32(tO + lane_addr + 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[32 + e] += __uint_as_float(v[e]);
+    }
+    if (p < P.N) {
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int e = 0; e < 64; ++e) o[e] *= inv;
+      store_row64_bf16(P.o_out + ((long long)b * P.N + p) * P.out_ld + h * 64, o);
+      P.lse[(long long)bh * P.N + p] = (m + log2f(l)) * 0.6931471805599453f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dq
+__global__ void __launch_bounds__(L_THREADS, 2)
+tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, sdp_full, ds_full, dq_full;
+  __shared__ uint64_t kv_full[L_STAGES_FWD], kv_empty[L_STAGES_FWD];
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Qs = smem;                       // 16 KB
+  uint8_t* dOs = Qs + 16384;                // 16 KB
+  uint8_t* dSs = dOs + 16384;               // 16 KB  [128 q x 64 keys]
+  uint8_t* KV = dSs + 16384;                // stages x (K 8 KB | V 8 KB)
+  const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
+  const int i0 = blockIdx.x * 128;
+  const int j_beg = (lc_lo(i0, P.W) / 64) * 64;
+  const int j_last = min(P.N - 1, i0 + 127);
+  const int ntiles = (j_last - j_beg) / 64 + 1;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1); mbar_init(&sdp_full, 1); mbar_init(&ds_full, 128); mbar_init(&dq_full, 1);
+    for (int i = 0; i < L_STAGES_FWD; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 4) { tmem_alloc(&tmem_base_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdQ = tmem_base + 128;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      prefetch_tmap(&P.qmap); prefetch_tmap(&P.kmap); prefetch_tmap(&P.vmap); prefetch_tmap(&P.domap);
+      mbar_expect_tx(&q_full, 32768);
+      tma_load_2d(Qs, &P.qmap, &q_full, h * 64, b * P.N + i0);
+      tma_load_2d(dOs, &P.domap, &q_full, h * 64, b * P.N + i0);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&kv_full[stage], 16384);
+        uint8_t* ks = KV + stage * 16384;
+        tma_load_2d(ks, &P.kmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
+        tma_load_2d(ks + 8192, &P.vmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
+        if (++stage == L_STAGES_FWD) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc_kk = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_km = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t qa = smem_u32(Qs), doa = smem_u32(dOs), dsa = smem_u32(dSs), kva = smem_u32(KV);
+      mbar_wait(&q_full, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&kv_full[stage], phase);
+        tc_fence_after();
+        mma_kk(tS, qa, kva + stage * 16384, idesc_kk, false);              // S = Q K^T
+        mma_kk(tdP, doa, kva + stage * 16384 + 8192, idesc_kk, false);     // dP = dO V^T
+        umma_commit(&sdp_full);
+        mbar_wait(&ds_full, (uint32_t)(t & 1));
+        tc_fence_after();
+        mma_km(tdQ, dsa, kva + stage * 16384, idesc_km, t > 0);            // dQ += dS K
+        umma_commit(&kv_empty[stage]);
+        if (++stage == L_STAGES_FWD) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&dq_full);
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const int p = i0 + r;
+    const int lo = lc_lo(p, P.W);
+    const bool row_ok = p < P.N;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float c2 = P.scale * LOG2E;
+    float lse2 = 0.f, delta = 0.f;
+    if (row_ok) {
+      lse2 = P.lse[(long long)bh * P.N + p] * LOG2E;
+      const long long ro = ((long long)b * P.N + p) * P.out_ld + h * 64;
+      delta = row_delta(P.out + ro, P.dout + ro);
+    }
+    for (int t = 0; t < ntiles; ++t) {
+      const int j0 = j_beg + t * 64;
+      mbar_wait(&sdp_full, (uint32_t)(t & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t vs[32], vd[32];
+        tmem_ld_32x32(tS + lane_addr + (uint32_t)(hh * 32), vs);
+        tmem_ld_32x32(tdP + lane_addr + (uint32_t)(hh * 32), vd);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int j = j0 + hh * 32 + c;
+          const bool ok = row_ok && (j <= p) && (j >= lo);
+          const float pr = ok ? ex2(__uint_as_float(vs[c]) * c2 - lse2) : 0.f;
+          f[c] = pr * (__uint_as_float(vd[c]) - delta) * P.scale;
+        }
+        st_sw128_32(dSs, r, hh * 32, f);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&ds_full);
+    }
+    mbar_wait(&dq_full, 0);
+    tc_fence_after();
+    float g[64];
+    {
+      uint32_t v[32];
+      tmem_ld_32x32(tdQ + lane_addr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) g[e] = __uint_as_float(v[e]);
+      tmem_ld_32x32(tdQ + lane_addr + 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) g[32 + e] = __uint_as_float(v[e]);
+    }
+    if (row_ok) store_row64_bf16(P.dq + ((long long)b * P.N + p) * P.ld + h * 64, g);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dk, dv
+__global__ void __launch_bounds__(L_THREADS, 2)
+tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t kv_full, sdp_full, ds_full, acc_full;
+  __shared__ uint64_t qd_full[L_STAGES_BWD], qd_empty[L_STAGES_BWD];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_lse2[2][64], s_delta[2][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Ks = smem;                       // 16 KB [128 keys x 64]
+  uint8_t* Vs = Ks + 16384;                 // 16 KB
+  uint8_t* PTs = Vs + 16384;                // 16 KB [128 keys x 64 queries]
+  uint8_t* dSTs = PTs + 16384;              // 16 KB
+  uint8_t* QD = dSTs + 16384;               // stages x (Q 8 KB | dO 8 KB)
+  const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
+  const int j0 = blockIdx.x * 128;
+  const int j_hi = min(P.N - 1, j0 + 127);
+  const int i_last = min(P.N - 1, (j_hi / P.W + 2) * P.W - 1);
+  const int ntiles = (i_last - j0) / 64 + 1;         // query tiles of 64 starting at j0
+
+  if (threadIdx.x == 0) {
+    mbar_init(&kv_full, 1); mbar_init(&sdp_full, 1); mbar_init(&ds_full, 128); mbar_init(&acc_full, 1);
+    for (int i = 0; i < L_STAGES_BWD; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 4) { tmem_alloc(&tmem_base_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tST = tmem_base, tdPT = tmem_base + 64, tdV = tmem_base + 128, tdK = tmem_base + 192;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      prefetch_tmap(&P.qmap); prefetch_tmap(&P.kmap); prefetch_tmap(&P.vmap); prefetch_tmap(&P.domap);
+      mbar_expect_tx(&kv_full, 32768);
+      tma_load_2d(Ks, &P.kmap, &kv_full, h * 64, b * P.N + j0);
+      tma_load_2d(Vs, &P.vmap, &kv_full, h * 64, b * P.N + j0);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&qd_empty[stage], phase ^ 1);
+        mbar_expect_tx(&qd_full[stage], 16384);
+        uint8_t* qs = QD + stage * 16384;
+        tma_load_2d(qs, &P.qmap, &qd_full[stage], h * 64, b * P.N + j0 + t * 64);
+        tma_load_2d(qs + 8192, &P.domap, &qd_full[stage], h * 64, b * P.N + j0 + t * 64);
+        if (++stage == L_STAGES_BWD) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc_kk = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_km = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t ka = smem_u32(Ks), va = smem_u32(Vs), pta = smem_u32(PTs), dsta = smem_u32(dSTs), qda = smem_u32(QD);
+      mbar_wait(&kv_full, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&qd_full[stage], phase);
+        tc_fence_after();
+        mma_kk(tST, ka, qda + stage * 16384, idesc_kk, false);             // S^T = K Q^T
+        mma_kk(tdPT, va, qda + stage * 16384 + 8192, idesc_kk, false);     // dP^T = V dO^T
+        umma_commit(&sdp_full);
+        mbar_wait(&ds_full, (uint32_t)(t & 1));
+        tc_fence_after();
+        mma_km(tdV, pta, qda + stage * 16384 + 8192, idesc_km, t > 0);     // dV += P^T dO
+        mma_km(tdK, dsta, qda + stage * 16384, idesc_km, t > 0);           // dK += dS^T Q
+        umma_commit(&qd_empty[stage]);
+        if (++stage == L_STAGES_BWD) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&acc_full);
+    }
+  } else {
+    const int r = warp * 32 + lane;          // key row
+    const int j = j0 + r;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float c2 = P.scale * LOG2E;
+    for (int t = 0; t < ntiles; ++t) {
+      const int q0 = j0 + t * 64;
+      const int buf = t & 1;
+      if (r < 64) {                          // per-query statistics of this query tile
+        const int p = q0 + r;
+        float l2 = 0.f, dl = 0.f;
+        if (p < P.N) {
+          l2 = P.lse[(long long)bh * P.N + p] * LOG2E;
+          const long long ro = ((long long)b * P.N + p) * P.out_ld + h * 64;
+          dl = row_delta(P.out + ro, P.dout + ro);
+        }
+        s_lse2[buf][r] = l2; s_delta[buf][r] = dl;
+      }
+      bar_softmax();
+      mbar_wait(&sdp_full, (uint32_t)(t & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t vs[32], vd[32];
+        tmem_ld_32x32(tST + lane_addr + (uint32_t)(hh * 32), vs);
+        tmem_ld_32x32(tdPT + lane_addr + (uint32_t)(hh * 32), vd);
+        tmem_ld_wait();
+        float fp[32], fd[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int p = q0 + hh * 32 + c;
+          const bool ok = (p < P.N) && (j <= p) && (j >= lc_lo(p, P.W)) && (j < P.N);
+          const float pr = ok ? ex2(__uint_as_float(vs[c]) * c2 - s_lse2[buf][hh * 32 + c]) : 0.f;
+          fp[c] = pr;
+          fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
+        }
+        st_sw128_32(PTs, r, hh * 32, fp);
+        st_sw128_32(dSTs, r, hh * 32, fd);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&ds_full);
+    }
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    float g[64];
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t ta = which ? tdK : tdV;
+      uint32_t v[32];
+      tmem_ld_32x32(ta + lane_addr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) g[e] = __uint_as_float(v[e]);
+      tmem_ld_32x32(ta + lane_addr + 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) g[32 + e] = __uint_as_float(v[e]);
+      if (j < P.N) store_row64_bf16((which ? P.dk : P.dv) + ((long long)b * P.N + j) * P.ld + h * 64, g);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ rotary (in place)
+template <typename T>
+__global__ void rotary_kernel(T* __restrict__ buf, long long ld, int B, int N, int H, int d, const float* __restrict__ inv_freq,
+                              int inverse) {
+  const int half = d / 2;
+  const long long total = (long long)B * N * H * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int dd = (int)(i % half);
+    const int hh = (int)((i / half) % H);
+    const long long row = i / ((long long)half * H);
+    const int n = (int)(row % N);
+    const long long o = row * ld + hh * d + dd;
+    float sn, cs;
+    sincosf((float)n * inv_freq[dd], &sn, &cs);
+    if (inverse) sn = -sn;
+    const float x1 = sa_ld(buf, o), x2 = sa_ld(buf, o + half);
+    sa_st(buf, o, x1 * cs - x2 * sn);
+    sa_st(buf, o + half, x2 * cs + x1 * sn);
+  }
+}
+
+std::once_flag g_once;
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+constexpr size_t SMEM_FWD = 16384 * 2 + L_STAGES_FWD * 16384 + 1024;
+constexpr size_t SMEM_DQ = 16384 * 3 + L_STAGES_FWD * 16384 + 1024;
+constexpr size_t SMEM_DKV = 16384 * 4 + L_STAGES_BWD * 16384 + 1024;
+
+void init_once() {
+  std::call_once(g_once, [] {
+    cudaFuncSetAttribute(tc_local_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD);
+    cudaFuncSetAttribute(tc_local_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQ);
+    cudaFuncSetAttribute(tc_local_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DKV);
+  });
+}
+
+int make_map(CUtensorMap* m, const void* base, const sa_local_desc* d, int ld, uint32_t box_rows) {
+  const uint64_t dims[2] = {(uint64_t)d->heads * 64, (uint64_t)d->batch * d->seq};
+  const uint64_t strides[2] = {2, (uint64_t)ld * 2};
+  const uint32_t box[2] = {64, box_rows};
+  return sa_make_tmap_bf16(m, base, 2, dims, strides, box);
+}
+
+void fill_common(LcParams& P, const sa_local_desc* d) {
+  P.B = d->batch; P.N = d->seq; P.H = d->heads; P.W = d->window; P.ld = d->ld; P.out_ld = d->out_ld;
+  P.scale = 1.0f / sqrtf((float)d->dim_head);
+  P.out = nullptr; P.dout = nullptr; P.o_out = nullptr; P.lse = nullptr; P.dq = P.dk = P.dv = nullptr;
+}
+
+}  // namespace
+
+bool sa_tc_local_supported(const sa_local_desc* d, const void* q, const void* k, const void* v, const float* inv_freq) {
+  if (d->act_dtype != SA_BF16 || d->dim_head != 64 || inv_freq != nullptr) return false;
+  if ((d->ld & 7) || (d->out_ld & 7) || !aligned16(q) || !aligned16(k) || !aligned16(v)) return false;
+  if ((long long)d->batch * d->heads > 65535 || d->window < 1) return false;
+  return sa_get_tmap_encode() != nullptr;
+}
+
+int sa_tc_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, const void* v, void* out, float* lse,
+                         cudaStream_t st) {
+  init_once();
+  sa_note_path(SA_PATH_TCGEN05);
+  if (!aligned16(out)) { sa_set_error("tc_local_fwd: output not 16-byte aligned"); return SA_ERR_INVALID; }
+  static thread_local LcParams P;
+  fill_common(P, d);
+  int rc;
+  if ((rc = make_map(&P.qmap, q, d, d->ld, 128)) != SA_OK) return rc;
+  if ((rc = make_map(&P.kmap, k, d, d->ld, 64)) != SA_OK) return rc;
+  if ((rc = make_map(&P.vmap, v, d, d->ld, 64)) != SA_OK) return rc;
+  P.o_out = (__nv_bfloat16*)out; P.lse = lse;
+  dim3 grid((unsigned)sa_cdiv(d->seq, 128), (unsigned)(d->batch * d->heads));
+  tc_local_fwd_kernel<<<grid, L_THREADS, SMEM_FWD, st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+int sa_tc_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, const void* v, const void* out,
+                         const void* dout, const float* lse, void* dq, void* dk, void* dv, cudaStream_t st) {
+  init_once();
+  sa_note_path(SA_PATH_TCGEN05);
+  if (!aligned16(out) || !aligned16(dout) || !aligned16(dq) || !aligned16(dk) || !aligned16(dv)) {
+    sa_set_error("tc_local_bwd: pointers not 16-byte aligned");
+    return SA_ERR_INVALID;
+  }
+  static thread_local LcParams P;
+  fill_common(P, d);
+  P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.lse = const_cast<float*>(lse);
+  P.dq = (__nv_bfloat16*)dq; P.dk = (__nv_bfloat16*)dk; P.dv = (__nv_bfloat16*)dv;
+  int rc;
+  // dq kernel: 128-row Q / dO boxes, 64-row K / V boxes
+  if ((rc = make_map(&P.qmap, q, d, d->ld, 128)) != SA_OK) return rc;
+  if ((rc = make_map(&P.domap, dout, d, d->out_ld, 128)) != SA_OK) return rc;
+  if ((rc = make_map(&P.kmap, k, d, d->ld, 64)) != SA_OK) return rc;
+  if ((rc = make_map(&P.vmap, v, d, d->ld, 64)) != SA_OK) return rc;
+  dim3 grid((unsigned)sa_cdiv(d->seq, 128), (unsigned)(d->batch * d->heads));
+  tc_local_bwd_dq_kernel<<<grid, L_THREADS, SMEM_DQ, st>>>(P);
+  SA_LAUNCH_CHECK();
+  // dkv kernel: 128-row K / V boxes, 64-row Q / dO boxes
+  if ((rc = make_map(&P.qmap, q, d, d->ld, 64)) != SA_OK) return rc;
+  if ((rc = make_map(&P.domap, dout, d, d->out_ld, 64)) != SA_OK) return rc;
+  if ((rc = make_map(&P.kmap, k, d, d->ld, 128)) != SA_OK) return rc;
+  if ((rc = make_map(&P.vmap, v, d, d->ld, 128)) != SA_OK) return rc;
+  tc_local_bwd_dkv_kernel<<<grid, L_THREADS, SMEM_DKV, st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+int sa_rotary_launch(void* buf, int dtype, int64_t ld, int batch, int seq, int heads, int dim_head, const float* inv_freq,
+                     int inverse, cudaStream_t st) {
+  const long long total = (long long)batch * seq * heads * (dim_head / 2);
+  long long blocks = sa_cdiv(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == SA_BF16)
+    rotary_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)buf, ld, batch, seq, heads, dim_head,
+                                                                   inv_freq, inverse);
+  else
+    rotary_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)buf, ld, batch, seq, heads, dim_head, inv_freq, inverse);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}

@@ -179,6 +179,12 @@ def favor_scan_bwd(d, qf, kf, vbuf, vcol, eps, out, dout, ocol, den, dqf, dkf, d
                                        _p(ws), ws.numel() * ws.element_size(), _stream()), "sa_favor_scan_bwd")
 
 
+def rotary(buf, col, batch, seq, heads, dim_head, inv_freq, inverse: bool) -> None:
+    """in-place rotary position term on `heads` head blocks of the row-major buffer starting at column `col`"""
+    _lib.check(lib().sa_rotary(_ptr(buf, col), _dt(buf.dtype), _rowmajor(buf), batch, seq, heads, dim_head, _p(inv_freq),
+                               int(inverse), _stream()), "sa_rotary")
+
+
 def local_attn_fwd(d, buf, qcol, kcol, vcol, inv_freq, out, ocol, lse) -> None:
     _lib.check(lib().sa_local_attn_fwd(C.byref(d), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol), _p(inv_freq),
                                        _ptr(out, ocol), _p(lse), _stream()), "sa_local_attn_fwd")
@@ -245,6 +251,6 @@ def _instrument(name, fn):
 
 
 for _n in ("gemm_nt", "gemm_tn", "embed_fwd", "embed_bwd", "layernorm_fwd", "layernorm_bwd", "ce_fwd_bwd", "cast2d",
-           "favor_kmax", "favor_featmap_fwd", "favor_featmap_bwd", "favor_scan_fwd", "favor_scan_bwd", "local_attn_fwd",
+           "rotary", "favor_kmax", "favor_featmap_fwd", "favor_featmap_bwd", "favor_scan_fwd", "favor_scan_bwd", "local_attn_fwd",
            "local_attn_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])

@@ -253,6 +253,59 @@ def test_local_attention_fwd_bwd_fp32(B, H, N, W, rot):
         _close(_rows_to_heads(dbuf[:, i * inner:(i + 1) * inner].cpu(), B, H), t.grad, 1e-4, name)
 
 
+@pytest.mark.parametrize("B,H,N,W", [(2, 2, 300, 40), (1, 3, 1000, 420), (1, 1, 150, 64), (2, 1, 130, 7), (1, 2, 1400, 420)])
+def test_tcgen05_local_attention_bf16(B, H, N, W):
+    """tcgen05 flash-style kernels (bf16 operands, bf16 P / dS re-staging, fp32 accumulation) vs the oracle on the same
+    bf16-rounded inputs; tolerance 2e-2 of the tensor's max (bf16 rounding of probabilities), not the fp32 claim."""
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(N + W)
+    d = 64
+    q, k, v = (_bf(torch.randn(B, H, N, d, generator=g)).requires_grad_(True) for _ in range(3))
+    w = _bf(torch.randn(B, H, N, d, generator=g))
+    out = po.local_attention(q, k, v, W, "none")
+    (out * w).sum().backward()
+    inner = H * d
+    buf = torch.cat([_heads_to_rows(t.detach()) for t in (q, k, v)], dim=1).cuda().bfloat16()
+    ldsc = pf.local_desc(B, N, H, d, W, 3 * inner, inner, torch.bfloat16)
+    O = torch.zeros(B * N, inner, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device="cuda")
+    pf.local_attn_fwd(ldsc, buf, 0, inner, 2 * inner, None, O, 0, lse)
+    assert ops.last_path() == 2, "tcgen05 local attention was not selected"
+    _close(_rows_to_heads(O.float().cpu(), B, H), out, 2e-2, "tc local out")
+    dbuf = torch.zeros_like(buf)
+    pf.local_attn_bwd(ldsc, buf, 0, inner, 2 * inner, None, O, _heads_to_rows(w).cuda().bfloat16(), 0, lse, dbuf)
+    assert ops.last_path() == 2
+    for i, (name, t) in enumerate((("dq", q), ("dk", k), ("dv", v))):
+        got = _rows_to_heads(dbuf[:, i * inner:(i + 1) * inner].float().cpu(), B, H)
+        scale = float(t.grad.abs().max())
+        err = float((got - t.grad).abs().max())
+        assert err <= 2e-2 * scale, f"tc local {name}: {err:.3e} vs max {scale:.3e}"
+    # the CUDA-core kernel on the same bf16 buffers agrees too (same masks, same window arithmetic)
+    ops.set_force_simt(True)
+    try:
+        O2 = torch.zeros_like(O); lse2 = torch.empty_like(lse)
+        pf.local_attn_fwd(ldsc, buf, 0, inner, 2 * inner, None, O2, 0, lse2)
+        assert ops.last_path() == 1
+    finally:
+        ops.set_force_simt(False)
+    _close(lse, lse2, 1e-3, "lse tc vs simt")
+
+
+def test_rotary_inplace_matches_oracle():
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(2)
+    B, H, N, d = 2, 3, 77, 64
+    q, k = torch.randn(B, H, N, d, generator=g), torch.randn(B, H, N, d, generator=g)
+    qr, kr = po.apply_rotary_pos_emb(q, k, po.sinusoidal_embeddings(N, d)[None, None])
+    buf = torch.cat([torch.zeros(B * N, 64), _heads_to_rows(q)], dim=1).cuda()
+    inv_freq = (1.0 / (10000 ** (torch.arange(0, d, 2).float() / d))).cuda()
+    pf.rotary(buf, 64, B, N, H, d, inv_freq, False)
+    _close(_rows_to_heads(buf[:, 64:].cpu(), B, H), qr, 1e-5, "rotary")
+    assert float(buf[:, :64].abs().max()) == 0.0
+    pf.rotary(buf, 64, B, N, H, d, inv_freq, True)
+    _close(_rows_to_heads(buf[:, 64:].cpu(), B, H), q, 1e-5, "rotary inverse")
+
+
 # ------------------------------------------------------------------------------------------------ ends
 def test_layernorm_ce_embed_fp32():
     ops, pf = _mods()
