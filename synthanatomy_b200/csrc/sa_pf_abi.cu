@@ -28,6 +28,17 @@ int sa_simt_local_attn_fwd(const sa_local_desc*, const void*, const void*, const
 int sa_simt_local_attn_bwd(const sa_local_desc*, const void*, const void*, const void*, const float*, const void*,
                            const void*, const float*, void*, void*, void*, cudaStream_t);
 
+bool sa_tc_favor_supported(const sa_favor_desc*);
+size_t sa_tc_favor_scan_workspace(const sa_favor_desc*, int);
+int sa_tc_favor_featmap_fwd(const sa_favor_desc*, int, const void*, const float*, const unsigned long long*,
+                            unsigned long long*, float, void*, int32_t*, cudaStream_t);
+int sa_tc_favor_featmap_bwd(const sa_favor_desc*, const void*, const float*, int, float, const void*, const void*,
+                            const int32_t*, void*, float*, cudaStream_t);
+int sa_tc_favor_scan_fwd(const sa_favor_desc*, const void*, const void*, const void*, float, void*, int, float*, void*,
+                         size_t, cudaStream_t);
+int sa_tc_favor_scan_bwd(const sa_favor_desc*, const void*, const void*, const void*, float, const void*, const void*,
+                         int, const float*, void*, void*, void*, void*, size_t, cudaStream_t);
+
 bool sa_tc_local_supported(const sa_local_desc*, const void*, const void*, const void*, const float*);
 int sa_tc_local_attn_fwd(const sa_local_desc*, const void*, const void*, const void*, void*, float*, cudaStream_t);
 int sa_tc_local_attn_bwd(const sa_local_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
@@ -63,6 +74,8 @@ extern "C" int sa_gemm_tn(int64_t m, int na, int nb, int dtype, const void* a, i
 extern "C" int sa_favor_kmax(const sa_favor_desc* d, const void* k, const float* proj, unsigned long long* kmax,
                              void* stream) {
   SA_CHECK_ARG(d && k && proj && kmax, "null pointer");
+  if (!sa_force_simt() && sa_tc_favor_supported(d))
+    return sa_tc_favor_featmap_fwd(d, 0, k, proj, nullptr, kmax, 0.f, nullptr, nullptr, sa_stream(stream));
   return sa_simt_favor_kmax(d, k, proj, kmax, sa_stream(stream));
 }
 
@@ -70,6 +83,8 @@ extern "C" int sa_favor_featmap_fwd(const sa_favor_desc* d, const void* x, const
                                     const unsigned long long* kmax, float eps, void* feat, int32_t* argmax, void* stream) {
   SA_CHECK_ARG(d && x && proj && feat, "null pointer");
   SA_CHECK_ARG(is_query ? argmax != nullptr : kmax != nullptr, "queries need argmax, keys need kmax");
+  if (!sa_force_simt() && sa_tc_favor_supported(d))
+    return sa_tc_favor_featmap_fwd(d, is_query ? 1 : 2, x, proj, kmax, nullptr, eps, feat, argmax, sa_stream(stream));
   return sa_simt_favor_featmap_fwd(d, x, proj, is_query, kmax, eps, feat, argmax, sa_stream(stream));
 }
 
@@ -78,6 +93,8 @@ extern "C" int sa_favor_featmap_bwd(const sa_favor_desc* d, const void* x, const
                                     void* stream) {
   SA_CHECK_ARG(d && x && proj && feat && dfeat && dx, "null pointer");
   SA_CHECK_ARG(is_query ? argmax != nullptr : gsum != nullptr, "queries need argmax, keys need gsum");
+  if (!sa_force_simt() && sa_tc_favor_supported(d))
+    return sa_tc_favor_featmap_bwd(d, x, proj, is_query, eps, feat, dfeat, argmax, dx, gsum, sa_stream(stream));
   return sa_simt_favor_featmap_bwd(d, x, proj, is_query, eps, feat, dfeat, argmax, dx, gsum, sa_stream(stream));
 }
 
@@ -89,12 +106,17 @@ extern "C" int sa_favor_kmax_fixup(const sa_favor_desc* d, const float* proj, co
 
 extern "C" size_t sa_favor_scan_workspace(const sa_favor_desc* d, int backward) {
   if (!d) return 0;
-  return sa_simt_favor_scan_workspace(d, backward);
+  // large enough for either path (the dispatch can change with sa_set_force_simt between the query and the call)
+  const size_t simt = sa_simt_favor_scan_workspace(d, backward);
+  const size_t tc = sa_tc_favor_supported(d) ? sa_tc_favor_scan_workspace(d, backward) : 0;
+  return simt > tc ? simt : tc;
 }
 
 extern "C" int sa_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps_cumsum,
                                  void* out, int out_ld, float* den, void* workspace, size_t ws_bytes, void* stream) {
   SA_CHECK_ARG(d && qf && kf && v && out && den && workspace, "null pointer");
+  if (!sa_force_simt() && sa_tc_favor_supported(d))
+    return sa_tc_favor_scan_fwd(d, qf, kf, v, eps_cumsum, out, out_ld, den, workspace, ws_bytes, sa_stream(stream));
   return sa_simt_favor_scan_fwd(d, qf, kf, v, eps_cumsum, out, out_ld, den, workspace, ws_bytes, sa_stream(stream));
 }
 
@@ -102,6 +124,9 @@ extern "C" int sa_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const v
                                  const void* out, const void* dout, int out_ld, const float* den, void* dqf, void* dkf,
                                  void* dv, void* workspace, size_t ws_bytes, void* stream) {
   SA_CHECK_ARG(d && qf && kf && v && out && dout && den && dqf && dkf && dv && workspace, "null pointer");
+  if (!sa_force_simt() && sa_tc_favor_supported(d))
+    return sa_tc_favor_scan_bwd(d, qf, kf, v, eps_cumsum, out, dout, out_ld, den, dqf, dkf, dv, workspace, ws_bytes,
+                                sa_stream(stream));
   return sa_simt_favor_scan_bwd(d, qf, kf, v, eps_cumsum, out, dout, out_ld, den, dqf, dkf, dv, workspace, ws_bytes,
                                 sa_stream(stream));
 }

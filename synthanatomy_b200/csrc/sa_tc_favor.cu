@@ -1,0 +1,1030 @@
+// tcgen05 FAVOR+ (global heads) for sm_100a: bf16 operands, fp32 accumulation in TMEM.
+//
+// Replaces performer_pytorch.softmax_kernel / causal_linear_attention (+ autograd) and fast_transformers'
+// CausalDotProduct, reached from /root/reference/src/networks/transformers/performer.py:270.  Same entry points and
+// tensor layouts as the CUDA-core path in sa_pf_favor_simt.cu (which stays the fp32 parity path).
+//
+// Every kernel works on one (batch, head, 128-token chunk).  A [128 rows x 64 cols] bf16 block with 128-byte rows and
+// the 128B swizzle is the unit of shared memory: the same bytes serve as a K-major operand (contraction over the 64
+// columns) and as an MN-major operand (contraction over the rows), so one TMA load / one register re-staging feeds
+// both kinds of product.  Feature tensors [bh][n][mp] are read as ceil(mp / 64) such blocks (TMA zero-fills past mp).
+//
+//   featmap_fwd   D = x P^T (MMA)  ->  r (exp(c D - c^2|x|^2/2 - stab) + eps)            (also the key-max pre-pass)
+//   chunk_state   Z^T[e'][f] = sum_tok W_aug[tok][e'] F[tok][f]   W_aug = [v | 1]  or  [dout/den | -delta/den]
+//   prefix        exclusive prefix (suffix) over chunks, fp32 -> bf16 states [80 rows][mp]; row 64 = the "1" column
+//   scan<0>       A = q' k'^T -> tril -> bf16;  O = q' S + tril(A) v;   out = O / den
+//   scan<1>       A^T = k' q'^T -> triu, * 1/den_i -> bf16;  dv = k' R + A^T dout
+//   dqk<0>        B = dout v^T - delta -> tril;  dq' = (dout S - delta ksum + B k') / den
+//   dqk<1>        B^T = (v dout^T - delta) / den -> triu;  dk' = v R + Rden + B^T q'
+//   featmap_bwd   dD = dfeat (feat - r eps) (- row sum at the arg-max for queries);  dx = c dD P - c^2 s x
+//
+// Warp roles (320 threads): warps 0-7 epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2),
+// warp 8 MMA issuer, warp 9 TMA producer.
+#include <mutex>
+
+#include "sa_pf_common.cuh"
+#include "sa_tc_common.cuh"
+
+using namespace satc;
+
+namespace {
+
+constexpr int F_THREADS = 320;
+constexpr int FC = 128;            // tokens per chunk
+constexpr int F_MAXBLK = 5;        // feature blocks of 64 (mp <= 320)
+constexpr int ST_ROWS = 80;        // rows of a bf16 state tile: 64 value columns, the "1" column, zero padding
+constexpr int SUM_ROWS = 65;       // rows of the fp32 chunk sums
+constexpr uint32_t BLK = 16384;    // [128 x 64] bf16 block
+constexpr uint32_t ST_BLK = ST_ROWS * 128;   // [80 x 64] bf16 block
+
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned int o) {
+  return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// 32 lanes x 16 columns of fp32
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ uint8_t* sw_row(uint8_t* block, int r) { return block + (r >> 3) * 1024 + (r & 7) * 128; }
+
+// write 32 / 16 consecutive columns starting at c0 (multiple of 16) of row r of a 128B-swizzled [rows][64] bf16 block
+__device__ __forceinline__ void st_sw_32(uint8_t* block, int r, int c0, const float (&f)[32]) {
+  uint8_t* row = sw_row(block, r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = (c0 >> 3) + i;
+    uint4 u;
+    u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]); u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+    u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]); u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+    *reinterpret_cast<uint4*>(row + ((ch ^ (r & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void st_sw_16(uint8_t* block, int r, int c0, const float (&f)[16]) {
+  uint8_t* row = sw_row(block, r);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int ch = (c0 >> 3) + i;
+    uint4 u;
+    u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]); u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+    u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]); u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+    *reinterpret_cast<uint4*>(row + ((ch ^ (r & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+// dot product of two 64-element bf16 rows in global memory
+__device__ __forceinline__ float row_dot64(const __nv_bfloat16* a, const __nv_bfloat16* b) {
+  const uint4* pa = reinterpret_cast<const uint4*>(a);
+  const uint4* pb = reinterpret_cast<const uint4*>(b);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float x[8], y[8];
+    unpack8(__ldg(pa + i), x); unpack8(__ldg(pb + i), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(x[j], y[j], acc);
+  }
+  return acc;
+}
+
+// P [m][64] fp32 (global) -> bf16 128B-swizzled [mp rows][64] block image (rows >= m are zero)
+__device__ __forceinline__ void stage_proj(uint8_t* Ps, const float* __restrict__ proj, int m, int mp, int tid) {
+  for (int idx = tid; idx < mp * 8; idx += 256) {
+    const int f = idx >> 3, ch = idx & 7;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (f < m) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(proj + f * 64 + ch * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(proj + f * 64 + ch * 8 + 4));
+      u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+    }
+    *reinterpret_cast<uint4*>(sw_row(Ps, f) + ((ch ^ (f & 7)) << 4)) = u;
+  }
+}
+
+struct FvParams {
+  CUtensorMap map_a, map_b, map_c, map_d, map_e, map_f;
+  int B, N, H, m, mp, nblk, tail;    // tail = valid columns of the last feature block
+  int ld, out_ld, nchunks, tmem_cols;
+  float c, r, eps;
+  const float* proj;
+  const unsigned long long* kmax_in;
+  unsigned long long* kmax_out;
+  const __nv_bfloat16* x;            // featmap input (head 0, column 0 of the block)
+  __nv_bfloat16* feat;               // featmap output / featmap_bwd: features
+  const __nv_bfloat16* dfeat;
+  int* argmax;
+  float* gsum;
+  int is_query;
+  const __nv_bfloat16* out;
+  const __nv_bfloat16* dout;
+  const float* den_in;
+  float* den_out;
+  __nv_bfloat16* o_out;              // scan<0>: out;  scan<1>: dv;  featmap_bwd: dx
+  __nv_bfloat16* df_out;             // dqk: dq' / dk'
+  float* sums;                       // chunk_state output
+};
+
+#define FV_PROLOGUE(NBAR_INIT)                                                              \
+  extern __shared__ uint8_t smem_raw[];                                                     \
+  __shared__ uint32_t tmem_base_slot;                                                       \
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                               \
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023); \
+  const int chunk = blockIdx.x, bh = blockIdx.y, b = bh / P.H, h = bh % P.H;                \
+  const int n0 = chunk * FC;                                                                \
+  (void)b; (void)h; (void)lane;                                                             \
+  if (threadIdx.x == 0) { NBAR_INIT; fence_mbar_init(); fence_proxy_async(); }              \
+  __syncthreads();
+
+#define FV_ALLOC()                                                                          \
+  if (warp == 8) { tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols); tmem_relinquish(); } \
+  tc_fence_before();                                                                        \
+  __syncthreads();                                                                          \
+  tc_fence_after();                                                                         \
+  const uint32_t tmem_base = tmem_base_slot;
+
+#define FV_EPILOGUE()                                                                       \
+  tc_fence_before();                                                                        \
+  __syncthreads();                                                                          \
+  if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+
+// issue D[128 x mp] (+)= A * B over the column parts (<= 256 columns per instruction).
+//   b_kmajor: B is [mp rows][64] K-major (rows contiguous, 128 B each);  else MN-major blocks `b_blk` bytes apart
+__device__ __forceinline__ void mma_cols(uint32_t tD, uint64_t desc_a, uint32_t b_addr, bool b_kmajor, uint32_t b_blk,
+                                         int mp, int a_mn, uint32_t accumulate) {
+  const int n0 = mp < 256 ? mp : 256;
+  if (b_kmajor) {
+    umma_bf16(tD, desc_a, make_smem_desc(b_addr, 16, 1024, 2), make_idesc_bf16(128, n0, a_mn, 0), accumulate);
+    if (mp > 256)
+      umma_bf16(tD + 256, desc_a, make_smem_desc(b_addr + 256 * 128, 16, 1024, 2), make_idesc_bf16(128, mp - 256, a_mn, 0),
+                accumulate);
+  } else {
+    umma_bf16(tD, desc_a, make_smem_desc(b_addr, b_blk, 1024, 2), make_idesc_bf16(128, n0, a_mn, 1), accumulate);
+    if (mp > 256)
+      umma_bf16(tD + 256, desc_a, make_smem_desc(b_addr + 4 * b_blk, b_blk, 1024, 2),
+                make_idesc_bf16(128, mp - 256, a_mn, 1), accumulate);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ feature map, forward
+// MODE 0: key-max pre-pass   1: queries (row max stabiliser, arg-max saved)   2: keys (global stabiliser)
+template <int MODE>
+__global__ void __launch_bounds__(F_THREADS, 1)
+tc_featmap_fwd_kernel(const __grid_constant__ FvParams P) {
+  __shared__ uint64_t x_full, p_ready, d_full;
+  __shared__ float s_red[2][FC];
+  __shared__ int s_arg[2][FC];
+  FV_PROLOGUE(mbar_init(&x_full, 1); mbar_init(&p_ready, 256); mbar_init(&d_full, 1));
+  uint8_t* Xs = smem;               // 16 KB
+  uint8_t* Ps = smem + BLK;         // mp x 128 B
+  if (warp == 9 && lane == 0) {
+    prefetch_tmap(&P.map_a);
+    mbar_expect_tx(&x_full, BLK);
+    tma_load_3d(Xs, &P.map_a, &x_full, h * 64, n0, b);
+  }
+  if (warp < 8) {
+    stage_proj(Ps, P.proj, P.m, P.mp, threadIdx.x);
+    fence_proxy_async();
+    mbar_arrive(&p_ready);
+  }
+  FV_ALLOC();
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_wait(&x_full, 0);
+      mbar_wait(&p_ready, 0);
+      tc_fence_after();
+      const uint32_t xa = smem_u32(Xs), pa = smem_u32(Ps);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        mma_cols(tmem_base, make_smem_desc(xa + k * 32, 16, 1024, 2), pa + k * 32, true, 0, P.mp, 0, k > 0);
+      umma_commit(&d_full);
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    const int n = n0 + r;
+    const bool row_ok = n < P.N;
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int U = P.mp >> 4, U0 = U >> 1;
+    const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
+    mbar_wait(&x_full, 0);
+    float diag = 0.f;
+    {
+      const uint8_t* row = sw_row(Xs, r);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(row + ((ch ^ (r & 7)) << 4)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) diag = fmaf(f[j], f[j], diag);
+      }
+      diag *= 0.5f * P.c * P.c;
+    }
+    mbar_wait(&d_full, 0);
+    tc_fence_after();
+    if (MODE == 0) {
+      float best = -INFINITY;
+      int bj = 0;
+      for (int u = u_beg; u < u_end; ++u) {
+        uint32_t v[16];
+        tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cix = 0; cix < 16; ++cix) {
+          const int j = u * 16 + cix;
+          const float dv = P.c * __uint_as_float(v[cix]);
+          if (j < P.m && dv > best) { best = dv; bj = j; }
+        }
+      }
+      unsigned long long packed = 0ull;
+      if (row_ok && best > -INFINITY) {
+        const unsigned int flat = (unsigned int)(((long long)bh * P.N + n) * P.m + bj);
+        packed = ((unsigned long long)f2ord(best) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, packed, o);
+        packed = other > packed ? other : packed;
+      }
+      if (lane == 0 && packed) atomicMax(P.kmax_out, packed);
+    } else {
+      float stab;
+      if (MODE == 1) {
+        float mx = -INFINITY;
+        int am = 0;
+        for (int u = u_beg; u < u_end; ++u) {
+          uint32_t v[16];
+          tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int cix = 0; cix < 16; ++cix) {
+            const int j = u * 16 + cix;
+            const float dv = __uint_as_float(v[cix]);
+            if (j < P.m && dv > mx) { mx = dv; am = j; }
+          }
+        }
+        s_red[hf][r] = mx; s_arg[hf][r] = am;
+        bar_epi();
+        const float m0 = s_red[0][r], m1 = s_red[1][r];
+        stab = P.c * fmaxf(m0, m1);
+        if (hf == 0 && row_ok) P.argmax[(long long)bh * P.N + n] = (m0 >= m1) ? s_arg[0][r] : s_arg[1][r];
+      } else {
+        stab = ord2f((unsigned int)(P.kmax_in[0] >> 32));
+      }
+      const float off = diag + stab;
+      __nv_bfloat16* dst = P.feat + ((long long)bh * P.N + n) * P.mp;
+      for (int u = u_beg; u < u_end; ++u) {
+        uint32_t v[16];
+        tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int cix = 0; cix < 16; ++cix) {
+          const int j = u * 16 + cix;
+          f[cix] = j < P.m ? P.r * (__expf(P.c * __uint_as_float(v[cix]) - off) + P.eps) : 0.f;
+        }
+        if (row_ok) {
+          reinterpret_cast<uint4*>(dst + u * 16)[0] = pack8(f);
+          reinterpret_cast<uint4*>(dst + u * 16)[1] = pack8(f + 8);
+        }
+      }
+    }
+  }
+  FV_EPILOGUE();
+}
+
+// ------------------------------------------------------------------------------------------------ chunk sums
+// sums[bh][chunk][e'][f] = sum_tok W_aug[tok][e'] F[tok][f]      (e' < 65)
+// MODE 0: W_aug = [v | 1]    MODE 1: W_aug = [dout / den | -(dout . out) / den]
+template <int MODE>
+__global__ void __launch_bounds__(F_THREADS, 1)
+tc_chunk_state_kernel(const __grid_constant__ FvParams P) {
+  __shared__ uint64_t f_full, w_ready, d_full;
+  FV_PROLOGUE(mbar_init(&f_full, 1); mbar_init(&w_ready, 256); mbar_init(&d_full, 1));
+  uint8_t* Ws = smem;                    // 2 blocks: W | aug
+  uint8_t* Fs = smem + 2 * BLK;          // nblk blocks
+  if (warp == 9 && lane == 0) {
+    prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b);
+    mbar_expect_tx(&f_full, (uint32_t)P.nblk * BLK + (MODE == 0 ? BLK : 0u));
+    for (int cb = 0; cb < P.nblk; ++cb) tma_load_3d(Fs + cb * BLK, &P.map_a, &f_full, cb * 64, n0, bh);
+    if (MODE == 0) tma_load_3d(Ws, &P.map_b, &f_full, h * 64, n0, b);
+  }
+  if (warp < 8) {
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    const int n = n0 + r;
+    // aug block: zero, then column 0
+    {
+      uint8_t* row = Ws + BLK + (r >> 3) * 1024 + (r & 7) * 128 + hf * 64;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(row + i * 16) = make_uint4(0, 0, 0, 0);
+    }
+    bar_epi();
+    float aug = 0.f;
+    if (MODE == 0) {
+      aug = 1.0f;
+    } else {
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = 0.f;
+      if (n < P.N) {
+        const long long ro = ((long long)b * P.N + n) * P.out_ld + h * 64;
+        const float inv = 1.0f / P.den_in[(long long)bh * P.N + n];
+        const float delta = row_dot64(P.out + ro, P.dout + ro);
+        aug = -delta * inv;
+        const uint4* pd = reinterpret_cast<const uint4*>(P.dout + ro + hf * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          unpack8(__ldg(pd + i), f + i * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[i * 8 + j] *= inv;
+        }
+      }
+      st_sw_32(Ws, r, hf * 32, f);
+    }
+    if (hf == 0) {
+      __nv_bfloat16* p0 = reinterpret_cast<__nv_bfloat16*>(sw_row(Ws + BLK, r) + (((0 ^ (r & 7))) << 4));
+      *p0 = __float2bfloat16_rn(aug);
+    }
+    fence_proxy_async();
+    mbar_arrive(&w_ready);
+  }
+  FV_ALLOC();
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_wait(&f_full, 0);
+      mbar_wait(&w_ready, 0);
+      tc_fence_after();
+      const uint32_t wa = smem_u32(Ws), fa = smem_u32(Fs);
+#pragma unroll
+      for (int k = 0; k < FC / 16; ++k)
+        mma_cols(tmem_base, make_smem_desc(wa + k * 2048, BLK, 1024, 2), fa + k * 2048, false, BLK, P.mp, 1, k > 0);
+      umma_commit(&d_full);
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;       // e'
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int U = P.mp >> 4, U0 = U >> 1;
+    const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
+    mbar_wait(&d_full, 0);
+    tc_fence_after();
+    if (q * 32 < SUM_ROWS) {           // warp-uniform: quadrants 0..2 hold rows < 65
+      float* dst = P.sums + (((long long)bh * P.nchunks + chunk) * SUM_ROWS + r) * P.mp;
+      for (int u = u_beg; u < u_end; ++u) {
+        uint32_t v[16];
+        tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
+        tmem_ld_wait();
+        if (r < SUM_ROWS) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(dst + u * 16)[i] =
+                make_float4(__uint_as_float(v[i * 4]), __uint_as_float(v[i * 4 + 1]), __uint_as_float(v[i * 4 + 2]),
+                            __uint_as_float(v[i * 4 + 3]));
+        }
+      }
+    }
+  }
+  FV_EPILOGUE();
+}
+
+// ------------------------------------------------------------------------------------------------ prefix over chunks
+// states[bh][chunk][80][mp] (bf16) = exclusive prefix (reverse: suffix) over chunks of sums[bh][chunk][65][mp];
+// forward: the "1" row (64) is seeded with eps (k_cumsum + eps);  rows 65..79 are zero.
+__global__ void fv_prefix_kernel(const float* __restrict__ sums, __nv_bfloat16* __restrict__ states, int nchunks, int mp,
+                                 int reverse, float eps) {
+  const int per = ST_ROWS * mp;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per) return;
+  const int bh = blockIdx.y;
+  const int e = i / mp, f = i % mp;
+  __nv_bfloat16* dst = states + (long long)bh * nchunks * per + i;
+  if (e >= SUM_ROWS) {
+    for (int cix = 0; cix < nchunks; ++cix) dst[(long long)cix * per] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const long long sper = (long long)SUM_ROWS * mp;
+  const float* src = sums + (long long)bh * nchunks * sper + (long long)e * mp + f;
+  float run = (!reverse && e == 64) ? eps : 0.f;
+  if (!reverse) {
+    for (int cix = 0; cix < nchunks; ++cix) {
+      const float v = src[cix * sper];
+      dst[(long long)cix * per] = __float2bfloat16_rn(run);
+      run += v;
+    }
+  } else {
+    for (int cix = nchunks - 1; cix >= 0; --cix) {
+      const float v = src[cix * sper];
+      dst[(long long)cix * per] = __float2bfloat16_rn(run);
+      run += v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ scan / dv
+// MODE 0 (forward):  X = q' (rows i), Y = k' (cols j), St = S, W = v:    out = (q' S + tril(q' k'^T) v) / den
+// MODE 1 (dv):       X = k' (rows j), Y = q' (cols i), St = R, W = dout: dv = k' R + triu(k' q'^T * 1/den_i) dout
+// maps: a = X features, b = Y features, c = states, d = W (head columns)
+constexpr uint32_t SC_STAGE = 2 * BLK + ST_BLK;      // 43008
+constexpr int SC_STAGES = 2;
+
+template <int MODE>
+__global__ void __launch_bounds__(F_THREADS, 2)
+tc_scan_kernel(const __grid_constant__ FvParams P) {
+  __shared__ uint64_t full[SC_STAGES], empty[SC_STAGES], w_full, a_full, am_ready, o_full;
+  __shared__ float s_vec[FC];
+  __shared__ float s_red[2][FC];
+  FV_PROLOGUE(for (int i = 0; i < SC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+              mbar_init(&w_full, 1); mbar_init(&a_full, 1); mbar_init(&am_ready, 256); mbar_init(&o_full, 1));
+  uint8_t* Ring = smem;
+  uint8_t* Ws = smem + SC_STAGES * SC_STAGE;
+  uint8_t* Am = smem;                    // 2 blocks, re-using stage 0 after the feature loop
+  constexpr int NST = MODE == 0 ? ST_ROWS : 64;
+  FV_ALLOC();
+  const uint32_t tA = tmem_base, tO = tmem_base + 128;
+  if (warp == 9) {
+    if (lane == 0) {
+      prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b); prefetch_tmap(&P.map_c); prefetch_tmap(&P.map_d);
+      mbar_expect_tx(&w_full, BLK);
+      tma_load_3d(Ws, &P.map_d, &w_full, h * 64, n0, b);
+      int stage = 0; uint32_t phase = 0;
+      for (int cb = 0; cb < P.nblk; ++cb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], SC_STAGE);
+        uint8_t* s = Ring + stage * SC_STAGE;
+        tma_load_3d(s, &P.map_a, &full[stage], cb * 64, n0, bh);
+        tma_load_3d(s + BLK, &P.map_b, &full[stage], cb * 64, n0, bh);
+        tma_load_2d(s + 2 * BLK, &P.map_c, &full[stage], cb * 64, (bh * P.nchunks + chunk) * ST_ROWS);
+        if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc_a = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_s = make_idesc_bf16(128, NST, 0, 0);
+      const uint32_t idesc_w = make_idesc_bf16(128, 64, 0, 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int cb = 0; cb < P.nblk; ++cb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t xa = smem_u32(Ring + stage * SC_STAGE), ya = xa + BLK, sa = xa + 2 * BLK;
+        const int ksteps = (cb == P.nblk - 1) ? (P.tail >> 4) : 4;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t dx = make_smem_desc(xa + k * 32, 16, 1024, 2);
+          umma_bf16(tA, dx, make_smem_desc(ya + k * 32, 16, 1024, 2), idesc_a, (cb | k) != 0);
+          umma_bf16(tO, dx, make_smem_desc(sa + k * 32, 16, 1024, 2), idesc_s, (cb | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&a_full);
+      mbar_wait(&am_ready, 0);
+      mbar_wait(&w_full, 0);
+      tc_fence_after();
+      const uint32_t ama = smem_u32(Am), wa = smem_u32(Ws);
+#pragma unroll
+      for (int k = 0; k < FC / 16; ++k)
+        umma_bf16(tO, make_smem_desc(ama + (k >> 2) * BLK + (k & 3) * 32, 16, 1024, 2),
+                  make_smem_desc(wa + k * 2048, BLK, 1024, 2), idesc_w, 1u);
+      umma_commit(&o_full);
+    }
+  } else {
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    const int n = n0 + r;
+    const bool row_ok = n < P.N;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    if (MODE == 1) {
+      if (hf == 0) s_vec[r] = row_ok ? 1.0f / P.den_in[(long long)bh * P.N + n] : 0.f;
+      bar_epi();
+    }
+    mbar_wait(&a_full, 0);
+    tc_fence_after();
+    float rowsum = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t v[32];
+      tmem_ld_32x32(tA + tlane + (uint32_t)(hf * 64 + hh * 32), v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int cix = 0; cix < 32; ++cix) {
+        const int cc = hf * 64 + hh * 32 + cix;
+        float val;
+        if (MODE == 0) val = (cc <= r) ? __uint_as_float(v[cix]) : 0.f;
+        else val = (cc >= r) ? __uint_as_float(v[cix]) * s_vec[cc] : 0.f;
+        val = bf16_round(val);
+        rowsum += val;
+        f[cix] = val;
+      }
+      st_sw_32(Am + hf * BLK, r, hh * 32, f);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(&am_ready);
+    if (MODE == 0) {
+      s_red[hf][r] = rowsum;
+      bar_epi();
+      rowsum = s_red[0][r] + s_red[1][r];
+    }
+    mbar_wait(&o_full, 0);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld_32x32(tO + tlane + (uint32_t)(hf * 32), v);
+    tmem_ld_wait();
+    float scale = 1.0f;
+    if (MODE == 0) {
+      uint32_t d16[16];
+      tmem_ld_32x16(tO + tlane + 64u, d16);
+      tmem_ld_wait();
+      const float den = __uint_as_float(d16[0]) + rowsum;
+      scale = 1.0f / den;
+      if (hf == 0 && row_ok) P.den_out[(long long)bh * P.N + n] = den;
+    }
+    if (row_ok) {
+      float f[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]) * scale;
+      const int ldo = MODE == 0 ? P.out_ld : P.ld;
+      uint4* dst = reinterpret_cast<uint4*>(P.o_out + ((long long)b * P.N + n) * ldo + h * 64 + hf * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = pack8(f + i * 8);
+    }
+  }
+  FV_EPILOGUE();
+}
+
+// ------------------------------------------------------------------------------------------------ dq' / dk'
+// MODE 0 (dq'): X = dout (rows i), Y = v (cols j), St = S, F = k':  dq' = (dout S - delta ksum + tril(dout v^T - delta) k') / den
+// MODE 1 (dk'): X = v (rows j), Y = dout (cols i), St = R, F = q':  dk' = v R + Rden + triu((v dout^T - delta_i) / den_i) q'
+// maps: a = X (head columns), b = Y (head columns), c = F features, d = states
+template <int MODE>
+__global__ void __launch_bounds__(F_THREADS, 1)
+tc_dqk_kernel(const __grid_constant__ FvParams P) {
+  __shared__ uint64_t xy_full, fs_full, b_full, bm_ready, d_full;
+  __shared__ float s_delta[FC], s_inv[FC];
+  FV_PROLOGUE(mbar_init(&xy_full, 1); mbar_init(&fs_full, 1); mbar_init(&b_full, 1); mbar_init(&bm_ready, 256);
+              mbar_init(&d_full, 1));
+  uint8_t* Xs = smem;
+  uint8_t* Ys = smem + BLK;
+  uint8_t* Bm = smem + 2 * BLK;          // 2 blocks
+  uint8_t* Fs = smem + 4 * BLK;          // nblk blocks
+  uint8_t* Ss = Fs + P.nblk * BLK;       // nblk state blocks
+  if (warp == 9 && lane == 0) {
+    prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b); prefetch_tmap(&P.map_c); prefetch_tmap(&P.map_d);
+    mbar_expect_tx(&xy_full, 2 * BLK);
+    tma_load_3d(Xs, &P.map_a, &xy_full, h * 64, n0, b);
+    tma_load_3d(Ys, &P.map_b, &xy_full, h * 64, n0, b);
+    mbar_expect_tx(&fs_full, (uint32_t)P.nblk * (BLK + ST_BLK));
+    for (int cb = 0; cb < P.nblk; ++cb) {
+      tma_load_3d(Fs + cb * BLK, &P.map_c, &fs_full, cb * 64, n0, bh);
+      tma_load_2d(Ss + cb * ST_BLK, &P.map_d, &fs_full, cb * 64, (bh * P.nchunks + chunk) * ST_ROWS);
+    }
+  }
+  FV_ALLOC();
+  const uint32_t tB = tmem_base, tD = tmem_base + 128;
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t xa = smem_u32(Xs), ya = smem_u32(Ys), bma = smem_u32(Bm), fa = smem_u32(Fs), sa = smem_u32(Ss);
+      mbar_wait(&xy_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tB, make_smem_desc(xa + k * 32, 16, 1024, 2), make_smem_desc(ya + k * 32, 16, 1024, 2),
+                  make_idesc_bf16(128, 128, 0, 0), k > 0);
+      umma_commit(&b_full);
+      mbar_wait(&fs_full, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)      // X . St   (contraction over the 64 value columns = rows of the state blocks)
+        mma_cols(tD, make_smem_desc(xa + k * 32, 16, 1024, 2), sa + k * 2048, false, ST_BLK, P.mp, 0, k > 0);
+      mbar_wait(&bm_ready, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < FC / 16; ++k)  // Bm . F  (contraction over the chunk's tokens)
+        mma_cols(tD, make_smem_desc(bma + (k >> 2) * BLK + (k & 3) * 32, 16, 1024, 2), fa + k * 2048, false, BLK, P.mp, 0, 1u);
+      umma_commit(&d_full);
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    const int n = n0 + r;
+    const bool row_ok = n < P.N;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    if (hf == 0) {
+      float dl = 0.f, iv = 0.f;
+      if (row_ok) {
+        const long long ro = ((long long)b * P.N + n) * P.out_ld + h * 64;
+        dl = row_dot64(P.out + ro, P.dout + ro);
+        iv = 1.0f / P.den_in[(long long)bh * P.N + n];
+      }
+      s_delta[r] = dl; s_inv[r] = iv;
+    }
+    bar_epi();
+    const float my_delta = s_delta[r], my_inv = s_inv[r];
+    mbar_wait(&b_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t v[32];
+      tmem_ld_32x32(tB + tlane + (uint32_t)(hf * 64 + hh * 32), v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int cix = 0; cix < 32; ++cix) {
+        const int cc = hf * 64 + hh * 32 + cix;
+        if (MODE == 0) f[cix] = (cc <= r) ? __uint_as_float(v[cix]) - my_delta : 0.f;
+        else f[cix] = (cc >= r) ? (__uint_as_float(v[cix]) - s_delta[cc]) * s_inv[cc] : 0.f;
+      }
+      st_sw_32(Bm + hf * BLK, r, hh * 32, f);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(&bm_ready);
+    mbar_wait(&fs_full, 0);
+    mbar_wait(&d_full, 0);
+    tc_fence_after();
+    const int U = P.mp >> 4, U0 = U >> 1;
+    const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
+    __nv_bfloat16* dst = P.df_out + ((long long)bh * P.N + n) * P.mp;
+    for (int u = u_beg; u < u_end; ++u) {
+      uint32_t v[16];
+      tmem_ld_32x16(tD + tlane + (uint32_t)(u * 16), v);
+      tmem_ld_wait();
+      // row 64 of the state block: the "1" column (k_cumsum + eps / Rden); row 64 is un-swizzled (64 & 7 == 0)
+      const uint4* vec = reinterpret_cast<const uint4*>(Ss + (u >> 2) * ST_BLK + 64 * 128 + (u & 3) * 32);
+      float s[16], f[16];
+      unpack8(vec[0], s); unpack8(vec[1], s + 8);
+#pragma unroll
+      for (int cix = 0; cix < 16; ++cix) {
+        const float acc = __uint_as_float(v[cix]);
+        f[cix] = MODE == 0 ? my_inv * (acc - my_delta * s[cix]) : acc + s[cix];
+      }
+      if (row_ok) {
+        reinterpret_cast<uint4*>(dst + u * 16)[0] = pack8(f);
+        reinterpret_cast<uint4*>(dst + u * 16)[1] = pack8(f + 8);
+      }
+    }
+  }
+  FV_EPILOGUE();
+}
+
+// ------------------------------------------------------------------------------------------------ feature map, backward
+__global__ void __launch_bounds__(F_THREADS, 1)
+tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
+  __shared__ uint64_t dd_ready, d_full;
+  __shared__ float s_red[2][FC];
+  FV_PROLOGUE(mbar_init(&dd_ready, 256); mbar_init(&d_full, 1));
+  uint8_t* Ds = smem;                          // nblk blocks: dD
+  uint8_t* Ps = smem + P.nblk * BLK;           // mp x 128 B
+  float ssum = 0.f;
+  if (warp < 8) {
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    const int n = n0 + r;
+    const bool row_ok = n < P.N;
+    stage_proj(Ps, P.proj, P.m, P.mp, threadIdx.x);
+    const int U = P.mp >> 4, U0 = U >> 1;
+    const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
+    const long long fo = ((long long)bh * P.N + n) * P.mp;
+    const float re = P.r * P.eps;
+    float part = 0.f;
+    for (int u = u_beg; u < u_end; ++u) {
+      float g[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) g[i] = 0.f;
+      if (row_ok) {
+        float a[16], d[16];
+        const uint4* pf = reinterpret_cast<const uint4*>(P.feat + fo + u * 16);
+        const uint4* pd = reinterpret_cast<const uint4*>(P.dfeat + fo + u * 16);
+        unpack8(__ldg(pf), a); unpack8(__ldg(pf + 1), a + 8);
+        unpack8(__ldg(pd), d); unpack8(__ldg(pd + 1), d + 8);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          g[i] = (u * 16 + i < P.m) ? d[i] * (a[i] - re) : 0.f;
+          part += g[i];
+        }
+      }
+      st_sw_16(Ds + (u >> 2) * BLK, r, (u & 3) * 16, g);
+    }
+    s_red[hf][r] = part;
+    bar_epi();
+    ssum = s_red[0][r] + s_red[1][r];
+    if (P.is_query) {
+      if (row_ok) {
+        const int am = P.argmax[(long long)bh * P.N + n];
+        const int ua = am >> 4;
+        if (ua >= u_beg && ua < u_end) {       // this thread staged that column: patch it
+          const float g = __bfloat162float(P.dfeat[fo + am]) * (__bfloat162float(P.feat[fo + am]) - re) - ssum;
+          const int cl = am & 63;
+          __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(sw_row(Ds + (am >> 6) * BLK, r) + (((cl >> 3) ^ (r & 7)) << 4)) + (cl & 7);
+          *p = __float2bfloat16_rn(g);
+        }
+      }
+    } else if (hf == 0) {
+      const float w = sa_warp_sum(ssum);
+      if (lane == 0) atomicAdd(P.gsum, w);
+    }
+    fence_proxy_async();
+    mbar_arrive(&dd_ready);
+  }
+  FV_ALLOC();
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_wait(&dd_ready, 0);
+      tc_fence_after();
+      const uint32_t da = smem_u32(Ds), pa = smem_u32(Ps);
+      const uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
+      const int ksteps = P.mp >> 4;
+      for (int ks = 0; ks < ksteps; ++ks)
+        umma_bf16(tmem_base, make_smem_desc(da + (ks >> 2) * BLK + (ks & 3) * 32, 16, 1024, 2),
+                  make_smem_desc(pa + ks * 2048, 8192, 1024, 2), idesc, ks > 0);
+      umma_commit(&d_full);
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    const int n = n0 + r;
+    mbar_wait(&d_full, 0);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32), v);
+    tmem_ld_wait();
+    if (n < P.N) {
+      const long long xo = ((long long)b * P.N + n) * P.ld + h * 64 + hf * 32;
+      const uint4* px = reinterpret_cast<const uint4*>(P.x + xo);
+      uint4* dst = reinterpret_cast<uint4*>(P.o_out + xo);
+      const float c2s = P.c * P.c * ssum;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float xv[8], f[8];
+        unpack8(__ldg(px + i), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = P.c * __uint_as_float(v[i * 8 + j]) - c2s * xv[j];
+        dst[i] = pack8(f);
+      }
+    }
+  }
+  FV_EPILOGUE();
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+std::once_flag g_once;
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int nblk_of(int mp) { return (mp + 63) / 64; }
+size_t smem_featmap(int mp) { return BLK + round_up((size_t)mp * 128, 1024) + 1024; }
+size_t smem_state(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + 1024; }
+constexpr size_t SMEM_SCAN = SC_STAGES * SC_STAGE + BLK + 1024;
+size_t smem_dqk(int mp) { return (size_t)4 * BLK + (size_t)nblk_of(mp) * (BLK + ST_BLK) + 1024; }
+size_t smem_fbwd(int mp) { return (size_t)nblk_of(mp) * BLK + round_up((size_t)mp * 128, 1024) + 1024; }
+constexpr size_t SMEM_MAX = 227 * 1024 - 4096;   // opt-in ceiling minus the static shared memory of the kernels
+
+void init_once() {
+  std::call_once(g_once, [] {
+    const int big = (int)SMEM_MAX;
+    cudaFuncSetAttribute(tc_featmap_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_featmap_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_featmap_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_chunk_state_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_chunk_state_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SCAN);
+    cudaFuncSetAttribute(tc_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SCAN);
+    cudaFuncSetAttribute(tc_dqk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_dqk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_featmap_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  });
+}
+
+int tmem_cols_for(int need) {
+  int c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+
+void fill_common(FvParams& P, const sa_favor_desc* d, int out_ld, float eps) {
+  P.B = d->batch; P.N = d->seq; P.H = d->heads; P.m = d->m; P.mp = d->mp; P.nblk = nblk_of(d->mp);
+  P.tail = d->mp - 64 * (P.nblk - 1);
+  P.ld = d->ld; P.out_ld = out_ld; P.nchunks = (int)sa_cdiv(d->seq, FC); P.tmem_cols = 32;
+  P.c = powf((float)d->dim_head, -0.25f);
+  P.r = powf((float)d->m, -0.5f);
+  P.eps = eps;
+  P.proj = nullptr; P.kmax_in = nullptr; P.kmax_out = nullptr; P.x = nullptr; P.feat = nullptr; P.dfeat = nullptr;
+  P.argmax = nullptr; P.gsum = nullptr; P.is_query = 0; P.out = nullptr; P.dout = nullptr; P.den_in = nullptr;
+  P.den_out = nullptr; P.o_out = nullptr; P.df_out = nullptr; P.sums = nullptr;
+}
+
+// [bh][n][mp] feature tensor: box = 64 columns x 128 tokens of one (batch, head)
+int feat_map(CUtensorMap* m, const void* base, const sa_favor_desc* d) {
+  const uint64_t dims[3] = {(uint64_t)d->mp, (uint64_t)d->seq, (uint64_t)d->batch * d->heads};
+  const uint64_t strides[3] = {2, (uint64_t)d->mp * 2, (uint64_t)d->seq * d->mp * 2};
+  const uint32_t box[3] = {64, FC, 1};
+  return sa_make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+// head columns of a row-major [batch * seq][ld] buffer (base = column 0 of head 0)
+int head_map(CUtensorMap* m, const void* base, const sa_favor_desc* d, int ld) {
+  const uint64_t dims[3] = {(uint64_t)d->heads * 64, (uint64_t)d->seq, (uint64_t)d->batch};
+  const uint64_t strides[3] = {2, (uint64_t)ld * 2, (uint64_t)d->seq * ld * 2};
+  const uint32_t box[3] = {64, FC, 1};
+  return sa_make_tmap_bf16(m, base, 3, dims, strides, box);
+}
+// bf16 states [bh * nchunks * 80][mp]: box = 64 columns x 80 rows
+int state_map(CUtensorMap* m, const void* base, const sa_favor_desc* d, int nchunks) {
+  const uint64_t dims[2] = {(uint64_t)d->mp, (uint64_t)d->batch * d->heads * nchunks * ST_ROWS};
+  const uint64_t strides[2] = {2, (uint64_t)d->mp * 2};
+  const uint32_t box[2] = {64, ST_ROWS};
+  return sa_make_tmap_bf16(m, base, 2, dims, strides, box);
+}
+
+size_t sums_bytes(const sa_favor_desc* d) {
+  return round_up((size_t)d->batch * d->heads * sa_cdiv(d->seq, FC) * SUM_ROWS * d->mp * sizeof(float), 1024);
+}
+size_t states_bytes(const sa_favor_desc* d) {
+  return round_up((size_t)d->batch * d->heads * sa_cdiv(d->seq, FC) * ST_ROWS * d->mp * sizeof(__nv_bfloat16), 1024);
+}
+
+dim3 fv_grid(const sa_favor_desc* d) { return dim3((unsigned)sa_cdiv(d->seq, FC), (unsigned)(d->batch * d->heads)); }
+
+// chunk sums + prefix:  mode 0: (kf, v) forward prefix;  mode 1: (qf, dout / den) suffix
+int launch_states(const sa_favor_desc* d, int mode, const void* feat, const void* w, const void* out, const void* dout,
+                  int out_ld, const float* den, float eps, float* sums, void* states, cudaStream_t st) {
+  static thread_local FvParams P;
+  fill_common(P, d, out_ld, eps);
+  int rc;
+  if ((rc = feat_map(&P.map_a, feat, d)) != SA_OK) return rc;
+  if (mode == 0 && (rc = head_map(&P.map_b, w, d, d->ld)) != SA_OK) return rc;
+  P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.sums = sums;
+  P.tmem_cols = tmem_cols_for(d->mp);
+  const size_t smem = smem_state(d->mp);
+  if (mode == 0) tc_chunk_state_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  else tc_chunk_state_kernel<1><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  SA_LAUNCH_CHECK();
+  const int per = ST_ROWS * d->mp;
+  dim3 pgrid((unsigned)sa_cdiv(per, 256), (unsigned)(d->batch * d->heads));
+  fv_prefix_kernel<<<pgrid, 256, 0, st>>>(sums, (__nv_bfloat16*)states, P.nchunks, d->mp, mode, eps);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+}  // namespace
+
+bool sa_tc_favor_supported(const sa_favor_desc* d) {
+  if (d->act_dtype != SA_BF16 || d->dim_head != 64) return false;
+  if (d->mp % 16 != 0 || d->mp < 16 || d->mp > 64 * F_MAXBLK || d->m > d->mp || d->m < 1) return false;
+  if (d->ld % 8 != 0) return false;
+  if ((long long)d->batch * d->heads > 65535) return false;
+  if ((long long)d->batch * d->heads * d->seq * d->m >= (1LL << 32)) return false;
+  return sa_get_tmap_encode() != nullptr;
+}
+
+size_t sa_tc_favor_scan_workspace(const sa_favor_desc* d, int backward) {
+  return sums_bytes(d) + (backward ? 2 : 1) * states_bytes(d);
+}
+
+int sa_tc_favor_featmap_fwd(const sa_favor_desc* d, int mode, const void* x, const float* proj,
+                            const unsigned long long* kmax_in, unsigned long long* kmax_out, float eps, void* feat,
+                            int32_t* argmax, cudaStream_t st) {
+  init_once();
+  sa_note_path(SA_PATH_TCGEN05);
+  if (!aligned16(x) || !aligned16(proj) || (feat && !aligned16(feat))) {
+    sa_set_error("tc_favor_featmap_fwd: pointers not 16-byte aligned");
+    return SA_ERR_INVALID;
+  }
+  static thread_local FvParams P;
+  fill_common(P, d, 0, eps);
+  int rc;
+  if ((rc = head_map(&P.map_a, x, d, d->ld)) != SA_OK) return rc;
+  P.proj = proj; P.kmax_in = kmax_in; P.kmax_out = kmax_out; P.feat = (__nv_bfloat16*)feat; P.argmax = argmax;
+  P.tmem_cols = tmem_cols_for(d->mp);
+  const size_t smem = smem_featmap(d->mp);
+  if (mode == 0) tc_featmap_fwd_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  else if (mode == 1) tc_featmap_fwd_kernel<1><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  else tc_featmap_fwd_kernel<2><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+int sa_tc_favor_featmap_bwd(const sa_favor_desc* d, const void* x, const float* proj, int is_query, float eps,
+                            const void* feat, const void* dfeat, const int32_t* argmax, void* dx, float* gsum,
+                            cudaStream_t st) {
+  init_once();
+  sa_note_path(SA_PATH_TCGEN05);
+  if (!aligned16(x) || !aligned16(proj) || !aligned16(feat) || !aligned16(dfeat) || !aligned16(dx)) {
+    sa_set_error("tc_favor_featmap_bwd: pointers not 16-byte aligned");
+    return SA_ERR_INVALID;
+  }
+  static thread_local FvParams P;
+  fill_common(P, d, 0, eps);
+  P.proj = proj; P.x = (const __nv_bfloat16*)x; P.feat = (__nv_bfloat16*)const_cast<void*>(feat);
+  P.dfeat = (const __nv_bfloat16*)dfeat; P.argmax = const_cast<int32_t*>(argmax); P.gsum = gsum; P.is_query = is_query;
+  P.o_out = (__nv_bfloat16*)dx;
+  P.tmem_cols = 64;
+  tc_featmap_bwd_kernel<<<fv_grid(d), F_THREADS, smem_fbwd(d->mp), st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+int sa_tc_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps, void* out,
+                         int out_ld, float* den, void* ws, size_t ws_bytes, cudaStream_t st) {
+  init_once();
+  sa_note_path(SA_PATH_TCGEN05);
+  if (ws_bytes < sa_tc_favor_scan_workspace(d, 0)) { sa_set_error("tc_favor_scan_fwd: workspace too small"); return SA_ERR_WORKSPACE; }
+  if (!aligned16(qf) || !aligned16(kf) || !aligned16(v) || !aligned16(out) || !aligned16(ws) || (out_ld & 7)) {
+    sa_set_error("tc_favor_scan_fwd: pointers / leading dimensions not 16-byte aligned");
+    return SA_ERR_INVALID;
+  }
+  float* sums = (float*)ws;
+  uint8_t* states = (uint8_t*)ws + sums_bytes(d);
+  int rc;
+  if ((rc = launch_states(d, 0, kf, v, nullptr, nullptr, out_ld, nullptr, eps, sums, states, st)) != SA_OK) return rc;
+  static thread_local FvParams P;
+  fill_common(P, d, out_ld, eps);
+  if ((rc = feat_map(&P.map_a, qf, d)) != SA_OK) return rc;
+  if ((rc = feat_map(&P.map_b, kf, d)) != SA_OK) return rc;
+  if ((rc = state_map(&P.map_c, states, d, P.nchunks)) != SA_OK) return rc;
+  if ((rc = head_map(&P.map_d, v, d, d->ld)) != SA_OK) return rc;
+  P.o_out = (__nv_bfloat16*)out; P.den_out = den;
+  P.tmem_cols = 256;
+  tc_scan_kernel<0><<<fv_grid(d), F_THREADS, SMEM_SCAN, st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps, const void* out,
+                         const void* dout, int out_ld, const float* den, void* dqf, void* dkf, void* dv, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+  init_once();
+  sa_note_path(SA_PATH_TCGEN05);
+  if (ws_bytes < sa_tc_favor_scan_workspace(d, 1)) { sa_set_error("tc_favor_scan_bwd: workspace too small"); return SA_ERR_WORKSPACE; }
+  if (!aligned16(qf) || !aligned16(kf) || !aligned16(v) || !aligned16(out) || !aligned16(dout) || !aligned16(dqf) ||
+      !aligned16(dkf) || !aligned16(dv) || !aligned16(ws) || (out_ld & 7)) {
+    sa_set_error("tc_favor_scan_bwd: pointers / leading dimensions not 16-byte aligned");
+    return SA_ERR_INVALID;
+  }
+  float* sums = (float*)ws;
+  uint8_t* stS = (uint8_t*)ws + sums_bytes(d);
+  uint8_t* stR = stS + states_bytes(d);
+  int rc;
+  if ((rc = launch_states(d, 0, kf, v, nullptr, nullptr, out_ld, nullptr, eps, sums, stS, st)) != SA_OK) return rc;
+  if ((rc = launch_states(d, 1, qf, nullptr, out, dout, out_ld, den, eps, sums, stR, st)) != SA_OK) return rc;
+  static thread_local FvParams P;
+  const size_t smem = smem_dqk(d->mp);
+  // dq'
+  fill_common(P, d, out_ld, eps);
+  if ((rc = head_map(&P.map_a, dout, d, out_ld)) != SA_OK) return rc;
+  if ((rc = head_map(&P.map_b, v, d, d->ld)) != SA_OK) return rc;
+  if ((rc = feat_map(&P.map_c, kf, d)) != SA_OK) return rc;
+  if ((rc = state_map(&P.map_d, stS, d, P.nchunks)) != SA_OK) return rc;
+  P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.df_out = (__nv_bfloat16*)dqf;
+  P.tmem_cols = tmem_cols_for(128 + d->mp);
+  tc_dqk_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  SA_LAUNCH_CHECK();
+  // dk'
+  if ((rc = head_map(&P.map_a, v, d, d->ld)) != SA_OK) return rc;
+  if ((rc = head_map(&P.map_b, dout, d, out_ld)) != SA_OK) return rc;
+  if ((rc = feat_map(&P.map_c, qf, d)) != SA_OK) return rc;
+  if ((rc = state_map(&P.map_d, stR, d, P.nchunks)) != SA_OK) return rc;
+  P.df_out = (__nv_bfloat16*)dkf;
+  tc_dqk_kernel<1><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  SA_LAUNCH_CHECK();
+  // dv
+  fill_common(P, d, out_ld, eps);
+  if ((rc = feat_map(&P.map_a, kf, d)) != SA_OK) return rc;
+  if ((rc = feat_map(&P.map_b, qf, d)) != SA_OK) return rc;
+  if ((rc = state_map(&P.map_c, stR, d, P.nchunks)) != SA_OK) return rc;
+  if ((rc = head_map(&P.map_d, dout, d, out_ld)) != SA_OK) return rc;
+  P.den_in = den; P.o_out = (__nv_bfloat16*)dv;
+  P.tmem_cols = 256;
+  tc_scan_kernel<1><<<fv_grid(d), F_THREADS, SMEM_SCAN, st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}

@@ -1,0 +1,143 @@
+"""GPU tests of the tcgen05 FAVOR+ kernels (csrc/sa_tc_favor.cu; bf16 operands, fp32 accumulation) through the C ABI,
+against the CPU oracle on the same bf16-rounded inputs.  Tolerances are stated per check: they are bf16 operand /
+re-staging tolerances (features, masked score tiles and chunk states are rounded to bf16 for the tensor cores),
+not the fp32 1e-4 parity claim -- that one is made by the CUDA-core path in test_gpu_performer.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import performer_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from synthanatomy_b200 import ops, pf_ops
+    return ops, pf_ops
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def _heads_to_rows(t):          # [B, H, N, d] -> [B*N, H*d]
+    B, H, N, d = t.shape
+    return t.permute(0, 2, 1, 3).reshape(B * N, H * d).contiguous()
+
+
+def _rows_to_heads(t, B, H):    # [B*N, H*d] -> [B, H, N, d]
+    M, C = t.shape
+    return t.view(B, M // B, H, C // H).permute(0, 2, 1, 3)
+
+
+def _rel(got, want, tol, what):
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    scale = max(float(want.abs().max()), 1e-12)
+    err = float((got - want).abs().max())
+    assert err <= tol * scale, f"{what}: max abs err {err:.3e} > {tol:.0e} * max |ref| {scale:.3e}"
+
+
+def _kmax_value(kmax):
+    packed = int(kmax.item()) & 0xFFFFFFFFFFFFFFFF
+    bits = packed >> 32
+    bits = bits ^ 0x80000000 if bits & 0x80000000 else (~bits) & 0xFFFFFFFF
+    return float(np.frombuffer(np.uint32(bits).tobytes(), dtype=np.float32)[0]), 0xFFFFFFFF - (packed & 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("B,H,N,m", [(2, 2, 300, 266), (1, 3, 1000, 266), (1, 1, 128, 266), (1, 2, 77, 40), (1, 1, 513, 100)])
+def test_tcgen05_favor_featmap_bf16(B, H, N, m):
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(N + m)
+    d, mp = 64, ((m + 15) // 16) * 16
+    q = _bf(torch.randn(B, H, N, d, generator=g)).requires_grad_(True)
+    k = _bf(torch.randn(B, H, N, d, generator=g)).requires_grad_(True)
+    P = _bf(po.gaussian_orthogonal_random_matrix(m, d, generator=g))      # the kernel stages P as bf16
+    wq, wk = _bf(torch.randn(B, H, N, m, generator=g)), _bf(torch.randn(B, H, N, m, generator=g))
+    qf, kf = po.softmax_kernel(q, P, True), po.softmax_kernel(k, P, False)
+    dk_all = k.detach() * d ** -0.25 @ P.t()
+    kmax_ref = float(dk_all.max())
+
+    ld = 2 * H * d + 8
+    buf = torch.zeros(B * N, ld)
+    buf[:, :H * d] = _heads_to_rows(q.detach()); buf[:, H * d:2 * H * d] = _heads_to_rows(k.detach())
+    buf = buf.cuda().bfloat16()
+    fd = pf.favor_desc(B, N, H, d, m, mp, ld, torch.bfloat16)
+    kmax = torch.zeros(1, dtype=torch.int64, device="cuda")
+    pf.favor_kmax(fd, buf, H * d, P.cuda(), kmax)
+    assert ops.last_path() == 2, "tcgen05 feature map was not selected"
+    val, flat = _kmax_value(kmax)
+    assert abs(val - kmax_ref) <= 1e-4 * max(1.0, abs(kmax_ref)), (val, kmax_ref)
+    assert abs(float(dk_all.flatten()[flat]) - kmax_ref) <= 1e-4 * max(1.0, abs(kmax_ref)), "arg-max position"
+    QF = torch.full((B, H, N, mp), 7.0, device="cuda", dtype=torch.bfloat16)
+    KF = torch.full((B, H, N, mp), 7.0, device="cuda", dtype=torch.bfloat16)
+    argq = torch.empty(B, H, N, dtype=torch.int32, device="cuda")
+    pf.favor_featmap_fwd(fd, buf, 0, P.cuda(), True, None, 1e-4, QF, argq)
+    pf.favor_featmap_fwd(fd, buf, H * d, P.cuda(), False, kmax, 1e-4, KF, None)
+    assert ops.last_path() == 2
+    _rel(QF[..., :m], qf, 1e-2, "q features"); _rel(KF[..., :m], kf, 1e-2, "k features")
+    if mp > m:
+        assert float(QF[..., m:].abs().max()) == 0.0 and float(KF[..., m:].abs().max()) == 0.0
+    dq_all = q.detach() * d ** -0.25 @ P.t()
+    picked = torch.gather(dq_all, -1, argq.cpu().long().unsqueeze(-1)).squeeze(-1)
+    assert float((picked - dq_all.max(-1).values).abs().max()) <= 1e-4, "query arg-max"
+
+    # backward: upstream gradients wq / wk, the features the kernel itself produced
+    ((qf * wq).sum() + (kf * wk).sum()).backward()
+    dQF = torch.zeros(B, H, N, mp); dQF[..., :m] = wq
+    dKF = torch.zeros(B, H, N, mp); dKF[..., :m] = wk
+    dbuf = torch.zeros(B * N, ld, device="cuda", dtype=torch.bfloat16)
+    gsum = torch.zeros(1, device="cuda")
+    pf.favor_featmap_bwd(fd, buf, 0, P.cuda(), True, 1e-4, QF, dQF.cuda().bfloat16(), argq, dbuf, 0, None)
+    pf.favor_featmap_bwd(fd, buf, H * d, P.cuda(), False, 1e-4, KF, dKF.cuda().bfloat16(), None, dbuf, H * d, gsum)
+    assert ops.last_path() == 2
+    pf.favor_kmax_fixup(fd, P.cuda(), kmax, gsum, dbuf, H * d)
+    _rel(_rows_to_heads(dbuf[:, :H * d].float().cpu(), B, H), q.grad, 2e-2, "dq")
+    _rel(_rows_to_heads(dbuf[:, H * d:2 * H * d].float().cpu(), B, H), k.grad, 2e-2, "dk")
+
+
+@pytest.mark.parametrize("B,H,N,m", [(2, 2, 300, 266), (1, 3, 1000, 266), (1, 1, 128, 266), (1, 2, 77, 40), (1, 1, 513, 100),
+                                     (1, 1, 1400, 266)])
+def test_tcgen05_favor_scan_bf16(B, H, N, m):
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(N + m)
+    d, mp = 64, ((m + 15) // 16) * 16
+    qf = _bf(torch.rand(B, H, N, m, generator=g) * 0.1 + 1e-3).requires_grad_(True)
+    kf = _bf(torch.rand(B, H, N, m, generator=g) * 0.1 + 1e-3).requires_grad_(True)
+    v = _bf(torch.randn(B, H, N, d, generator=g)).requires_grad_(True)
+    w = _bf(torch.randn(B, H, N, d, generator=g))
+    out = po.causal_linear_attention(qf, kf, v)
+    (out * w).sum().backward()
+
+    QF = torch.zeros(B, H, N, mp); QF[..., :m] = qf.detach()
+    KF = torch.zeros(B, H, N, mp); KF[..., :m] = kf.detach()
+    QF, KF = QF.cuda().bfloat16(), KF.cuda().bfloat16()
+    ld = H * d + 16
+    vbuf = torch.zeros(B * N, ld); vbuf[:, 16:] = _heads_to_rows(v.detach()); vbuf = vbuf.cuda().bfloat16()
+    fd = pf.favor_desc(B, N, H, d, m, mp, ld, torch.bfloat16)
+    ws = torch.empty(pf.favor_scan_workspace(fd, True), dtype=torch.uint8, device="cuda")
+    O = torch.zeros(B * N, H * d + 64, device="cuda", dtype=torch.bfloat16)
+    den = torch.empty(B, H, N, device="cuda")
+    pf.favor_scan_fwd(fd, QF, KF, vbuf, 16, 1e-6, O, 64, den, ws)
+    assert ops.last_path() == 2, "tcgen05 scan was not selected"
+    den_ref = (qf.detach() * (kf.detach().cumsum(-2) + 1e-6)).sum(-1)
+    _rel(den, den_ref, 1e-2, "den")
+    _rel(_rows_to_heads(O[:, 64:].float().cpu(), B, H), out, 2e-2, "scan out")
+
+    # backward on the exact (oracle) forward output, so that the comparison isolates the backward kernels
+    Oref = torch.zeros(B * N, H * d + 64); Oref[:, 64:] = _heads_to_rows(out.detach()); Oref = Oref.cuda().bfloat16()
+    dO = torch.zeros(B * N, H * d + 64); dO[:, 64:] = _heads_to_rows(w); dO = dO.cuda().bfloat16()
+    dQF = torch.full_like(QF, 7.0); dKF = torch.full_like(KF, 7.0)
+    dv = torch.zeros(B * N, ld, device="cuda", dtype=torch.bfloat16)
+    pf.favor_scan_bwd(fd, QF, KF, vbuf, 16, 1e-6, Oref, dO, 64, den_ref.cuda().contiguous(), dQF, dKF, dv, 16, ws)
+    assert ops.last_path() == 2
+    _rel(dQF[..., :m], qf.grad, 3e-2, "dq'"); _rel(dKF[..., :m], kf.grad, 3e-2, "dk'")
+    _rel(_rows_to_heads(dv[:, 16:].float().cpu(), B, H), v.grad, 3e-2, "dv")
+    # and the CUDA-core kernels on the same bf16 buffers agree (same entry points, other dispatch)
+    ops.set_force_simt(True)
+    try:
+        O2 = torch.zeros_like(O); den2 = torch.empty_like(den)
+        pf.favor_scan_fwd(fd, QF, KF, vbuf, 16, 1e-6, O2, 64, den2, ws)
+        assert ops.last_path() == 1
+    finally:
+        ops.set_force_simt(False)
+    _rel(den, den2, 1e-2, "den tc vs simt")
