@@ -477,6 +477,9 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
   } else {
     const int r = warp * 32 + lane;          // key row
     const int j = j0 + r;
+    // key j is seen by queries p with j <= p and floor(p / W) - 1 <= floor(j / W)  <=>  p <= (floor(j / W) + 2) W - 1
+    // (one division per thread instead of one per score)
+    const int p_hi = (j < P.N) ? min(P.N - 1, (j / P.W + 2) * P.W - 1) : -1;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const float c2 = P.scale * LOG2E;
     for (int t = 0; t < ntiles; ++t) {
@@ -505,7 +508,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int p = q0 + hh * 32 + c;
-          const bool ok = (p < P.N) && (j <= p) && (j >= lc_lo(p, P.W)) && (j < P.N);
+          const bool ok = (j <= p) && (p <= p_hi);
           const float pr = ok ? ex2(__uint_as_float(vs[c]) * c2 - s_lse2[buf][hh * 32 + c]) : 0.f;
           fp[c] = pr;
           fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
@@ -544,20 +547,22 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
 template <typename T>
 __global__ void rotary_kernel(T* __restrict__ buf, long long ld, int B, int N, int H, int d, const float* __restrict__ inv_freq,
                               int inverse) {
+  // one thread per (row, frequency): the sine / cosine pair is shared by all heads of the row
   const int half = d / 2;
-  const long long total = (long long)B * N * H * half;
+  const long long total = (long long)B * N * half;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int dd = (int)(i % half);
-    const int hh = (int)((i / half) % H);
-    const long long row = i / ((long long)half * H);
+    const long long row = i / half;
     const int n = (int)(row % N);
-    const long long o = row * ld + hh * d + dd;
     float sn, cs;
     sincosf((float)n * inv_freq[dd], &sn, &cs);
     if (inverse) sn = -sn;
-    const float x1 = sa_ld(buf, o), x2 = sa_ld(buf, o + half);
-    sa_st(buf, o, x1 * cs - x2 * sn);
-    sa_st(buf, o + half, x2 * cs + x1 * sn);
+    for (int hh = 0; hh < H; ++hh) {
+      const long long o = row * ld + hh * d + dd;
+      const float x1 = sa_ld(buf, o), x2 = sa_ld(buf, o + half);
+      sa_st(buf, o, x1 * cs - x2 * sn);
+      sa_st(buf, o + half, x2 * cs + x1 * sn);
+    }
   }
 }
 
@@ -649,7 +654,7 @@ int sa_tc_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, c
 
 int sa_rotary_launch(void* buf, int dtype, int64_t ld, int batch, int seq, int heads, int dim_head, const float* inv_freq,
                      int inverse, cudaStream_t st) {
-  const long long total = (long long)batch * seq * heads * (dim_head / 2);
+  const long long total = (long long)batch * seq * (dim_head / 2);
   long long blocks = sa_cdiv(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (dtype == SA_BF16)
