@@ -119,6 +119,17 @@ int sa_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* kf, co
 int sa_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps_cumsum,
                       const void* out, const void* dout, int out_ld, const float* den, void* dqf, void* dkf, void* dv,
                       void* workspace, size_t ws_bytes, void* stream);
+/* Variants that keep the per-chunk prefix states S of the forward pass for the backward pass instead of recomputing
+ * them.  sa_favor_scan_states_bytes() is the size of that buffer (0 when the selected path does not save states: pass
+ * NULL then); the contents are opaque and only valid for the same descriptor and k', v. */
+size_t sa_favor_scan_states_bytes(const sa_favor_desc* d);
+int sa_favor_scan_fwd_save(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps_cumsum,
+                           void* out, int out_ld, float* den, void* workspace, size_t ws_bytes, void* states,
+                           size_t states_bytes, void* stream);
+int sa_favor_scan_bwd_saved(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps_cumsum,
+                            const void* out, const void* dout, int out_ld, const float* den, void* dqf, void* dkf,
+                            void* dv, void* workspace, size_t ws_bytes, const void* states, size_t states_bytes,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Local-window heads.  Replaces local_attention.LocalAttention.forward (window w, causal, look_backward = 1,

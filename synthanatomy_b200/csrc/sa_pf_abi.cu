@@ -34,10 +34,11 @@ int sa_tc_favor_featmap_fwd(const sa_favor_desc*, int, const void*, const float*
                             unsigned long long*, float, void*, int32_t*, cudaStream_t);
 int sa_tc_favor_featmap_bwd(const sa_favor_desc*, const void*, const float*, int, float, const void*, const void*,
                             const int32_t*, void*, float*, cudaStream_t);
+size_t sa_tc_favor_states_bytes(const sa_favor_desc*);
 int sa_tc_favor_scan_fwd(const sa_favor_desc*, const void*, const void*, const void*, float, void*, int, float*, void*,
-                         size_t, cudaStream_t);
+                         size_t, void*, cudaStream_t);
 int sa_tc_favor_scan_bwd(const sa_favor_desc*, const void*, const void*, const void*, float, const void*, const void*,
-                         int, const float*, void*, void*, void*, void*, size_t, cudaStream_t);
+                         int, const float*, void*, void*, void*, void*, size_t, const void*, cudaStream_t);
 
 bool sa_tc_local_supported(const sa_local_desc*, const void*, const void*, const void*, const float*);
 int sa_tc_local_attn_fwd(const sa_local_desc*, const void*, const void*, const void*, void*, float*, cudaStream_t);
@@ -112,23 +113,47 @@ extern "C" size_t sa_favor_scan_workspace(const sa_favor_desc* d, int backward) 
   return simt > tc ? simt : tc;
 }
 
+extern "C" size_t sa_favor_scan_states_bytes(const sa_favor_desc* d) {
+  if (!d || sa_force_simt() || !sa_tc_favor_supported(d)) return 0;
+  return sa_tc_favor_states_bytes(d);
+}
+
+extern "C" int sa_favor_scan_fwd_save(const sa_favor_desc* d, const void* qf, const void* kf, const void* v,
+                                      float eps_cumsum, void* out, int out_ld, float* den, void* workspace,
+                                      size_t ws_bytes, void* states, size_t states_bytes, void* stream) {
+  SA_CHECK_ARG(d && qf && kf && v && out && den && workspace, "null pointer");
+  if (!sa_force_simt() && sa_tc_favor_supported(d)) {
+    SA_CHECK_ARG(!states || states_bytes >= sa_tc_favor_states_bytes(d), "states buffer too small");
+    return sa_tc_favor_scan_fwd(d, qf, kf, v, eps_cumsum, out, out_ld, den, workspace, ws_bytes, states, sa_stream(stream));
+  }
+  SA_CHECK_ARG(!states, "the CUDA-core path does not save states (sa_favor_scan_states_bytes() == 0)");
+  return sa_simt_favor_scan_fwd(d, qf, kf, v, eps_cumsum, out, out_ld, den, workspace, ws_bytes, sa_stream(stream));
+}
+
 extern "C" int sa_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps_cumsum,
                                  void* out, int out_ld, float* den, void* workspace, size_t ws_bytes, void* stream) {
-  SA_CHECK_ARG(d && qf && kf && v && out && den && workspace, "null pointer");
-  if (!sa_force_simt() && sa_tc_favor_supported(d))
-    return sa_tc_favor_scan_fwd(d, qf, kf, v, eps_cumsum, out, out_ld, den, workspace, ws_bytes, sa_stream(stream));
-  return sa_simt_favor_scan_fwd(d, qf, kf, v, eps_cumsum, out, out_ld, den, workspace, ws_bytes, sa_stream(stream));
+  return sa_favor_scan_fwd_save(d, qf, kf, v, eps_cumsum, out, out_ld, den, workspace, ws_bytes, nullptr, 0, stream);
+}
+
+extern "C" int sa_favor_scan_bwd_saved(const sa_favor_desc* d, const void* qf, const void* kf, const void* v,
+                                       float eps_cumsum, const void* out, const void* dout, int out_ld, const float* den,
+                                       void* dqf, void* dkf, void* dv, void* workspace, size_t ws_bytes,
+                                       const void* states, size_t states_bytes, void* stream) {
+  SA_CHECK_ARG(d && qf && kf && v && out && dout && den && dqf && dkf && dv && workspace, "null pointer");
+  if (!sa_force_simt() && sa_tc_favor_supported(d)) {
+    SA_CHECK_ARG(!states || states_bytes >= sa_tc_favor_states_bytes(d), "states buffer too small");
+    return sa_tc_favor_scan_bwd(d, qf, kf, v, eps_cumsum, out, dout, out_ld, den, dqf, dkf, dv, workspace, ws_bytes, states,
+                                sa_stream(stream));
+  }
+  return sa_simt_favor_scan_bwd(d, qf, kf, v, eps_cumsum, out, dout, out_ld, den, dqf, dkf, dv, workspace, ws_bytes,
+                                sa_stream(stream));
 }
 
 extern "C" int sa_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps_cumsum,
                                  const void* out, const void* dout, int out_ld, const float* den, void* dqf, void* dkf,
                                  void* dv, void* workspace, size_t ws_bytes, void* stream) {
-  SA_CHECK_ARG(d && qf && kf && v && out && dout && den && dqf && dkf && dv && workspace, "null pointer");
-  if (!sa_force_simt() && sa_tc_favor_supported(d))
-    return sa_tc_favor_scan_bwd(d, qf, kf, v, eps_cumsum, out, dout, out_ld, den, dqf, dkf, dv, workspace, ws_bytes,
-                                sa_stream(stream));
-  return sa_simt_favor_scan_bwd(d, qf, kf, v, eps_cumsum, out, dout, out_ld, den, dqf, dkf, dv, workspace, ws_bytes,
-                                sa_stream(stream));
+  return sa_favor_scan_bwd_saved(d, qf, kf, v, eps_cumsum, out, dout, out_ld, den, dqf, dkf, dv, workspace, ws_bytes,
+                                 nullptr, 0, stream);
 }
 
 extern "C" int sa_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, const void* v,

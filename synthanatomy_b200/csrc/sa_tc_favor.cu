@@ -196,90 +196,97 @@ __device__ __forceinline__ void mma_cols(uint32_t tD, uint64_t desc_a, uint32_t 
 
 // ------------------------------------------------------------------------------------------------ feature map, forward
 // MODE 0: key-max pre-pass   1: queries (row max stabiliser, arg-max saved)   2: keys (global stabiliser)
+// Persistent: one CTA per SM stages P once, then walks (batch, head, chunk) tiles; the x tiles arrive through a
+// two-stage TMA ring, so the load of tile i+1 overlaps the MMA / epilogue of tile i.
 template <int MODE>
 __global__ void __launch_bounds__(F_THREADS, 1)
 tc_featmap_fwd_kernel(const __grid_constant__ FvParams P) {
-  __shared__ uint64_t x_full, p_ready, d_full;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ uint64_t x_full[2], x_empty[2], p_ready, d_full, d_empty;
   __shared__ float s_red[2][FC];
   __shared__ int s_arg[2][FC];
-  FV_PROLOGUE(mbar_init(&x_full, 1); mbar_init(&p_ready, 256); mbar_init(&d_full, 1));
-  uint8_t* Xs = smem;               // 16 KB
-  uint8_t* Ps = smem + BLK;         // mp x 128 B
-  if (warp == 9 && lane == 0) {
-    prefetch_tmap(&P.map_a);
-    mbar_expect_tx(&x_full, BLK);
-    tma_load_3d(Xs, &P.map_a, &x_full, h * 64, n0, b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Xs = smem;               // 2 x 16 KB
+  uint8_t* Ps = smem + 2 * BLK;     // mp x 128 B
+  const int total = P.nchunks * P.B * P.H;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 256); }
+    mbar_init(&p_ready, 256); mbar_init(&d_full, 1); mbar_init(&d_empty, 256);
+    fence_mbar_init();
+    fence_proxy_async();
   }
+  __syncthreads();
   if (warp < 8) {
     stage_proj(Ps, P.proj, P.m, P.mp, threadIdx.x);
     fence_proxy_async();
     mbar_arrive(&p_ready);
   }
   FV_ALLOC();
-  if (warp == 8) {
+  if (warp == 9) {
     if (lane == 0) {
-      mbar_wait(&x_full, 0);
-      mbar_wait(&p_ready, 0);
-      tc_fence_after();
-      const uint32_t xa = smem_u32(Xs), pa = smem_u32(Ps);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        mma_cols(tmem_base, make_smem_desc(xa + k * 32, 16, 1024, 2), pa + k * 32, true, 0, P.mp, 0, k > 0);
-      umma_commit(&d_full);
+      prefetch_tmap(&P.map_a);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        const int bh = tile / P.nchunks, chunk = tile % P.nchunks;
+        mbar_wait(&x_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1));
+        mbar_expect_tx(&x_full[s], BLK);
+        tma_load_3d(Xs + s * BLK, &P.map_a, &x_full[s], (bh % P.H) * 64, chunk * FC, bh / P.H);
+      }
     }
-  } else if (warp < 8) {
+  } else if (warp == 8) {
+    if (lane == 0) {
+      mbar_wait(&p_ready, 0);
+      const uint32_t pa = smem_u32(Ps);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        mbar_wait(&x_full[s], (uint32_t)((it >> 1) & 1));
+        mbar_wait(&d_empty, (uint32_t)((it & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t xa = smem_u32(Xs + s * BLK);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_cols(tmem_base, make_smem_desc(xa + k * 32, 16, 1024, 2), pa + k * 32, true, 0, P.mp, 0, k > 0);
+        umma_commit(&d_full);
+      }
+    }
+  } else {
     const int q = warp & 3, hf = warp >> 2;
     const int r = q * 32 + lane;
-    const int n = n0 + r;
-    const bool row_ok = n < P.N;
     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
     const int U = P.mp >> 4, U0 = U >> 1;
     const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
-    mbar_wait(&x_full, 0);
-    float diag = 0.f;
-    {
-      const uint8_t* row = sw_row(Xs, r);
+    float stab_k = 0.f;
+    if (MODE == 2) stab_k = ord2f((unsigned int)(P.kmax_in[0] >> 32));
+    unsigned long long best_packed = 0ull;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int bh = tile / P.nchunks, chunk = tile % P.nchunks;
+      const int n = chunk * FC + r;
+      const bool row_ok = n < P.N;
+      mbar_wait(&x_full[s], (uint32_t)((it >> 1) & 1));
+      float diag = 0.f;
+      if (MODE != 0) {
+        const uint8_t* row = sw_row(Xs + s * BLK, r);
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(row + ((ch ^ (r & 7)) << 4)), f);
+        for (int ch = 0; ch < 8; ++ch) {
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4*>(row + ((ch ^ (r & 7)) << 4)), f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) diag = fmaf(f[j], f[j], diag);
-      }
-      diag *= 0.5f * P.c * P.c;
-    }
-    mbar_wait(&d_full, 0);
-    tc_fence_after();
-    if (MODE == 0) {
-      float best = -INFINITY;
-      int bj = 0;
-      for (int u = u_beg; u < u_end; ++u) {
-        uint32_t v[16];
-        tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int cix = 0; cix < 16; ++cix) {
-          const int j = u * 16 + cix;
-          const float dv = P.c * __uint_as_float(v[cix]);
-          if (j < P.m && dv > best) { best = dv; bj = j; }
+          for (int j = 0; j < 8; ++j) diag = fmaf(f[j], f[j], diag);
         }
+        diag *= 0.5f * P.c * P.c;
       }
-      unsigned long long packed = 0ull;
-      if (row_ok && best > -INFINITY) {
-        const unsigned int flat = (unsigned int)(((long long)bh * P.N + n) * P.m + bj);
-        packed = ((unsigned long long)f2ord(best) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, packed, o);
-        packed = other > packed ? other : packed;
-      }
-      if (lane == 0 && packed) atomicMax(P.kmax_out, packed);
-    } else {
-      float stab;
-      if (MODE == 1) {
-        float mx = -INFINITY;
-        int am = 0;
+      mbar_wait(&d_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      mbar_arrive(&x_empty[s]);        // the MMA has consumed the x tile and this thread has read its row
+      if (MODE == 0) {
+        float best = -INFINITY;
+        int bj = 0;
         for (int u = u_beg; u < u_end; ++u) {
           uint32_t v[16];
           tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
@@ -287,35 +294,68 @@ tc_featmap_fwd_kernel(const __grid_constant__ FvParams P) {
 #pragma unroll
           for (int cix = 0; cix < 16; ++cix) {
             const int j = u * 16 + cix;
-            const float dv = __uint_as_float(v[cix]);
-            if (j < P.m && dv > mx) { mx = dv; am = j; }
+            const float dv = P.c * __uint_as_float(v[cix]);
+            if (j < P.m && dv > best) { best = dv; bj = j; }
           }
         }
-        s_red[hf][r] = mx; s_arg[hf][r] = am;
-        bar_epi();
-        const float m0 = s_red[0][r], m1 = s_red[1][r];
-        stab = P.c * fmaxf(m0, m1);
-        if (hf == 0 && row_ok) P.argmax[(long long)bh * P.N + n] = (m0 >= m1) ? s_arg[0][r] : s_arg[1][r];
+        if (row_ok && best > -INFINITY) {
+          const unsigned int flat = (unsigned int)(((long long)bh * P.N + n) * P.m + bj);
+          const unsigned long long packed = ((unsigned long long)f2ord(best) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+          best_packed = packed > best_packed ? packed : best_packed;
+        }
       } else {
-        stab = ord2f((unsigned int)(P.kmax_in[0] >> 32));
-      }
-      const float off = diag + stab;
-      __nv_bfloat16* dst = P.feat + ((long long)bh * P.N + n) * P.mp;
-      for (int u = u_beg; u < u_end; ++u) {
-        uint32_t v[16];
-        tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
-        tmem_ld_wait();
-        float f[16];
+        float stab;
+        if (MODE == 1) {
+          float mx = -INFINITY;
+          int am = 0;
+          for (int u = u_beg; u < u_end; ++u) {
+            uint32_t v[16];
+            tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
+            tmem_ld_wait();
 #pragma unroll
-        for (int cix = 0; cix < 16; ++cix) {
-          const int j = u * 16 + cix;
-          f[cix] = j < P.m ? P.r * (__expf(P.c * __uint_as_float(v[cix]) - off) + P.eps) : 0.f;
+            for (int cix = 0; cix < 16; ++cix) {
+              const int j = u * 16 + cix;
+              const float dv = __uint_as_float(v[cix]);
+              if (j < P.m && dv > mx) { mx = dv; am = j; }
+            }
+          }
+          bar_epi();                     // the previous tile's readers of s_red / s_arg are done
+          s_red[hf][r] = mx; s_arg[hf][r] = am;
+          bar_epi();
+          const float m0 = s_red[0][r], m1 = s_red[1][r];
+          stab = P.c * fmaxf(m0, m1);
+          if (hf == 0 && row_ok) P.argmax[(long long)bh * P.N + n] = (m0 >= m1) ? s_arg[0][r] : s_arg[1][r];
+        } else {
+          stab = stab_k;
         }
-        if (row_ok) {
-          reinterpret_cast<uint4*>(dst + u * 16)[0] = pack8(f);
-          reinterpret_cast<uint4*>(dst + u * 16)[1] = pack8(f + 8);
+        const float off = diag + stab;
+        __nv_bfloat16* dst = P.feat + ((long long)bh * P.N + n) * P.mp;
+        for (int u = u_beg; u < u_end; ++u) {
+          uint32_t v[16];
+          tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int cix = 0; cix < 16; ++cix) {
+            const int j = u * 16 + cix;
+            f[cix] = j < P.m ? P.r * (__expf(P.c * __uint_as_float(v[cix]) - off) + P.eps) : 0.f;
+          }
+          if (row_ok) {
+            reinterpret_cast<uint4*>(dst + u * 16)[0] = pack8(f);
+            reinterpret_cast<uint4*>(dst + u * 16)[1] = pack8(f + 8);
+          }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&d_empty);
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best_packed, o);
+        best_packed = other > best_packed ? other : best_packed;
+      }
+      if (lane == 0 && best_packed) atomicMax(P.kmax_out, best_packed);
     }
   }
   FV_EPILOGUE();
@@ -698,99 +738,131 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ feature map, backward
+// Persistent (one CTA per SM, P staged once).  Per tile: the epilogue warps stage dD = dfeat (feat - r eps) as bf16
+// (16-byte global loads, three 16-column units in flight per thread), the MMA warp forms dD P, the epilogue warps
+// finish dx = c dD P - c^2 s x.
 __global__ void __launch_bounds__(F_THREADS, 1)
 tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_base_slot;
   __shared__ uint64_t dd_ready, d_full;
   __shared__ float s_red[2][FC];
-  FV_PROLOGUE(mbar_init(&dd_ready, 256); mbar_init(&d_full, 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Ds = smem;                          // nblk blocks: dD
   uint8_t* Ps = smem + P.nblk * BLK;           // mp x 128 B
-  float ssum = 0.f;
-  if (warp < 8) {
-    const int q = warp & 3, hf = warp >> 2;
-    const int r = q * 32 + lane;
-    const int n = n0 + r;
-    const bool row_ok = n < P.N;
-    stage_proj(Ps, P.proj, P.m, P.mp, threadIdx.x);
-    const int U = P.mp >> 4, U0 = U >> 1;
-    const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
-    const long long fo = ((long long)bh * P.N + n) * P.mp;
-    const float re = P.r * P.eps;
-    float part = 0.f;
-    for (int u = u_beg; u < u_end; ++u) {
-      float g[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) g[i] = 0.f;
-      if (row_ok) {
-        float a[16], d[16];
-        const uint4* pf = reinterpret_cast<const uint4*>(P.feat + fo + u * 16);
-        const uint4* pd = reinterpret_cast<const uint4*>(P.dfeat + fo + u * 16);
-        unpack8(__ldg(pf), a); unpack8(__ldg(pf + 1), a + 8);
-        unpack8(__ldg(pd), d); unpack8(__ldg(pd + 1), d + 8);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          g[i] = (u * 16 + i < P.m) ? d[i] * (a[i] - re) : 0.f;
-          part += g[i];
-        }
-      }
-      st_sw_16(Ds + (u >> 2) * BLK, r, (u & 3) * 16, g);
-    }
-    s_red[hf][r] = part;
-    bar_epi();
-    ssum = s_red[0][r] + s_red[1][r];
-    if (P.is_query) {
-      if (row_ok) {
-        const int am = P.argmax[(long long)bh * P.N + n];
-        const int ua = am >> 4;
-        if (ua >= u_beg && ua < u_end) {       // this thread staged that column: patch it
-          const float g = __bfloat162float(P.dfeat[fo + am]) * (__bfloat162float(P.feat[fo + am]) - re) - ssum;
-          const int cl = am & 63;
-          __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(sw_row(Ds + (am >> 6) * BLK, r) + (((cl >> 3) ^ (r & 7)) << 4)) + (cl & 7);
-          *p = __float2bfloat16_rn(g);
-        }
-      }
-    } else if (hf == 0) {
-      const float w = sa_warp_sum(ssum);
-      if (lane == 0) atomicAdd(P.gsum, w);
-    }
+  const int total = P.nchunks * P.B * P.H;
+  if (threadIdx.x == 0) {
+    mbar_init(&dd_ready, 256); mbar_init(&d_full, 1);
+    fence_mbar_init();
     fence_proxy_async();
-    mbar_arrive(&dd_ready);
   }
+  __syncthreads();
+  if (warp < 8) stage_proj(Ps, P.proj, P.m, P.mp, threadIdx.x);
   FV_ALLOC();
   if (warp == 8) {
     if (lane == 0) {
-      mbar_wait(&dd_ready, 0);
-      tc_fence_after();
       const uint32_t da = smem_u32(Ds), pa = smem_u32(Ps);
       const uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
       const int ksteps = P.mp >> 4;
-      for (int ks = 0; ks < ksteps; ++ks)
-        umma_bf16(tmem_base, make_smem_desc(da + (ks >> 2) * BLK + (ks & 3) * 32, 16, 1024, 2),
-                  make_smem_desc(pa + ks * 2048, 8192, 1024, 2), idesc, ks > 0);
-      umma_commit(&d_full);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        mbar_wait(&dd_ready, (uint32_t)(it & 1));
+        tc_fence_after();
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_bf16(tmem_base, make_smem_desc(da + (ks >> 2) * BLK + (ks & 3) * 32, 16, 1024, 2),
+                    make_smem_desc(pa + ks * 2048, 8192, 1024, 2), idesc, ks > 0);
+        umma_commit(&d_full);
+      }
     }
   } else if (warp < 8) {
     const int q = warp & 3, hf = warp >> 2;
     const int r = q * 32 + lane;
-    const int n = n0 + r;
-    mbar_wait(&d_full, 0);
-    tc_fence_after();
-    uint32_t v[32];
-    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32), v);
-    tmem_ld_wait();
-    if (n < P.N) {
-      const long long xo = ((long long)b * P.N + n) * P.ld + h * 64 + hf * 32;
-      const uint4* px = reinterpret_cast<const uint4*>(P.x + xo);
-      uint4* dst = reinterpret_cast<uint4*>(P.o_out + xo);
-      const float c2s = P.c * P.c * ssum;
+    const int U = P.mp >> 4, U0 = U >> 1;
+    const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
+    const float re = P.r * P.eps;
+    float gacc = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int bh = tile / P.nchunks, chunk = tile % P.nchunks;
+      const int b = bh / P.H, h = bh % P.H;
+      const int n = chunk * FC + r;
+      const bool row_ok = n < P.N;
+      const long long fo = ((long long)bh * P.N + n) * P.mp;
+      float part = 0.f;
+      for (int u0 = u_beg; u0 < u_end; u0 += 3) {
+        uint4 ra[3][2], rd[3][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float xv[8], f[8];
-        unpack8(__ldg(px + i), xv);
+        for (int k = 0; k < 3; ++k) {
+          if (u0 + k < u_end && row_ok) {
+            const uint4* pf = reinterpret_cast<const uint4*>(P.feat + fo + (u0 + k) * 16);
+            const uint4* pd = reinterpret_cast<const uint4*>(P.dfeat + fo + (u0 + k) * 16);
+            ra[k][0] = __ldg(pf); ra[k][1] = __ldg(pf + 1);
+            rd[k][0] = __ldg(pd); rd[k][1] = __ldg(pd + 1);
+          } else {
+            ra[k][0] = ra[k][1] = rd[k][0] = rd[k][1] = make_uint4(0, 0, 0, 0);
+          }
+        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = P.c * __uint_as_float(v[i * 8 + j]) - c2s * xv[j];
-        dst[i] = pack8(f);
+        for (int k = 0; k < 3; ++k) {
+          const int u = u0 + k;
+          if (u < u_end) {
+            float a[16], d[16], g[16];
+            unpack8(ra[k][0], a); unpack8(ra[k][1], a + 8);
+            unpack8(rd[k][0], d); unpack8(rd[k][1], d + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              g[i] = (row_ok && u * 16 + i < P.m) ? d[i] * (a[i] - re) : 0.f;
+              part += g[i];
+            }
+            st_sw_16(Ds + (u >> 2) * BLK, r, (u & 3) * 16, g);
+          }
+        }
       }
+      bar_epi();                               // readers of s_red of the previous tile are done
+      s_red[hf][r] = part;
+      bar_epi();
+      const float ssum = s_red[0][r] + s_red[1][r];
+      if (P.is_query) {
+        if (row_ok) {
+          const int am = P.argmax[(long long)bh * P.N + n];
+          const int ua = am >> 4;
+          if (ua >= u_beg && ua < u_end) {     // this thread staged that column: patch it
+            const float g = __bfloat162float(P.dfeat[fo + am]) * (__bfloat162float(P.feat[fo + am]) - re) - ssum;
+            const int cl = am & 63;
+            __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(sw_row(Ds + (am >> 6) * BLK, r) + (((cl >> 3) ^ (r & 7)) << 4)) + (cl & 7);
+            *p = __float2bfloat16_rn(g);
+          }
+        }
+      } else if (hf == 0) {
+        gacc += ssum;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&dd_ready);
+      mbar_wait(&d_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32), v);
+      tmem_ld_wait();
+      if (row_ok) {
+        const long long xo = ((long long)b * P.N + n) * P.ld + h * 64 + hf * 32;
+        const uint4* px = reinterpret_cast<const uint4*>(P.x + xo);
+        uint4* dst = reinterpret_cast<uint4*>(P.o_out + xo);
+        const float c2s = P.c * P.c * ssum;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float xv[8], f[8];
+          unpack8(__ldg(px + i), xv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = P.c * __uint_as_float(v[i * 8 + j]) - c2s * xv[j];
+          dst[i] = pack8(f);
+        }
+      }
+    }
+    if (!P.is_query && hf == 0) {
+      const float w = sa_warp_sum(gacc);
+      if (lane == 0) atomicAdd(P.gsum, w);
     }
   }
   FV_EPILOGUE();
@@ -802,7 +874,16 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int nblk_of(int mp) { return (mp + 63) / 64; }
-size_t smem_featmap(int mp) { return BLK + round_up((size_t)mp * 128, 1024) + 1024; }
+int sa_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = 148;
+  }
+  return n;
+}
+size_t smem_featmap(int mp) { return 2 * BLK + round_up((size_t)mp * 128, 1024) + 1024; }
 size_t smem_state(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + 1024; }
 constexpr size_t SMEM_SCAN = SC_STAGES * SC_STAGE + BLK + 1024;
 size_t smem_dqk(int mp) { return (size_t)4 * BLK + (size_t)nblk_of(mp) * (BLK + ST_BLK) + 1024; }
@@ -926,9 +1007,11 @@ int sa_tc_favor_featmap_fwd(const sa_favor_desc* d, int mode, const void* x, con
   P.proj = proj; P.kmax_in = kmax_in; P.kmax_out = kmax_out; P.feat = (__nv_bfloat16*)feat; P.argmax = argmax;
   P.tmem_cols = tmem_cols_for(d->mp);
   const size_t smem = smem_featmap(d->mp);
-  if (mode == 0) tc_featmap_fwd_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
-  else if (mode == 1) tc_featmap_fwd_kernel<1><<<fv_grid(d), F_THREADS, smem, st>>>(P);
-  else tc_featmap_fwd_kernel<2><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  const int total = P.nchunks * d->batch * d->heads;
+  const dim3 grid((unsigned)(total < sa_sm_count() ? total : sa_sm_count()));
+  if (mode == 0) tc_featmap_fwd_kernel<0><<<grid, F_THREADS, smem, st>>>(P);
+  else if (mode == 1) tc_featmap_fwd_kernel<1><<<grid, F_THREADS, smem, st>>>(P);
+  else tc_featmap_fwd_kernel<2><<<grid, F_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -948,13 +1031,16 @@ int sa_tc_favor_featmap_bwd(const sa_favor_desc* d, const void* x, const float* 
   P.dfeat = (const __nv_bfloat16*)dfeat; P.argmax = const_cast<int32_t*>(argmax); P.gsum = gsum; P.is_query = is_query;
   P.o_out = (__nv_bfloat16*)dx;
   P.tmem_cols = 64;
-  tc_featmap_bwd_kernel<<<fv_grid(d), F_THREADS, smem_fbwd(d->mp), st>>>(P);
+  const int total = P.nchunks * d->batch * d->heads;
+  tc_featmap_bwd_kernel<<<dim3((unsigned)(total < sa_sm_count() ? total : sa_sm_count())), F_THREADS, smem_fbwd(d->mp), st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
 
+size_t sa_tc_favor_states_bytes(const sa_favor_desc* d) { return states_bytes(d); }
+
 int sa_tc_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps, void* out,
-                         int out_ld, float* den, void* ws, size_t ws_bytes, cudaStream_t st) {
+                         int out_ld, float* den, void* ws, size_t ws_bytes, void* states_out, cudaStream_t st) {
   init_once();
   sa_note_path(SA_PATH_TCGEN05);
   if (ws_bytes < sa_tc_favor_scan_workspace(d, 0)) { sa_set_error("tc_favor_scan_fwd: workspace too small"); return SA_ERR_WORKSPACE; }
@@ -963,7 +1049,8 @@ int sa_tc_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* kf,
     return SA_ERR_INVALID;
   }
   float* sums = (float*)ws;
-  uint8_t* states = (uint8_t*)ws + sums_bytes(d);
+  uint8_t* states = states_out ? (uint8_t*)states_out : (uint8_t*)ws + sums_bytes(d);
+  if (!aligned16(states)) { sa_set_error("tc_favor_scan_fwd: states buffer not 16-byte aligned"); return SA_ERR_INVALID; }
   int rc;
   if ((rc = launch_states(d, 0, kf, v, nullptr, nullptr, out_ld, nullptr, eps, sums, states, st)) != SA_OK) return rc;
   static thread_local FvParams P;
@@ -981,7 +1068,7 @@ int sa_tc_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* kf,
 
 int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps, const void* out,
                          const void* dout, int out_ld, const float* den, void* dqf, void* dkf, void* dv, void* ws,
-                         size_t ws_bytes, cudaStream_t st) {
+                         size_t ws_bytes, const void* states_in, cudaStream_t st) {
   init_once();
   sa_note_path(SA_PATH_TCGEN05);
   if (ws_bytes < sa_tc_favor_scan_workspace(d, 1)) { sa_set_error("tc_favor_scan_bwd: workspace too small"); return SA_ERR_WORKSPACE; }
@@ -994,7 +1081,12 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   uint8_t* stS = (uint8_t*)ws + sums_bytes(d);
   uint8_t* stR = stS + states_bytes(d);
   int rc;
-  if ((rc = launch_states(d, 0, kf, v, nullptr, nullptr, out_ld, nullptr, eps, sums, stS, st)) != SA_OK) return rc;
+  if (states_in) {      // prefix states saved by the forward call: no recomputation
+    if (!aligned16(states_in)) { sa_set_error("tc_favor_scan_bwd: states buffer not 16-byte aligned"); return SA_ERR_INVALID; }
+    stS = (uint8_t*)const_cast<void*>(states_in);
+  } else if ((rc = launch_states(d, 0, kf, v, nullptr, nullptr, out_ld, nullptr, eps, sums, stS, st)) != SA_OK) {
+    return rc;
+  }
   if ((rc = launch_states(d, 1, qf, nullptr, out, dout, out_ld, den, eps, sums, stR, st)) != SA_OK) return rc;
   static thread_local FvParams P;
   const size_t smem = smem_dqk(d->mp);

@@ -311,7 +311,7 @@ class _PerformerFn(torch.autograd.Function):
             qkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
             pf_ops.gemm_nt(xa, Wqkv, out_act=qkv)
             attn = torch.empty((M, D.inner), device=dev, dtype=dt)
-            qf = kf = argq = kmax = den = lse = proj = inv_freq = None
+            qf = kf = argq = kmax = den = lse = proj = inv_freq = states = None
             if D.gh > 0:
                 proj = attn_mod.fast_attention.projection_matrix
                 kmax = torch.zeros((1,), device=dev, dtype=torch.int64)
@@ -322,7 +322,10 @@ class _PerformerFn(torch.autograd.Function):
                 pf_ops.favor_featmap_fwd(fd, qkv, 0, proj, True, None, net.eps_feature, qf, argq)
                 pf_ops.favor_featmap_fwd(fd, qkv, D.inner, proj, False, kmax, net.eps_feature, kf, None)
                 den = torch.empty((B, D.gh, N), device=dev, dtype=f32)
-                pf_ops.favor_scan_fwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, 0, den, ws)
+                # the tcgen05 path can keep its per-chunk prefix states for the backward scan (no recomputation)
+                nst = pf_ops.favor_scan_states_bytes(fd) if need_grad else 0
+                states = torch.empty((nst,), device=dev, dtype=torch.uint8) if nst else None
+                pf_ops.favor_scan_fwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, 0, den, ws, states)
             if D.lh > 0:
                 inv_freq = attn_mod.local_attn.rel_pos.inv_freq if attn_mod.local_attn.rel_pos is not None else None
                 lse = torch.empty((B, D.lh, N), device=dev, dtype=f32)
@@ -351,7 +354,7 @@ class _PerformerFn(torch.autograd.Function):
                 xa = torch.empty((M, D.dim), device=dev, dtype=dt)
                 pf_ops.gemm_nt(h, W2_, bias=b2, scale_dev=g_f, resid=x32, out_f32=x32, out_act=xa)
             if need_grad:
-                saved.append((xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq))
+                saved.append((xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq, states))
                 weights.append((Wqkv, Wo_, W1_, W2_))
         # ---- final LayerNorm + logits (performer.py:273-286)
         nw, nb, Wout, bout = p[base + 10 * D.depth: base + 10 * D.depth + 4]
@@ -425,7 +428,7 @@ class _PerformerFn(torch.autograd.Function):
         for li in range(D.depth - 1, -1, -1):
             o = base + 10 * li
             g_a, _Wq, _Wk, _Wv, _Wo, g_f, _W1, b1, _W2, b2 = p[o:o + 10]
-            xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq = ctx.saved[li]
+            xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq, states = ctx.saved[li]
             Wqkv, Wo_, W1_, W2_ = ctx.weights[li]
             ctx.saved[li] = None
             # ---- feed-forward sub-layer: x_out = x + g_f * (gelu(x W1^T + b1) W2^T + b2)
@@ -461,8 +464,10 @@ class _PerformerFn(torch.autograd.Function):
             if D.gh > 0:
                 dqf = torch.empty_like(qf)
                 dkf = torch.empty_like(kf)
+                if states is not None and pf_ops.favor_scan_states_bytes(fd) == 0:
+                    states = None          # the dispatch changed since the forward pass: recompute
                 pf_ops.favor_scan_bwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, dattn, 0, den, dqf, dkf, dqkv,
-                                      2 * D.inner, ws)
+                                      2 * D.inner, ws, states)
                 gsum = torch.zeros((1,), device=dev, dtype=f32)
                 pf_ops.favor_featmap_bwd(fd, qkv, 0, proj, True, net.eps_feature, qf, dqf, argq, dqkv, 0, None)
                 pf_ops.favor_featmap_bwd(fd, qkv, D.inner, proj, False, net.eps_feature, kf, dkf, None, dqkv, D.inner, gsum)

@@ -166,17 +166,25 @@ def favor_scan_workspace(d, backward: bool) -> int:
     return int(lib().sa_favor_scan_workspace(C.byref(d), int(backward)))
 
 
-def favor_scan_fwd(d, qf, kf, vbuf, vcol, eps, out, ocol, den, ws) -> None:
-    _lib.check(lib().sa_favor_scan_fwd(C.byref(d), _p(qf), _p(kf), _ptr(vbuf, vcol), float(eps), _ptr(out, ocol),
-                                       _rowmajor(out), _p(den), _p(ws), ws.numel() * ws.element_size(), _stream()),
+def favor_scan_states_bytes(d) -> int:
+    """bytes of the prefix-state buffer the forward scan can keep for the backward scan (0: the selected path recomputes)"""
+    return int(lib().sa_favor_scan_states_bytes(C.byref(d)))
+
+
+def favor_scan_fwd(d, qf, kf, vbuf, vcol, eps, out, ocol, den, ws, states=None) -> None:
+    _lib.check(lib().sa_favor_scan_fwd_save(C.byref(d), _p(qf), _p(kf), _ptr(vbuf, vcol), float(eps), _ptr(out, ocol),
+                                            _rowmajor(out), _p(den), _p(ws), ws.numel() * ws.element_size(), _p(states),
+                                            0 if states is None else states.numel() * states.element_size(), _stream()),
                "sa_favor_scan_fwd")
 
 
-def favor_scan_bwd(d, qf, kf, vbuf, vcol, eps, out, dout, ocol, den, dqf, dkf, dbuf, dvcol, ws) -> None:
+def favor_scan_bwd(d, qf, kf, vbuf, vcol, eps, out, dout, ocol, den, dqf, dkf, dbuf, dvcol, ws, states=None) -> None:
     assert _rowmajor(out) == _rowmajor(dout)
-    _lib.check(lib().sa_favor_scan_bwd(C.byref(d), _p(qf), _p(kf), _ptr(vbuf, vcol), float(eps), _ptr(out, ocol),
-                                       _ptr(dout, ocol), _rowmajor(out), _p(den), _p(dqf), _p(dkf), _ptr(dbuf, dvcol),
-                                       _p(ws), ws.numel() * ws.element_size(), _stream()), "sa_favor_scan_bwd")
+    _lib.check(lib().sa_favor_scan_bwd_saved(C.byref(d), _p(qf), _p(kf), _ptr(vbuf, vcol), float(eps), _ptr(out, ocol),
+                                             _ptr(dout, ocol), _rowmajor(out), _p(den), _p(dqf), _p(dkf),
+                                             _ptr(dbuf, dvcol), _p(ws), ws.numel() * ws.element_size(), _p(states),
+                                             0 if states is None else states.numel() * states.element_size(), _stream()),
+               "sa_favor_scan_bwd")
 
 
 def rotary(buf, col, batch, seq, heads, dim_head, inv_freq, inverse: bool) -> None:

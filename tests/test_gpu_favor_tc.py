@@ -132,6 +132,16 @@ def test_tcgen05_favor_scan_bf16(B, H, N, m):
     assert ops.last_path() == 2
     _rel(dQF[..., :m], qf.grad, 3e-2, "dq'"); _rel(dKF[..., :m], kf.grad, 3e-2, "dk'")
     _rel(_rows_to_heads(dv[:, 16:].float().cpu(), B, H), v.grad, 3e-2, "dv")
+    # saved prefix states (forward -> backward) give the same gradients as the recomputing call, bit for bit
+    nst = pf.favor_scan_states_bytes(fd)
+    assert nst > 0
+    states = torch.empty(nst, dtype=torch.uint8, device="cuda")
+    O3 = torch.zeros_like(O); den3 = torch.empty_like(den)
+    pf.favor_scan_fwd(fd, QF, KF, vbuf, 16, 1e-6, O3, 64, den3, ws, states)
+    assert torch.equal(O3, O) and torch.equal(den3, den)
+    dQF3 = torch.full_like(QF, 7.0); dKF3 = torch.full_like(KF, 7.0); dv3 = torch.zeros_like(dv)
+    pf.favor_scan_bwd(fd, QF, KF, vbuf, 16, 1e-6, Oref, dO, 64, den_ref.cuda().contiguous(), dQF3, dKF3, dv3, 16, ws, states)
+    assert torch.equal(dQF3, dQF) and torch.equal(dKF3, dKF) and torch.equal(dv3, dv)
     # and the CUDA-core kernels on the same bf16 buffers agree (same entry points, other dispatch)
     ops.set_force_simt(True)
     try:
