@@ -44,6 +44,11 @@ __device__ __forceinline__ unsigned int f2ord(float f) {
 __device__ __forceinline__ float ord2f(unsigned int o) {
   return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
 }
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -53,6 +58,17 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+// shared -> global tensor store (bulk async group); rows / columns outside the tensor are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // 32 lanes x 16 columns of fp32
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -209,7 +225,8 @@ tc_featmap_fwd_kernel(const __grid_constant__ FvParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Xs = smem;               // 2 x 16 KB
-  uint8_t* Ps = smem + 2 * BLK;     // mp x 128 B
+  uint8_t* Os = smem + 2 * BLK;     // nblk blocks: the bf16 feature tile on its way out (TMA store)
+  uint8_t* Ps = Os + P.nblk * BLK;  // mp x 128 B
   const int total = P.nchunks * P.B * P.H;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 256); }
@@ -284,71 +301,84 @@ tc_featmap_fwd_kernel(const __grid_constant__ FvParams P) {
       mbar_wait(&d_full, (uint32_t)(it & 1));
       tc_fence_after();
       mbar_arrive(&x_empty[s]);        // the MMA has consumed the x tile and this thread has read its row
-      if (MODE == 0) {
-        float best = -INFINITY;
-        int bj = 0;
+      // raw maximum of this thread's columns (unit-level bookkeeping: one FMNMX per element), located afterwards
+      float mx = -INFINITY;
+      int au = u_beg;
+      if (MODE != 2) {
         for (int u = u_beg; u < u_end; ++u) {
           uint32_t v[16];
           tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
           tmem_ld_wait();
+          float um = -INFINITY;
+          if (u * 16 + 16 <= P.m) {
 #pragma unroll
-          for (int cix = 0; cix < 16; ++cix) {
-            const int j = u * 16 + cix;
-            const float dv = P.c * __uint_as_float(v[cix]);
-            if (j < P.m && dv > best) { best = dv; bj = j; }
+            for (int cix = 0; cix < 16; ++cix) um = fmaxf(um, __uint_as_float(v[cix]));
+          } else {
+#pragma unroll
+            for (int cix = 0; cix < 16; ++cix) um = fmaxf(um, (u * 16 + cix < P.m) ? __uint_as_float(v[cix]) : -INFINITY);
           }
+          if (um > mx) { mx = um; au = u; }
         }
-        if (row_ok && best > -INFINITY) {
-          const unsigned int flat = (unsigned int)(((long long)bh * P.N + n) * P.m + bj);
-          const unsigned long long packed = ((unsigned long long)f2ord(best) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
+      }
+      int am = 0;
+      if (MODE != 2) {                     // first column of unit `au` that holds the maximum
+        uint32_t v[16];
+        tmem_ld_32x16(tbase + (uint32_t)(au * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cix = 15; cix >= 0; --cix)
+          if (__uint_as_float(v[cix]) == mx && au * 16 + cix < P.m) am = cix;
+        am += au * 16;
+      }
+      if (MODE == 0) {
+        if (row_ok && mx > -INFINITY) {
+          const unsigned int flat = (unsigned int)(((long long)bh * P.N + n) * P.m + am);
+          const unsigned long long packed = ((unsigned long long)f2ord(P.c * mx) << 32) | (unsigned long long)(0xFFFFFFFFu - flat);
           best_packed = packed > best_packed ? packed : best_packed;
         }
       } else {
         float stab;
         if (MODE == 1) {
-          float mx = -INFINITY;
-          int am = 0;
-          for (int u = u_beg; u < u_end; ++u) {
-            uint32_t v[16];
-            tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int cix = 0; cix < 16; ++cix) {
-              const int j = u * 16 + cix;
-              const float dv = __uint_as_float(v[cix]);
-              if (j < P.m && dv > mx) { mx = dv; am = j; }
-            }
-          }
           bar_epi();                     // the previous tile's readers of s_red / s_arg are done
           s_red[hf][r] = mx; s_arg[hf][r] = am;
-          bar_epi();
+        }
+        if (threadIdx.x == 0) tma_store_wait_read();     // the previous tile's store has read the staging buffer
+        bar_epi();
+        if (MODE == 1) {
           const float m0 = s_red[0][r], m1 = s_red[1][r];
           stab = P.c * fmaxf(m0, m1);
           if (hf == 0 && row_ok) P.argmax[(long long)bh * P.N + n] = (m0 >= m1) ? s_arg[0][r] : s_arg[1][r];
         } else {
           stab = stab_k;
         }
-        const float off = diag + stab;
-        __nv_bfloat16* dst = P.feat + ((long long)bh * P.N + n) * P.mp;
+        // r (exp(c D - off) + eps) = r 2^(D c log2e - off log2e) + r eps
+        const float kc = P.c * 1.4426950408889634f;
+        const float koff = (diag + stab) * 1.4426950408889634f;
+        const float reps = P.r * P.eps;
         for (int u = u_beg; u < u_end; ++u) {
           uint32_t v[16];
           tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
           tmem_ld_wait();
           float f[16];
 #pragma unroll
-          for (int cix = 0; cix < 16; ++cix) {
-            const int j = u * 16 + cix;
-            f[cix] = j < P.m ? P.r * (__expf(P.c * __uint_as_float(v[cix]) - off) + P.eps) : 0.f;
+          for (int cix = 0; cix < 16; ++cix) f[cix] = fmaf(P.r, ex2f(fmaf(__uint_as_float(v[cix]), kc, -koff)), reps);
+          if (u * 16 + 16 > P.m) {
+#pragma unroll
+            for (int cix = 0; cix < 16; ++cix) f[cix] = (u * 16 + cix < P.m) ? f[cix] : 0.f;
           }
-          if (row_ok) {
-            reinterpret_cast<uint4*>(dst + u * 16)[0] = pack8(f);
-            reinterpret_cast<uint4*>(dst + u * 16)[1] = pack8(f + 8);
-          }
+          st_sw_16(Os + (u >> 2) * BLK, r, (u & 3) * 16, f);
+        }
+        fence_proxy_async();
+        bar_epi();
+        if (threadIdx.x == 0) {
+          for (int cb = 0; cb < P.nblk; ++cb) tma_store_3d(&P.map_b, Os + cb * BLK, cb * 64, chunk * FC, bh);
+          tma_store_commit();
         }
       }
       tc_fence_before();
       mbar_arrive(&d_empty);
     }
+    if (MODE != 0 && threadIdx.x == 0) tma_store_wait_all();
     if (MODE == 0) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -883,7 +913,7 @@ int sa_sm_count() {
   }
   return n;
 }
-size_t smem_featmap(int mp) { return 2 * BLK + round_up((size_t)mp * 128, 1024) + 1024; }
+size_t smem_featmap(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + round_up((size_t)mp * 128, 1024) + 1024; }
 size_t smem_state(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + 1024; }
 constexpr size_t SMEM_SCAN = SC_STAGES * SC_STAGE + BLK + 1024;
 size_t smem_dqk(int mp) { return (size_t)4 * BLK + (size_t)nblk_of(mp) * (BLK + ST_BLK) + 1024; }
@@ -1004,6 +1034,7 @@ int sa_tc_favor_featmap_fwd(const sa_favor_desc* d, int mode, const void* x, con
   fill_common(P, d, 0, eps);
   int rc;
   if ((rc = head_map(&P.map_a, x, d, d->ld)) != SA_OK) return rc;
+  if (feat && (rc = feat_map(&P.map_b, feat, d)) != SA_OK) return rc;
   P.proj = proj; P.kmax_in = kmax_in; P.kmax_out = kmax_out; P.feat = (__nv_bfloat16*)feat; P.argmax = argmax;
   P.tmem_cols = tmem_cols_for(d->mp);
   const size_t smem = smem_featmap(d->mp);
