@@ -301,33 +301,40 @@ tc_featmap_fwd_kernel(const __grid_constant__ FvParams P) {
       mbar_wait(&d_full, (uint32_t)(it & 1));
       tc_fence_after();
       mbar_arrive(&x_empty[s]);        // the MMA has consumed the x tile and this thread has read its row
-      // raw maximum of this thread's columns (unit-level bookkeeping: one FMNMX per element), located afterwards
+      // raw maximum of this thread's columns: unit-level bookkeeping (one FMNMX per element, the 16 values of the best
+      // unit are kept in registers), the first arg-max is located afterwards.  (tcgen05.ld is warp-collective: its
+      // address must not depend on the lane, so the best unit cannot simply be re-read.)
       float mx = -INFINITY;
-      int au = u_beg;
+      int am = 0;
       if (MODE != 2) {
+        int au = u_beg;
+        float best[16];
+#pragma unroll
+        for (int cix = 0; cix < 16; ++cix) best[cix] = -INFINITY;
         for (int u = u_beg; u < u_end; ++u) {
           uint32_t v[16];
           tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
           tmem_ld_wait();
-          float um = -INFINITY;
+          float w[16];
           if (u * 16 + 16 <= P.m) {
 #pragma unroll
-            for (int cix = 0; cix < 16; ++cix) um = fmaxf(um, __uint_as_float(v[cix]));
+            for (int cix = 0; cix < 16; ++cix) w[cix] = __uint_as_float(v[cix]);
           } else {
 #pragma unroll
-            for (int cix = 0; cix < 16; ++cix) um = fmaxf(um, (u * 16 + cix < P.m) ? __uint_as_float(v[cix]) : -INFINITY);
+            for (int cix = 0; cix < 16; ++cix) w[cix] = (u * 16 + cix < P.m) ? __uint_as_float(v[cix]) : -INFINITY;
           }
-          if (um > mx) { mx = um; au = u; }
+          float um = w[0];
+#pragma unroll
+          for (int cix = 1; cix < 16; ++cix) um = fmaxf(um, w[cix]);
+          const bool better = um > mx;
+          mx = better ? um : mx;
+          au = better ? u : au;
+#pragma unroll
+          for (int cix = 0; cix < 16; ++cix) best[cix] = better ? w[cix] : best[cix];
         }
-      }
-      int am = 0;
-      if (MODE != 2) {                     // first column of unit `au` that holds the maximum
-        uint32_t v[16];
-        tmem_ld_32x16(tbase + (uint32_t)(au * 16), v);
-        tmem_ld_wait();
 #pragma unroll
         for (int cix = 15; cix >= 0; --cix)
-          if (__uint_as_float(v[cix]) == mx && au * 16 + cix < P.m) am = cix;
+          if (best[cix] == mx) am = cix;
         am += au * 16;
       }
       if (MODE == 0) {
