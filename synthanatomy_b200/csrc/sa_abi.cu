@@ -11,6 +11,9 @@ int sa_simt_conv3d_fwd(const sa_conv_desc*, const void*, const void*, const floa
                        void*, cudaStream_t);
 int sa_simt_conv3d_wgrad(const sa_conv_desc*, const void*, const void*, float*, cudaStream_t);
 bool sa_tc_conv3d_supported(const sa_conv_desc*);
+bool sa_tc_conv3_supported(const sa_conv_desc*);
+int sa_tc_conv3_fwd(const sa_conv_desc*, const void*, const void*, const float*, const void*, const void*, int, void*,
+                    cudaStream_t);
 int sa_tc_conv3d_fwd(const sa_conv_desc*, const void*, const void*, const float*, const void*, const void*, int, void*,
                      cudaStream_t);
 bool sa_tc_wgrad_supported(const sa_conv_desc*);
@@ -97,6 +100,7 @@ extern "C" int sa_conv3d_fwd(const sa_conv_desc* d, const void* x, const void* w
   if (rc != SA_OK) return rc;
   SA_CHECK_ARG(x && wp && y, "null pointer");
   cudaStream_t st = sa_stream(stream);
+  if (!sa_force_simt() && sa_tc_conv3_supported(d)) return sa_tc_conv3_fwd(d, x, wp, bias, addend, mask, relu, y, st);
   if (!sa_force_simt() && sa_tc_conv3d_supported(d)) return sa_tc_conv3d_fwd(d, x, wp, bias, addend, mask, relu, y, st);
   return sa_simt_conv3d_fwd(d, x, wp, bias, addend, mask, relu, y, st);
 }

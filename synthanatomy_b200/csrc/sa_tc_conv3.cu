@@ -1,0 +1,289 @@
+// tcgen05 implicit-GEMM for the stride-1 3x3x3 convolutions (and their data gradients) of the VQ-VAE, sm_100a.
+//
+// The general shift-GEMM kernel (sa_tc_conv.cu) reloads a 128-position activation box and a weight slice for every
+// tap: 32 KB of L2 -> shared memory traffic per four 128x128x16 MMAs = 128 B / clk / SM, three times what the L2 can
+// feed 148 SMs.  This kernel cuts the traffic per MMA by 2.2x:
+//
+//   * tile = 8 x 4 x 8 output positions (256 rows = TWO 128-row accumulators that share every weight slice),
+//   * for a fixed (dh, dw) the three depth taps read ONE activation box that is two planes deeper (10 x 4 x 8): a
+//     depth shift is a whole number of 32-row planes = 4 KB, so the shifted A operand is the same shared-memory box
+//     at a 1024-byte-aligned offset -- no re-load, the 128B swizzle atoms stay intact,
+//   * persistent CTAs (one per SM) with two TMEM accumulator stages (2 x 256 columns): the epilogue of tile i runs
+//     under the MMAs of tile i+1.
+//
+// Per pipeline stage (one (dh, dw, 64-channel chunk)): A box 40 KB + 3 weight slices (3 x N x 128 B) for 24 MMAs.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = epilogue
+// (TMEM lane quadrant = warp & 3, accumulator half = (warp - 2) >> 2).
+//
+// Reference call sites replaced: cuDNN fprop / dgrad behind the 3x3x3 nn.Conv3d of ResidualLayer and of the
+// encoder / decoder heads, /root/reference/src/networks/vqvae/baseline.py:153-160, 242-244, 258.
+#include <mutex>
+#include <stdlib.h>
+
+#include "sa_tc_common.cuh"
+
+using namespace satc;
+
+namespace {
+
+constexpr int C3_THREADS = 320;
+constexpr int C3_TD = 8, C3_TH = 4, C3_TW = 8;
+constexpr int C3_PLANE = C3_TH * C3_TW;                  // 32 rows
+constexpr uint32_t C3_PLANE_BYTES = C3_PLANE * 128;      // 4 KB
+constexpr uint32_t C3_A_BYTES = (C3_TD + 2) * C3_PLANE_BYTES;   // 40 KB
+constexpr int C3_STAGES = 2;
+
+struct C3Params {
+  CUtensorMap amap, wmap;
+  int N, cchunks;
+  int gD, gH, gW, ntd, nth, ntw, batch, total_tiles;
+  int pe;                   // effective padding (tap offset = t - pe)
+  int wrow[27];             // first row of each tap's [N][c_in] slice in the packed weight matrix
+  int relu;
+  const float* bias;
+  const __nv_bfloat16* addend;
+  const __nv_bfloat16* mask;
+  __nv_bfloat16* y;
+};
+
+__global__ void __launch_bounds__(C3_THREADS, 1)
+tc_conv3_kernel(const __grid_constant__ C3Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[C3_STAGES], empty_bar[C3_STAGES];
+  __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b_bytes = (uint32_t)P.N * 128;
+  const uint32_t stage_bytes = C3_A_BYTES + 3 * b_bytes;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int iters = 9 * P.cchunks;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < C3_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) { tmem_alloc(&tmem_base_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      prefetch_tmap(&P.wmap);
+      prefetch_tmap(&P.amap);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tw_i = t % P.ntw; t /= P.ntw;
+        const int th_i = t % P.nth; t /= P.nth;
+        const int td_i = t % P.ntd; t /= P.ntd;
+        const int b = t;
+        const int g0d = td_i * C3_TD, g0h = th_i * C3_TH, g0w = tw_i * C3_TW;
+        for (int it = 0; it < iters; ++it) {
+          const int hw = it / P.cchunks, cc = it - hw * P.cchunks;
+          const int dh = hw / 3, dw = hw - dh * 3;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          tma_load_5d(sa, &P.amap, &full_bar[stage], cc * 64, g0w + dw - P.pe, g0h + dh - P.pe, g0d - P.pe, b);
+#pragma unroll
+          for (int dd = 0; dd < 3; ++dd)
+            tma_load_2d(sa + C3_A_BYTES + dd * b_bytes, &P.wmap, &full_bar[stage], cc * 64, P.wrow[(dd * 3 + dh) * 3 + dw]);
+          if (++stage == C3_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, P.N, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * 256);
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + C3_A_BYTES;
+#pragma unroll
+          for (int dd = 0; dd < 3; ++dd) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t a0 = sa + (uint32_t)(dd + 4 * half) * C3_PLANE_BYTES;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d0 + (uint32_t)(half * 128), make_smem_desc(a0 + k * 32, 16, 1024, 2),
+                          make_smem_desc(sb + dd * b_bytes + k * 32, 16, 1024, 2), idesc, (it | dd | k) != 0);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C3_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: TMEM -> regs -> bf16 NDHWC
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    const int r = quad * 32 + lane;                       // row of this half's accumulator
+    const int dz = half * 4 + (r >> 5), hy = (r >> 3) & 3, wx = r & 7;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int tw_i = t % P.ntw; t /= P.ntw;
+      const int th_i = t % P.nth; t /= P.nth;
+      const int td_i = t % P.ntd; t /= P.ntd;
+      const int b = t;
+      const int gd = td_i * C3_TD + dz, gh = th_i * C3_TH + hy, gw = tw_i * C3_TW + wx;
+      const bool valid = gd < P.gD && gh < P.gH && gw < P.gW;
+      const int64_t obase = ((((int64_t)b * P.gD + gd) * P.gH + gh) * P.gW + gw) * P.N;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      for (int c0 = 0; c0 < P.N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + half * 128 + c0), v);
+        tmem_ld_wait();
+        if (valid) {
+          const int nc = min(32, P.N - c0);      // N is a multiple of 16
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (P.bias) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (q * 4 < nc) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + c0) + q);
+                f[q * 4 + 0] += bb.x; f[q * 4 + 1] += bb.y; f[q * 4 + 2] += bb.z; f[q * 4 + 3] += bb.w;
+              }
+            }
+          }
+          if (P.addend) {
+            const uint4* ap = reinterpret_cast<const uint4*>(P.addend + obase + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < nc) {
+                const uint4 u = __ldg(ap + q);
+                f[q * 8 + 0] += bf16lo(u.x); f[q * 8 + 1] += bf16hi(u.x);
+                f[q * 8 + 2] += bf16lo(u.y); f[q * 8 + 3] += bf16hi(u.y);
+                f[q * 8 + 4] += bf16lo(u.z); f[q * 8 + 5] += bf16hi(u.z);
+                f[q * 8 + 6] += bf16lo(u.w); f[q * 8 + 7] += bf16hi(u.w);
+              }
+            }
+          }
+          if (P.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (P.mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(P.mask + obase + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < nc) {
+                const uint4 u = __ldg(mp + q);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!(bf16lo(w[e]) > 0.f)) f[q * 8 + 2 * e] = 0.f;
+                  if (!(bf16hi(w[e]) > 0.f)) f[q * 8 + 2 * e + 1] = 0.f;
+                }
+              }
+            }
+          }
+          uint4* yp = reinterpret_cast<uint4*>(P.y + obase + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q * 8 < nc) {
+              uint4 u;
+              u.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+              u.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+              u.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+              u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+              yp[q] = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+std::once_flag g_c3_once;
+int g_c3_sms = 148;
+
+}  // namespace
+
+bool sa_tc_conv3_supported(const sa_conv_desc* d) {
+  if (d->act_dtype != SA_BF16 || d->ksize != 3 || d->stride != 1) return false;
+  if (d->c_in % 64 != 0 || d->c_out % 16 != 0 || d->c_out < 16 || d->c_out > 128) return false;
+  const int pe = d->transposed ? 2 - d->pad : d->pad;
+  if (pe < 0 || pe > 2) return false;
+  for (int i = 0; i < 3; ++i) if (d->out_dhw[i] != d->in_dhw[i] + 2 * pe - 2) return false;
+  if (const char* e = getenv("SA_TC_CONV3")) { if (e[0] == '0') return false; }   // A/B switch for benchmarking
+  return sa_get_tmap_encode() != nullptr;
+}
+
+int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const float* bias, const void* addend,
+                    const void* mask, int relu, void* y, cudaStream_t st) {
+  std::call_once(g_c3_once, [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) g_c3_sms = v;
+    cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  });
+  sa_note_path(SA_PATH_TCGEN05);
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) { sa_set_error("tc_conv3: bias not 16-byte aligned"); return SA_ERR_INVALID; }
+  static thread_local C3Params P;
+  const int iD = d->in_dhw[0], iH = d->in_dhw[1], iW = d->in_dhw[2];
+  P.N = d->c_out;
+  P.cchunks = d->c_in / 64;
+  P.gD = d->out_dhw[0]; P.gH = d->out_dhw[1]; P.gW = d->out_dhw[2];
+  P.ntd = (int)sa_cdiv(P.gD, C3_TD); P.nth = (int)sa_cdiv(P.gH, C3_TH); P.ntw = (int)sa_cdiv(P.gW, C3_TW);
+  P.batch = d->batch;
+  const int64_t total = (int64_t)P.ntd * P.nth * P.ntw * d->batch;
+  if (total >= (1LL << 31)) { sa_set_error("tc_conv3: too many tiles"); return SA_ERR_UNSUPPORTED; }
+  P.total_tiles = (int)total;
+  P.pe = d->transposed ? 2 - d->pad : d->pad;
+  for (int t = 0; t < 27; ++t) P.wrow[t] = (d->transposed ? 26 - t : t) * d->c_out;    // flipped taps for the transposed form
+  P.relu = relu; P.bias = bias;
+  P.addend = (const __nv_bfloat16*)addend; P.mask = (const __nv_bfloat16*)mask; P.y = (__nv_bfloat16*)y;
+  {
+    const uint64_t dims[2] = {(uint64_t)d->c_in, (uint64_t)27 * d->c_out};
+    const uint64_t strides[2] = {2, (uint64_t)d->c_in * 2};
+    const uint32_t box[2] = {64, (uint32_t)d->c_out};
+    int rc = sa_make_tmap_bf16(&P.wmap, wp, 2, dims, strides, box);
+    if (rc != SA_OK) return rc;
+  }
+  {
+    const uint64_t C = (uint64_t)d->c_in;
+    const uint64_t dims[5] = {C, (uint64_t)iW, (uint64_t)iH, (uint64_t)iD, (uint64_t)d->batch};
+    const uint64_t strides[5] = {2, C * 2, (uint64_t)iW * C * 2, (uint64_t)iH * iW * C * 2, (uint64_t)iD * iH * iW * C * 2};
+    const uint32_t box[5] = {64, C3_TW, C3_TH, C3_TD + 2, 1};
+    int rc = sa_make_tmap_bf16(&P.amap, x, 5, dims, strides, box);
+    if (rc != SA_OK) return rc;
+  }
+  const size_t stage_bytes = (size_t)C3_A_BYTES + 3 * (size_t)P.N * 128;
+  const size_t smem = C3_STAGES * stage_bytes + 1024;
+  const unsigned grid = (unsigned)(P.total_tiles < g_c3_sms ? P.total_tiles : g_c3_sms);
+  tc_conv3_kernel<<<grid, C3_THREADS, smem, st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
