@@ -11,6 +11,8 @@ int sa_simt_conv3d_fwd(const sa_conv_desc*, const void*, const void*, const floa
                        void*, cudaStream_t);
 int sa_simt_conv3d_wgrad(const sa_conv_desc*, const void*, const void*, float*, cudaStream_t);
 bool sa_tc_conv3d_supported(const sa_conv_desc*);
+bool sa_tc_wgrad3_supported(const sa_conv_desc*);
+int sa_tc_conv3d_wgrad3(const sa_conv_desc*, const void*, const void*, float*, cudaStream_t);
 bool sa_tc_conv3_supported(const sa_conv_desc*);
 int sa_tc_conv3_fwd(const sa_conv_desc*, const void*, const void*, const float*, const void*, const void*, int, void*,
                     cudaStream_t);
@@ -116,6 +118,7 @@ extern "C" int sa_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void*
     const size_t n = (size_t)d->ksize * d->ksize * d->ksize * d->c_out * d->c_in;
     SA_CUDA(cudaMemsetAsync(dwp, 0, n * sizeof(float), st));
   }
+  if (!sa_force_simt() && sa_tc_wgrad3_supported(d)) return sa_tc_conv3d_wgrad3(d, p, q, dwp, st);
   if (!sa_force_simt() && sa_tc_wgrad_supported(d)) return sa_tc_conv3d_wgrad(d, p, q, dwp, st);
   return sa_simt_conv3d_wgrad(d, p, q, dwp, st);
 }
