@@ -283,8 +283,13 @@ def vqvae_b200(args, world, rank, local, dev):
         flop = 2.0 * pos * 27 * 128 * 128                    # algorithmic FLOPs of one 3x3x3 128->128 launch
         avg_ms = sum(dt) / len(dt)
         ach = flop / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "tc_conv_kernel (3x3x3 128->128 @ level 1, fwd + dgrad launches)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one level-1 launch from the committed
+        # `ncu --set full` capture (profiles/r1_vqvae_ncu_conv3.txt); algorithmic bytes = bf16 NDHWC in + out
+        traffic = 2.894e9 if (full and B == 8) else None
+        roof = {"bound": "tensor", "kernel": "tc_conv3_kernel (3x3x3 128->128 @ level 1, fwd + dgrad launches)",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "traffic_source": "profiles/r1_vqvae_ncu_conv3.txt (ncu, same kernel and shape; not measured in this run)",
+                "algorithmic_bytes_per_launch": 2.0 * pos * 128 * 2,
                 "launches_timed": len(dt), "avg_ms": avg_ms, "flop_per_launch": flop, "peak_source": peak_src}
     step_flop = 3 * FLOP_PER_VOL_FWD * B * (vol[0] * vol[1] * vol[2]) / (160 * 224 * 160)
     out = {
@@ -535,7 +540,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     ops.lib()   # fail loudly here if the CUDA library is missing
     out = vqvae_b200(args, world, rank, local, dev) if args.workload in ("vqvae", "both") else None
     if args.workload in ("performer", "both"):
