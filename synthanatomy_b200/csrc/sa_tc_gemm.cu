@@ -68,6 +68,38 @@ __device__ __forceinline__ void st32_f32(float* p, const float (&f)[32]) {
   for (int i = 0; i < 8; ++i) q[i] = make_float4(f[i * 4 + 0], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
 }
 
+// GELU(x) = x Phi(x) and GELU'(x) = Phi(x) + x phi(x) with Phi through erf(|x| / sqrt 2) = 1 - poly(t) e^{-x^2/2},
+// t = 1 / (1 + p |x| / sqrt 2)  (Abramowitz & Stegun 7.1.26, |error| < 1.5e-7): one reciprocal, one ex2 and a
+// handful of FMAs instead of libm erff (+ expf for the derivative, which shares the exponential here).  Used by the
+// bf16 tensor-core epilogue only (outputs are rounded to bf16, 2^-9); the fp32 parity path keeps erff.
+__device__ __forceinline__ void fast_phi(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x);
+  const float z = ax * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170f * x * x));     // e^{-x^2/2}
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, e, 1.0f);                 // erf(|x| / sqrt 2)
+  const float half = 0.5f * erf_abs;
+  cdf = x >= 0.f ? 0.5f + half : 0.5f - half;
+  pdf = 0.39894228040143268f * e;
+}
+__device__ __forceinline__ float fast_gelu(float x) {
+  float c, p;
+  fast_phi(x, c, p);
+  return x * c;
+}
+__device__ __forceinline__ float fast_gelu_grad(float x) {
+  float c, p;
+  fast_phi(x, c, p);
+  return fmaf(x, p, c);
+}
+
 __global__ void __launch_bounds__(G_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -189,11 +221,11 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
           if (e.act == SA_ACT_GELU_FWD) {
             st32_bf16(reinterpret_cast<T*>(e.pre) + o, f);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = sa_gelu(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = fast_gelu(f[j]);
           } else if (e.act == SA_ACT_GELU_BWD) {
             ld32_bf16(reinterpret_cast<const T*>(e.pre) + o, t);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= sa_gelu_grad(t[j]);
+            for (int j = 0; j < 32; ++j) f[j] *= fast_gelu_grad(t[j]);
           }
           if (e.resid) {
             ld32_f32(e.resid + o, t);
