@@ -31,11 +31,12 @@ constexpr int C3_TD = 8, C3_TH = 4, C3_TW = 8;
 constexpr int C3_PLANE = C3_TH * C3_TW;                  // 32 rows
 constexpr uint32_t C3_PLANE_BYTES = C3_PLANE * 128;      // 4 KB
 constexpr uint32_t C3_A_BYTES = (C3_TD + 2) * C3_PLANE_BYTES;   // 40 KB
-constexpr int C3_STAGES = 2;
+constexpr int C3_MAX_STAGES = 4;
 
 struct C3Params {
   CUtensorMap amap, wmap;
   int N, cchunks;
+  int ksz, stages;          // 3 (27 taps, depth-fused) or 1 (pointwise); pipeline stages
   int gD, gH, gW, ntd, nth, ntw, batch, total_tiles;
   int pe;                   // effective padding (tap offset = t - pe)
   int wrow[27];             // first row of each tap's [N][c_in] slice in the packed weight matrix
@@ -49,18 +50,20 @@ struct C3Params {
 __global__ void __launch_bounds__(C3_THREADS, 1)
 tc_conv3_kernel(const __grid_constant__ C3Params P) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[C3_STAGES], empty_bar[C3_STAGES];
+  __shared__ uint64_t full_bar[C3_MAX_STAGES], empty_bar[C3_MAX_STAGES];
   __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_bytes = (uint32_t)P.N * 128;
-  const uint32_t stage_bytes = C3_A_BYTES + 3 * b_bytes;
+  const int ksz = P.ksz;                                   // taps per axis; the ksz depth taps share one A box
+  const uint32_t a_bytes = (uint32_t)(C3_TD + ksz - 1) * C3_PLANE_BYTES;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)ksz * b_bytes;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int iters = 9 * P.cchunks;
+  const int iters = ksz * ksz * P.cchunks;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < C3_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
     fence_mbar_init();
     fence_proxy_async();
@@ -86,15 +89,14 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
         const int g0d = td_i * C3_TD, g0h = th_i * C3_TH, g0w = tw_i * C3_TW;
         for (int it = 0; it < iters; ++it) {
           const int hw = it / P.cchunks, cc = it - hw * P.cchunks;
-          const int dh = hw / 3, dw = hw - dh * 3;
+          const int dh = hw / ksz, dw = hw - dh * ksz;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], stage_bytes);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           tma_load_5d(sa, &P.amap, &full_bar[stage], cc * 64, g0w + dw - P.pe, g0h + dh - P.pe, g0d - P.pe, b);
-#pragma unroll
-          for (int dd = 0; dd < 3; ++dd)
-            tma_load_2d(sa + C3_A_BYTES + dd * b_bytes, &P.wmap, &full_bar[stage], cc * 64, P.wrow[(dd * 3 + dh) * 3 + dw]);
-          if (++stage == C3_STAGES) { stage = 0; phase ^= 1; }
+          for (int dd = 0; dd < ksz; ++dd)
+            tma_load_2d(sa + a_bytes + dd * b_bytes, &P.wmap, &full_bar[stage], cc * 64, P.wrow[(dd * ksz + dh) * ksz + dw]);
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -112,9 +114,8 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + C3_A_BYTES;
-#pragma unroll
-          for (int dd = 0; dd < 3; ++dd) {
+          const uint32_t sb = sa + a_bytes;
+          for (int dd = 0; dd < ksz; ++dd) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const uint32_t a0 = sa + (uint32_t)(dd + 4 * half) * C3_PLANE_BYTES;
@@ -125,7 +126,7 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == C3_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -232,11 +233,12 @@ int g_c3_sms = 148;
 }  // namespace
 
 bool sa_tc_conv3_supported(const sa_conv_desc* d) {
-  if (d->act_dtype != SA_BF16 || d->ksize != 3 || d->stride != 1) return false;
+  if (d->act_dtype != SA_BF16 || !(d->ksize == 3 || d->ksize == 1) || d->stride != 1) return false;
   if (d->c_in % 64 != 0 || d->c_out % 16 != 0 || d->c_out < 16 || d->c_out > 128) return false;
-  const int pe = d->transposed ? 2 - d->pad : d->pad;
-  if (pe < 0 || pe > 2) return false;
-  for (int i = 0; i < 3; ++i) if (d->out_dhw[i] != d->in_dhw[i] + 2 * pe - 2) return false;
+  const int k = d->ksize;
+  const int pe = d->transposed ? k - 1 - d->pad : d->pad;
+  if (pe < 0 || pe > k - 1) return false;
+  for (int i = 0; i < 3; ++i) if (d->out_dhw[i] != d->in_dhw[i] + 2 * pe - (k - 1)) return false;
   if (const char* e = getenv("SA_TC_CONV3")) { if (e[0] == '0') return false; }   // A/B switch for benchmarking
   return sa_get_tmap_encode() != nullptr;
 }
@@ -261,12 +263,14 @@ int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const 
   const int64_t total = (int64_t)P.ntd * P.nth * P.ntw * d->batch;
   if (total >= (1LL << 31)) { sa_set_error("tc_conv3: too many tiles"); return SA_ERR_UNSUPPORTED; }
   P.total_tiles = (int)total;
-  P.pe = d->transposed ? 2 - d->pad : d->pad;
-  for (int t = 0; t < 27; ++t) P.wrow[t] = (d->transposed ? 26 - t : t) * d->c_out;    // flipped taps for the transposed form
+  const int k = d->ksize, taps = k * k * k;
+  P.ksz = k;
+  P.pe = d->transposed ? k - 1 - d->pad : d->pad;
+  for (int t = 0; t < taps; ++t) P.wrow[t] = (d->transposed ? taps - 1 - t : t) * d->c_out;   // flipped taps: transposed form
   P.relu = relu; P.bias = bias;
   P.addend = (const __nv_bfloat16*)addend; P.mask = (const __nv_bfloat16*)mask; P.y = (__nv_bfloat16*)y;
   {
-    const uint64_t dims[2] = {(uint64_t)d->c_in, (uint64_t)27 * d->c_out};
+    const uint64_t dims[2] = {(uint64_t)d->c_in, (uint64_t)taps * d->c_out};
     const uint64_t strides[2] = {2, (uint64_t)d->c_in * 2};
     const uint32_t box[2] = {64, (uint32_t)d->c_out};
     int rc = sa_make_tmap_bf16(&P.wmap, wp, 2, dims, strides, box);
@@ -276,12 +280,17 @@ int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const 
     const uint64_t C = (uint64_t)d->c_in;
     const uint64_t dims[5] = {C, (uint64_t)iW, (uint64_t)iH, (uint64_t)iD, (uint64_t)d->batch};
     const uint64_t strides[5] = {2, C * 2, (uint64_t)iW * C * 2, (uint64_t)iH * iW * C * 2, (uint64_t)iD * iH * iW * C * 2};
-    const uint32_t box[5] = {64, C3_TW, C3_TH, C3_TD + 2, 1};
+    const uint32_t box[5] = {64, C3_TW, C3_TH, (uint32_t)(C3_TD + k - 1), 1};
     int rc = sa_make_tmap_bf16(&P.amap, x, 5, dims, strides, box);
     if (rc != SA_OK) return rc;
   }
-  const size_t stage_bytes = (size_t)C3_A_BYTES + 3 * (size_t)P.N * 128;
-  const size_t smem = C3_STAGES * stage_bytes + 1024;
+  const size_t stage_bytes = (size_t)(C3_TD + k - 1) * C3_PLANE_BYTES + (size_t)k * P.N * 128;
+  int stages = (int)((227 * 1024 - 2048 - 1024) / stage_bytes);
+  if (stages > C3_MAX_STAGES) stages = C3_MAX_STAGES;
+  if (stages > k * k * P.cchunks) stages = k * k * P.cchunks;
+  if (stages < 1) { sa_set_error("tc_conv3: stage does not fit shared memory"); return SA_ERR_UNSUPPORTED; }
+  P.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024;
   const unsigned grid = (unsigned)(P.total_tiles < g_c3_sms ? P.total_tiles : g_c3_sms);
   tc_conv3_kernel<<<grid, C3_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
