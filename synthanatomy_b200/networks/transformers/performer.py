@@ -181,13 +181,59 @@ class ProjectionUpdater(nn.Module):
     def fix_projections_(self):
         self.feature_redraw_interval = None
 
+    def __getstate__(self):      # the prefetch thread / pinned buffers are rebuilt on demand (deepcopy, pickling)
+        st = dict(self.__dict__)
+        for k in ("_pins", "_pin_events", "_gen", "_pool", "_next"):
+            st.pop(k, None)
+        return st
+
+    def _draw_all_into(self, slot: int, mods):
+        """host side of a redraw: QR draws of every layer into pinned buffer `slot` (runs on the prefetch thread)"""
+        evs = self._pin_events
+        if evs[slot] is not None:
+            evs[slot].synchronize()            # the copies issued from this buffer two redraws ago have executed
+        for i, m in enumerate(mods):
+            self._pins[slot][i].copy_(gaussian_orthogonal_random_matrix(m.nb_features, m.dim_heads, m.ortho_scaling,
+                                                                        generator=self._gen))
+        return slot
+
+    def _redraw_all(self):
+        """Redraw every layer's projection matrix.  The QR factorisations run on the host like the reference's
+        (performer-pytorch draws on the CPU and copies), but off the critical path: the matrices of the NEXT redraw are
+        drawn by a background thread into pinned memory while the device works, and a redraw itself is only a batch of
+        asynchronous H2D copies.  Draws come from a private generator seeded once from torch's global RNG, so a run is
+        reproducible under torch.manual_seed."""
+        mods = [m for m in self.instance.modules() if isinstance(m, FastAttention)]
+        if not mods:
+            return
+        dev = mods[0].projection_matrix.device
+        if dev.type != "cuda":
+            for m in mods:
+                m.redraw_projection_matrix()
+            return
+        shape = (len(mods),) + tuple(mods[0].projection_matrix.shape)
+        st = self.__dict__
+        if st.get("_pins") is None or tuple(st["_pins"][0].shape) != shape:
+            import concurrent.futures as cf
+            st["_pins"] = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+            st["_pin_events"] = [None, None]
+            st["_gen"] = torch.Generator().manual_seed(int(torch.randint(0, 2 ** 62, (1,)).item()))
+            st["_pool"] = cf.ThreadPoolExecutor(max_workers=1)
+            st["_next"] = st["_pool"].submit(self._draw_all_into, 0, mods)
+        slot = self._next.result()
+        with torch.no_grad():
+            for i, m in enumerate(mods):
+                m.projection_matrix.copy_(self._pins[slot][i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pin_events[slot] = ev
+        self._next = self._pool.submit(self._draw_all_into, 1 - slot, mods)
+
     def redraw_projections(self):
         if not self.training:
             return
         if self.feature_redraw_interval is not None and self._calls >= self.feature_redraw_interval:
-            for mod in self.instance.modules():
-                if isinstance(mod, FastAttention):
-                    mod.redraw_projection_matrix()
+            self._redraw_all()
             self._calls = 0
             self.calls_since_last_redraw.zero_()
             return
