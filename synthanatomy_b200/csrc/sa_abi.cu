@@ -59,8 +59,8 @@ sa_tmap_encode_fn sa_get_tmap_encode() {
   return fn;
 }
 
-int sa_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+int sa_make_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box) {
   sa_tmap_encode_fn enc = sa_get_tmap_encode();
   if (!enc) { sa_set_error("cuTensorMapEncodeTiled entry point not available"); return SA_ERR_CUDA; }
   cuuint64_t gdims[5], gstr[4];
@@ -70,7 +70,8 @@ int sa_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64
   if (reinterpret_cast<uintptr_t>(base) & 15) { sa_set_error("tensor map base not 16-byte aligned"); return SA_ERR_INVALID; }
   for (int i = 1; i < rank; ++i)
     if (strides_bytes[i] & 15) { sa_set_error("tensor map stride %d not a multiple of 16 bytes", i); return SA_ERR_INVALID; }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
+  const CUtensorMapDataType dt = dtype == SA_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -80,6 +81,11 @@ int sa_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64
     return SA_ERR_CUDA;
   }
   return SA_OK;
+}
+
+int sa_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  return sa_make_tmap(out, SA_BF16, base, rank, dims, strides_bytes, box);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -169,3 +169,6 @@ sa_tmap_encode_fn sa_get_tmap_encode();
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides[0] is implied (2 bytes).
 int sa_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box);
+// same for dtype SA_BF16 / SA_F32 (the innermost box extent must span at most 128 bytes)
+int sa_make_tmap(CUtensorMap* out, int dtype, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box);

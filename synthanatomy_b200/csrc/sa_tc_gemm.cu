@@ -13,6 +13,7 @@
 // Reference call sites replaced: cuBLAS behind nn.Linear forward / backward of performer-pytorch SelfAttention
 // (to_q/to_k/to_v/to_out), FeedForward (w1, w2) and /root/reference/src/networks/transformers/performer.py:221,286.
 #include <mutex>
+#include <stdlib.h>
 
 #include "sa_pf_common.cuh"
 #include "sa_tc_common.cuh"
@@ -28,6 +29,8 @@ constexpr int G_STAGES = 4;
 
 struct NtParams {
   CUtensorMap amap, bmap;
+  CUtensorMap omap_act, omap_b;   // TMA-store maps: out_act (bf16, 64 x 32 boxes); `pre` (bf16) or out_f32 (fp32, 32 x 32 boxes)
+  int stages, tma_out;            // pipeline stages; 1 = outputs leave through shared-memory staging + TMA stores
   long long m;
   int n, k;
   int BN, m_tiles, n_tiles, kblocks;
@@ -66,6 +69,36 @@ __device__ __forceinline__ void st32_f32(float* p, const float (&f)[32]) {
   float4* q = reinterpret_cast<float4*>(p);
 #pragma unroll
   for (int i = 0; i < 8; ++i) q[i] = make_float4(f[i * 4 + 0], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 32 bf16 columns [c0, c0 + 32) of row r of a 128B-swizzled [32 rows][64 cols] staging block
+__device__ __forceinline__ void stage_bf16_32(uint8_t* block, int r, int c0, const float (&f)[32]) {
+  uint8_t* row = block + r * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = (c0 >> 3) + i;
+    uint4 u;
+    u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]); u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+    u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]); u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+    *reinterpret_cast<uint4*>(row + ((ch ^ (r & 7)) << 4)) = u;
+  }
+}
+// 32 fp32 columns of row r of a 128B-swizzled [32 rows][32 cols] staging block
+__device__ __forceinline__ void stage_f32_32(uint8_t* block, int r, const float (&f)[32]) {
+  uint8_t* row = block + r * 128;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
 }
 
 // GELU(x) = x Phi(x) and GELU'(x) = Phi(x) + x phi(x) with Phi through erf(|x| / sqrt 2) = 1 - poly(t) e^{-x^2/2},
@@ -118,7 +151,7 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
   const int total_tiles = P.m_tiles * P.n_tiles;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < G_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
     fence_mbar_init();
     fence_proxy_async();
@@ -145,7 +178,7 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           tma_load_2d(sa, &P.amap, &full_bar[stage], kb * G_BK, mt * G_BM);
           tma_load_2d(sa + a_bytes, &P.bmap, &full_bar[stage], kb * G_BK, nt * P.BN);
-          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -170,7 +203,7 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
             umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -185,24 +218,92 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
     const int half = ew >> 2;                 // which half of the tile's columns
     const int half_cols = P.BN / 2;           // BN is a multiple of 16 -> halves are multiples of 8
     const float st = e.scale * (e.scale_dev ? __ldg(e.scale_dev) : 1.0f);
+    uint8_t* stgA = smem + (size_t)P.stages * stage_bytes + (size_t)ew * 8192;   // out_act block   [32 rows][64 bf16]
+    uint8_t* stgB = stgA + 4096;                                               // pre block / out_f32 chunk
     float dot = 0.f;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
       const long long row = (long long)mt * G_BM + quad * 32 + lane;
+      const int row0 = mt * G_BM + quad * 32;
       const bool row_ok = row < P.m;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       for (int cc = 0; cc < half_cols; cc += 32) {
         const int ct = half * half_cols + cc;             // column inside the tile
         const int col = nt * P.BN + ct;                   // global column
+        if (P.vec == 3) continue;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * P.BN + ct), v);
         tmem_ld_wait();
+        if (P.vec == 2) continue;                         // SA_GEMM_NOEPI=1: mainloop-only timing experiment
         const int nc = min(min(32, half_cols - cc), P.n - col);
-        if (!row_ok || nc <= 0) continue;
+        if (nc <= 0) continue;                             // warp-uniform
+        if (!P.tma_out && !row_ok) continue;               // (the staging path needs every lane)
         const long long o = row * e.ldo + col;
-        if (P.vec && nc == 32) {
+        if (P.tma_out) {
+          // Outputs leave through 128B-swizzled shared-memory staging blocks and TMA stores: the per-thread stores
+          // (thread = row) would touch 32 different 128-byte lines per instruction; the bulk stores write whole rows.
+          // Rows past m / nothing past n (n % 32 == 0 on this path) are clipped by the TMA unit.
+          float f[32], t[32];
+          const int ci = cc >> 5;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (e.bias) {
+            ld32_f32(e.bias + col, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += t[j];
+          }
+          if (e.dot_with && row_ok) {
+            ld32_bf16(reinterpret_cast<const T*>(e.dot_with) + o, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dot = fmaf(f[j], t[j], dot);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= st;
+          if (e.act == SA_ACT_GELU_FWD) {
+            if ((ci & 1) == 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
+            stage_bf16_32(stgB, lane, (ci & 1) * 32, f);
+            if (ci & 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&P.omap_b, stgB, col - 32, row0); bulk_commit(); }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fast_gelu(f[j]);
+          } else if (e.act == SA_ACT_GELU_BWD) {
+            if (row_ok) {
+              ld32_bf16(reinterpret_cast<const T*>(e.pre) + o, t);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= fast_gelu_grad(t[j]);
+            }
+          }
+          if (e.resid && row_ok) {
+            ld32_f32(e.resid + o, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += t[j];
+          }
+          if (e.out_f32) {
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            stage_f32_32(stgB, lane, f);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&P.omap_b, stgB, col, row0); bulk_commit(); }
+          }
+          if (e.out_act) {
+            // single output: the two staging blocks alternate (wait only for the store issued two blocks ago)
+            const bool solo = !e.out_f32 && e.act != SA_ACT_GELU_FWD;
+            uint8_t* sbuf = (solo && (ci & 2)) ? stgB : stgA;
+            if ((ci & 1) == 0 && solo) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
+            stage_bf16_32(sbuf, lane, (ci & 1) * 32, f);
+            if (ci & 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&P.omap_act, sbuf, col - 32, row0); bulk_commit(); }
+            }
+          }
+        } else if (P.vec && nc == 32) {
           float f[32], t[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -249,6 +350,7 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
       dot = sa_warp_sum(dot);
       if (lane == 0) atomicAdd(e.dot_out, dot);
     }
+    if (P.tma_out && lane == 0) bulk_wait0();
   }
 
   tc_fence_before();
@@ -423,11 +525,38 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
   const void* ptrs[] = {e.bias, e.dot_with, e.pre, e.resid, e.out_f32, e.out_act};
   for (const void* p : ptrs) vec = vec && aligned16(p);
   P.vec = vec ? 1 : 0;
+  if (const char* env = getenv("SA_GEMM_NOEPI")) { if (env[0] == '1') P.vec = 2; }
+  if (const char* env = getenv("SA_GEMM_NOEPI")) { if (env[0] == '2') P.vec = 3; }
   int rc = make_2d(&P.amap, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, G_BK, G_BM);
   if (rc != SA_OK) return rc;
   rc = make_2d(&P.bmap, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, G_BK, (uint32_t)P.BN);
   if (rc != SA_OK) return rc;
-  const size_t smem = (size_t)G_STAGES * (G_BM * 128 + (size_t)P.BN * 128) + 1024;
+  // TMA-store epilogue: whole 64-column blocks per warp, at most one "second" output (pre or out_f32)
+  P.tma_out = (vec && P.vec != 2 && P.vec != 3 && P.BN % 128 == 0 && n % 64 == 0 && (e.out_act || e.out_f32) &&
+               !(e.out_f32 && e.act == SA_ACT_GELU_FWD)) ? 1 : 0;
+  if (const char* env = getenv("SA_GEMM_TMA_OUT")) { if (env[0] == '0') P.tma_out = 0; }
+  const size_t stage_bytes = G_BM * 128 + (size_t)P.BN * 128;
+  P.stages = G_STAGES;
+  const size_t stg_bytes = P.tma_out ? 8 * 8192 : 0;
+  while (P.stages > 2 && (size_t)P.stages * stage_bytes + stg_bytes + 1024 > (size_t)g_max_smem - 2048) --P.stages;
+  if (P.tma_out) {
+    const uint64_t dims[2] = {(uint64_t)n, (uint64_t)m};
+    if (e.out_act) {
+      const uint64_t strides[2] = {2, (uint64_t)e.ldo * 2};
+      const uint32_t box[2] = {64, 32};
+      if ((rc = sa_make_tmap(&P.omap_act, SA_BF16, e.out_act, 2, dims, strides, box)) != SA_OK) return rc;
+    }
+    if (e.act == SA_ACT_GELU_FWD) {
+      const uint64_t strides[2] = {2, (uint64_t)e.ldo * 2};
+      const uint32_t box[2] = {64, 32};
+      if ((rc = sa_make_tmap(&P.omap_b, SA_BF16, e.pre, 2, dims, strides, box)) != SA_OK) return rc;
+    } else if (e.out_f32) {
+      const uint64_t strides[2] = {4, (uint64_t)e.ldo * 4};
+      const uint32_t box[2] = {32, 32};
+      if ((rc = sa_make_tmap(&P.omap_b, SA_F32, e.out_f32, 2, dims, strides, box)) != SA_OK) return rc;
+    }
+  }
+  const size_t smem = (size_t)P.stages * stage_bytes + stg_bytes + 1024;
   const int total = P.m_tiles * P.n_tiles;
   const unsigned grid = (unsigned)(total < g_sms ? total : g_sms);
   tc_gemm_nt_kernel<<<grid, G_THREADS, smem, st>>>(P);
