@@ -751,7 +751,7 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
     tc_fence_after();
     const int U = P.mp >> 4, U0 = U >> 1;
     const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
-    __nv_bfloat16* dst = P.df_out + ((long long)bh * P.N + n) * P.mp;
+    // the result tile leaves through the (now idle) feature blocks and TMA stores: whole rows instead of 32-byte pieces
     for (int u = u_beg; u < u_end; ++u) {
       uint32_t v[16];
       tmem_ld_32x16(tD + tlane + (uint32_t)(u * 16), v);
@@ -765,31 +765,38 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
         const float acc = __uint_as_float(v[cix]);
         f[cix] = MODE == 0 ? my_inv * (acc - my_delta * s[cix]) : acc + s[cix];
       }
-      if (row_ok) {
-        reinterpret_cast<uint4*>(dst + u * 16)[0] = pack8(f);
-        reinterpret_cast<uint4*>(dst + u * 16)[1] = pack8(f + 8);
-      }
+      st_sw_16(Fs + (u >> 2) * BLK, r, (u & 3) * 16, f);
+    }
+    fence_proxy_async();
+    bar_epi();
+    if (threadIdx.x == 0) {
+      for (int cb = 0; cb < P.nblk; ++cb) tma_store_3d(&P.map_e, Fs + cb * BLK, cb * 64, n0, bh);
+      tma_store_commit();
+      tma_store_wait_all();
     }
   }
   FV_EPILOGUE();
 }
 
 // ------------------------------------------------------------------------------------------------ feature map, backward
-// Persistent (one CTA per SM, P staged once).  Per tile: the epilogue warps stage dD = dfeat (feat - r eps) as bf16
-// (16-byte global loads, three 16-column units in flight per thread), the MMA warp forms dD P, the epilogue warps
-// finish dx = c dD P - c^2 s x.
+// Persistent (one CTA per SM, P staged once).  Per tile the producer warp TMA-loads the feature tile and its gradient
+// tile (the next tile's loads overlap this tile's MMA / epilogue); the epilogue warps turn the gradient tile IN PLACE into
+// dD = dfeat (feat - r eps) (bf16, own row: conflict-free swizzled 16-byte accesses), the MMA warp forms dD P, the
+// epilogue warps finish dx = c dD P - c^2 s x.
 __global__ void __launch_bounds__(F_THREADS, 1)
 tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ uint64_t dd_ready, d_full;
+  __shared__ uint64_t a_full, g_full, a_empty, g_empty, dd_ready, d_full;
   __shared__ float s_red[2][FC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Ds = smem;                          // nblk blocks: dD
-  uint8_t* Ps = smem + P.nblk * BLK;           // mp x 128 B
+  uint8_t* Ds = smem;                          // nblk blocks: dfeat tile, then dD in place
+  uint8_t* As = smem + P.nblk * BLK;           // nblk blocks: feat tile
+  uint8_t* Ps = As + P.nblk * BLK;             // mp x 128 B
   const int total = P.nchunks * P.B * P.H;
   if (threadIdx.x == 0) {
+    mbar_init(&a_full, 1); mbar_init(&g_full, 1); mbar_init(&a_empty, 256); mbar_init(&g_empty, 1);
     mbar_init(&dd_ready, 256); mbar_init(&d_full, 1);
     fence_mbar_init();
     fence_proxy_async();
@@ -797,7 +804,22 @@ tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
   __syncthreads();
   if (warp < 8) stage_proj(Ps, P.proj, P.m, P.mp, threadIdx.x);
   FV_ALLOC();
-  if (warp == 8) {
+  if (warp == 9) {
+    if (lane == 0) {
+      prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int bh = tile / P.nchunks, chunk = tile % P.nchunks;
+        const uint32_t par = (uint32_t)((it & 1) ^ 1);
+        mbar_wait(&a_empty, par);                  // the epilogue warps have read the previous feature tile
+        mbar_expect_tx(&a_full, (uint32_t)P.nblk * BLK);
+        for (int cb = 0; cb < P.nblk; ++cb) tma_load_3d(As + cb * BLK, &P.map_a, &a_full, cb * 64, chunk * FC, bh);
+        mbar_wait(&g_empty, par);                  // the MMAs of the previous tile have read dD
+        mbar_expect_tx(&g_full, (uint32_t)P.nblk * BLK);
+        for (int cb = 0; cb < P.nblk; ++cb) tma_load_3d(Ds + cb * BLK, &P.map_b, &g_full, cb * 64, chunk * FC, bh);
+      }
+    }
+  } else if (warp == 8) {
     if (lane == 0) {
       const uint32_t da = smem_u32(Ds), pa = smem_u32(Ps);
       const uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
@@ -809,6 +831,7 @@ tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
         for (int ks = 0; ks < ksteps; ++ks)
           umma_bf16(tmem_base, make_smem_desc(da + (ks >> 2) * BLK + (ks & 3) * 32, 16, 1024, 2),
                     make_smem_desc(pa + ks * 2048, 8192, 1024, 2), idesc, ks > 0);
+        umma_commit(&g_empty);
         umma_commit(&d_full);
       }
     }
@@ -825,51 +848,47 @@ tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
       const int b = bh / P.H, h = bh % P.H;
       const int n = chunk * FC + r;
       const bool row_ok = n < P.N;
-      const long long fo = ((long long)bh * P.N + n) * P.mp;
-      float part = 0.f;
-      for (int u0 = u_beg; u0 < u_end; u0 += 3) {
-        uint4 ra[3][2], rd[3][2];
+      int am = -1;
+      if (P.is_query && row_ok) am = P.argmax[(long long)bh * P.N + n];
+      mbar_wait(&a_full, (uint32_t)(it & 1));
+      mbar_wait(&g_full, (uint32_t)(it & 1));
+      float part = 0.f, g_am = 0.f;
+      for (int u = u_beg; u < u_end; ++u) {
+        uint8_t* rowd = sw_row(Ds + (u >> 2) * BLK, r);
+        const uint8_t* rowa = sw_row(As + (u >> 2) * BLK, r);
+        const int c0 = ((u & 3) * 16) >> 3;
+        uint4* pd0 = reinterpret_cast<uint4*>(rowd + ((c0 ^ (r & 7)) << 4));
+        uint4* pd1 = reinterpret_cast<uint4*>(rowd + (((c0 + 1) ^ (r & 7)) << 4));
+        float a[16], d[16], g[16];
+        unpack8(*reinterpret_cast<const uint4*>(rowa + ((c0 ^ (r & 7)) << 4)), a);
+        unpack8(*reinterpret_cast<const uint4*>(rowa + (((c0 + 1) ^ (r & 7)) << 4)), a + 8);
+        unpack8(*pd0, d); unpack8(*pd1, d + 8);
+        if (u * 16 + 16 <= P.m) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          if (u0 + k < u_end && row_ok) {
-            const uint4* pf = reinterpret_cast<const uint4*>(P.feat + fo + (u0 + k) * 16);
-            const uint4* pd = reinterpret_cast<const uint4*>(P.dfeat + fo + (u0 + k) * 16);
-            ra[k][0] = __ldg(pf); ra[k][1] = __ldg(pf + 1);
-            rd[k][0] = __ldg(pd); rd[k][1] = __ldg(pd + 1);
-          } else {
-            ra[k][0] = ra[k][1] = rd[k][0] = rd[k][1] = make_uint4(0, 0, 0, 0);
-          }
+          for (int i = 0; i < 16; ++i) g[i] = d[i] * (a[i] - re);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) g[i] = (u * 16 + i < P.m) ? d[i] * (a[i] - re) : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int u = u0 + k;
-          if (u < u_end) {
-            float a[16], d[16], g[16];
-            unpack8(ra[k][0], a); unpack8(ra[k][1], a + 8);
-            unpack8(rd[k][0], d); unpack8(rd[k][1], d + 8);
+        for (int i = 0; i < 16; ++i) part += g[i];
+        if ((am >> 4) == u) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              g[i] = (row_ok && u * 16 + i < P.m) ? d[i] * (a[i] - re) : 0.f;
-              part += g[i];
-            }
-            st_sw_16(Ds + (u >> 2) * BLK, r, (u & 3) * 16, g);
-          }
+          for (int i = 0; i < 16; ++i) g_am = ((am & 15) == i) ? g[i] : g_am;
         }
+        *pd0 = pack8(g); *pd1 = pack8(g + 8);
       }
-      bar_epi();                               // readers of s_red of the previous tile are done
+      mbar_arrive(&a_empty);                    // this thread is done with the feature tile
+      bar_epi();                                // readers of s_red of the previous tile are done
       s_red[hf][r] = part;
       bar_epi();
-      const float ssum = s_red[0][r] + s_red[1][r];
+      const float ssum = row_ok ? s_red[0][r] + s_red[1][r] : 0.f;
       if (P.is_query) {
-        if (row_ok) {
-          const int am = P.argmax[(long long)bh * P.N + n];
-          const int ua = am >> 4;
-          if (ua >= u_beg && ua < u_end) {     // this thread staged that column: patch it
-            const float g = __bfloat162float(P.dfeat[fo + am]) * (__bfloat162float(P.feat[fo + am]) - re) - ssum;
-            const int cl = am & 63;
-            __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(sw_row(Ds + (am >> 6) * BLK, r) + (((cl >> 3) ^ (r & 7)) << 4)) + (cl & 7);
-            *p = __float2bfloat16_rn(g);
-          }
+        const int ua = am >> 4;
+        if (am >= 0 && ua >= u_beg && ua < u_end) {      // this thread staged that column: patch it
+          const int cl = am & 63;
+          __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(sw_row(Ds + (am >> 6) * BLK, r) + (((cl >> 3) ^ (r & 7)) << 4)) + (cl & 7);
+          *p = __float2bfloat16_rn(g_am - ssum);
         }
       } else if (hf == 0) {
         gacc += ssum;
@@ -924,7 +943,7 @@ size_t smem_featmap(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + round_up(
 size_t smem_state(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + 1024; }
 constexpr size_t SMEM_SCAN = SC_STAGES * SC_STAGE + BLK + 1024;
 size_t smem_dqk(int mp) { return (size_t)4 * BLK + (size_t)nblk_of(mp) * (BLK + ST_BLK) + 1024; }
-size_t smem_fbwd(int mp) { return (size_t)nblk_of(mp) * BLK + round_up((size_t)mp * 128, 1024) + 1024; }
+size_t smem_fbwd(int mp) { return (size_t)2 * nblk_of(mp) * BLK + round_up((size_t)mp * 128, 1024) + 1024; }
 constexpr size_t SMEM_MAX = 227 * 1024 - 4096;   // opt-in ceiling minus the static shared memory of the kernels
 
 void init_once() {
@@ -1068,6 +1087,9 @@ int sa_tc_favor_featmap_bwd(const sa_favor_desc* d, const void* x, const float* 
   P.proj = proj; P.x = (const __nv_bfloat16*)x; P.feat = (__nv_bfloat16*)const_cast<void*>(feat);
   P.dfeat = (const __nv_bfloat16*)dfeat; P.argmax = const_cast<int32_t*>(argmax); P.gsum = gsum; P.is_query = is_query;
   P.o_out = (__nv_bfloat16*)dx;
+  int rc;
+  if ((rc = feat_map(&P.map_a, feat, d)) != SA_OK) return rc;
+  if ((rc = feat_map(&P.map_b, dfeat, d)) != SA_OK) return rc;
   P.tmem_cols = 64;
   const int total = P.nchunks * d->batch * d->heads;
   tc_featmap_bwd_kernel<<<dim3((unsigned)(total < sa_sm_count() ? total : sa_sm_count())), F_THREADS, smem_fbwd(d->mp), st>>>(P);
@@ -1135,6 +1157,7 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   if ((rc = feat_map(&P.map_c, kf, d)) != SA_OK) return rc;
   if ((rc = state_map(&P.map_d, stS, d, P.nchunks)) != SA_OK) return rc;
   P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.df_out = (__nv_bfloat16*)dqf;
+  if ((rc = feat_map(&P.map_e, dqf, d)) != SA_OK) return rc;
   P.tmem_cols = tmem_cols_for(128 + d->mp);
   tc_dqk_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
@@ -1144,6 +1167,7 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   if ((rc = feat_map(&P.map_c, qf, d)) != SA_OK) return rc;
   if ((rc = state_map(&P.map_d, stR, d, P.nchunks)) != SA_OK) return rc;
   P.df_out = (__nv_bfloat16*)dkf;
+  if ((rc = feat_map(&P.map_e, dkf, d)) != SA_OK) return rc;
   tc_dqk_kernel<1><<<fv_grid(d), F_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
   // dv
