@@ -195,6 +195,8 @@ tc_local_fwd_kernel(const __grid_constant__ LcParams P) {
       mbar_wait(&s_full[t & 1], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       const uint32_t ts = tS0 + lane_addr + (uint32_t)((t & 1) * 64);
+      // interior tiles (every key of the tile is visible to this row) skip the per-score mask arithmetic
+      const bool full = (j0 + 63 <= p) && (j0 >= lo) && (p < P.N);
       // pass 1 over the S row: running maximum (TMEM reads are cheap; keeps the register footprint at 2 CTAs / SM)
       float mt = -INFINITY;
 #pragma unroll
@@ -202,11 +204,18 @@ tc_local_fwd_kernel(const __grid_constant__ LcParams P) {
         uint32_t v[32];
         tmem_ld_32x32(ts + (uint32_t)(hh * 32), v);
         tmem_ld_wait();
+        if (full) {
+          float mr = __uint_as_float(v[0]);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int j = j0 + hh * 32 + c;
-          const bool ok = (j <= p) && (j >= lo) && (p < P.N);
-          mt = fmaxf(mt, ok ? __uint_as_float(v[c]) * c2 : -INFINITY);
+          for (int c = 1; c < 32; ++c) mr = fmaxf(mr, __uint_as_float(v[c]));
+          mt = fmaxf(mt, mr * c2);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int j = j0 + hh * 32 + c;
+            const bool ok = (j <= p) && (j >= lo) && (p < P.N);
+            mt = fmaxf(mt, ok ? __uint_as_float(v[c]) * c2 : -INFINITY);
+          }
         }
       }
       const float m_new = fmaxf(m, mt);
@@ -232,12 +241,20 @@ tc_local_fwd_kernel(const __grid_constant__ LcParams P) {
         tmem_ld_32x32(ts + (uint32_t)(hh * 32), v);
         tmem_ld_wait();
         float f[32];
+        if (full) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int j = j0 + hh * 32 + c;
-          const bool ok = (j <= p) && (j >= lo) && (p < P.N);
-          f[c] = ok ? ex2(__uint_as_float(v[c]) * c2 - m_safe) : 0.f;
-          ps += f[c];
+          for (int c = 0; c < 32; ++c) {
+            f[c] = ex2(fmaf(__uint_as_float(v[c]), c2, -m_safe));
+            ps += f[c];
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int j = j0 + hh * 32 + c;
+            const bool ok = (j <= p) && (j >= lo) && (p < P.N);
+            f[c] = ok ? ex2(fmaf(__uint_as_float(v[c]), c2, -m_safe)) : 0.f;
+            ps += f[c];
+          }
         }
         st_sw128_32(Ps, r, hh * 32, f);
       }
@@ -372,7 +389,7 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
         for (int c = 0; c < 32; ++c) {
           const int j = j0 + hh * 32 + c;
           const bool ok = row_ok && (j <= p) && (j >= lo);
-          const float pr = ok ? ex2(__uint_as_float(vs[c]) * c2 - lse2) : 0.f;
+          const float pr = ok ? ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) : 0.f;
           f[c] = pr * (__uint_as_float(vd[c]) - delta) * P.scale;
         }
         st_sw128_32(dSs, r, hh * 32, f);
@@ -509,7 +526,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
         for (int c = 0; c < 32; ++c) {
           const int p = q0 + hh * 32 + c;
           const bool ok = (j <= p) && (p <= p_hi);
-          const float pr = ok ? ex2(__uint_as_float(vs[c]) * c2 - s_lse2[buf][hh * 32 + c]) : 0.f;
+          const float pr = ok ? ex2(fmaf(__uint_as_float(vs[c]), c2, -s_lse2[buf][hh * 32 + c])) : 0.f;
           fp[c] = pr;
           fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
         }
