@@ -167,6 +167,7 @@ struct FvParams {
   __nv_bfloat16* o_out;              // scan<0>: out;  scan<1>: dv;  featmap_bwd: dx
   __nv_bfloat16* df_out;             // dqk: dq' / dk'
   float* sums;                       // chunk_state output
+  const __nv_bfloat16* st_vec;       // dqk: the bf16 states (their row 64 is read directly)
 };
 
 #define FV_PROLOGUE(NBAR_INIT)                                                              \
@@ -402,16 +403,21 @@ tc_featmap_fwd_kernel(const __grid_constant__ FvParams P) {
 // sums[bh][chunk][e'][f] = sum_tok W_aug[tok][e'] F[tok][f]      (e' < 65)
 // MODE 0: W_aug = [v | 1]    MODE 1: W_aug = [dout / den | -(dout . out) / den]
 template <int MODE>
-__global__ void __launch_bounds__(F_THREADS, 1)
+__global__ void __launch_bounds__(F_THREADS, 2)
 tc_chunk_state_kernel(const __grid_constant__ FvParams P) {
   __shared__ uint64_t f_full, w_ready, d_full;
   FV_PROLOGUE(mbar_init(&f_full, 1); mbar_init(&w_ready, 256); mbar_init(&d_full, 1));
   uint8_t* Ws = smem;                    // 2 blocks: W | aug
-  uint8_t* Fs = smem + 2 * BLK;          // nblk blocks
+  uint8_t* Fs = smem + 2 * BLK;          // this CTA's feature blocks
+  // gridDim.z CTAs split the feature blocks of a chunk (fewer TMEM columns / less shared memory per CTA: 2+ CTAs per SM)
+  const int cb_beg = (gridDim.z > 1 && blockIdx.z == 1) ? 2 : 0;
+  const int cb_end = (gridDim.z > 1 && blockIdx.z == 0) ? 2 : P.nblk;
+  const int nb = cb_end - cb_beg;
+  const int ncols = min(P.mp, cb_end * 64) - cb_beg * 64;       // feature columns of this CTA (multiple of 16, <= 192)
   if (warp == 9 && lane == 0) {
     prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b);
-    mbar_expect_tx(&f_full, (uint32_t)P.nblk * BLK + (MODE == 0 ? BLK : 0u));
-    for (int cb = 0; cb < P.nblk; ++cb) tma_load_3d(Fs + cb * BLK, &P.map_a, &f_full, cb * 64, n0, bh);
+    mbar_expect_tx(&f_full, (uint32_t)nb * BLK + (MODE == 0 ? BLK : 0u));
+    for (int cb = 0; cb < nb; ++cb) tma_load_3d(Fs + cb * BLK, &P.map_a, &f_full, (cb_beg + cb) * 64, n0, bh);
     if (MODE == 0) tma_load_3d(Ws, &P.map_b, &f_full, h * 64, n0, b);
   }
   if (warp < 8) {
@@ -461,21 +467,23 @@ tc_chunk_state_kernel(const __grid_constant__ FvParams P) {
       mbar_wait(&w_ready, 0);
       tc_fence_after();
       const uint32_t wa = smem_u32(Ws), fa = smem_u32(Fs);
+      const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
 #pragma unroll
       for (int k = 0; k < FC / 16; ++k)
-        mma_cols(tmem_base, make_smem_desc(wa + k * 2048, BLK, 1024, 2), fa + k * 2048, false, BLK, P.mp, 1, k > 0);
+        umma_bf16(tmem_base, make_smem_desc(wa + k * 2048, BLK, 1024, 2), make_smem_desc(fa + k * 2048, BLK, 1024, 2), idesc,
+                  k > 0);
       umma_commit(&d_full);
     }
   } else if (warp < 8) {
     const int q = warp & 3, hf = warp >> 2;
     const int r = q * 32 + lane;       // e'
     const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int U = P.mp >> 4, U0 = U >> 1;
+    const int U = ncols >> 4, U0 = U >> 1;
     const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
     mbar_wait(&d_full, 0);
     tc_fence_after();
     if (q * 32 < SUM_ROWS) {           // warp-uniform: quadrants 0..2 hold rows < 65
-      float* dst = P.sums + (((long long)bh * P.nchunks + chunk) * SUM_ROWS + r) * P.mp;
+      float* dst = P.sums + (((long long)bh * P.nchunks + chunk) * SUM_ROWS + r) * P.mp + cb_beg * 64;
       for (int u = u_beg; u < u_end; ++u) {
         uint32_t v[16];
         tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
@@ -663,34 +671,48 @@ tc_scan_kernel(const __grid_constant__ FvParams P) {
 // MODE 0 (dq'): X = dout (rows i), Y = v (cols j), St = S, F = k':  dq' = (dout S - delta ksum + tril(dout v^T - delta) k') / den
 // MODE 1 (dk'): X = v (rows j), Y = dout (cols i), St = R, F = q':  dk' = v R + Rden + triu((v dout^T - delta_i) / den_i) q'
 // maps: a = X (head columns), b = Y (head columns), c = F features, d = states
+// The feature blocks (64 features each) stream through a two-stage TMA ring together with the matching state block; each
+// gets its own [128 x 64] accumulator (two TMEM buffers), so the epilogue of block c runs under the MMAs of block c + 1
+// and the loads of block c + 2.  100 KB of shared memory and 256 TMEM columns: two CTAs per SM.
+constexpr uint32_t DQ_STAGE = BLK + ST_BLK;      // 26 KB
+constexpr int DQ_STAGES = 2;
+constexpr size_t SMEM_DQK = 3 * BLK + DQ_STAGES * DQ_STAGE + 1024;
+
 template <int MODE>
-__global__ void __launch_bounds__(F_THREADS, 1)
+__global__ void __launch_bounds__(F_THREADS, 2)
 tc_dqk_kernel(const __grid_constant__ FvParams P) {
-  __shared__ uint64_t xy_full, fs_full, b_full, bm_ready, d_full;
+  __shared__ uint64_t xy_full, b_full, bm_ready, ring_full[DQ_STAGES], ring_empty[DQ_STAGES], acc_full[2], acc_empty[2];
   __shared__ float s_delta[FC], s_inv[FC];
-  FV_PROLOGUE(mbar_init(&xy_full, 1); mbar_init(&fs_full, 1); mbar_init(&b_full, 1); mbar_init(&bm_ready, 256);
-              mbar_init(&d_full, 1));
+  FV_PROLOGUE(mbar_init(&xy_full, 1); mbar_init(&b_full, 1); mbar_init(&bm_ready, 256);
+              for (int i = 0; i < DQ_STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+              for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); });
   uint8_t* Xs = smem;
-  uint8_t* Ys = smem + BLK;
-  uint8_t* Bm = smem + 2 * BLK;          // 2 blocks
-  uint8_t* Fs = smem + 4 * BLK;          // nblk blocks
-  uint8_t* Ss = Fs + P.nblk * BLK;       // nblk state blocks
+  uint8_t* Bm = smem + BLK;              // 2 blocks; the first one holds Y until B' = X Y^T has been formed
+  uint8_t* Ys = Bm;
+  uint8_t* Ring = smem + 3 * BLK;
   if (warp == 9 && lane == 0) {
     prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b); prefetch_tmap(&P.map_c); prefetch_tmap(&P.map_d);
     mbar_expect_tx(&xy_full, 2 * BLK);
     tma_load_3d(Xs, &P.map_a, &xy_full, h * 64, n0, b);
     tma_load_3d(Ys, &P.map_b, &xy_full, h * 64, n0, b);
-    mbar_expect_tx(&fs_full, (uint32_t)P.nblk * (BLK + ST_BLK));
-    for (int cb = 0; cb < P.nblk; ++cb) {
-      tma_load_3d(Fs + cb * BLK, &P.map_c, &fs_full, cb * 64, n0, bh);
-      tma_load_2d(Ss + cb * ST_BLK, &P.map_d, &fs_full, cb * 64, (bh * P.nchunks + chunk) * ST_ROWS);
-    }
   }
   FV_ALLOC();
   const uint32_t tB = tmem_base, tD = tmem_base + 128;
-  if (warp == 8) {
+  if (warp == 9) {
+    if (lane == 0) {       // (after the CTA-wide barrier of the TMEM allocation: this loop waits on the MMA warp)
+      int stage = 0; uint32_t phase = 0;
+      for (int cb = 0; cb < P.nblk; ++cb) {
+        mbar_wait(&ring_empty[stage], phase ^ 1);
+        mbar_expect_tx(&ring_full[stage], DQ_STAGE);
+        uint8_t* sp = Ring + stage * DQ_STAGE;
+        tma_load_3d(sp, &P.map_c, &ring_full[stage], cb * 64, n0, bh);
+        tma_load_2d(sp + BLK, &P.map_d, &ring_full[stage], cb * 64, (bh * P.nchunks + chunk) * ST_ROWS);
+        if (++stage == DQ_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 8) {
     if (lane == 0) {
-      const uint32_t xa = smem_u32(Xs), ya = smem_u32(Ys), bma = smem_u32(Bm), fa = smem_u32(Fs), sa = smem_u32(Ss);
+      const uint32_t xa = smem_u32(Xs), ya = smem_u32(Ys), bma = smem_u32(Bm);
       mbar_wait(&xy_full, 0);
       tc_fence_after();
 #pragma unroll
@@ -698,17 +720,27 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
         umma_bf16(tB, make_smem_desc(xa + k * 32, 16, 1024, 2), make_smem_desc(ya + k * 32, 16, 1024, 2),
                   make_idesc_bf16(128, 128, 0, 0), k > 0);
       umma_commit(&b_full);
-      mbar_wait(&fs_full, 0);
-      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      for (int cb = 0; cb < P.nblk; ++cb) {
+        const int ncols = (cb == P.nblk - 1) ? P.tail : 64;
+        const uint32_t idesc = make_idesc_bf16(128, ncols, 0, 1);
+        const uint32_t td = tD + (uint32_t)((cb & 1) * 64);
+        mbar_wait(&ring_full[stage], phase);
+        mbar_wait(&acc_empty[cb & 1], (uint32_t)(((cb >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t fa = smem_u32(Ring + stage * DQ_STAGE), sa = fa + BLK;
 #pragma unroll
-      for (int k = 0; k < 4; ++k)      // X . St   (contraction over the 64 value columns = rows of the state blocks)
-        mma_cols(tD, make_smem_desc(xa + k * 32, 16, 1024, 2), sa + k * 2048, false, ST_BLK, P.mp, 0, k > 0);
-      mbar_wait(&bm_ready, 0);
-      tc_fence_after();
+        for (int k = 0; k < 4; ++k)      // X . St_c  (contraction over the 64 value columns = rows of the state block)
+          umma_bf16(td, make_smem_desc(xa + k * 32, 16, 1024, 2), make_smem_desc(sa + k * 2048, ST_BLK, 1024, 2), idesc, k > 0);
+        if (cb == 0) { mbar_wait(&bm_ready, 0); tc_fence_after(); }
 #pragma unroll
-      for (int k = 0; k < FC / 16; ++k)  // Bm . F  (contraction over the chunk's tokens)
-        mma_cols(tD, make_smem_desc(bma + (k >> 2) * BLK + (k & 3) * 32, 16, 1024, 2), fa + k * 2048, false, BLK, P.mp, 0, 1u);
-      umma_commit(&d_full);
+        for (int k = 0; k < FC / 16; ++k)  // Bm . F_c  (contraction over the chunk's tokens)
+          umma_bf16(td, make_smem_desc(bma + (k >> 2) * BLK + (k & 3) * 32, 16, 1024, 2),
+                    make_smem_desc(fa + k * 2048, BLK, 1024, 2), idesc, 1u);
+        umma_commit(&ring_empty[stage]);
+        umma_commit(&acc_full[cb & 1]);
+        if (++stage == DQ_STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp < 8) {
     const int q = warp & 3, hf = warp >> 2;
@@ -746,33 +778,35 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(&bm_ready);
-    mbar_wait(&fs_full, 0);
-    mbar_wait(&d_full, 0);
-    tc_fence_after();
-    const int U = P.mp >> 4, U0 = U >> 1;
-    const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
-    // the result tile leaves through the (now idle) feature blocks and TMA stores: whole rows instead of 32-byte pieces
-    for (int u = u_beg; u < u_end; ++u) {
-      uint32_t v[16];
-      tmem_ld_32x16(tD + tlane + (uint32_t)(u * 16), v);
-      tmem_ld_wait();
-      // row 64 of the state block: the "1" column (k_cumsum + eps / Rden); row 64 is un-swizzled (64 & 7 == 0)
-      const uint4* vec = reinterpret_cast<const uint4*>(Ss + (u >> 2) * ST_BLK + 64 * 128 + (u & 3) * 32);
-      float s[16], f[16];
-      unpack8(vec[0], s); unpack8(vec[1], s + 8);
+    // the "1" row of the states (k_cumsum + eps / Rden), read from global memory (L2-resident: the TMA loads fetch it too)
+    const __nv_bfloat16* vecrow = P.st_vec + ((long long)(bh * P.nchunks + chunk) * ST_ROWS + 64) * P.mp;
+    __nv_bfloat16* dst = P.df_out + ((long long)bh * P.N + n) * P.mp;
+    for (int cb = 0; cb < P.nblk; ++cb) {
+      const int ncols = (cb == P.nblk - 1) ? P.tail : 64;
+      mbar_wait(&acc_full[cb & 1], (uint32_t)((cb >> 1) & 1));
+      tc_fence_after();
+      if (hf * 32 < ncols) {                 // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tD + tlane + (uint32_t)((cb & 1) * 64 + hf * 32), v);
+        tmem_ld_wait();
+        const int c0 = cb * 64 + hf * 32;
+        const int nv = min(32, ncols - hf * 32) >> 3;      // 16-byte output vectors (8 columns each)
 #pragma unroll
-      for (int cix = 0; cix < 16; ++cix) {
-        const float acc = __uint_as_float(v[cix]);
-        f[cix] = MODE == 0 ? my_inv * (acc - my_delta * s[cix]) : acc + s[cix];
+        for (int i = 0; i < 4; ++i) {
+          if (i < nv) {
+            float sv[8], f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(vecrow + c0) + i), sv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float acc = __uint_as_float(v[i * 8 + j]);
+              f[j] = MODE == 0 ? my_inv * (acc - my_delta * sv[j]) : acc + sv[j];
+            }
+            if (row_ok) reinterpret_cast<uint4*>(dst + c0)[i] = pack8(f);
+          }
+        }
       }
-      st_sw_16(Fs + (u >> 2) * BLK, r, (u & 3) * 16, f);
-    }
-    fence_proxy_async();
-    bar_epi();
-    if (threadIdx.x == 0) {
-      for (int cb = 0; cb < P.nblk; ++cb) tma_store_3d(&P.map_e, Fs + cb * BLK, cb * 64, n0, bh);
-      tma_store_commit();
-      tma_store_wait_all();
+      tc_fence_before();
+      mbar_arrive(&acc_empty[cb & 1]);
     }
   }
   FV_EPILOGUE();
@@ -956,8 +990,8 @@ void init_once() {
     cudaFuncSetAttribute(tc_chunk_state_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(tc_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SCAN);
     cudaFuncSetAttribute(tc_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SCAN);
-    cudaFuncSetAttribute(tc_dqk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(tc_dqk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_dqk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQK);
+    cudaFuncSetAttribute(tc_dqk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQK);
     cudaFuncSetAttribute(tc_featmap_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   });
 }
@@ -977,7 +1011,7 @@ void fill_common(FvParams& P, const sa_favor_desc* d, int out_ld, float eps) {
   P.eps = eps;
   P.proj = nullptr; P.kmax_in = nullptr; P.kmax_out = nullptr; P.x = nullptr; P.feat = nullptr; P.dfeat = nullptr;
   P.argmax = nullptr; P.gsum = nullptr; P.is_query = 0; P.out = nullptr; P.dout = nullptr; P.den_in = nullptr;
-  P.den_out = nullptr; P.o_out = nullptr; P.df_out = nullptr; P.sums = nullptr;
+  P.den_out = nullptr; P.o_out = nullptr; P.df_out = nullptr; P.sums = nullptr; P.st_vec = nullptr;
 }
 
 // [bh][n][mp] feature tensor: box = 64 columns x 128 tokens of one (batch, head)
@@ -1020,10 +1054,18 @@ int launch_states(const sa_favor_desc* d, int mode, const void* feat, const void
   if ((rc = feat_map(&P.map_a, feat, d)) != SA_OK) return rc;
   if (mode == 0 && (rc = head_map(&P.map_b, w, d, d->ld)) != SA_OK) return rc;
   P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.sums = sums;
+  dim3 grid = fv_grid(d);
+  size_t smem = smem_state(d->mp);
   P.tmem_cols = tmem_cols_for(d->mp);
-  const size_t smem = smem_state(d->mp);
-  if (mode == 0) tc_chunk_state_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
-  else tc_chunk_state_kernel<1><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  if (P.nblk >= 3) {        // split the feature blocks {0, 1} | {2 ..} over two CTAs
+    grid.z = 2;
+    const int nbmax = P.nblk - 2 > 2 ? P.nblk - 2 : 2;
+    smem = (size_t)(2 + nbmax) * BLK + 1024;
+    const int c1 = d->mp - 128;
+    P.tmem_cols = tmem_cols_for(c1 > 128 ? c1 : 128);
+  }
+  if (mode == 0) tc_chunk_state_kernel<0><<<grid, F_THREADS, smem, st>>>(P);
+  else tc_chunk_state_kernel<1><<<grid, F_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
   const int per = ST_ROWS * d->mp;
   dim3 pgrid((unsigned)sa_cdiv(per, 256), (unsigned)(d->batch * d->heads));
@@ -1149,7 +1191,7 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   }
   if ((rc = launch_states(d, 1, qf, nullptr, out, dout, out_ld, den, eps, sums, stR, st)) != SA_OK) return rc;
   static thread_local FvParams P;
-  const size_t smem = smem_dqk(d->mp);
+  const size_t smem = SMEM_DQK;
   // dq'
   fill_common(P, d, out_ld, eps);
   if ((rc = head_map(&P.map_a, dout, d, out_ld)) != SA_OK) return rc;
@@ -1157,8 +1199,8 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   if ((rc = feat_map(&P.map_c, kf, d)) != SA_OK) return rc;
   if ((rc = state_map(&P.map_d, stS, d, P.nchunks)) != SA_OK) return rc;
   P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.df_out = (__nv_bfloat16*)dqf;
-  if ((rc = feat_map(&P.map_e, dqf, d)) != SA_OK) return rc;
-  P.tmem_cols = tmem_cols_for(128 + d->mp);
+  P.st_vec = (const __nv_bfloat16*)stS;
+  P.tmem_cols = 256;
   tc_dqk_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
   // dk'
@@ -1167,7 +1209,7 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   if ((rc = feat_map(&P.map_c, qf, d)) != SA_OK) return rc;
   if ((rc = state_map(&P.map_d, stR, d, P.nchunks)) != SA_OK) return rc;
   P.df_out = (__nv_bfloat16*)dkf;
-  if ((rc = feat_map(&P.map_e, dkf, d)) != SA_OK) return rc;
+  P.st_vec = (const __nv_bfloat16*)stR;
   tc_dqk_kernel<1><<<fv_grid(d), F_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
   // dv
