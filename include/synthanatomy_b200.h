@@ -85,6 +85,15 @@ int sa_conv3d_fwd(const sa_conv_desc* d, const void* x, const void* wp, const fl
 int sa_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void* q, float* dwp, int accumulate,
                     void* stream);
 
+/* Fused backward of the pointwise (1x1x1, 128 -> 128 channels) convolution of a ResidualLayer
+ * (/root/reference/src/networks/vqvae/baseline.py:153-160: y = relu(x + conv1x1(h)), h = relu(conv3x3x3(x))).
+ * g [m][c_out] = gradient w.r.t. the pre-activation of y, h [m][c_in] the saved activation (bf16, NDHWC flattened to
+ * m positions), wp_t = sa_pack_weight(w1, transpose = 1).  One pass produces
+ *   dh[m][c_in] = (g W1) * (h > 0),   dwp[c_out][c_in] += g^T h,   dbias[c_out] += column sums of g
+ * (dwp / dbias are accumulated into: zero them first).  Replaces three launches of the general entry points. */
+int sa_conv1x1_bwd_fused(int64_t m, int c_out, int c_in, const void* g, const void* h, const void* wp_t, void* dh,
+                         float* dwp, float* dbias, void* stream);
+
 /* dst[t'][a][b] = src[a][b][t] (transpose == 0) or dst[t'][b][a] = src[a][b][t] (transpose == 1),
  * t' = flip ? taps-1-t : t.  src is the torch layout (fp32, [A][B][taps]); dst is sa_dtype dst_dtype.
  * sa_unpack_wgrad is the exact inverse on fp32 data (dst[a][b][t] (+)= src[...]), used to scatter dWp

@@ -185,10 +185,14 @@ def _stack_backward(ops_list, saved, params, g, in_is_relu: bool, need_dx: bool)
             x, h = saved[i]
             w3, w1 = params[o], params[o + 2]
             # y = relu(x + conv1(h) + b1), h = relu(conv3(x) + b3); g already carries the (y > 0) mask
-            grads[o + 2] = ops.conv_wgrad(op.c1.spec, h, g, w1)
-            grads[o + 3] = ops.bias_grad(g)
             wp1_t = ops.pack_weight(w1, True, g.dtype)
-            dh = ops.conv_dgrad(op.c1.spec, g, wp1_t, h.shape[1:4], None, h)            # * (h > 0)
+            if ops.conv1x1_bwd_fused_supported(op.c1.spec, g):
+                # one pass over g and h: dh = dgrad(g) * (h > 0), dW1, db1
+                dh, grads[o + 2], grads[o + 3] = ops.conv1x1_bwd_fused(op.c1.spec, g, h, wp1_t, w1)
+            else:
+                grads[o + 2] = ops.conv_wgrad(op.c1.spec, h, g, w1)
+                grads[o + 3] = ops.bias_grad(g)
+                dh = ops.conv_dgrad(op.c1.spec, g, wp1_t, h.shape[1:4], None, h)        # * (h > 0)
             grads[o] = ops.conv_wgrad(op.c3.spec, x, dh, w3)
             grads[o + 1] = ops.bias_grad(dh)
             if want_dx:

@@ -54,7 +54,12 @@ def last_path() -> int:
     return int(lib().sa_last_path())
 
 
+_FORCE_SIMT = False
+
+
 def set_force_simt(on: bool) -> None:
+    global _FORCE_SIMT
+    _FORCE_SIMT = bool(on)
     lib().sa_set_force_simt(1 if on else 0)
 
 
@@ -182,6 +187,22 @@ def conv_wgrad(spec: ConvSpec, x: torch.Tensor, dy: torch.Tensor, weight_like: t
     dwp = torch.empty((taps, d.c_out, d.c_in), device=x.device, dtype=torch.float32)
     _lib.check(lib().sa_conv3d_wgrad(C.byref(d), _p(pp), _p(qq), _p(dwp), 0, _stream()), "sa_conv3d_wgrad")
     return unpack_wgrad(dwp, weight_like, transpose=False)
+
+
+def conv1x1_bwd_fused_supported(spec: ConvSpec, g: torch.Tensor) -> bool:
+    return (spec.k == 1 and spec.s == 1 and spec.p == 0 and spec.kind == "conv" and spec.cin == 128 and spec.cout == 128
+            and g.dtype == torch.bfloat16 and not _FORCE_SIMT)
+
+
+def conv1x1_bwd_fused(spec: ConvSpec, g: torch.Tensor, h: torch.Tensor, wp_t: torch.Tensor, weight_like: torch.Tensor):
+    """One pass over g and h: dh = dgrad(g) * (h > 0), dW (torch layout of `weight_like`, fp32) and db."""
+    m = g.numel() // spec.cout
+    dh = torch.empty_like(h)
+    dwp = torch.zeros((1, spec.cout, spec.cin), device=g.device, dtype=torch.float32)
+    db = torch.zeros((spec.cout,), device=g.device, dtype=torch.float32)
+    _lib.check(lib().sa_conv1x1_bwd_fused(m, spec.cout, spec.cin, _p(g), _p(h), _p(wp_t), _p(dh), _p(dwp), _p(db),
+                                          _stream()), "sa_conv1x1_bwd_fused")
+    return dh, unpack_wgrad(dwp, weight_like, transpose=False), db
 
 
 def _i3(v):

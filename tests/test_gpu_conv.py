@@ -200,3 +200,31 @@ def test_tcgen05_epilogue_fusions():
     assert ops.last_path() == 2
     ref = (F.conv_transpose3d(x, w, None, padding=1) + add) * (msk > 0)
     torch.testing.assert_close(_from_ndhwc(dx), ref, rtol=2 ** -7, atol=2e-3 * float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 8, 8), (2, 5, 7, 10), (1, 16, 16, 24)])
+def test_tcgen05_pointwise_backward_fused(shape):
+    """sa_conv1x1_bwd_fused (dh with the ReLU mask of h, dW1, db1 in one pass) against torch autograd on the same
+    bf16-rounded tensors, and against the three general entry points it replaces."""
+    ops = _ops()
+    g_ = torch.Generator().manual_seed(23)
+    B, D, H, W = shape
+    C = 128
+    h = _bf(torch.randn(B, C, D, H, W, generator=g_)).requires_grad_(True)     # pre-ReLU sign pattern matters: use h itself
+    w = _bf(torch.randn(C, C, 1, 1, 1, generator=g_) * 0.05).requires_grad_(True)
+    b = torch.zeros(C, requires_grad=True)
+    gy = _bf(torch.randn(B, C, D, H, W, generator=g_))
+    hr = F.relu(h)
+    y = F.conv3d(hr, w, b)
+    y.backward(gy)
+    spec = ops.ConvSpec("conv", C, C, 1, 1, 0)
+    gd, hd = _to_ndhwc(gy, torch.bfloat16), _to_ndhwc(hr.detach(), torch.bfloat16)
+    wp_t = ops.pack_weight(w.detach().cuda(), True, torch.bfloat16)
+    assert ops.conv1x1_bwd_fused_supported(spec, gd)
+    dh, dw, db = ops.conv1x1_bwd_fused(spec, gd, hd, wp_t, w.detach().cuda())
+    assert ops.last_path() == 2
+    torch.testing.assert_close(_from_ndhwc(dh), h.grad, rtol=2 ** -7, atol=2e-3 * float(h.grad.abs().max()))
+    torch.testing.assert_close(dw.cpu(), w.grad, rtol=1e-3, atol=1e-3 * float(w.grad.abs().max()))
+    torch.testing.assert_close(db.cpu(), b.grad, rtol=1e-3, atol=1e-3 * float(b.grad.abs().max()))
+    dh2 = ops.conv_dgrad(spec, gd, wp_t, (D, H, W), None, hd)
+    assert torch.equal(dh2, dh)

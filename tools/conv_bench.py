@@ -48,6 +48,9 @@ def main():
     print(f"{tag} wgrad3x3x3             {t:8.3f} ms  {f3 / t / 1e9:8.1f} TFLOP/s", flush=True)
     t = timeit(lambda: ops.conv_wgrad(s1, x, dy, w1))
     print(f"{tag} wgrad1x1x1             {t:8.3f} ms  {f1 / t / 1e9:8.1f} TFLOP/s", flush=True)
+    wp1t = ops.pack_weight(w1, True, torch.bfloat16)
+    t = timeit(lambda: ops.conv1x1_bwd_fused(s1, dy, x, wp1t, w1))
+    print(f"{tag} 1x1x1 fused bwd        {t:8.3f} ms  {2 * f1 / t / 1e9:8.1f} TFLOP/s  {3 * pos * C * 2 / t / 1e6:8.1f} GB/s", flush=True)
     t = timeit(lambda: ops.bias_grad(dy))
     print(f"{tag} bias_grad              {t:8.3f} ms  {pos * C * 2 / t / 1e6:8.1f} GB/s", flush=True)
     # strided pair
