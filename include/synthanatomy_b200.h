@@ -93,6 +93,10 @@ int sa_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void* q, float* 
  * (dwp / dbias are accumulated into: zero them first).  Replaces three launches of the general entry points. */
 int sa_conv1x1_bwd_fused(int64_t m, int c_out, int c_in, const void* g, const void* h, const void* wp_t, void* dh,
                          float* dwp, float* dbias, void* stream);
+/* Streaming forward twin: y[m][c_out] = relu?(x W^T + bias + addend), wp = sa_pack_weight(w, transpose = 0)
+ * (128 -> 128 channels; the residual `addend` is required). */
+int sa_conv1x1_fwd_fused(int64_t m, int c_out, int c_in, const void* x, const void* wp, const float* bias,
+                         const void* addend, int relu, void* y, void* stream);
 
 /* dst[t'][a][b] = src[a][b][t] (transpose == 0) or dst[t'][b][a] = src[a][b][t] (transpose == 1),
  * t' = flip ? taps-1-t : t.  src is the torch layout (fp32, [A][B][taps]); dst is sa_dtype dst_dtype.

@@ -34,6 +34,8 @@ struct PwParams {
   int tiles;
   float* dwp;
   float* dbias;
+  const float* bias;     // forward mode
+  int relu;
 };
 
 __device__ __forceinline__ void pw_tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -44,8 +46,11 @@ __device__ __forceinline__ void pw_tma_store_2d(const CUtensorMap* m, const void
 }
 __device__ __forceinline__ void pw_bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// MODE 0: the fused backward above.   MODE 1: the forward  y = relu(h W1^T + b1 + x)  with the same streaming structure
+// ("g" tile = h, "h" tile = the residual addend x; no weight / bias gradient products).
+template <int MODE>
 __global__ void __launch_bounds__(PW_THREADS, 1)
-tc_pw_bwd_kernel(const __grid_constant__ PwParams P) {
+tc_pw_kernel(const __grid_constant__ PwParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full, full_bar[PW_STAGES], empty_bar[PW_STAGES], dh_full[2], dh_empty[2], final_full;
   __shared__ uint32_t tmem_base_slot;
@@ -123,12 +128,14 @@ tc_pw_bwd_kernel(const __grid_constant__ PwParams P) {
             umma_bf16(tDh + (uint32_t)(bsel * 128), make_smem_desc(ga + kb * PW_BLK + k * 32, 16, 1024, 2),
                       make_smem_desc(wa + kb * PW_BLK + k * 32, 16, 1024, 2), idesc_kk, (kb | k) != 0);
         umma_commit(&dh_full[bsel]);
-        // dW1 += g^T h, db1 += g^T 1: both operands MN-major (contraction over the 128 positions: 8 k-steps)
+        if (MODE == 0) {
+          // dW1 += g^T h, db1 += g^T 1: both operands MN-major (contraction over the 128 positions: 8 k-steps)
 #pragma unroll
-        for (int j = 0; j < PW_M / 16; ++j) {
-          const uint64_t da = make_smem_desc(ga + j * 2048, PW_BLK, 1024, 2);
-          umma_bf16(tDw, da, make_smem_desc(ha + j * 2048, PW_BLK, 1024, 2), idesc_mm, (it | j) != 0);
-          umma_bf16(tDb, da, make_smem_desc(oa + j * 2048, PW_BLK, 1024, 2), idesc_m1, (it | j) != 0);
+          for (int j = 0; j < PW_M / 16; ++j) {
+            const uint64_t da = make_smem_desc(ga + j * 2048, PW_BLK, 1024, 2);
+            umma_bf16(tDw, da, make_smem_desc(ha + j * 2048, PW_BLK, 1024, 2), idesc_mm, (it | j) != 0);
+            umma_bf16(tDb, da, make_smem_desc(oa + j * 2048, PW_BLK, 1024, 2), idesc_m1, (it | j) != 0);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == PW_STAGES) { stage = 0; phase ^= 1; }
@@ -164,10 +171,26 @@ tc_pw_bwd_kernel(const __grid_constant__ PwParams P) {
           const uint4 hm = *reinterpret_cast<const uint4*>(hrow + ((ch ^ (r & 7)) << 4));
           const uint32_t w[4] = {hm.x, hm.y, hm.z, hm.w};
           float f[8];
+          if (MODE == 0) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            f[2 * e] = bf16lo(w[e]) > 0.f ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
-            f[2 * e + 1] = bf16hi(w[e]) > 0.f ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
+            for (int e = 0; e < 4; ++e) {
+              f[2 * e] = bf16lo(w[e]) > 0.f ? __uint_as_float(v[i * 8 + 2 * e]) : 0.f;
+              f[2 * e + 1] = bf16hi(w[e]) > 0.f ? __uint_as_float(v[i * 8 + 2 * e + 1]) : 0.f;
+            }
+          } else {
+            const int c0 = half * 64 + ch * 8;
+            const float4 b0 = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b1 = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + c0 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[2 * e] = __uint_as_float(v[i * 8 + 2 * e]) + bb[2 * e] + bf16lo(w[e]);
+              f[2 * e + 1] = __uint_as_float(v[i * 8 + 2 * e + 1]) + bb[2 * e + 1] + bf16hi(w[e]);
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
           }
           uint4 u;
           u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
@@ -188,7 +211,7 @@ tc_pw_bwd_kernel(const __grid_constant__ PwParams P) {
       if (++stage == PW_STAGES) stage = 0;
     }
     if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (my_tiles > 0) {
+    if (MODE == 0 && my_tiles > 0) {
       // dW1 / db1 partials of this CTA: lane = n
       mbar_wait(&final_full, 0);
       tc_fence_after();
@@ -240,7 +263,8 @@ extern "C" int sa_conv1x1_bwd_fused(int64_t m, int c_out, int c_in, const void* 
     int dev = 0, v = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) g_pw_sms = v;
-    cudaFuncSetAttribute(tc_pw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    cudaFuncSetAttribute(tc_pw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    cudaFuncSetAttribute(tc_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   });
   sa_note_path(SA_PATH_TCGEN05);
   static thread_local PwParams P;
@@ -254,7 +278,42 @@ extern "C" int sa_conv1x1_bwd_fused(int64_t m, int c_out, int c_in, const void* 
   if ((rc = pw_map(&P.wmap, wp_t, 128, 128, 128)) != SA_OK) return rc;
   const size_t smem = (size_t)(2 + 1 + 2 + PW_STAGES * 4) * PW_BLK + 1024;
   const unsigned grid = (unsigned)(P.tiles < g_pw_sms ? P.tiles : g_pw_sms);
-  tc_pw_bwd_kernel<<<grid, PW_THREADS, smem, sa_stream(stream)>>>(P);
+  P.bias = nullptr; P.relu = 0;
+  tc_pw_kernel<0><<<grid, PW_THREADS, smem, sa_stream(stream)>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+// y [m][128] = relu?(x W^T + bias + addend):  x [m][128], wp [128 (c_out)][128 (c_in)] bf16 (sa_pack_weight, no transpose),
+// addend [m][128] bf16 (the residual input).  The streaming forward twin of sa_conv1x1_bwd_fused.
+extern "C" int sa_conv1x1_fwd_fused(int64_t m, int c_out, int c_in, const void* x, const void* wp, const float* bias,
+                                    const void* addend, int relu, void* y, void* stream) {
+  SA_CHECK_ARG(x && wp && addend && y, "null pointer");
+  SA_CHECK_ARG(m > 0, "bad sizes");
+  SA_UNSUPPORTED(c_out != 128 || c_in != 128, "the fused pointwise forward is built for 128 -> 128 channels");
+  SA_UNSUPPORTED(m >= (1LL << 31) - 256, "too many positions");
+  SA_CHECK_ARG(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "bias not 16-byte aligned");
+  if (!sa_get_tmap_encode()) { sa_set_error("cuTensorMapEncodeTiled unavailable"); return SA_ERR_CUDA; }
+  std::call_once(g_pw_once, [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) g_pw_sms = v;
+    cudaFuncSetAttribute(tc_pw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    cudaFuncSetAttribute(tc_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  });
+  sa_note_path(SA_PATH_TCGEN05);
+  static thread_local PwParams P;
+  P.m = m;
+  P.tiles = (int)sa_cdiv(m, PW_M);
+  P.dwp = nullptr; P.dbias = nullptr; P.bias = bias; P.relu = relu;
+  int rc;
+  if ((rc = pw_map(&P.gmap, x, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;
+  if ((rc = pw_map(&P.hmap, addend, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;
+  if ((rc = pw_map(&P.omap, y, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;
+  if ((rc = pw_map(&P.wmap, wp, 128, 128, 128)) != SA_OK) return rc;
+  const size_t smem = (size_t)(2 + 1 + 2 + PW_STAGES * 4) * PW_BLK + 1024;
+  const unsigned grid = (unsigned)(P.tiles < g_pw_sms ? P.tiles : g_pw_sms);
+  tc_pw_kernel<1><<<grid, PW_THREADS, smem, sa_stream(stream)>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

@@ -119,7 +119,10 @@ def _stack_forward(ops_list, x: torch.Tensor, params: Sequence[torch.Tensor], sa
             wp3 = ops.pack_weight(w3, False, dt)
             wp1 = ops.pack_weight(w1, False, dt)
             h = ops.conv_forward(op.c3.spec, x, wp3, b3, None, True)
-            y = ops.conv_forward(op.c1.spec, h, wp1, b1, x, True)   # relu(x + conv1x1(h))
+            if ops.conv1x1_bwd_fused_supported(op.c1.spec, h):
+                y = ops.conv1x1_fwd_fused(op.c1.spec, h, wp1, b1, x, True)   # relu(x + conv1x1(h)), streaming kernel
+            else:
+                y = ops.conv_forward(op.c1.spec, h, wp1, b1, x, True)   # relu(x + conv1x1(h))
             saved.append((x, h) if save else None)
             x = y
     return x, saved

@@ -205,6 +205,16 @@ def conv1x1_bwd_fused(spec: ConvSpec, g: torch.Tensor, h: torch.Tensor, wp_t: to
     return dh, unpack_wgrad(dwp, weight_like, transpose=False), db
 
 
+def conv1x1_fwd_fused(spec: ConvSpec, x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor],
+                      addend: torch.Tensor, relu: bool) -> torch.Tensor:
+    """y = relu?(conv1x1(x) + bias + addend) through the streaming pointwise kernel (128 -> 128 channels, bf16)."""
+    m = x.numel() // spec.cin
+    y = torch.empty_like(addend)
+    _lib.check(lib().sa_conv1x1_fwd_fused(m, spec.cout, spec.cin, _p(x), _p(wp), _p(bias), _p(addend), int(relu), _p(y),
+                                          _stream()), "sa_conv1x1_fwd_fused")
+    return y
+
+
 def _i3(v):
     return (C.c_int * 3)(*[int(a) for a in v])
 

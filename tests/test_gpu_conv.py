@@ -228,3 +228,10 @@ def test_tcgen05_pointwise_backward_fused(shape):
     torch.testing.assert_close(db.cpu(), b.grad, rtol=1e-3, atol=1e-3 * float(b.grad.abs().max()))
     dh2 = ops.conv_dgrad(spec, gd, wp_t, (D, H, W), None, hd)
     assert torch.equal(dh2, dh)
+    # the streaming forward twin: relu(conv1x1(h) + b + x) == the general entry point, bit for bit
+    bias = torch.randn(C, generator=g_).cuda()
+    xd = _to_ndhwc(_bf(torch.randn(B, C, D, H, W, generator=g_)), torch.bfloat16)
+    wp = ops.pack_weight(w.detach().cuda(), False, torch.bfloat16)
+    y1 = ops.conv1x1_fwd_fused(spec, hd, wp, bias, xd, True)
+    y2 = ops.conv_forward(spec, hd, wp, bias, xd, True)
+    assert torch.equal(y1, y2)
