@@ -33,13 +33,20 @@ constexpr uint32_t C3_PLANE_BYTES = C3_PLANE * 128;      // 4 KB
 constexpr uint32_t C3_A_BYTES = (C3_TD + 2) * C3_PLANE_BYTES;   // 40 KB
 constexpr int C3_MAX_STAGES = 4;
 
+// one pipeline iteration per (group, 64-channel chunk): ONE activation box (ndd + 7 planes deep) serves ndd depth taps
+struct C3Group {
+  int8_t map, od, oh, ow;   // activation view and box origin relative to the tile origin
+  int32_t wrow[3];          // first row of each depth tap's [N][c_in] slice in the packed weight matrix
+};
+
 struct C3Params {
-  CUtensorMap amap, wmap;
-  int N, cchunks;
-  int ksz, stages;          // 3 (27 taps, depth-fused) or 1 (pointwise); pipeline stages
-  int gD, gH, gW, ntd, nth, ntw, batch, total_tiles;
-  int pe;                   // effective padding (tap offset = t - pe)
-  int wrow[27];             // first row of each tap's [N][c_in] slice in the packed weight matrix
+  CUtensorMap amap[8];
+  CUtensorMap wmap;
+  C3Group groups[32];
+  int ngroups, ndd;
+  int N, cchunks, stages;
+  int gD, gH, gW, ntd, nth, ntw, batch, total_tiles;   // tile grid
+  int oD, oH, oW, os, oqd, oqh, oqw;                   // output position = g * os + oq
   int relu;
   const float* bias;
   const __nv_bfloat16* addend;
@@ -56,11 +63,11 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_bytes = (uint32_t)P.N * 128;
-  const int ksz = P.ksz;                                   // taps per axis; the ksz depth taps share one A box
-  const uint32_t a_bytes = (uint32_t)(C3_TD + ksz - 1) * C3_PLANE_BYTES;
-  const uint32_t stage_bytes = a_bytes + (uint32_t)ksz * b_bytes;
+  const int ndd = P.ndd;                                   // depth taps that share one A box
+  const uint32_t a_bytes = (uint32_t)(C3_TD + ndd - 1) * C3_PLANE_BYTES;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)ndd * b_bytes;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int iters = ksz * ksz * P.cchunks;
+  const int iters = P.ngroups * P.cchunks;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -78,7 +85,7 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       prefetch_tmap(&P.wmap);
-      prefetch_tmap(&P.amap);
+      prefetch_tmap(&P.amap[0]);
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         int t = tile;
@@ -88,14 +95,14 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
         const int b = t;
         const int g0d = td_i * C3_TD, g0h = th_i * C3_TH, g0w = tw_i * C3_TW;
         for (int it = 0; it < iters; ++it) {
-          const int hw = it / P.cchunks, cc = it - hw * P.cchunks;
-          const int dh = hw / ksz, dw = hw - dh * ksz;
+          const int gi = it / P.cchunks, cc = it - gi * P.cchunks;
+          const C3Group g = P.groups[gi];
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], stage_bytes);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          tma_load_5d(sa, &P.amap, &full_bar[stage], cc * 64, g0w + dw - P.pe, g0h + dh - P.pe, g0d - P.pe, b);
-          for (int dd = 0; dd < ksz; ++dd)
-            tma_load_2d(sa + a_bytes + dd * b_bytes, &P.wmap, &full_bar[stage], cc * 64, P.wrow[(dd * ksz + dh) * ksz + dw]);
+          tma_load_5d(sa, &P.amap[g.map], &full_bar[stage], cc * 64, g0w + g.ow, g0h + g.oh, g0d + g.od, b);
+          for (int dd = 0; dd < ndd; ++dd)
+            tma_load_2d(sa + a_bytes + dd * b_bytes, &P.wmap, &full_bar[stage], cc * 64, g.wrow[dd]);
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -115,7 +122,7 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          for (int dd = 0; dd < ksz; ++dd) {
+          for (int dd = 0; dd < ndd; ++dd) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const uint32_t a0 = sa + (uint32_t)(dd + 4 * half) * C3_PLANE_BYTES;
@@ -148,7 +155,8 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
       const int b = t;
       const int gd = td_i * C3_TD + dz, gh = th_i * C3_TH + hy, gw = tw_i * C3_TW + wx;
       const bool valid = gd < P.gD && gh < P.gH && gw < P.gW;
-      const int64_t obase = ((((int64_t)b * P.gD + gd) * P.gH + gh) * P.gW + gw) * P.N;
+      const int64_t obase = ((((int64_t)b * P.oD + (gd * P.os + P.oqd)) * P.oH + (gh * P.os + P.oqh)) * P.oW +
+                             (gw * P.os + P.oqw)) * P.N;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       for (int c0 = 0; c0 < P.N; c0 += 32) {
@@ -232,15 +240,63 @@ int g_c3_sms = 148;
 
 }  // namespace
 
+namespace {
+
+int c3_act_map(CUtensorMap* m, const void* base, int C, int D, int H, int W, int B, int sub, int pd, int ph, int pw, int planes) {
+  // view X[b, d*sub + pd, h*sub + ph, w*sub + pw, c]; dims innermost first
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)(W / sub), (uint64_t)(H / sub), (uint64_t)(D / sub), (uint64_t)B};
+  const uint64_t es = 2;
+  const uint64_t strides[5] = {es, (uint64_t)C * es * sub, (uint64_t)W * C * es * sub, (uint64_t)H * W * C * es * sub,
+                               (uint64_t)D * H * W * C * es};
+  const uint32_t box[5] = {64, C3_TW, C3_TH, (uint32_t)planes, 1};
+  const uint8_t* p = (const uint8_t*)base + ((uint64_t)pd * H * W + (uint64_t)ph * W + pw) * C * es;
+  return sa_make_tmap_bf16(m, p, 5, dims, strides, box);
+}
+
+int c3_launch(C3Params& P, int batch, cudaStream_t st) {
+  P.ntd = (int)sa_cdiv(P.gD, C3_TD); P.nth = (int)sa_cdiv(P.gH, C3_TH); P.ntw = (int)sa_cdiv(P.gW, C3_TW);
+  P.batch = batch;
+  const int64_t total = (int64_t)P.ntd * P.nth * P.ntw * batch;
+  if (total >= (1LL << 31)) { sa_set_error("tc_conv3: too many tiles"); return SA_ERR_UNSUPPORTED; }
+  P.total_tiles = (int)total;
+  const size_t stage_bytes = (size_t)(C3_TD + P.ndd - 1) * C3_PLANE_BYTES + (size_t)P.ndd * P.N * 128;
+  int stages = (int)((227 * 1024 - 2048 - 1024) / stage_bytes);
+  if (stages > C3_MAX_STAGES) stages = C3_MAX_STAGES;
+  if (stages > P.ngroups * P.cchunks) stages = P.ngroups * P.cchunks;
+  if (stages < 1) { sa_set_error("tc_conv3: stage does not fit shared memory"); return SA_ERR_UNSUPPORTED; }
+  P.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024;
+  const unsigned grid = (unsigned)(P.total_tiles < g_c3_sms ? P.total_tiles : g_c3_sms);
+  tc_conv3_kernel<<<grid, C3_THREADS, smem, st>>>(P);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+}  // namespace
+
+// stride-1 k = 3 / k = 1 convs (and their transposed forms), 4/2/1 strided convs and 4/2/1 transposed convs
 bool sa_tc_conv3_supported(const sa_conv_desc* d) {
-  if (d->act_dtype != SA_BF16 || !(d->ksize == 3 || d->ksize == 1) || d->stride != 1) return false;
+  if (d->act_dtype != SA_BF16) return false;
   if (d->c_in % 64 != 0 || d->c_out % 16 != 0 || d->c_out < 16 || d->c_out > 128) return false;
-  const int k = d->ksize;
-  const int pe = d->transposed ? k - 1 - d->pad : d->pad;
-  if (pe < 0 || pe > k - 1) return false;
-  for (int i = 0; i < 3; ++i) if (d->out_dhw[i] != d->in_dhw[i] + 2 * pe - (k - 1)) return false;
   if (const char* e = getenv("SA_TC_CONV3")) { if (e[0] == '0') return false; }   // A/B switch for benchmarking
-  return sa_get_tmap_encode() != nullptr;
+  if (!sa_get_tmap_encode()) return false;
+  const int k = d->ksize;
+  if (d->stride == 1 && (k == 3 || k == 1)) {
+    const int pe = d->transposed ? k - 1 - d->pad : d->pad;
+    if (pe < 0 || pe > k - 1) return false;
+    for (int i = 0; i < 3; ++i) if (d->out_dhw[i] != d->in_dhw[i] + 2 * pe - (k - 1)) return false;
+    return true;
+  }
+  if (d->stride == 2 && k == 4 && d->pad == 1) {
+    if (const char* e = getenv("SA_TC_CONV3_S2")) { if (e[0] == '0') return false; }
+    if (!d->transposed) {
+      for (int i = 0; i < 3; ++i) if (d->in_dhw[i] % 2 || d->out_dhw[i] * 2 != d->in_dhw[i]) return false;
+    } else {
+      for (int i = 0; i < 3; ++i) if (d->out_dhw[i] != d->in_dhw[i] * 2) return false;
+    }
+    return true;
+  }
+  return false;
 }
 
 int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const float* bias, const void* addend,
@@ -255,18 +311,10 @@ int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const 
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) { sa_set_error("tc_conv3: bias not 16-byte aligned"); return SA_ERR_INVALID; }
   static thread_local C3Params P;
   const int iD = d->in_dhw[0], iH = d->in_dhw[1], iW = d->in_dhw[2];
+  const int k = d->ksize, taps = k * k * k;
   P.N = d->c_out;
   P.cchunks = d->c_in / 64;
-  P.gD = d->out_dhw[0]; P.gH = d->out_dhw[1]; P.gW = d->out_dhw[2];
-  P.ntd = (int)sa_cdiv(P.gD, C3_TD); P.nth = (int)sa_cdiv(P.gH, C3_TH); P.ntw = (int)sa_cdiv(P.gW, C3_TW);
-  P.batch = d->batch;
-  const int64_t total = (int64_t)P.ntd * P.nth * P.ntw * d->batch;
-  if (total >= (1LL << 31)) { sa_set_error("tc_conv3: too many tiles"); return SA_ERR_UNSUPPORTED; }
-  P.total_tiles = (int)total;
-  const int k = d->ksize, taps = k * k * k;
-  P.ksz = k;
-  P.pe = d->transposed ? k - 1 - d->pad : d->pad;
-  for (int t = 0; t < taps; ++t) P.wrow[t] = (d->transposed ? taps - 1 - t : t) * d->c_out;   // flipped taps: transposed form
+  P.oD = d->out_dhw[0]; P.oH = d->out_dhw[1]; P.oW = d->out_dhw[2];
   P.relu = relu; P.bias = bias;
   P.addend = (const __nv_bfloat16*)addend; P.mask = (const __nv_bfloat16*)mask; P.y = (__nv_bfloat16*)y;
   {
@@ -276,23 +324,70 @@ int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const 
     int rc = sa_make_tmap_bf16(&P.wmap, wp, 2, dims, strides, box);
     if (rc != SA_OK) return rc;
   }
-  {
-    const uint64_t C = (uint64_t)d->c_in;
-    const uint64_t dims[5] = {C, (uint64_t)iW, (uint64_t)iH, (uint64_t)iD, (uint64_t)d->batch};
-    const uint64_t strides[5] = {2, C * 2, (uint64_t)iW * C * 2, (uint64_t)iH * iW * C * 2, (uint64_t)iD * iH * iW * C * 2};
-    const uint32_t box[5] = {64, C3_TW, C3_TH, (uint32_t)(C3_TD + k - 1), 1};
-    int rc = sa_make_tmap_bf16(&P.amap, x, 5, dims, strides, box);
-    if (rc != SA_OK) return rc;
+  int rc;
+  if (d->stride == 1) {
+    // k x k (dh, dw) groups, each with the k depth taps in one box
+    const int pe = d->transposed ? k - 1 - d->pad : d->pad;
+    P.ndd = k; P.ngroups = k * k;
+    P.gD = P.oD; P.gH = P.oH; P.gW = P.oW;
+    P.os = 1; P.oqd = P.oqh = P.oqw = 0;
+    if ((rc = c3_act_map(&P.amap[0], x, d->c_in, iD, iH, iW, d->batch, 1, 0, 0, 0, C3_TD + k - 1)) != SA_OK) return rc;
+    for (int dh = 0; dh < k; ++dh)
+      for (int dw = 0; dw < k; ++dw) {
+        C3Group& g = P.groups[dh * k + dw];
+        g.map = 0; g.od = (int8_t)(-pe); g.oh = (int8_t)(dh - pe); g.ow = (int8_t)(dw - pe);
+        for (int dd = 0; dd < k; ++dd) {
+          const int t = (dd * k + dh) * k + dw;
+          g.wrow[dd] = (d->transposed ? taps - 1 - t : t) * d->c_out;    // flipped taps: transposed form
+        }
+      }
+    return c3_launch(P, d->batch, st);
   }
-  const size_t stage_bytes = (size_t)(C3_TD + k - 1) * C3_PLANE_BYTES + (size_t)k * P.N * 128;
-  int stages = (int)((227 * 1024 - 2048 - 1024) / stage_bytes);
-  if (stages > C3_MAX_STAGES) stages = C3_MAX_STAGES;
-  if (stages > k * k * P.cchunks) stages = k * k * P.cchunks;
-  if (stages < 1) { sa_set_error("tc_conv3: stage does not fit shared memory"); return SA_ERR_UNSUPPORTED; }
-  P.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024;
-  const unsigned grid = (unsigned)(P.total_tiles < g_c3_sms ? P.total_tiles : g_c3_sms);
-  tc_conv3_kernel<<<grid, C3_THREADS, smem, st>>>(P);
-  SA_LAUNCH_CHECK();
+  // ---- 4/2/1: per dimension tap t <-> (parity view, offset):  0: (odd, -1)  1: (even, 0)  2: (odd, 0)  3: (even, +1)
+  auto par = [](int t) { return (t & 1) ? 0 : 1; };
+  auto off = [](int t) { return t == 0 ? -1 : (t == 3 ? 1 : 0); };
+  P.ndd = 2;
+  if (!d->transposed) {
+    // strided conv: i = 2 g - 1 + t.  The two depth taps of one parity ({0, 2}: offsets -1, 0; {1, 3}: offsets 0, +1) share a box
+    P.gD = P.oD; P.gH = P.oH; P.gW = P.oW;
+    P.os = 1; P.oqd = P.oqh = P.oqw = 0;
+    for (int m = 0; m < 8; ++m)
+      if ((rc = c3_act_map(&P.amap[m], x, d->c_in, iD, iH, iW, d->batch, 2, (m >> 2) & 1, (m >> 1) & 1, m & 1, C3_TD + 1)) != SA_OK)
+        return rc;
+    int gi = 0;
+    for (int pd = 0; pd < 2; ++pd)
+      for (int th = 0; th < 4; ++th)
+        for (int tw = 0; tw < 4; ++tw) {
+          C3Group& g = P.groups[gi++];
+          const int td0 = pd ? 0 : 1, td1 = pd ? 2 : 3;       // odd-parity view: taps 0, 2   even: taps 1, 3
+          g.map = (int8_t)((pd << 2) | (par(th) << 1) | par(tw));
+          g.od = (int8_t)off(td0); g.oh = (int8_t)off(th); g.ow = (int8_t)off(tw);
+          g.wrow[0] = ((td0 * 4 + th) * 4 + tw) * d->c_out;
+          g.wrow[1] = ((td1 * 4 + th) * 4 + tw) * d->c_out;
+          g.wrow[2] = 0;
+        }
+    P.ngroups = gi;
+    return c3_launch(P, d->batch, st);
+  }
+  // transposed 4/2/1: output parity phase q -> two taps per dim:  q=0: (t=3, off -1), (t=1, off 0)   q=1: (t=2, off 0), (t=0, off +1)
+  P.gD = iD; P.gH = iH; P.gW = iW;
+  P.os = 2;
+  if ((rc = c3_act_map(&P.amap[0], x, d->c_in, iD, iH, iW, d->batch, 1, 0, 0, 0, C3_TD + 1)) != SA_OK) return rc;
+  static const int tap_of[2][2] = {{3, 1}, {2, 0}};      // ordered by increasing offset
+  static const int off_of[2][2] = {{-1, 0}, {0, 1}};
+  for (int q = 0; q < 8; ++q) {
+    const int qd = (q >> 2) & 1, qh = (q >> 1) & 1, qw = q & 1;
+    P.oqd = qd; P.oqh = qh; P.oqw = qw;
+    P.ngroups = 4;
+    for (int j = 0; j < 4; ++j) {
+      const int jh = (j >> 1) & 1, jw = j & 1;
+      C3Group& g = P.groups[j];
+      g.map = 0; g.od = (int8_t)off_of[qd][0]; g.oh = (int8_t)off_of[qh][jh]; g.ow = (int8_t)off_of[qw][jw];
+      for (int dd = 0; dd < 2; ++dd)
+        g.wrow[dd] = ((tap_of[qd][dd] * 4 + tap_of[qh][jh]) * 4 + tap_of[qw][jw]) * d->c_out;
+      g.wrow[2] = 0;
+    }
+    if ((rc = c3_launch(P, d->batch, st)) != SA_OK) return rc;
+  }
   return SA_OK;
 }

@@ -467,11 +467,9 @@ tc_chunk_state_kernel(const __grid_constant__ FvParams P) {
       mbar_wait(&w_ready, 0);
       tc_fence_after();
       const uint32_t wa = smem_u32(Ws), fa = smem_u32(Fs);
-      const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
 #pragma unroll
-      for (int k = 0; k < FC / 16; ++k)
-        umma_bf16(tmem_base, make_smem_desc(wa + k * 2048, BLK, 1024, 2), make_smem_desc(fa + k * 2048, BLK, 1024, 2), idesc,
-                  k > 0);
+      for (int k = 0; k < FC / 16; ++k)      // (two instructions per k-step when this CTA owns more than 256 columns)
+        mma_cols(tmem_base, make_smem_desc(wa + k * 2048, BLK, 1024, 2), fa + k * 2048, false, BLK, ncols, 1, k > 0);
       umma_commit(&d_full);
     }
   } else if (warp < 8) {
@@ -1057,7 +1055,8 @@ int launch_states(const sa_favor_desc* d, int mode, const void* feat, const void
   dim3 grid = fv_grid(d);
   size_t smem = smem_state(d->mp);
   P.tmem_cols = tmem_cols_for(d->mp);
-  if (P.nblk >= 3) {        // split the feature blocks {0, 1} | {2 ..} over two CTAs
+  if (P.nblk >= 3 && mode == 0) {   // split the feature blocks {0, 1} | {2 ..} over two CTAs (mode 1 builds its W operand
+                                    // from global memory per CTA: splitting would duplicate that work)
     grid.z = 2;
     const int nbmax = P.nblk - 2 > 2 ? P.nblk - 2 : 2;
     smem = (size_t)(2 + nbmax) * BLK + 1024;
