@@ -158,6 +158,11 @@ int sa_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, cons
                       void* out, float* lse, void* stream);
 int sa_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, const void* v, const float* inv_freq,
                       const void* out, const void* dout, const float* lse, void* dq, void* dk, void* dv, void* stream);
+/* Same, with an optional scratch buffer delta_ws [batch][heads][seq] fp32 (may be NULL): the dq kernel leaves
+ * delta = dO . O per query there and the dk/dv kernel reads it back instead of recomputing it for every key tile. */
+int sa_local_attn_bwd_ws(const sa_local_desc* d, const void* q, const void* k, const void* v, const float* inv_freq,
+                         const void* out, const void* dout, const float* lse, void* dq, void* dk, void* dv,
+                         float* delta_ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Output head: nn.LayerNorm (performer.py:273) and cross-entropy over the logits

@@ -43,7 +43,7 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc*, const void*, const void*, const v
 bool sa_tc_local_supported(const sa_local_desc*, const void*, const void*, const void*, const float*);
 int sa_tc_local_attn_fwd(const sa_local_desc*, const void*, const void*, const void*, void*, float*, cudaStream_t);
 int sa_tc_local_attn_bwd(const sa_local_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
-                         void*, void*, void*, cudaStream_t);
+                         void*, void*, void*, float*, cudaStream_t);
 int sa_rotary_launch(void*, int, int64_t, int, int, int, int, const float*, int, cudaStream_t);
 
 extern "C" int sa_gemm_nt(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
@@ -164,13 +164,19 @@ extern "C" int sa_local_attn_fwd(const sa_local_desc* d, const void* q, const vo
   return sa_simt_local_attn_fwd(d, q, k, v, inv_freq, out, lse, sa_stream(stream));
 }
 
+extern "C" int sa_local_attn_bwd_ws(const sa_local_desc* d, const void* q, const void* k, const void* v,
+                                    const float* inv_freq, const void* out, const void* dout, const float* lse, void* dq,
+                                    void* dk, void* dv, float* delta_ws, void* stream) {
+  SA_CHECK_ARG(d && q && k && v && out && dout && lse && dq && dk && dv, "null pointer");
+  if (!sa_force_simt() && sa_tc_local_supported(d, q, k, v, inv_freq))
+    return sa_tc_local_attn_bwd(d, q, k, v, out, dout, lse, dq, dk, dv, delta_ws, sa_stream(stream));
+  return sa_simt_local_attn_bwd(d, q, k, v, inv_freq, out, dout, lse, dq, dk, dv, sa_stream(stream));
+}
+
 extern "C" int sa_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, const void* v,
                                  const float* inv_freq, const void* out, const void* dout, const float* lse, void* dq,
                                  void* dk, void* dv, void* stream) {
-  SA_CHECK_ARG(d && q && k && v && out && dout && lse && dq && dk && dv, "null pointer");
-  if (!sa_force_simt() && sa_tc_local_supported(d, q, k, v, inv_freq))
-    return sa_tc_local_attn_bwd(d, q, k, v, out, dout, lse, dq, dk, dv, sa_stream(stream));
-  return sa_simt_local_attn_bwd(d, q, k, v, inv_freq, out, dout, lse, dq, dk, dv, sa_stream(stream));
+  return sa_local_attn_bwd_ws(d, q, k, v, inv_freq, out, dout, lse, dq, dk, dv, nullptr, stream);
 }
 
 extern "C" int sa_rotary(void* buf, int dtype, int64_t ld, int batch, int seq, int heads, int dim_head,

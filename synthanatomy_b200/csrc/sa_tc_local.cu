@@ -40,6 +40,7 @@ struct LcParams {
   __nv_bfloat16* dq;
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
+  float* delta_ws;           // optional [batch * heads][seq]: delta = dO . O per query, written by the dq kernel for the dk/dv kernel
 };
 
 __device__ __forceinline__ int lc_lo(int p, int W) { const int w = p / W - 1; return (w > 0 ? w : 0) * W; }
@@ -373,6 +374,7 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
       lse2 = P.lse[(long long)bh * P.N + p] * LOG2E;
       const long long ro = ((long long)b * P.N + p) * P.out_ld + h * 64;
       delta = row_delta(P.out + ro, P.dout + ro);
+      if (P.delta_ws) P.delta_ws[(long long)bh * P.N + p] = delta;
     }
     for (int t = 0; t < ntiles; ++t) {
       const int j0 = j_beg + t * 64;
@@ -499,19 +501,29 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
     const int p_hi = (j < P.N) ? min(P.N - 1, (j / P.W + 2) * P.W - 1) : -1;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const float c2 = P.scale * LOG2E;
-    for (int t = 0; t < ntiles; ++t) {
-      const int q0 = j0 + t * 64;
-      const int buf = t & 1;
-      if (r < 64) {                          // per-query statistics of this query tile
-        const int p = q0 + r;
-        float l2 = 0.f, dl = 0.f;
-        if (p < P.N) {
-          l2 = P.lse[(long long)bh * P.N + p] * LOG2E;
+    // per-query statistics (log-sum-exp, delta = dO . O) of a query tile: threads 0..63, one query each.  With the
+    // delta workspace (filled by the dq kernel) both are coalesced 4-byte loads and the next tile's pair is fetched
+    // while this tile is processed; without it delta is recomputed from the two 128-byte rows.
+    auto load_stats = [&](int tt, float& l2, float& dl) {
+      l2 = 0.f; dl = 0.f;
+      const int p = j0 + tt * 64 + r;
+      if (r < 64 && tt < ntiles && p < P.N) {
+        l2 = P.lse[(long long)bh * P.N + p] * LOG2E;
+        if (P.delta_ws) {
+          dl = P.delta_ws[(long long)bh * P.N + p];
+        } else {
           const long long ro = ((long long)b * P.N + p) * P.out_ld + h * 64;
           dl = row_delta(P.out + ro, P.dout + ro);
         }
-        s_lse2[buf][r] = l2; s_delta[buf][r] = dl;
       }
+    };
+    float nl2, ndl;
+    load_stats(0, nl2, ndl);
+    for (int t = 0; t < ntiles; ++t) {
+      const int q0 = j0 + t * 64;
+      const int buf = t & 1;
+      if (r < 64) { s_lse2[buf][r] = nl2; s_delta[buf][r] = ndl; }
+      if (P.delta_ws) load_stats(t + 1, nl2, ndl);      // in flight during this tile
       bar_softmax();
       mbar_wait(&sdp_full, (uint32_t)(t & 1));
       tc_fence_after();
@@ -536,6 +548,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&ds_full);
+      if (!P.delta_ws) load_stats(t + 1, nl2, ndl);
     }
     mbar_wait(&acc_full, 0);
     tc_fence_after();
@@ -609,6 +622,7 @@ void fill_common(LcParams& P, const sa_local_desc* d) {
   P.B = d->batch; P.N = d->seq; P.H = d->heads; P.W = d->window; P.ld = d->ld; P.out_ld = d->out_ld;
   P.scale = 1.0f / sqrtf((float)d->dim_head);
   P.out = nullptr; P.dout = nullptr; P.o_out = nullptr; P.lse = nullptr; P.dq = P.dk = P.dv = nullptr;
+  P.delta_ws = nullptr;
 }
 
 }  // namespace
@@ -639,7 +653,8 @@ int sa_tc_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, c
 }
 
 int sa_tc_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, const void* v, const void* out,
-                         const void* dout, const float* lse, void* dq, void* dk, void* dv, cudaStream_t st) {
+                         const void* dout, const float* lse, void* dq, void* dk, void* dv, float* delta_ws,
+                         cudaStream_t st) {
   init_once();
   sa_note_path(SA_PATH_TCGEN05);
   if (!aligned16(out) || !aligned16(dout) || !aligned16(dq) || !aligned16(dk) || !aligned16(dv)) {
@@ -650,6 +665,7 @@ int sa_tc_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, c
   fill_common(P, d);
   P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.lse = const_cast<float*>(lse);
   P.dq = (__nv_bfloat16*)dq; P.dk = (__nv_bfloat16*)dk; P.dv = (__nv_bfloat16*)dv;
+  P.delta_ws = delta_ws;
   int rc;
   // dq kernel: 128-row Q / dO boxes, 64-row K / V boxes
   if ((rc = make_map(&P.qmap, q, d, d->ld, 128)) != SA_OK) return rc;

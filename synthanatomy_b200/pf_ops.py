@@ -199,9 +199,10 @@ def local_attn_fwd(d, buf, qcol, kcol, vcol, inv_freq, out, ocol, lse) -> None:
 
 
 def local_attn_bwd(d, buf, qcol, kcol, vcol, inv_freq, out, dout, ocol, lse, dbuf) -> None:
-    _lib.check(lib().sa_local_attn_bwd(C.byref(d), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol), _p(inv_freq),
-                                       _ptr(out, ocol), _ptr(dout, ocol), _p(lse), _ptr(dbuf, qcol), _ptr(dbuf, kcol),
-                                       _ptr(dbuf, vcol), _stream()), "sa_local_attn_bwd")
+    delta_ws = torch.empty_like(lse)       # scratch: delta = dO . O per query, handed from the dq to the dk/dv kernel
+    _lib.check(lib().sa_local_attn_bwd_ws(C.byref(d), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol), _p(inv_freq),
+                                          _ptr(out, ocol), _ptr(dout, ocol), _p(lse), _ptr(dbuf, qcol), _ptr(dbuf, kcol),
+                                          _ptr(dbuf, vcol), _p(delta_ws), _stream()), "sa_local_attn_bwd")
 
 
 # ------------------------------------------------------------------------------------------------
