@@ -151,6 +151,9 @@ typedef struct sa_local_desc {
  * inverse != 0 applies the transpose (the backward of the map).  buf: [batch * seq][ld], act dtype. */
 int sa_rotary(void* buf, int dtype, int64_t ld, int batch, int seq, int heads, int dim_head, const float* inv_freq,
               int inverse, void* stream);
+/* The q and the k head blocks of one row-major buffer in ONE launch: the second block starts k_offset elements after the first. */
+int sa_rotary_qk(void* buf, int dtype, int64_t ld, int64_t k_offset, int batch, int seq, int heads, int dim_head,
+                 const float* inv_freq, int inverse, void* stream);
 
 /* inv_freq == NULL: q and k already carry the position term (sa_rotary) or none is wanted; the tcgen05 kernels take
  * this form only. */

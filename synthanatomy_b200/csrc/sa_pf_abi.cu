@@ -45,6 +45,7 @@ int sa_tc_local_attn_fwd(const sa_local_desc*, const void*, const void*, const v
 int sa_tc_local_attn_bwd(const sa_local_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
                          void*, void*, void*, float*, cudaStream_t);
 int sa_rotary_launch(void*, int, int64_t, int, int, int, int, const float*, int, cudaStream_t);
+int sa_rotary_qk_launch(void*, int, int64_t, int64_t, int, int, int, int, const float*, int, cudaStream_t);
 
 extern "C" int sa_gemm_nt(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
                           const sa_gemm_epilogue* epi, int64_t ldo, void* stream) {
@@ -186,4 +187,13 @@ extern "C" int sa_rotary(void* buf, int dtype, int64_t ld, int batch, int seq, i
                "bad sizes");
   SA_CHECK_ARG(dtype == SA_F32 || dtype == SA_BF16, "bad dtype");
   return sa_rotary_launch(buf, dtype, ld, batch, seq, heads, dim_head, inv_freq, inverse, sa_stream(stream));
+}
+
+extern "C" int sa_rotary_qk(void* buf, int dtype, int64_t ld, int64_t k_offset, int batch, int seq, int heads, int dim_head,
+                            const float* inv_freq, int inverse, void* stream) {
+  SA_CHECK_ARG(buf && inv_freq, "null pointer");
+  SA_CHECK_ARG(batch > 0 && seq > 0 && heads > 0 && dim_head > 0 && (dim_head & 1) == 0 && k_offset >= (int64_t)heads * dim_head &&
+                   ld >= k_offset + (int64_t)heads * dim_head, "bad sizes");
+  SA_CHECK_ARG(dtype == SA_F32 || dtype == SA_BF16, "bad dtype");
+  return sa_rotary_qk_launch(buf, dtype, ld, k_offset, batch, seq, heads, dim_head, inv_freq, inverse, sa_stream(stream));
 }

@@ -596,6 +596,69 @@ __global__ void rotary_kernel(T* __restrict__ buf, long long ld, int B, int N, i
   }
 }
 
+// q and k blocks in one launch: one thread per (row, frequency); the sine / cosine pair is shared by both blocks and all heads
+template <typename T>
+__global__ void rotary_qk_kernel(T* __restrict__ buf, long long ld, long long k_offset, int B, int N, int H, int d,
+                                 const float* __restrict__ inv_freq, int inverse) {
+  const int half = d / 2;
+  const long long total = (long long)B * N * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int dd = (int)(i % half);
+    const long long row = i / half;
+    const int n = (int)(row % N);
+    float sn, cs;
+    sincosf((float)n * inv_freq[dd], &sn, &cs);
+    if (inverse) sn = -sn;
+#pragma unroll 2
+    for (int blk = 0; blk < 2; ++blk) {
+      const long long o0 = row * ld + (blk ? k_offset : 0) + dd;
+      for (int hh = 0; hh < H; ++hh) {
+        const long long o = o0 + hh * d;
+        const float x1 = sa_ld(buf, o), x2 = sa_ld(buf, o + half);
+        sa_st(buf, o, x1 * cs - x2 * sn);
+        sa_st(buf, o + half, x2 * cs + x1 * sn);
+      }
+    }
+  }
+}
+
+// bf16, d = 64: 8 rows per CTA; the 8 x 32 sine / cosine pairs go through shared memory, the data moves in 16-byte vectors
+__global__ void __launch_bounds__(256)
+rotary_qk_vec_kernel(__nv_bfloat16* __restrict__ buf, long long ld, long long k_offset, long long rows, int N, int H,
+                     const float* __restrict__ inv_freq, int inverse) {
+  __shared__ float s_cs[8][32], s_sn[8][32];
+  const long long row0 = (long long)blockIdx.x * 8;
+  {
+    const int rr = threadIdx.x >> 5, dd = threadIdx.x & 31;
+    const long long row = row0 + rr;
+    float sn = 0.f, cs = 1.f;
+    if (row < rows) sincosf((float)(int)(row % N) * inv_freq[dd], &sn, &cs);
+    s_cs[rr][dd] = cs; s_sn[rr][dd] = inverse ? -sn : sn;
+  }
+  __syncthreads();
+  const int per_row = 2 * H * 4;                 // vector items per row: (block, head, 8-frequency group)
+  for (int e = threadIdx.x; e < 8 * per_row; e += 256) {
+    const int rr = e / per_row, it = e - rr * per_row;
+    const long long row = row0 + rr;
+    if (row >= rows) continue;
+    const int g8 = it & 3, hh = (it >> 2) % H, blk = it / (4 * H);
+    __nv_bfloat16* p1 = buf + row * ld + (blk ? k_offset : 0) + hh * 64 + g8 * 8;
+    uint4 u1 = *reinterpret_cast<const uint4*>(p1), u2 = *reinterpret_cast<const uint4*>(p1 + 32);
+    uint32_t* a = reinterpret_cast<uint32_t*>(&u1);
+    uint32_t* b = reinterpret_cast<uint32_t*>(&u2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float c0 = s_cs[rr][g8 * 8 + 2 * j], c1 = s_cs[rr][g8 * 8 + 2 * j + 1];
+      const float s0 = s_sn[rr][g8 * 8 + 2 * j], s1 = s_sn[rr][g8 * 8 + 2 * j + 1];
+      const float x1l = satc::bf16lo(a[j]), x1h = satc::bf16hi(a[j]), x2l = satc::bf16lo(b[j]), x2h = satc::bf16hi(b[j]);
+      a[j] = satc::pack_bf16x2(x1l * c0 - x2l * s0, x1h * c1 - x2h * s1);
+      b[j] = satc::pack_bf16x2(x2l * c0 + x1l * s0, x2h * c1 + x1h * s1);
+    }
+    *reinterpret_cast<uint4*>(p1) = u1;
+    *reinterpret_cast<uint4*>(p1 + 32) = u2;
+  }
+}
+
 std::once_flag g_once;
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -695,6 +758,27 @@ int sa_rotary_launch(void* buf, int dtype, int64_t ld, int batch, int seq, int h
                                                                    inv_freq, inverse);
   else
     rotary_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)buf, ld, batch, seq, heads, dim_head, inv_freq, inverse);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+int sa_rotary_qk_launch(void* buf, int dtype, int64_t ld, int64_t k_offset, int batch, int seq, int heads, int dim_head,
+                        const float* inv_freq, int inverse, cudaStream_t st) {
+  const long long total = (long long)batch * seq * (dim_head / 2);
+  long long blocks = sa_cdiv(total, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  const bool vec_ok = dtype == SA_BF16 && dim_head == 64 && (ld % 8) == 0 && (k_offset % 8) == 0 &&
+                      (reinterpret_cast<uintptr_t>(buf) & 15) == 0 && heads <= 64;
+  if (vec_ok) {
+    const long long rows = (long long)batch * seq;
+    rotary_qk_vec_kernel<<<(unsigned)sa_cdiv(rows, 8), 256, 0, st>>>((__nv_bfloat16*)buf, ld, k_offset, rows, seq, heads,
+                                                                     inv_freq, inverse);
+  } else if (dtype == SA_BF16)
+    rotary_qk_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((__nv_bfloat16*)buf, ld, k_offset, batch, seq, heads,
+                                                                      dim_head, inv_freq, inverse);
+  else
+    rotary_qk_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)buf, ld, k_offset, batch, seq, heads, dim_head, inv_freq,
+                                                              inverse);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

@@ -377,8 +377,7 @@ class _PerformerFn(torch.autograd.Function):
                 lse = torch.empty((B, D.lh, N), device=dev, dtype=f32)
                 c0 = D.gh * D.dh
                 if inv_freq is not None:       # rotary position term, in place: the saved q / k of the local heads are rotated
-                    pf_ops.rotary(qkv, c0, B, N, D.lh, D.dh, inv_freq, False)
-                    pf_ops.rotary(qkv, D.inner + c0, B, N, D.lh, D.dh, inv_freq, False)
+                    pf_ops.rotary_qk(qkv, c0, D.inner + c0, B, N, D.lh, D.dh, inv_freq, False)
                 pf_ops.local_attn_fwd(ld_, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, c0, lse)
             if is32:
                 xn_ = torch.empty((M, D.dim), device=dev, dtype=f32)
@@ -505,8 +504,7 @@ class _PerformerFn(torch.autograd.Function):
                 c0 = D.gh * D.dh
                 pf_ops.local_attn_bwd(ld_, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, dattn, c0, lse, dqkv)
                 if inv_freq is not None:       # transpose of the rotary map on the gradients of the rotated q / k
-                    pf_ops.rotary(dqkv, c0, B, N, D.lh, D.dh, inv_freq, True)
-                    pf_ops.rotary(dqkv, D.inner + c0, B, N, D.lh, D.dh, inv_freq, True)
+                    pf_ops.rotary_qk(dqkv, c0, D.inner + c0, B, N, D.lh, D.dh, inv_freq, True)
             if D.gh > 0:
                 dqf = torch.empty_like(qf)
                 dkf = torch.empty_like(kf)

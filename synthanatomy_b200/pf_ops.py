@@ -193,6 +193,12 @@ def rotary(buf, col, batch, seq, heads, dim_head, inv_freq, inverse: bool) -> No
                                int(inverse), _stream()), "sa_rotary")
 
 
+def rotary_qk(buf, qcol, kcol, batch, seq, heads, dim_head, inv_freq, inverse: bool) -> None:
+    """rotary position term on the q block (column qcol) and the k block (column kcol) of one buffer, one launch"""
+    _lib.check(lib().sa_rotary_qk(_ptr(buf, qcol), _dt(buf.dtype), _rowmajor(buf), kcol - qcol, batch, seq, heads, dim_head,
+                                  _p(inv_freq), int(inverse), _stream()), "sa_rotary_qk")
+
+
 def local_attn_fwd(d, buf, qcol, kcol, vcol, inv_freq, out, ocol, lse) -> None:
     _lib.check(lib().sa_local_attn_fwd(C.byref(d), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol), _p(inv_freq),
                                        _ptr(out, ocol), _p(lse), _stream()), "sa_local_attn_fwd")
@@ -260,6 +266,6 @@ def _instrument(name, fn):
 
 
 for _n in ("gemm_nt", "gemm_tn", "embed_fwd", "embed_bwd", "layernorm_fwd", "layernorm_bwd", "ce_fwd_bwd", "cast2d",
-           "rotary", "favor_kmax", "favor_featmap_fwd", "favor_featmap_bwd", "favor_scan_fwd", "favor_scan_bwd", "local_attn_fwd",
+           "rotary", "rotary_qk", "favor_kmax", "favor_featmap_fwd", "favor_featmap_bwd", "favor_scan_fwd", "favor_scan_bwd", "local_attn_fwd",
            "local_attn_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])
