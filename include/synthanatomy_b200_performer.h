@@ -168,6 +168,26 @@ int sa_local_attn_bwd_ws(const sa_local_desc* d, const void* q, const void* k, c
                          float* delta_ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Autoregressive sampling with recurrent state.  The reference re-runs the whole network
+ * on the growing prefix for every sampled token (src/networks/transformers/transformer.py:58-101); these entry points
+ * advance the attention state of one layer by ONE position and return what the prefix forward returns at its last
+ * position.  q / k / v: the [batch][ld] rows of the new position (column 0 of head 0 of each block).
+ *
+ * sa_favor_decode_step (global heads): t = number of keys already absorbed (= position of the new token).
+ *   mhist[t] = ordered-uint encoding of the key stabiliser after t keys (mhist[0] = encoding of -inf = 0x007FFFFF,
+ *   later entries zero); Se [batch*heads][m][64], ze [batch*heads][m], S1 [batch*heads][64] fp32, zero before position 0;
+ *   scratch: (2 * batch * heads * m + batch * heads) floats.
+ * sa_local_decode_step (local heads): kcache / vcache [batch][nmax][heads * 64] (act dtype) receive the rotated key and
+ *   the value of position p, which then attends the cached positions (floor(p / w) - 1) w .. p.
+ * ---------------------------------------------------------------------------------------------- */
+int sa_favor_decode_step(int batch, int heads, int m, int dtype, int t, const void* q, const void* k, const void* v, int ld,
+                         const float* proj, float eps, float eps_cumsum, unsigned int* mhist, float* scratch, float* Se,
+                         float* ze, float* S1, void* out, int out_ld, void* stream);
+int sa_local_decode_step(int batch, int heads, int window, int dtype, int p, int nmax, const void* q, const void* k,
+                         const void* v, int ld, const float* inv_freq, void* kcache, void* vcache, void* out, int out_ld,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Output head: nn.LayerNorm (performer.py:273) and cross-entropy over the logits
  * (inferer/transformer.py:29 + losses/transformer/transformer.py:24-33).
  * ---------------------------------------------------------------------------------------------- */

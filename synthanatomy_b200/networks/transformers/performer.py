@@ -537,6 +537,100 @@ class _PerformerFn(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+class _Decoder:
+    """Recurrent-state evaluation of the network, one position per call.
+
+    ``step(tokens_t, t)`` returns the logits the reference obtains from a forward over the prefix ``x[:, :t + 1]`` at
+    its last position (src/networks/transformers/transformer.py:20-56) -- including the prefix-dependent key stabiliser
+    of the FAVOR+ heads -- at O(1) attention work per token: the global heads carry S = sum k' (x) v in a split form that
+    can be re-normalised exactly when the stabiliser moves, the local heads keep a key / value cache.  Eval mode only
+    (no projection redraw, no dropout)."""
+
+    def __init__(self, net: "Performer", batch: int, max_len: int, dt: torch.dtype):
+        dev = net.token_emb.weight.device
+        self.net, self.B, self.max_len, self.dt = net, batch, max_len, dt
+        D = self.D = _Dims(net, batch, 1, dt)
+        f32 = torch.float32
+        self.sp_idx = net._sp_idx(max_len, dev)            # [n_axes, max_len] (coordinate of position n - 1, -1 at BOS)
+        self.layers = []
+        for li in range(D.depth):
+            att = net.performer.net.layers[li][0]
+            ff = net.performer.net.layers[li][1]
+            a = att.fn
+            st = dict(
+                g_a=att.g.detach(), g_f=ff.g.detach(),
+                Wqkv=_as(torch.cat((a.to_q.weight, a.to_k.weight, a.to_v.weight), dim=0).detach(), dt),
+                Wo=_as(a.to_out.weight.detach(), dt), W1=_as(ff.fn.fn.w1.weight.detach(), dt), b1=ff.fn.fn.w1.bias.detach(),
+                W2=_as(ff.fn.fn.w2.weight.detach(), dt), b2=ff.fn.fn.w2.bias.detach())
+            if D.gh > 0:
+                st["proj"] = a.fast_attention.projection_matrix
+                mh = torch.zeros((max_len + 2,), device=dev, dtype=torch.int32)
+                mh[0] = 0x007FFFFF                           # ordered-uint encoding of -inf
+                st["mhist"] = mh
+                st["Se"] = torch.zeros((batch * D.gh, D.m, D.dh), device=dev, dtype=f32)
+                st["ze"] = torch.zeros((batch * D.gh, D.m), device=dev, dtype=f32)
+                st["S1"] = torch.zeros((batch * D.gh, D.dh), device=dev, dtype=f32)
+            if D.lh > 0:
+                st["inv_freq"] = a.local_attn.rel_pos.inv_freq if a.local_attn.rel_pos is not None else None
+                st["kc"] = torch.zeros((batch, max_len, D.lh * D.dh), device=dev, dtype=dt)
+                st["vc"] = torch.zeros((batch, max_len, D.lh * D.dh), device=dev, dtype=dt)
+            self.layers.append(st)
+        self.scratch = torch.empty((2 * batch * max(D.gh, 1) * D.m + batch * max(D.gh, 1),), device=dev, dtype=f32)
+        self.Wout = _as(net.to_out.weight.detach(), dt)
+
+    @torch.no_grad()
+    def step(self, tokens_t: torch.Tensor, t: int) -> torch.Tensor:
+        """tokens_t [B] (the token at position t) -> logits [B, num_tokens] of position t"""
+        net, D, B, dt = self.net, self.D, self.B, self.dt
+        assert 0 <= t < self.max_len
+        dev = tokens_t.device
+        f32 = torch.float32
+        is32 = dt == f32
+        x32 = torch.empty((B, D.dim), device=dev, dtype=f32)
+        xa = x32 if is32 else torch.empty((B, D.dim), device=dev, dtype=dt)
+        sp = None if self.sp_idx is None else self.sp_idx[:, t:t + 1].contiguous()
+        pf_ops.embed_fwd(tokens_t.long().view(B, 1).contiguous(), sp, net.token_emb.weight.detach(),
+                         [m.emb.weight.detach() for m in net.spatial_position_emb], net.pos_emb.emb.weight.detach()[t:],
+                         x32, None if is32 else xa)
+        for st in self.layers:
+            qkv = torch.empty((B, 3 * D.inner), device=dev, dtype=dt)
+            pf_ops.gemm_nt(xa, st["Wqkv"], out_act=qkv)
+            attn = torch.empty((B, D.inner), device=dev, dtype=dt)
+            if D.gh > 0:
+                pf_ops.favor_decode_step(B, D.gh, D.m, t, qkv, 0, D.inner, 2 * D.inner, st["proj"], net.eps_feature,
+                                         net.eps_cumsum, st["mhist"], self.scratch, st["Se"], st["ze"], st["S1"], attn, 0)
+            if D.lh > 0:
+                c0 = D.gh * D.dh
+                pf_ops.local_decode_step(B, D.lh, D.W, t, self.max_len, qkv, c0, D.inner + c0, 2 * D.inner + c0,
+                                         st["inv_freq"], st["kc"], st["vc"], attn, c0)
+            if is32:
+                xn = torch.empty((B, D.dim), device=dev, dtype=f32)
+                pf_ops.gemm_nt(attn, st["Wo"], scale_dev=st["g_a"], resid=x32, out_f32=xn)
+                x32 = xa = xn
+            else:
+                xa = torch.empty((B, D.dim), device=dev, dtype=dt)
+                pf_ops.gemm_nt(attn, st["Wo"], scale_dev=st["g_a"], resid=x32, out_f32=x32, out_act=xa)
+            u = torch.empty((B, D.ff), device=dev, dtype=dt)
+            h = torch.empty((B, D.ff), device=dev, dtype=dt)
+            pf_ops.gemm_nt(xa, st["W1"], bias=st["b1"], act=SA_ACT_GELU_FWD, pre=u, out_act=h)
+            if is32:
+                xn = torch.empty((B, D.dim), device=dev, dtype=f32)
+                pf_ops.gemm_nt(h, st["W2"], bias=st["b2"], scale_dev=st["g_f"], resid=x32, out_f32=xn)
+                x32 = xa = xn
+            else:
+                xa = torch.empty((B, D.dim), device=dev, dtype=dt)
+                pf_ops.gemm_nt(h, st["W2"], bias=st["b2"], scale_dev=st["g_f"], resid=x32, out_f32=x32, out_act=xa)
+        mean = torch.empty((B,), device=dev, dtype=f32)
+        rstd = torch.empty((B,), device=dev, dtype=f32)
+        enc32 = torch.empty((B, D.dim), device=dev, dtype=f32) if is32 else None
+        xn = enc32 if is32 else torch.empty((B, D.dim), device=dev, dtype=dt)
+        pf_ops.layernorm_fwd(x32, net.norm.weight.detach(), net.norm.bias.detach(), 1e-5, enc32, None if is32 else xn, mean,
+                             rstd)
+        logits = torch.empty((B, D.V), device=dev, dtype=f32)
+        pf_ops.gemm_nt(xn, self.Wout, bias=net.to_out.bias.detach(), out_f32=logits)
+        return logits
+
+
 class Performer(TransformerBase):
     """NOTE: All tensor logic assumes the following ordering [Batch, Length, Channel] (as the reference)."""
 
@@ -668,6 +762,49 @@ class Performer(TransformerBase):
         if self.compute_dtype is not None:
             return self.compute_dtype
         return torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
+
+    def make_decoder(self, batch: int, max_len: int) -> _Decoder:
+        """recurrent-state evaluator for sampling: ``decoder.step(tokens_t, t) -> logits [batch, num_tokens]``"""
+        return _Decoder(self, batch, max_len, self._dtype())
+
+    @torch.no_grad()
+    def sample(self, prefix: torch.Tensor, conditioning: torch.Tensor = None, temperature: float = 1.0,
+               sample: bool = True, top_k: Optional[int] = None, recurrent: Optional[bool] = None) -> torch.Tensor:
+        """``TransformerBase.sample`` (reference transformer.py:58-101), same arguments, evaluated with recurrent
+        attention state: one position per step instead of one forward over the whole prefix per step (O(N) instead of
+        O(N^2) layer evaluations).  With one attention layer the result is the reference's; with deeper stacks it
+        agrees up to the reference's own non-causal coupling through the prefix-dependent key stabiliser (see
+        ``_Decoder`` and tests/test_gpu_performer.py::test_recurrent_decoder_matches_prefix_forward).
+        ``recurrent=False`` (default taken from ``self.recurrent_sampling``; also used for conditioning / a CPU
+        module) runs the reference's loop of full forwards."""
+        if recurrent is None:
+            recurrent = getattr(self, "recurrent_sampling", True)
+        if not recurrent or conditioning is not None or not prefix.is_cuda:
+            return super().sample(prefix, conditioning=conditioning, temperature=temperature, sample=sample, top_k=top_k)
+        self.eval()
+        steps = int(np.prod(self.ordering.dimensions))
+        B, P = prefix.shape
+        dec = self.make_decoder(B, max(1, P + steps - 1))     # the last sampled token is never fed back
+        logits = None
+        for t in range(P):
+            logits = dec.step(prefix[:, t], t)
+        out = []
+        for k in range(steps):
+            lg = logits / temperature
+            if top_k is not None:
+                lg = self._top_k_logits(lg, top_k)
+            probs = torch.softmax(lg, dim=-1)
+            if sample:
+                ix = torch.multinomial(probs, num_samples=1)
+            else:
+                _, ix = torch.topk(probs, k=1, dim=-1)
+            out.append(ix)
+            if k + 1 < steps:
+                logits = dec.step(ix[:, 0], P + k)
+        x = torch.cat(out, dim=1)
+        x = x[:, self.ordering.get_revert_sequence_ordering()]
+        x = x.reshape(x.shape[0], *self.ordering.dimensions)
+        return torch.squeeze(x, 1)
 
     def forward(self, x: torch.Tensor, conditionings: Sequence[torch.Tensor] = None, return_encodings: bool = False,
                 **kwargs):

@@ -199,6 +199,22 @@ def rotary_qk(buf, qcol, kcol, batch, seq, heads, dim_head, inv_freq, inverse: b
                                   _p(inv_freq), int(inverse), _stream()), "sa_rotary_qk")
 
 
+def favor_decode_step(batch, heads, m, t, buf, qcol, kcol, vcol, proj, eps, eps_cumsum, mhist, scratch, Se, ze, S1, out,
+                      ocol) -> None:
+    """advance the FAVOR+ state of one layer by the position whose q / k / v rows are in `buf` ([batch, ld])"""
+    _lib.check(lib().sa_favor_decode_step(batch, heads, m, _dt(buf.dtype), t, _ptr(buf, qcol), _ptr(buf, kcol),
+                                          _ptr(buf, vcol), _rowmajor(buf), _p(proj), float(eps), float(eps_cumsum),
+                                          _p(mhist), _p(scratch), _p(Se), _p(ze), _p(S1), _ptr(out, ocol), _rowmajor(out),
+                                          _stream()), "sa_favor_decode_step")
+
+
+def local_decode_step(batch, heads, window, p, nmax, buf, qcol, kcol, vcol, inv_freq, kcache, vcache, out, ocol) -> None:
+    """append position p to the local-head caches of one layer and attend its window"""
+    _lib.check(lib().sa_local_decode_step(batch, heads, window, _dt(buf.dtype), p, nmax, _ptr(buf, qcol), _ptr(buf, kcol),
+                                          _ptr(buf, vcol), _rowmajor(buf), _p(inv_freq), _p(kcache), _p(vcache),
+                                          _ptr(out, ocol), _rowmajor(out), _stream()), "sa_local_decode_step")
+
+
 def local_attn_fwd(d, buf, qcol, kcol, vcol, inv_freq, out, ocol, lse) -> None:
     _lib.check(lib().sa_local_attn_fwd(C.byref(d), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol), _p(inv_freq),
                                        _ptr(out, ocol), _p(lse), _stream()), "sa_local_attn_fwd")

@@ -460,3 +460,51 @@ def test_sampling_loop_and_adam_step():
     # Adam's first step is lr * sign(g) wherever |g| >> eps: compare where the gradient is not tiny
     big = grads_ref[k].abs() > 1e-6
     _close(dict(net.named_parameters())[k].detach().cpu()[big], want_p[big], 1e-4, "adam")
+
+
+CASES["tiny_depth1"] = (dict(CASES["tiny"][0], depth=1), CASES["tiny"][1])
+
+
+@pytest.mark.parametrize("name,dtype,tol", [("tiny_depth1", None, 1e-4), ("ragged_window", None, 1e-4),
+                                            ("global_only", None, 1e-4), ("tiny_depth1", torch.bfloat16, 5e-2),
+                                            ("tiny", None, 2e-2)])
+def test_recurrent_decoder_matches_prefix_forward(name, dtype, tol):
+    """the recurrent-state decoder (one position per call) against the quantity the reference's
+    sampling loop uses: the logits of a forward over the prefix x[:, :t+1] at its last position.
+
+    One attention layer: exact (1e-4 in fp32), including the prefix-dependent global key stabiliser of the FAVOR+
+    heads (the carried sums are re-normalised when it moves).  Deeper stacks: the reference itself is not causal --
+    extending the prefix moves the stabiliser and thereby (through the +eps of the feature map) the outputs of EARLIER
+    positions of a layer, which the next layer's keys / values are made of -- so no O(1)-state evaluation can reproduce
+    it bit for bit; the stated tolerance (2e-2 of max |logit| with the ReZero gates opened to 0.7 / -0.4 to amplify the
+    effect) bounds that coupling."""
+    kw, grid = CASES[name]
+    cfg, sd, net, seqs, x_in, y = _build(kw, grid, 21, compute_dtype=dtype)
+    net = net.cuda().eval()
+    x = x_in.cuda()
+    n = x.shape[1]
+    dec = net.make_decoder(x.shape[0], n)
+    checks = sorted(set([0, 1, 2, 5, kw["local_window_size"], kw["local_window_size"] + 1, 2 * kw["local_window_size"] + 3,
+                         n // 2, n - 1]))
+    with torch.no_grad():
+        for t in range(n):
+            lg = dec.step(x[:, t], t)
+            if t in checks and t < n:
+                ref = net(x[:, :t + 1])[:, -1]
+                scale = max(1.0, float(ref.abs().max()))
+                err = float((lg - ref).abs().max())
+                assert err <= tol * scale, f"position {t}: decoder logits differ from the prefix forward by {err:.3e}"
+    if dtype is None and kw["depth"] == 1:      # and from the CPU oracle's prefix forward at the last position
+        want = po.forward(sd, cfg, x_in, seqs)[:, -1]
+        _close(lg, want, 1e-4, "decoder vs oracle at the last position")
+
+
+def test_recurrent_sampling_equals_full_forward_sampling():
+    kw, grid = CASES["tiny_depth1"]
+    cfg, sd, net, seqs, x_in, y = _build(kw, grid, 23)
+    net = net.cuda().eval()
+    prefix = torch.full((2, 1), cfg.num_tokens - 1, dtype=torch.long, device="cuda")
+    a = net.sample(prefix, sample=False)
+    b = net.sample(prefix, sample=False, recurrent=False)
+    assert tuple(a.shape) == (2, *grid)
+    assert torch.equal(a, b)
