@@ -180,12 +180,18 @@ int sa_local_attn_bwd_ws(const sa_local_desc* d, const void* q, const void* k, c
  * sa_local_decode_step (local heads): kcache / vcache [batch][nmax][heads * 64] (act dtype) receive the rotated key and
  *   the value of position p, which then attends the cached positions (floor(p / w) - 1) w .. p.
  * ---------------------------------------------------------------------------------------------- */
-int sa_favor_decode_step(int batch, int heads, int m, int dtype, int t, const void* q, const void* k, const void* v, int ld,
-                         const float* proj, float eps, float eps_cumsum, unsigned int* mhist, float* scratch, float* Se,
-                         float* ze, float* S1, void* out, int out_ld, void* stream);
-int sa_local_decode_step(int batch, int heads, int window, int dtype, int p, int nmax, const void* q, const void* k,
-                         const void* v, int ld, const float* inv_freq, void* kcache, void* vcache, void* out, int out_ld,
-                         void* stream);
+int sa_favor_decode_step(int batch, int heads, int m, int dtype, int t, const int* t_dev, const void* q, const void* k,
+                         const void* v, int ld, const float* proj, float eps, float eps_cumsum, unsigned int* mhist,
+                         float* scratch, float* Se, float* ze, float* S1, void* out, int out_ld, void* stream);
+int sa_local_decode_step(int batch, int heads, int window, int dtype, int p, const int* p_dev, int nmax, const void* q,
+                         const void* k, const void* v, int ld, const float* inv_freq, void* kcache, void* vcache, void* out,
+                         int out_ld, void* stream);
+/* Embedding of ONE position (performer.py:241-268): tokens [batch] int64, sp_idx [n_axes][sp_ld] as in sa_embed_fwd.
+ * In all three entry points a non-NULL t_dev / p_dev (device int) overrides the host position, so that one captured
+ * CUDA graph of a decoding step can be replayed for every position. */
+int sa_embed_step(const int64_t* tokens, const int32_t* sp_idx, int n_axes, int sp_ld, const float* tok_w,
+                  const float* const* sp_w, const float* pos_w, int batch, int dim, int t, const int* t_dev, float* x_f32,
+                  void* x_act, int act_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Output head: nn.LayerNorm (performer.py:273) and cross-entropy over the logits

@@ -5,6 +5,8 @@
 int sa_simt_gemm_nt(int64_t, int, int, int, const void*, int64_t, const void*, int64_t, const SaEpi&, cudaStream_t);
 int sa_simt_gemm_tn(int64_t, int, int, int, const void*, int64_t, const void*, int64_t, const float*, float, float*,
                     cudaStream_t);
+bool sa_skinny_gemm_nt_supported(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb);
+int sa_skinny_gemm_nt(int64_t, int, int, int, const void*, int64_t, const void*, int64_t, const SaEpi&, cudaStream_t);
 bool sa_tc_gemm_nt_supported(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb);
 int sa_tc_gemm_nt(int64_t, int, int, const void*, int64_t, const void*, int64_t, const SaEpi&, cudaStream_t);
 bool sa_tc_gemm_tn_supported(int64_t m, int na, int nb, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb);
@@ -57,6 +59,8 @@ extern "C" int sa_gemm_nt(int64_t m, int n, int k, int dtype, const void* a, int
   SA_CHECK_ARG(!epi->dot_with == !epi->dot_out, "dot_with / dot_out must come together");
   const SaEpi e = sa_make_epi(epi, ldo);
   cudaStream_t st = sa_stream(stream);
+  // a handful of rows (one decoding position per batch element): weight-streaming kernel, either dtype
+  if (sa_skinny_gemm_nt_supported(m, n, k, dtype, a, lda, b, ldb)) return sa_skinny_gemm_nt(m, n, k, dtype, a, lda, b, ldb, e, st);
   if (!sa_force_simt() && sa_tc_gemm_nt_supported(m, n, k, dtype, a, lda, b, ldb)) return sa_tc_gemm_nt(m, n, k, a, lda, b, ldb, e, st);
   return sa_simt_gemm_nt(m, n, k, dtype, a, lda, b, ldb, e, st);
 }

@@ -51,6 +51,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 struct FsArgs {
   int B, H, m, ld, out_ld, t;      // t = number of keys already in the state (position of the new token)
+  const int* t_dev;                // when set, the position is read from device memory (CUDA-graph replay of a step)
   float c, r, eps, eps_cumsum;
 };
 
@@ -61,6 +62,7 @@ favor_step_project_kernel(FsArgs a, const T* __restrict__ q, const T* __restrict
                           unsigned int* __restrict__ mhist, float* __restrict__ dq, float* __restrict__ dk,
                           float* __restrict__ qmax) {
   __shared__ float sq[64], sk[64], red[8];
+  if (a.t_dev) a.t = *a.t_dev;
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   if (threadIdx.x < 64) {
     sq[threadIdx.x] = a.c * sa_ld(q, (long long)b * a.ld + h * 64 + threadIdx.x);
@@ -69,10 +71,14 @@ favor_step_project_kernel(FsArgs a, const T* __restrict__ q, const T* __restrict
   __syncthreads();
   float mq = -INFINITY, mk = -INFINITY;
   for (int f = threadIdx.x; f < a.m; f += blockDim.x) {
-    const float* p = proj + (long long)f * 64;
+    const float4* p = reinterpret_cast<const float4*>(proj + (long long)f * 64);
     float aq = 0.f, ak = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < 64; ++e) { const float pv = __ldg(p + e); aq = fmaf(sq[e], pv, aq); ak = fmaf(sk[e], pv, ak); }
+#pragma unroll
+    for (int e4 = 0; e4 < 16; ++e4) {
+      const float4 pv = __ldg(p + e4);
+      aq = fmaf(sq[4 * e4], pv.x, aq); aq = fmaf(sq[4 * e4 + 1], pv.y, aq); aq = fmaf(sq[4 * e4 + 2], pv.z, aq); aq = fmaf(sq[4 * e4 + 3], pv.w, aq);
+      ak = fmaf(sk[4 * e4], pv.x, ak); ak = fmaf(sk[4 * e4 + 1], pv.y, ak); ak = fmaf(sk[4 * e4 + 2], pv.z, ak); ak = fmaf(sk[4 * e4 + 3], pv.w, ak);
+    }
     dq[(long long)bh * a.m + f] = aq; dk[(long long)bh * a.m + f] = ak;
     mq = fmaxf(mq, aq); mk = fmaxf(mk, ak);
   }
@@ -99,6 +105,7 @@ favor_step_update_kernel(FsArgs a, const T* __restrict__ q, const T* __restrict_
   float* s1 = sv + 64;             // [64] updated S1
   float* part = s1 + 64;           // [4][64] partial numerators
   __shared__ float red[8];
+  if (a.t_dev) a.t = *a.t_dev;
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int t = threadIdx.x;
   float nq = 0.f, nk = 0.f;
@@ -131,10 +138,22 @@ favor_step_update_kernel(FsArgs a, const T* __restrict__ q, const T* __restrict_
   float num = 0.f;
   float* srow = Se + (long long)bh * a.m * 64;
   const float reps1 = a.eps * s1[e];
-  for (int f = g; f < a.m; f += 4) {
-    const float s = srow[(long long)f * 64 + e] * scale + ef[f] * sv[e];
-    srow[(long long)f * 64 + e] = s;
-    num = fmaf(qf[f], a.r * (s + reps1), num);
+  for (int f0 = g; f0 < a.m; f0 += 32) {          // 8 state rows per pass: the loads are issued before the stores
+    float sold[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int f = f0 + 4 * u;
+      sold[u] = f < a.m ? srow[(long long)f * 64 + e] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int f = f0 + 4 * u;
+      if (f < a.m) {
+        const float s = sold[u] * scale + ef[f] * sv[e];
+        srow[(long long)f * 64 + e] = s;
+        num = fmaf(qf[f], a.r * (s + reps1), num);
+      }
+    }
   }
   part[g * 64 + e] = num;
   __syncthreads();
@@ -146,6 +165,7 @@ favor_step_update_kernel(FsArgs a, const T* __restrict__ q, const T* __restrict_
 
 struct LsArgs {
   int B, H, W, ld, out_ld, p, nmax;   // p = position of the new token, nmax = rows of the caches per batch element
+  const int* p_dev;                   // when set, the position is read from device memory
   float scale;
   int rotary;
 };
@@ -160,6 +180,7 @@ local_step_kernel(LsArgs a, const T* __restrict__ q, const T* __restrict__ k, co
   float* sc = sq + 64;             // [2 W] scores
   float* part = sc + 2 * a.W;      // [2][64]
   __shared__ float red[4];
+  if (a.p_dev) a.p = *a.p_dev;
   const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
   const int t = threadIdx.x;
   const long long crow = ((long long)b * a.nmax + a.p) * (a.H * 64) + h * 64;
@@ -225,16 +246,17 @@ local_step_kernel(LsArgs a, const T* __restrict__ q, const T* __restrict__ k, co
 // q / k / v: [batch][ld] rows of the new position (column 0 of head 0 of each block); proj [m][64] fp32;
 // mhist [>= t + 2] ordered-uint key maxima (mhist[0] must hold the encoding of -inf, later entries zero);
 // scratch: 2 * batch * heads * m + batch * heads floats;  Se [batch*heads][m][64], ze [batch*heads][m], S1 [batch*heads][64].
-extern "C" int sa_favor_decode_step(int batch, int heads, int m, int dtype, int t, const void* q, const void* k, const void* v,
-                                    int ld, const float* proj, float eps, float eps_cumsum, unsigned int* mhist, float* scratch,
-                                    float* Se, float* ze, float* S1, void* out, int out_ld, void* stream) {
+extern "C" int sa_favor_decode_step(int batch, int heads, int m, int dtype, int t, const int* t_dev, const void* q,
+                                    const void* k, const void* v, int ld, const float* proj, float eps, float eps_cumsum,
+                                    unsigned int* mhist, float* scratch, float* Se, float* ze, float* S1, void* out,
+                                    int out_ld, void* stream) {
   SA_CHECK_ARG(q && k && v && proj && mhist && scratch && Se && ze && S1 && out, "null pointer");
   SA_CHECK_ARG(batch > 0 && heads > 0 && m > 0 && m <= 1024 && t >= 0, "bad sizes");
   SA_CHECK_ARG(dtype == SA_F32 || dtype == SA_BF16, "bad dtype");
   cudaStream_t st = sa_stream(stream);
   sa_note_path(SA_PATH_SIMT);
   FsArgs a;
-  a.B = batch; a.H = heads; a.m = m; a.ld = ld; a.out_ld = out_ld; a.t = t;
+  a.B = batch; a.H = heads; a.m = m; a.ld = ld; a.out_ld = out_ld; a.t = t; a.t_dev = t_dev;
   a.c = powf(64.0f, -0.25f); a.r = powf((float)m, -0.5f); a.eps = eps; a.eps_cumsum = eps_cumsum;
   float* dq = scratch;
   float* dk = dq + (size_t)batch * heads * m;
@@ -259,9 +281,9 @@ extern "C" int sa_favor_decode_step(int batch, int heads, int m, int dtype, int 
 }
 
 // kcache / vcache: [batch][nmax][heads * 64] (act dtype); position p must be < nmax.
-extern "C" int sa_local_decode_step(int batch, int heads, int window, int dtype, int p, int nmax, const void* q, const void* k,
-                                    const void* v, int ld, const float* inv_freq, void* kcache, void* vcache, void* out,
-                                    int out_ld, void* stream) {
+extern "C" int sa_local_decode_step(int batch, int heads, int window, int dtype, int p, const int* p_dev, int nmax,
+                                    const void* q, const void* k, const void* v, int ld, const float* inv_freq, void* kcache,
+                                    void* vcache, void* out, int out_ld, void* stream) {
   SA_CHECK_ARG(q && k && v && kcache && vcache && out, "null pointer");
   SA_CHECK_ARG(batch > 0 && heads > 0 && window > 0 && p >= 0 && p < nmax, "bad sizes");
   SA_CHECK_ARG(dtype == SA_F32 || dtype == SA_BF16, "bad dtype");
@@ -269,7 +291,7 @@ extern "C" int sa_local_decode_step(int batch, int heads, int window, int dtype,
   cudaStream_t st = sa_stream(stream);
   sa_note_path(SA_PATH_SIMT);
   LsArgs a;
-  a.B = batch; a.H = heads; a.W = window; a.ld = ld; a.out_ld = out_ld; a.p = p; a.nmax = nmax;
+  a.B = batch; a.H = heads; a.W = window; a.ld = ld; a.out_ld = out_ld; a.p = p; a.nmax = nmax; a.p_dev = p_dev;
   a.scale = 0.125f; a.rotary = inv_freq != nullptr;
   const size_t smem = sizeof(float) * ((size_t)64 + 2 * window + 128);
   const unsigned grid = (unsigned)(batch * heads);
@@ -284,6 +306,49 @@ extern "C" int sa_local_decode_step(int batch, int heads, int window, int dtype,
                                                               (const __nv_bfloat16*)v, inv_freq, (__nv_bfloat16*)kcache,
                                                               (__nv_bfloat16*)vcache, (__nv_bfloat16*)out);
   }
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+namespace {
+struct EsPtrs { const float* sp_w[3]; };
+
+template <typename T>
+__global__ void embed_step_kernel(const long long* __restrict__ tokens, const int* __restrict__ sp_idx, int n_axes, int sp_ld,
+                                  const float* __restrict__ tok_w, EsPtrs sp, const float* __restrict__ pos_w, int B, int dim,
+                                  int t, const int* __restrict__ t_dev, float* __restrict__ x_f32, T* __restrict__ x_act) {
+  if (t_dev) t = *t_dev;
+  const int total = B * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % dim, b = i / dim;
+    float v = tok_w[tokens[b] * dim + c];
+    for (int a = 0; a < n_axes; ++a) {
+      const int s = sp_idx[a * sp_ld + t];
+      if (s >= 0) v += sp.sp_w[a][(long long)s * dim + c];
+    }
+    v += pos_w[(long long)t * dim + c];
+    if (x_f32) x_f32[i] = v;
+    if (x_act) sa_st(x_act, i, v);
+  }
+}
+}  // namespace
+
+// embedding of ONE position t (read from t_dev when given): tokens [batch] int64, sp_idx [n_axes][sp_ld] as in sa_embed_fwd
+extern "C" int sa_embed_step(const int64_t* tokens, const int32_t* sp_idx, int n_axes, int sp_ld, const float* tok_w,
+                             const float* const* sp_w, const float* pos_w, int batch, int dim, int t, const int* t_dev,
+                             float* x_f32, void* x_act, int act_dtype, void* stream) {
+  SA_CHECK_ARG(tokens && tok_w && pos_w && (x_f32 || x_act), "null pointer");
+  SA_CHECK_ARG(n_axes >= 0 && n_axes <= 3 && (n_axes == 0 || (sp_idx && sp_w)), "bad spatial axes");
+  EsPtrs sp = {};
+  for (int a = 0; a < n_axes; ++a) sp.sp_w[a] = sp_w[a];
+  const unsigned grid = (unsigned)sa_cdiv((int64_t)batch * dim, 256);
+  if (act_dtype == SA_BF16)
+    embed_step_kernel<__nv_bfloat16><<<grid, 256, 0, sa_stream(stream)>>>((const long long*)tokens, sp_idx, n_axes, sp_ld, tok_w,
+                                                                          sp, pos_w, batch, dim, t, t_dev, x_f32,
+                                                                          (__nv_bfloat16*)x_act);
+  else
+    embed_step_kernel<float><<<grid, 256, 0, sa_stream(stream)>>>((const long long*)tokens, sp_idx, n_axes, sp_ld, tok_w, sp,
+                                                                  pos_w, batch, dim, t, t_dev, x_f32, (float*)x_act);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

@@ -158,3 +158,86 @@ int sa_simt_gemm_tn(int64_t m, int na, int nb, int dtype, const void* a, int64_t
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// "Skinny" NT GEMM for a handful of rows (m <= 8): the decoding step of autoregressive sampling multiplies one token per
+// batch element with every weight matrix.  Weight-bandwidth bound: one warp per output column streams that weight row
+// with 16-byte loads (the few A rows stay in L1), fp32 accumulation, warp reduction, then lane i finishes row i with the
+// shared epilogue.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int SK_MAXM = 8;
+
+__device__ __forceinline__ void sk_load8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void sk_load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+skinny_gemm_nt_kernel(int m, int n, int k, const T* __restrict__ A, long long lda, const T* __restrict__ B, long long ldb,
+                      SaEpi e) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= n) return;
+  float acc[SK_MAXM];
+#pragma unroll
+  for (int i = 0; i < SK_MAXM; ++i) acc[i] = 0.f;
+  const T* brow = B + (long long)j * ldb;
+  for (int k0 = lane * 8; k0 < k; k0 += 256) {
+    float w[8];
+    sk_load8(brow + k0, w);
+#pragma unroll
+    for (int i = 0; i < SK_MAXM; ++i) {
+      if (i < m) {
+        float a[8];
+        sk_load8(A + (long long)i * lda + k0, a);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[i] = fmaf(a[q], w[q], acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < SK_MAXM; ++i) acc[i] = sa_warp_sum(acc[i]);
+  const float st = e.scale * (e.scale_dev ? __ldg(e.scale_dev) : 1.0f);
+  float mine = 0.f;
+#pragma unroll
+  for (int i = 0; i < SK_MAXM; ++i) mine = (lane == i) ? acc[i] : mine;
+  float dot = 0.f;
+  if (lane < m) dot = sa_epi_elem<T>(e, lane, j, mine, st);
+  if (e.dot_out) {
+    dot = sa_warp_sum(dot);
+    if (lane == 0) atomicAdd(e.dot_out, dot);
+  }
+}
+
+}  // namespace
+
+bool sa_skinny_gemm_nt_supported(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb) {
+  if (m < 1 || m > SK_MAXM || n < 1 || k < 8 || (k & 7)) return false;
+  const int64_t al = dtype == SA_BF16 ? 8 : 4;      // elements per 16 bytes
+  if ((lda % al) || (ldb % al)) return false;
+  if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15)) return false;
+  return true;
+}
+
+int sa_skinny_gemm_nt(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
+                      const SaEpi& e, cudaStream_t st) {
+  sa_note_path(SA_PATH_SIMT);
+  const unsigned grid = (unsigned)sa_cdiv(n, 8);
+  if (dtype == SA_BF16)
+    skinny_gemm_nt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((int)m, n, k, (const __nv_bfloat16*)a, lda,
+                                                               (const __nv_bfloat16*)b, ldb, e);
+  else
+    skinny_gemm_nt_kernel<float><<<grid, 256, 0, st>>>((int)m, n, k, (const float*)a, lda, (const float*)b, ldb, e);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}

@@ -577,58 +577,91 @@ class _Decoder:
             self.layers.append(st)
         self.scratch = torch.empty((2 * batch * max(D.gh, 1) * D.m + batch * max(D.gh, 1),), device=dev, dtype=f32)
         self.Wout = _as(net.to_out.weight.detach(), dt)
+        # static buffers of one step (the step is captured into a CUDA graph after a few eager calls and replayed:
+        # ~200 launches per position would otherwise be bound by the host)
+        is32 = dt == f32
+        self.tok = torch.zeros((batch,), device=dev, dtype=torch.int64)
+        self.t_dev = torch.zeros((1,), device=dev, dtype=torch.int32)
+        self.x32 = [torch.empty((batch, D.dim), device=dev, dtype=f32) for _ in range(2)]
+        self.xa = None if is32 else torch.empty((batch, D.dim), device=dev, dtype=dt)
+        self.qkv = torch.empty((batch, 3 * D.inner), device=dev, dtype=dt)
+        self.attn = torch.empty((batch, D.inner), device=dev, dtype=dt)
+        self.u = torch.empty((batch, D.ff), device=dev, dtype=dt)
+        self.h = torch.empty((batch, D.ff), device=dev, dtype=dt)
+        self.mean = torch.empty((batch,), device=dev, dtype=f32)
+        self.rstd = torch.empty((batch,), device=dev, dtype=f32)
+        self.xn = torch.empty((batch, D.dim), device=dev, dtype=f32 if is32 else dt)
+        self.logits = torch.empty((batch, D.V), device=dev, dtype=f32)
+        self.tok_w = net.token_emb.weight.detach()
+        self.sp_ws = [m.emb.weight.detach() for m in net.spatial_position_emb]
+        self.pos_w = net.pos_emb.emb.weight.detach()
+        self.graph = None
+        self.calls = 0
+        import os
+        self.use_graph = os.environ.get("SA_DECODE_GRAPH", "1") != "0"
+
+    def _step_impl(self) -> None:
+        """one position: everything reads the position from self.t_dev and the tokens from self.tok"""
+        net, D, B, dt = self.net, self.D, self.B, self.dt
+        is32 = dt == torch.float32
+        cur = 0
+        x32 = self.x32[cur]
+        pf_ops.embed_step(self.tok, self.sp_idx, self.tok_w, self.sp_ws, self.pos_w, 0, self.t_dev, x32,
+                          None if is32 else self.xa)
+        xa = x32 if is32 else self.xa
+        for st in self.layers:
+            pf_ops.gemm_nt(xa, st["Wqkv"], out_act=self.qkv)
+            if D.gh > 0:
+                pf_ops.favor_decode_step(B, D.gh, D.m, 0, self.t_dev, self.qkv, 0, D.inner, 2 * D.inner, st["proj"],
+                                         net.eps_feature, net.eps_cumsum, st["mhist"], self.scratch, st["Se"], st["ze"],
+                                         st["S1"], self.attn, 0)
+            if D.lh > 0:
+                c0 = D.gh * D.dh
+                pf_ops.local_decode_step(B, D.lh, D.W, 0, self.t_dev, self.max_len, self.qkv, c0, D.inner + c0,
+                                         2 * D.inner + c0, st["inv_freq"], st["kc"], st["vc"], self.attn, c0)
+            if is32:
+                nxt = self.x32[cur ^ 1]
+                pf_ops.gemm_nt(self.attn, st["Wo"], scale_dev=st["g_a"], resid=x32, out_f32=nxt)
+                cur ^= 1
+                x32 = xa = nxt
+            else:
+                pf_ops.gemm_nt(self.attn, st["Wo"], scale_dev=st["g_a"], resid=x32, out_f32=x32, out_act=self.xa)
+            pf_ops.gemm_nt(xa, st["W1"], bias=st["b1"], act=SA_ACT_GELU_FWD, pre=self.u, out_act=self.h)
+            if is32:
+                nxt = self.x32[cur ^ 1]
+                pf_ops.gemm_nt(self.h, st["W2"], bias=st["b2"], scale_dev=st["g_f"], resid=x32, out_f32=nxt)
+                cur ^= 1
+                x32 = xa = nxt
+            else:
+                pf_ops.gemm_nt(self.h, st["W2"], bias=st["b2"], scale_dev=st["g_f"], resid=x32, out_f32=x32, out_act=self.xa)
+        pf_ops.layernorm_fwd(x32, net.norm.weight.detach(), net.norm.bias.detach(), 1e-5, self.xn if is32 else None,
+                             None if is32 else self.xn, self.mean, self.rstd)
+        pf_ops.gemm_nt(self.xn, self.Wout, bias=net.to_out.bias.detach(), out_f32=self.logits)
 
     @torch.no_grad()
     def step(self, tokens_t: torch.Tensor, t: int) -> torch.Tensor:
-        """tokens_t [B] (the token at position t) -> logits [B, num_tokens] of position t"""
-        net, D, B, dt = self.net, self.D, self.B, self.dt
+        """tokens_t [B] (the token at position t) -> logits [B, num_tokens] of position t.  Positions must be fed in
+        order 0, 1, 2, ...; the returned tensor is a static buffer that the next call overwrites."""
         assert 0 <= t < self.max_len
-        dev = tokens_t.device
-        f32 = torch.float32
-        is32 = dt == f32
-        x32 = torch.empty((B, D.dim), device=dev, dtype=f32)
-        xa = x32 if is32 else torch.empty((B, D.dim), device=dev, dtype=dt)
-        sp = None if self.sp_idx is None else self.sp_idx[:, t:t + 1].contiguous()
-        pf_ops.embed_fwd(tokens_t.long().view(B, 1).contiguous(), sp, net.token_emb.weight.detach(),
-                         [m.emb.weight.detach() for m in net.spatial_position_emb], net.pos_emb.emb.weight.detach()[t:],
-                         x32, None if is32 else xa)
-        for st in self.layers:
-            qkv = torch.empty((B, 3 * D.inner), device=dev, dtype=dt)
-            pf_ops.gemm_nt(xa, st["Wqkv"], out_act=qkv)
-            attn = torch.empty((B, D.inner), device=dev, dtype=dt)
-            if D.gh > 0:
-                pf_ops.favor_decode_step(B, D.gh, D.m, t, qkv, 0, D.inner, 2 * D.inner, st["proj"], net.eps_feature,
-                                         net.eps_cumsum, st["mhist"], self.scratch, st["Se"], st["ze"], st["S1"], attn, 0)
-            if D.lh > 0:
-                c0 = D.gh * D.dh
-                pf_ops.local_decode_step(B, D.lh, D.W, t, self.max_len, qkv, c0, D.inner + c0, 2 * D.inner + c0,
-                                         st["inv_freq"], st["kc"], st["vc"], attn, c0)
-            if is32:
-                xn = torch.empty((B, D.dim), device=dev, dtype=f32)
-                pf_ops.gemm_nt(attn, st["Wo"], scale_dev=st["g_a"], resid=x32, out_f32=xn)
-                x32 = xa = xn
-            else:
-                xa = torch.empty((B, D.dim), device=dev, dtype=dt)
-                pf_ops.gemm_nt(attn, st["Wo"], scale_dev=st["g_a"], resid=x32, out_f32=x32, out_act=xa)
-            u = torch.empty((B, D.ff), device=dev, dtype=dt)
-            h = torch.empty((B, D.ff), device=dev, dtype=dt)
-            pf_ops.gemm_nt(xa, st["W1"], bias=st["b1"], act=SA_ACT_GELU_FWD, pre=u, out_act=h)
-            if is32:
-                xn = torch.empty((B, D.dim), device=dev, dtype=f32)
-                pf_ops.gemm_nt(h, st["W2"], bias=st["b2"], scale_dev=st["g_f"], resid=x32, out_f32=xn)
-                x32 = xa = xn
-            else:
-                xa = torch.empty((B, D.dim), device=dev, dtype=dt)
-                pf_ops.gemm_nt(h, st["W2"], bias=st["b2"], scale_dev=st["g_f"], resid=x32, out_f32=x32, out_act=xa)
-        mean = torch.empty((B,), device=dev, dtype=f32)
-        rstd = torch.empty((B,), device=dev, dtype=f32)
-        enc32 = torch.empty((B, D.dim), device=dev, dtype=f32) if is32 else None
-        xn = enc32 if is32 else torch.empty((B, D.dim), device=dev, dtype=dt)
-        pf_ops.layernorm_fwd(x32, net.norm.weight.detach(), net.norm.bias.detach(), 1e-5, enc32, None if is32 else xn, mean,
-                             rstd)
-        logits = torch.empty((B, D.V), device=dev, dtype=f32)
-        pf_ops.gemm_nt(xn, self.Wout, bias=net.to_out.bias.detach(), out_f32=logits)
-        return logits
+        self.tok.copy_(tokens_t.view(-1))
+        self.t_dev.fill_(t)
+        if self.graph is not None:
+            self.graph.replay()
+            return self.logits
+        self._step_impl()
+        self.calls += 1
+        if self.use_graph and self.calls == 3:       # kernels / allocations are warm: capture one step for replay
+            try:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._step_impl()
+                self.graph = g
+            except Exception:                        # capture is an optimisation only
+                self.graph = None
+                self.use_graph = False
+                torch.cuda.synchronize()
+        return self.logits
 
 
 class Performer(TransformerBase):

@@ -199,20 +199,29 @@ def rotary_qk(buf, qcol, kcol, batch, seq, heads, dim_head, inv_freq, inverse: b
                                   _p(inv_freq), int(inverse), _stream()), "sa_rotary_qk")
 
 
-def favor_decode_step(batch, heads, m, t, buf, qcol, kcol, vcol, proj, eps, eps_cumsum, mhist, scratch, Se, ze, S1, out,
-                      ocol) -> None:
+def favor_decode_step(batch, heads, m, t, t_dev, buf, qcol, kcol, vcol, proj, eps, eps_cumsum, mhist, scratch, Se, ze, S1,
+                      out, ocol) -> None:
     """advance the FAVOR+ state of one layer by the position whose q / k / v rows are in `buf` ([batch, ld])"""
-    _lib.check(lib().sa_favor_decode_step(batch, heads, m, _dt(buf.dtype), t, _ptr(buf, qcol), _ptr(buf, kcol),
+    _lib.check(lib().sa_favor_decode_step(batch, heads, m, _dt(buf.dtype), t, _p(t_dev), _ptr(buf, qcol), _ptr(buf, kcol),
                                           _ptr(buf, vcol), _rowmajor(buf), _p(proj), float(eps), float(eps_cumsum),
                                           _p(mhist), _p(scratch), _p(Se), _p(ze), _p(S1), _ptr(out, ocol), _rowmajor(out),
                                           _stream()), "sa_favor_decode_step")
 
 
-def local_decode_step(batch, heads, window, p, nmax, buf, qcol, kcol, vcol, inv_freq, kcache, vcache, out, ocol) -> None:
+def local_decode_step(batch, heads, window, p, p_dev, nmax, buf, qcol, kcol, vcol, inv_freq, kcache, vcache, out,
+                      ocol) -> None:
     """append position p to the local-head caches of one layer and attend its window"""
-    _lib.check(lib().sa_local_decode_step(batch, heads, window, _dt(buf.dtype), p, nmax, _ptr(buf, qcol), _ptr(buf, kcol),
-                                          _ptr(buf, vcol), _rowmajor(buf), _p(inv_freq), _p(kcache), _p(vcache),
-                                          _ptr(out, ocol), _rowmajor(out), _stream()), "sa_local_decode_step")
+    _lib.check(lib().sa_local_decode_step(batch, heads, window, _dt(buf.dtype), p, _p(p_dev), nmax, _ptr(buf, qcol),
+                                          _ptr(buf, kcol), _ptr(buf, vcol), _rowmajor(buf), _p(inv_freq), _p(kcache),
+                                          _p(vcache), _ptr(out, ocol), _rowmajor(out), _stream()), "sa_local_decode_step")
+
+
+def embed_step(tokens, sp_idx, tok_w, sp_ws, pos_w, t, t_dev, x_f32, x_act) -> None:
+    """embedding of one position (host t, or the device int t_dev) for a [batch] vector of tokens"""
+    act = x_act if x_act is not None else x_f32
+    _lib.check(lib().sa_embed_step(_p(tokens), _p(sp_idx), len(sp_ws), 0 if sp_idx is None else sp_idx.shape[1], _p(tok_w),
+                                   _ptr_array(sp_ws), _p(pos_w), tokens.shape[0], tok_w.shape[1], t, _p(t_dev), _p(x_f32),
+                                   _p(x_act), _dt(act.dtype), _stream()), "sa_embed_step")
 
 
 def local_attn_fwd(d, buf, qcol, kcol, vcol, inv_freq, out, ocol, lse) -> None:
