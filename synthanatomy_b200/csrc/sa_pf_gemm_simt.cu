@@ -181,41 +181,75 @@ __device__ __forceinline__ void sk_load8(const __nv_bfloat16* p, float (&f)[8]) 
   f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 
+// ksplit (1, 2, 4 or 8) warps share one output column (interleaved K slices, partial sums through shared memory), so that
+// narrow outputs (n = 512) still fill the machine: 8 / ksplit columns per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256)
-skinny_gemm_nt_kernel(int m, int n, int k, const T* __restrict__ A, long long lda, const T* __restrict__ B, long long ldb,
-                      SaEpi e) {
+skinny_gemm_nt_kernel(int m, int n, int k, int ksplit, const T* __restrict__ A, long long lda, const T* __restrict__ B,
+                      long long ldb, SaEpi e) {
+  __shared__ float s_part[8][SK_MAXM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + warp;
-  if (j >= n) return;
+  const int cpc = 8 / ksplit;
+  const int cl = warp / ksplit, kp = warp - cl * ksplit;
+  const int j = blockIdx.x * cpc + cl;
+  const bool col_ok = j < n;
   float acc[SK_MAXM];
 #pragma unroll
   for (int i = 0; i < SK_MAXM; ++i) acc[i] = 0.f;
-  const T* brow = B + (long long)j * ldb;
-  for (int k0 = lane * 8; k0 < k; k0 += 256) {
-    float w[8];
-    sk_load8(brow + k0, w);
+  if (col_ok) {
+    const T* brow = B + (long long)j * ldb;
+    const int kstep = ksplit * 256;
+    int k0 = (kp * 32 + lane) * 8;
+    for (; k0 + kstep < k; k0 += 2 * kstep) {           // two weight vectors in flight
+      float w0[8], w1[8];
+      sk_load8(brow + k0, w0);
+      sk_load8(brow + k0 + kstep, w1);
 #pragma unroll
-    for (int i = 0; i < SK_MAXM; ++i) {
-      if (i < m) {
-        float a[8];
-        sk_load8(A + (long long)i * lda + k0, a);
+      for (int i = 0; i < SK_MAXM; ++i) {
+        if (i < m) {
+          float a0[8], a1[8];
+          sk_load8(A + (long long)i * lda + k0, a0);
+          sk_load8(A + (long long)i * lda + k0 + kstep, a1);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[i] = fmaf(a[q], w[q], acc[i]);
+          for (int q = 0; q < 8; ++q) acc[i] = fmaf(a0[q], w0[q], acc[i]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[i] = fmaf(a1[q], w1[q], acc[i]);
+        }
+      }
+    }
+    for (; k0 < k; k0 += kstep) {
+      float w[8];
+      sk_load8(brow + k0, w);
+#pragma unroll
+      for (int i = 0; i < SK_MAXM; ++i) {
+        if (i < m) {
+          float a[8];
+          sk_load8(A + (long long)i * lda + k0, a);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[i] = fmaf(a[q], w[q], acc[i]);
+        }
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < SK_MAXM; ++i) acc[i] = sa_warp_sum(acc[i]);
-  const float st = e.scale * (e.scale_dev ? __ldg(e.scale_dev) : 1.0f);
   float mine = 0.f;
 #pragma unroll
   for (int i = 0; i < SK_MAXM; ++i) mine = (lane == i) ? acc[i] : mine;
+  if (ksplit > 1) {
+    if (lane < SK_MAXM) s_part[warp][lane] = mine;
+    __syncthreads();
+    if (kp == 0 && lane < SK_MAXM) {
+      mine = 0.f;
+      for (int p = 0; p < ksplit; ++p) mine += s_part[warp + p][lane];
+    }
+  }
+  const float st = e.scale * (e.scale_dev ? __ldg(e.scale_dev) : 1.0f);
   float dot = 0.f;
-  if (lane < m) dot = sa_epi_elem<T>(e, lane, j, mine, st);
-  if (e.dot_out) {
+  if (kp == 0 && col_ok && lane < m) dot = sa_epi_elem<T>(e, lane, j, mine, st);
+  if (e.dot_out && kp == 0) {
     dot = sa_warp_sum(dot);
-    if (lane == 0) atomicAdd(e.dot_out, dot);
+    if (lane == 0 && col_ok) atomicAdd(e.dot_out, dot);
   }
 }
 
@@ -232,12 +266,15 @@ bool sa_skinny_gemm_nt_supported(int64_t m, int n, int k, int dtype, const void*
 int sa_skinny_gemm_nt(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
                       const SaEpi& e, cudaStream_t st) {
   sa_note_path(SA_PATH_SIMT);
-  const unsigned grid = (unsigned)sa_cdiv(n, 8);
+  // enough CTAs for ~2 per SM: narrow outputs split K over the warps of a CTA
+  int ksplit = 1;
+  while (ksplit < 8 && sa_cdiv(n, 8 / ksplit) < 296 && k >= 512 * ksplit) ksplit *= 2;
+  const unsigned grid = (unsigned)sa_cdiv(n, 8 / ksplit);
   if (dtype == SA_BF16)
-    skinny_gemm_nt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((int)m, n, k, (const __nv_bfloat16*)a, lda,
+    skinny_gemm_nt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((int)m, n, k, ksplit, (const __nv_bfloat16*)a, lda,
                                                                (const __nv_bfloat16*)b, ldb, e);
   else
-    skinny_gemm_nt_kernel<float><<<grid, 256, 0, st>>>((int)m, n, k, (const float*)a, lda, (const float*)b, ldb, e);
+    skinny_gemm_nt_kernel<float><<<grid, 256, 0, st>>>((int)m, n, k, ksplit, (const float*)a, lda, (const float*)b, ldb, e);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
