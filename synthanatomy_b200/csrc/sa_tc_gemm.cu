@@ -30,7 +30,9 @@ constexpr int G_STAGES = 4;
 struct NtParams {
   CUtensorMap amap, bmap;
   CUtensorMap omap_act, omap_b;   // TMA-store maps: out_act (bf16, 64 x 32 boxes); `pre` (bf16) or out_f32 (fp32, 32 x 32 boxes)
+  CUtensorMap imap_a, imap_b;     // TMA-load maps of epilogue inputs: `pre` and `dot_with` (bf16 blocks) or `resid` (fp32 chunks)
   int stages, tma_out;            // pipeline stages; 1 = outputs leave through shared-memory staging + TMA stores
+  int tma_in;                     // 1: GELU' epilogue reads pre / dot_with blocks through TMA; 2: residual chunks through TMA
   long long m;
   int n, k;
   int BN, m_tiles, n_tiles, kblocks;
@@ -101,6 +103,26 @@ __device__ __forceinline__ void stage_f32_32(uint8_t* block, int r, const float 
     *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
 }
 
+// read back 32 bf16 / fp32 columns of row r of a staged block (inverse of stage_bf16_32 / stage_f32_32)
+__device__ __forceinline__ void unstage_bf16_32(const uint8_t* block, int r, int c0, float (&f)[32]) {
+  const uint8_t* row = block + r * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = (c0 >> 3) + i;
+    const uint4 u = *reinterpret_cast<const uint4*>(row + ((ch ^ (r & 7)) << 4));
+    f[i * 8 + 0] = bf16lo(u.x); f[i * 8 + 1] = bf16hi(u.x); f[i * 8 + 2] = bf16lo(u.y); f[i * 8 + 3] = bf16hi(u.y);
+    f[i * 8 + 4] = bf16lo(u.z); f[i * 8 + 5] = bf16hi(u.z); f[i * 8 + 6] = bf16lo(u.w); f[i * 8 + 7] = bf16hi(u.w);
+  }
+}
+__device__ __forceinline__ void unstage_f32_32(const uint8_t* block, int r, float (&f)[32]) {
+  const uint8_t* row = block + r * 128;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 u = *reinterpret_cast<const float4*>(row + ((i ^ (r & 7)) << 4));
+    f[i * 4] = u.x; f[i * 4 + 1] = u.y; f[i * 4 + 2] = u.z; f[i * 4 + 3] = u.w;
+  }
+}
+
 // GELU(x) = x Phi(x) and GELU'(x) = Phi(x) + x phi(x) with Phi through erf(|x| / sqrt 2) = 1 - poly(t) e^{-x^2/2},
 // t = 1 / (1 + p |x| / sqrt 2)  (Abramowitz & Stegun 7.1.26, |error| < 1.5e-7): one reciprocal, one ex2 and a
 // handful of FMAs instead of libm erff (+ expf for the derivative, which shares the exponential here).  Used by the
@@ -140,6 +162,7 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
   __shared__ uint64_t empty_bar[G_STAGES];
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint64_t in_bar[8];            // one per epilogue warp: TMA loads of epilogue inputs
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -153,6 +176,7 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+    for (int i = 0; i < 8; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -221,6 +245,7 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
     uint8_t* stgA = smem + (size_t)P.stages * stage_bytes + (size_t)ew * 8192;   // out_act block   [32 rows][64 bf16]
     uint8_t* stgB = stgA + 4096;                                               // pre block / out_f32 chunk
     float dot = 0.f;
+    uint32_t in_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
@@ -249,6 +274,40 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
           const int ci = cc >> 5;
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (P.tma_in == 1) {
+            // GELU' epilogue (du = g (dx W2^T) gelu'(u), dot = sum (dx W2^T) h): the u and h blocks of this warp arrive by
+            // TMA in stgA / stgB, du is formed in place over u and leaves by TMA
+            if ((ci & 1) == 0) {
+              if (lane == 0) {
+                bulk_wait_read0();
+                mbar_expect_tx(&in_bar[ew], 8192);
+                tma_load_2d(stgA, &P.imap_a, &in_bar[ew], col, row0);
+                tma_load_2d(stgB, &P.imap_b, &in_bar[ew], col, row0);
+              }
+              mbar_wait(&in_bar[ew], in_phase);
+              in_phase ^= 1;
+            }
+            if (e.bias) {
+              ld32_f32(e.bias + col, t);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += t[j];
+            }
+            unstage_bf16_32(stgB, lane, (ci & 1) * 32, t);
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dot = fmaf(f[j], t[j], dot);
+            }
+            unstage_bf16_32(stgA, lane, (ci & 1) * 32, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] * st * fast_gelu_grad(t[j]);
+            stage_bf16_32(stgA, lane, (ci & 1) * 32, f);
+            if (ci & 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&P.omap_act, stgA, col - 32, row0); bulk_commit(); }
+            }
+            continue;
+          }
           if (e.bias) {
             ld32_f32(e.bias + col, t);
 #pragma unroll
@@ -278,13 +337,25 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
               for (int j = 0; j < 32; ++j) f[j] *= fast_gelu_grad(t[j]);
             }
           }
-          if (e.resid && row_ok) {
+          if (P.tma_in == 2) {
+            // residual chunk of this warp through TMA into stgB; out_f32 is then formed in place
+            if (lane == 0) {
+              bulk_wait_read0();
+              mbar_expect_tx(&in_bar[ew], 4096);
+              tma_load_2d(stgB, &P.imap_a, &in_bar[ew], col, row0);
+            }
+            mbar_wait(&in_bar[ew], in_phase);
+            in_phase ^= 1;
+            unstage_f32_32(stgB, lane, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += t[j];
+          } else if (e.resid && row_ok) {
             ld32_f32(e.resid + o, t);
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += t[j];
           }
           if (e.out_f32) {
-            if (lane == 0) bulk_wait_read0();
+            if (P.tma_in != 2) { if (lane == 0) bulk_wait_read0(); }
             __syncwarp();
             stage_f32_32(stgB, lane, f);
             fence_proxy_async();
@@ -554,6 +625,23 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
       const uint64_t strides[2] = {4, (uint64_t)e.ldo * 4};
       const uint32_t box[2] = {32, 32};
       if ((rc = sa_make_tmap(&P.omap_b, SA_F32, e.out_f32, 2, dims, strides, box)) != SA_OK) return rc;
+    }
+  }
+  P.tma_in = 0;
+  if (P.tma_out) {
+    const uint64_t dims[2] = {(uint64_t)n, (uint64_t)m};
+    const bool want = !getenv("SA_GEMM_TMA_IN") || getenv("SA_GEMM_TMA_IN")[0] != '0';
+    if (want && e.act == SA_ACT_GELU_BWD && e.dot_with && e.out_act && !e.out_f32 && !e.resid) {
+      const uint64_t strides[2] = {2, (uint64_t)e.ldo * 2};
+      const uint32_t box[2] = {64, 32};
+      if ((rc = sa_make_tmap(&P.imap_a, SA_BF16, e.pre, 2, dims, strides, box)) != SA_OK) return rc;
+      if ((rc = sa_make_tmap(&P.imap_b, SA_BF16, e.dot_with, 2, dims, strides, box)) != SA_OK) return rc;
+      P.tma_in = 1;
+    } else if (want && e.resid && e.out_f32 && e.act == SA_ACT_NONE) {
+      const uint64_t strides[2] = {4, (uint64_t)e.ldo * 4};
+      const uint32_t box[2] = {32, 32};
+      if ((rc = sa_make_tmap(&P.imap_a, SA_F32, e.resid, 2, dims, strides, box)) != SA_OK) return rc;
+      P.tma_in = 2;
     }
   }
   const size_t smem = (size_t)P.stages * stage_bytes + stg_bytes + 1024;
