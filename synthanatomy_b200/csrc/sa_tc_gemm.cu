@@ -257,11 +257,9 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
       for (int cc = 0; cc < half_cols; cc += 32) {
         const int ct = half * half_cols + cc;             // column inside the tile
         const int col = nt * P.BN + ct;                   // global column
-        if (P.vec == 3) continue;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * P.BN + ct), v);
         tmem_ld_wait();
-        if (P.vec == 2) continue;                         // SA_GEMM_NOEPI=1: mainloop-only timing experiment
         const int nc = min(min(32, half_cols - cc), P.n - col);
         if (nc <= 0) continue;                             // warp-uniform
         if (!P.tma_out && !row_ok) continue;               // (the staging path needs every lane)
@@ -596,14 +594,12 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
   const void* ptrs[] = {e.bias, e.dot_with, e.pre, e.resid, e.out_f32, e.out_act};
   for (const void* p : ptrs) vec = vec && aligned16(p);
   P.vec = vec ? 1 : 0;
-  if (const char* env = getenv("SA_GEMM_NOEPI")) { if (env[0] == '1') P.vec = 2; }
-  if (const char* env = getenv("SA_GEMM_NOEPI")) { if (env[0] == '2') P.vec = 3; }
   int rc = make_2d(&P.amap, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, G_BK, G_BM);
   if (rc != SA_OK) return rc;
   rc = make_2d(&P.bmap, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, G_BK, (uint32_t)P.BN);
   if (rc != SA_OK) return rc;
   // TMA-store epilogue: whole 64-column blocks per warp, at most one "second" output (pre or out_f32)
-  P.tma_out = (vec && P.vec != 2 && P.vec != 3 && P.BN % 128 == 0 && n % 64 == 0 && (e.out_act || e.out_f32) &&
+  P.tma_out = (vec && P.BN % 128 == 0 && n % 64 == 0 && (e.out_act || e.out_f32) &&
                !(e.out_f32 && e.act == SA_ACT_GELU_FWD)) ? 1 : 0;
   if (const char* env = getenv("SA_GEMM_TMA_OUT")) { if (env[0] == '0') P.tma_out = 0; }
   const size_t stage_bytes = G_BM * 128 + (size_t)P.BN * 128;
