@@ -146,6 +146,20 @@ __device__ __forceinline__ void stage_proj(uint8_t* Ps, const float* __restrict_
   }
 }
 
+// delta[bh][n] = dout[n] . out[n] and 1 / den[bh][n], once per backward pass (four kernels need them per row)
+__global__ void fv_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                const float* __restrict__ den, float2* __restrict__ dinv, int B, int N, int H, int out_ld) {
+  const long long total = (long long)B * N * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(i % H);
+    const long long row = i / H;                  // b * N + n
+    const int n = (int)(row % N), b = (int)(row / N);
+    const long long ro = row * out_ld + h * 64;
+    const long long o = ((long long)b * H + h) * N + n;
+    dinv[o] = make_float2(row_dot64(out + ro, dout + ro), 1.0f / den[o]);
+  }
+}
+
 struct FvParams {
   CUtensorMap map_a, map_b, map_c, map_d, map_e, map_f;
   int B, N, H, m, mp, nblk, tail;    // tail = valid columns of the last feature block
@@ -168,6 +182,7 @@ struct FvParams {
   __nv_bfloat16* df_out;             // dqk: dq' / dk'
   float* sums;                       // chunk_state output
   const __nv_bfloat16* st_vec;       // dqk: the bf16 states (their row 64 is read directly)
+  const float2* dinv;                // backward: per (batch, head, position) {delta = dout . out, 1 / den}
 };
 
 #define FV_PROLOGUE(NBAR_INIT)                                                              \
@@ -440,9 +455,9 @@ tc_chunk_state_kernel(const __grid_constant__ FvParams P) {
       for (int i = 0; i < 32; ++i) f[i] = 0.f;
       if (n < P.N) {
         const long long ro = ((long long)b * P.N + n) * P.out_ld + h * 64;
-        const float inv = 1.0f / P.den_in[(long long)bh * P.N + n];
-        const float delta = row_dot64(P.out + ro, P.dout + ro);
-        aug = -delta * inv;
+        const float2 di = __ldg(P.dinv + (long long)bh * P.N + n);
+        const float inv = di.y;
+        aug = -di.x * inv;
         const uint4* pd = reinterpret_cast<const uint4*>(P.dout + ro + hf * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -606,7 +621,7 @@ tc_scan_kernel(const __grid_constant__ FvParams P) {
     const bool row_ok = n < P.N;
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     if (MODE == 1) {
-      if (hf == 0) s_vec[r] = row_ok ? 1.0f / P.den_in[(long long)bh * P.N + n] : 0.f;
+      if (hf == 0) s_vec[r] = row_ok ? __ldg(P.dinv + (long long)bh * P.N + n).y : 0.f;
       bar_epi();
     }
     mbar_wait(&a_full, 0);
@@ -749,9 +764,8 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
     if (hf == 0) {
       float dl = 0.f, iv = 0.f;
       if (row_ok) {
-        const long long ro = ((long long)b * P.N + n) * P.out_ld + h * 64;
-        dl = row_dot64(P.out + ro, P.dout + ro);
-        iv = 1.0f / P.den_in[(long long)bh * P.N + n];
+        const float2 di = __ldg(P.dinv + (long long)bh * P.N + n);
+        dl = di.x; iv = di.y;
       }
       s_delta[r] = dl; s_inv[r] = iv;
     }
@@ -1009,7 +1023,7 @@ void fill_common(FvParams& P, const sa_favor_desc* d, int out_ld, float eps) {
   P.eps = eps;
   P.proj = nullptr; P.kmax_in = nullptr; P.kmax_out = nullptr; P.x = nullptr; P.feat = nullptr; P.dfeat = nullptr;
   P.argmax = nullptr; P.gsum = nullptr; P.is_query = 0; P.out = nullptr; P.dout = nullptr; P.den_in = nullptr;
-  P.den_out = nullptr; P.o_out = nullptr; P.df_out = nullptr; P.sums = nullptr; P.st_vec = nullptr;
+  P.den_out = nullptr; P.o_out = nullptr; P.df_out = nullptr; P.sums = nullptr; P.st_vec = nullptr; P.dinv = nullptr;
 }
 
 // [bh][n][mp] feature tensor: box = 64 columns x 128 tokens of one (batch, head)
@@ -1045,18 +1059,18 @@ dim3 fv_grid(const sa_favor_desc* d) { return dim3((unsigned)sa_cdiv(d->seq, FC)
 
 // chunk sums + prefix:  mode 0: (kf, v) forward prefix;  mode 1: (qf, dout / den) suffix
 int launch_states(const sa_favor_desc* d, int mode, const void* feat, const void* w, const void* out, const void* dout,
-                  int out_ld, const float* den, float eps, float* sums, void* states, cudaStream_t st) {
+                  int out_ld, const float* den, float eps, float* sums, void* states, cudaStream_t st,
+                  const float2* dinv = nullptr) {
   static thread_local FvParams P;
   fill_common(P, d, out_ld, eps);
   int rc;
   if ((rc = feat_map(&P.map_a, feat, d)) != SA_OK) return rc;
   if (mode == 0 && (rc = head_map(&P.map_b, w, d, d->ld)) != SA_OK) return rc;
-  P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.sums = sums;
+  P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.sums = sums; P.dinv = dinv;
   dim3 grid = fv_grid(d);
   size_t smem = smem_state(d->mp);
   P.tmem_cols = tmem_cols_for(d->mp);
-  if (P.nblk >= 3 && mode == 0) {   // split the feature blocks {0, 1} | {2 ..} over two CTAs (mode 1 builds its W operand
-                                    // from global memory per CTA: splitting would duplicate that work)
+  if (P.nblk >= 3) {        // split the feature blocks {0, 1} | {2 ..} over two CTAs
     grid.z = 2;
     const int nbmax = P.nblk - 2 > 2 ? P.nblk - 2 : 2;
     smem = (size_t)(2 + nbmax) * BLK + 1024;
@@ -1084,8 +1098,11 @@ bool sa_tc_favor_supported(const sa_favor_desc* d) {
   return sa_get_tmap_encode() != nullptr;
 }
 
+size_t dinv_bytes(const sa_favor_desc* d) {
+  return round_up((size_t)d->batch * d->heads * d->seq * sizeof(float2), 1024);
+}
 size_t sa_tc_favor_scan_workspace(const sa_favor_desc* d, int backward) {
-  return sums_bytes(d) + (backward ? 2 : 1) * states_bytes(d);
+  return sums_bytes(d) + (backward ? 2 * states_bytes(d) + dinv_bytes(d) : states_bytes(d));
 }
 
 int sa_tc_favor_featmap_fwd(const sa_favor_desc* d, int mode, const void* x, const float* proj,
@@ -1188,7 +1205,16 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   } else if ((rc = launch_states(d, 0, kf, v, nullptr, nullptr, out_ld, nullptr, eps, sums, stS, st)) != SA_OK) {
     return rc;
   }
-  if ((rc = launch_states(d, 1, qf, nullptr, out, dout, out_ld, den, eps, sums, stR, st)) != SA_OK) return rc;
+  float2* dinv = reinterpret_cast<float2*>(stR + states_bytes(d));
+  {
+    const long long total = (long long)d->batch * d->seq * d->heads;
+    long long blocks = sa_cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    fv_delta_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, den, dinv, d->batch,
+                                                      d->seq, d->heads, out_ld);
+    SA_LAUNCH_CHECK();
+  }
+  if ((rc = launch_states(d, 1, qf, nullptr, out, dout, out_ld, den, eps, sums, stR, st, dinv)) != SA_OK) return rc;
   static thread_local FvParams P;
   const size_t smem = SMEM_DQK;
   // dq'
@@ -1199,6 +1225,7 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   if ((rc = state_map(&P.map_d, stS, d, P.nchunks)) != SA_OK) return rc;
   P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.df_out = (__nv_bfloat16*)dqf;
   P.st_vec = (const __nv_bfloat16*)stS;
+  P.dinv = dinv;
   P.tmem_cols = 256;
   tc_dqk_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
@@ -1217,7 +1244,7 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   if ((rc = feat_map(&P.map_b, qf, d)) != SA_OK) return rc;
   if ((rc = state_map(&P.map_c, stR, d, P.nchunks)) != SA_OK) return rc;
   if ((rc = head_map(&P.map_d, dout, d, out_ld)) != SA_OK) return rc;
-  P.den_in = den; P.o_out = (__nv_bfloat16*)dv;
+  P.den_in = den; P.o_out = (__nv_bfloat16*)dv; P.dinv = dinv;
   P.tmem_cols = 256;
   tc_scan_kernel<1><<<fv_grid(d), F_THREADS, SMEM_SCAN, st>>>(P);
   SA_LAUNCH_CHECK();
