@@ -825,139 +825,150 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ feature map, backward
-// Persistent (one CTA per SM, P staged once).  Per tile the producer warp TMA-loads the feature tile and its gradient
-// tile (the next tile's loads overlap this tile's MMA / epilogue); the epilogue warps turn the gradient tile IN PLACE into
-// dD = dfeat (feat - r eps) (bf16, own row: conflict-free swizzled 16-byte accesses), the MMA warp forms dD P, the
-// epilogue warps finish dx = c dD P - c^2 s x.
+// Persistent (one CTA per SM, P staged once), pipelined over the feature blocks: the producer warp streams (feat, dfeat)
+// blocks of 64 features through a four-stage TMA ring; the epilogue warps turn each dfeat block IN PLACE into
+// dD = dfeat (feat - r eps) (bf16, own row: conflict-free swizzled 16-byte accesses) and hand it to the MMA warp, which
+// accumulates dD P over the blocks in one of two TMEM buffers; when a tile's last block is in, the epilogue warps finish
+// dx = c (dD P - s P[argmax]) - c^2 s x  (the arg-max term of the non-detached query stabiliser is applied here, with the
+// same bf16 P row the MMA used) while the blocks of the next tile are already streaming.
+constexpr int FB_STAGES = 4;
+constexpr uint32_t FB_STAGE = 2 * BLK;       // feat block | dfeat block
+
 __global__ void __launch_bounds__(F_THREADS, 1)
 tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ uint64_t a_full, g_full, a_empty, g_empty, dd_ready, d_full;
+  __shared__ uint64_t full[FB_STAGES], ready[FB_STAGES], empty[FB_STAGES], d_full[2], d_empty[2];
   __shared__ float s_red[2][FC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Ds = smem;                          // nblk blocks: dfeat tile, then dD in place
-  uint8_t* As = smem + P.nblk * BLK;           // nblk blocks: feat tile
-  uint8_t* Ps = As + P.nblk * BLK;             // mp x 128 B
+  uint8_t* Ring = smem;                                  // FB_STAGES x (feat block | dfeat block -> dD block)
+  uint8_t* Ps = smem + FB_STAGES * FB_STAGE;             // mp x 128 B
   const int total = P.nchunks * P.B * P.H;
   if (threadIdx.x == 0) {
-    mbar_init(&a_full, 1); mbar_init(&g_full, 1); mbar_init(&a_empty, 256); mbar_init(&g_empty, 1);
-    mbar_init(&dd_ready, 256); mbar_init(&d_full, 1);
+    for (int i = 0; i < FB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&ready[i], 256); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 256); }
     fence_mbar_init();
     fence_proxy_async();
   }
   __syncthreads();
-  if (warp < 8) stage_proj(Ps, P.proj, P.m, P.mp, threadIdx.x);
+  if (warp < 8) { stage_proj(Ps, P.proj, P.m, P.mp, threadIdx.x); fence_proxy_async(); }
   FV_ALLOC();
   if (warp == 9) {
     if (lane == 0) {
       prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int bh = tile / P.nchunks, chunk = tile % P.nchunks;
-        const uint32_t par = (uint32_t)((it & 1) ^ 1);
-        mbar_wait(&a_empty, par);                  // the epilogue warps have read the previous feature tile
-        mbar_expect_tx(&a_full, (uint32_t)P.nblk * BLK);
-        for (int cb = 0; cb < P.nblk; ++cb) tma_load_3d(As + cb * BLK, &P.map_a, &a_full, cb * 64, chunk * FC, bh);
-        mbar_wait(&g_empty, par);                  // the MMAs of the previous tile have read dD
-        mbar_expect_tx(&g_full, (uint32_t)P.nblk * BLK);
-        for (int cb = 0; cb < P.nblk; ++cb) tma_load_3d(Ds + cb * BLK, &P.map_b, &g_full, cb * 64, chunk * FC, bh);
+        for (int cb = 0; cb < P.nblk; ++cb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], FB_STAGE);
+          uint8_t* sp = Ring + stage * FB_STAGE;
+          tma_load_3d(sp, &P.map_a, &full[stage], cb * 64, chunk * FC, bh);
+          tma_load_3d(sp + BLK, &P.map_b, &full[stage], cb * 64, chunk * FC, bh);
+          if (++stage == FB_STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 8) {
     if (lane == 0) {
-      const uint32_t da = smem_u32(Ds), pa = smem_u32(Ps);
+      const uint32_t pa = smem_u32(Ps);
       const uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);
-      const int ksteps = P.mp >> 4;
+      int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        mbar_wait(&dd_ready, (uint32_t)(it & 1));
-        tc_fence_after();
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_bf16(tmem_base, make_smem_desc(da + (ks >> 2) * BLK + (ks & 3) * 32, 16, 1024, 2),
-                    make_smem_desc(pa + ks * 2048, 8192, 1024, 2), idesc, ks > 0);
-        umma_commit(&g_empty);
-        umma_commit(&d_full);
+        const int bsel = it & 1;
+        mbar_wait(&d_empty[bsel], (uint32_t)(((it >> 1) & 1) ^ 1));
+        for (int cb = 0; cb < P.nblk; ++cb) {
+          mbar_wait(&ready[stage], phase);
+          tc_fence_after();
+          const uint32_t da = smem_u32(Ring + stage * FB_STAGE + BLK);
+          const int ksteps = (cb == P.nblk - 1) ? (P.tail >> 4) : 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base + (uint32_t)(bsel * 64), make_smem_desc(da + k * 32, 16, 1024, 2),
+                      make_smem_desc(pa + (cb * 4 + k) * 2048, 8192, 1024, 2), idesc, (cb | k) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == FB_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&d_full[bsel]);
       }
     }
   } else if (warp < 8) {
     const int q = warp & 3, hf = warp >> 2;
     const int r = q * 32 + lane;
-    const int U = P.mp >> 4, U0 = U >> 1;
-    const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
     const float re = P.r * P.eps;
     float gacc = 0.f;
+    int stage = 0; uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int bsel = it & 1;
       const int bh = tile / P.nchunks, chunk = tile % P.nchunks;
       const int b = bh / P.H, h = bh % P.H;
       const int n = chunk * FC + r;
       const bool row_ok = n < P.N;
       int am = -1;
       if (P.is_query && row_ok) am = P.argmax[(long long)bh * P.N + n];
-      mbar_wait(&a_full, (uint32_t)(it & 1));
-      mbar_wait(&g_full, (uint32_t)(it & 1));
-      float part = 0.f, g_am = 0.f;
-      for (int u = u_beg; u < u_end; ++u) {
-        uint8_t* rowd = sw_row(Ds + (u >> 2) * BLK, r);
-        const uint8_t* rowa = sw_row(As + (u >> 2) * BLK, r);
-        const int c0 = ((u & 3) * 16) >> 3;
-        uint4* pd0 = reinterpret_cast<uint4*>(rowd + ((c0 ^ (r & 7)) << 4));
-        uint4* pd1 = reinterpret_cast<uint4*>(rowd + (((c0 + 1) ^ (r & 7)) << 4));
-        float a[16], d[16], g[16];
-        unpack8(*reinterpret_cast<const uint4*>(rowa + ((c0 ^ (r & 7)) << 4)), a);
-        unpack8(*reinterpret_cast<const uint4*>(rowa + (((c0 + 1) ^ (r & 7)) << 4)), a + 8);
-        unpack8(*pd0, d); unpack8(*pd1, d + 8);
-        if (u * 16 + 16 <= P.m) {
+      float part = 0.f;
+      for (int cb = 0; cb < P.nblk; ++cb) {
+        mbar_wait(&full[stage], phase);
+        uint8_t* sp = Ring + stage * FB_STAGE;
+        const int ncols = (cb == P.nblk - 1) ? P.tail : 64;
+        if (hf * 32 < ncols) {
+          const uint8_t* rowa = sw_row(sp, r);
+          uint8_t* rowd = sw_row(sp + BLK, r);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) g[i] = d[i] * (a[i] - re);
-        } else {
+          for (int i = 0; i < 4; ++i) {
+            const int col0 = hf * 32 + i * 8;                 // column inside the block
+            if (col0 < ncols) {
+              const int ch = col0 >> 3;
+              uint4* pd = reinterpret_cast<uint4*>(rowd + ((ch ^ (r & 7)) << 4));
+              float a[8], d[8], g[8];
+              unpack8(*reinterpret_cast<const uint4*>(rowa + ((ch ^ (r & 7)) << 4)), a);
+              unpack8(*pd, d);
+              const int f0 = cb * 64 + col0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) g[i] = (u * 16 + i < P.m) ? d[i] * (a[i] - re) : 0.f;
+              for (int j = 0; j < 8; ++j) {
+                g[j] = (f0 + j < P.m) ? d[j] * (a[j] - re) : 0.f;
+                part += g[j];
+              }
+              *pd = pack8(g);
+            }
+          }
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) part += g[i];
-        if ((am >> 4) == u) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) g_am = ((am & 15) == i) ? g[i] : g_am;
-        }
-        *pd0 = pack8(g); *pd1 = pack8(g + 8);
+        fence_proxy_async();
+        mbar_arrive(&ready[stage]);
+        if (++stage == FB_STAGES) { stage = 0; phase ^= 1; }
       }
-      mbar_arrive(&a_empty);                    // this thread is done with the feature tile
       bar_epi();                                // readers of s_red of the previous tile are done
       s_red[hf][r] = part;
       bar_epi();
       const float ssum = row_ok ? s_red[0][r] + s_red[1][r] : 0.f;
-      if (P.is_query) {
-        const int ua = am >> 4;
-        if (am >= 0 && ua >= u_beg && ua < u_end) {      // this thread staged that column: patch it
-          const int cl = am & 63;
-          __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(sw_row(Ds + (am >> 6) * BLK, r) + (((cl >> 3) ^ (r & 7)) << 4)) + (cl & 7);
-          *p = __float2bfloat16_rn(g_am - ssum);
-        }
-      } else if (hf == 0) {
-        gacc += ssum;
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&dd_ready);
-      mbar_wait(&d_full, (uint32_t)(it & 1));
+      if (!P.is_query && hf == 0) gacc += ssum;
+      mbar_wait(&d_full[bsel], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32), v);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(bsel * 64 + hf * 32), v);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&d_empty[bsel]);
       if (row_ok) {
         const long long xo = ((long long)b * P.N + n) * P.ld + h * 64 + hf * 32;
         const uint4* px = reinterpret_cast<const uint4*>(P.x + xo);
         uint4* dst = reinterpret_cast<uint4*>(P.o_out + xo);
         const float c2s = P.c * P.c * ssum;
+        const uint8_t* prow = am >= 0 ? sw_row(Ps, am) : nullptr;     // bf16 P row of the arg-max feature (64 columns)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float xv[8], f[8];
+          float xv[8], f[8], pv[8];
           unpack8(__ldg(px + i), xv);
+          if (prow) {
+            unpack8(*reinterpret_cast<const uint4*>(prow + (((hf * 4 + i) ^ (am & 7)) << 4)), pv);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = P.c * __uint_as_float(v[i * 8 + j]) - c2s * xv[j];
+            for (int j = 0; j < 8; ++j) pv[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = P.c * (__uint_as_float(v[i * 8 + j]) - ssum * pv[j]) - c2s * xv[j];
           dst[i] = pack8(f);
         }
       }
@@ -989,7 +1000,7 @@ size_t smem_featmap(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + round_up(
 size_t smem_state(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + 1024; }
 constexpr size_t SMEM_SCAN = SC_STAGES * SC_STAGE + BLK + 1024;
 size_t smem_dqk(int mp) { return (size_t)4 * BLK + (size_t)nblk_of(mp) * (BLK + ST_BLK) + 1024; }
-size_t smem_fbwd(int mp) { return (size_t)2 * nblk_of(mp) * BLK + round_up((size_t)mp * 128, 1024) + 1024; }
+size_t smem_fbwd(int mp) { return (size_t)FB_STAGES * FB_STAGE + round_up((size_t)mp * 128, 1024) + 1024; }
 constexpr size_t SMEM_MAX = 227 * 1024 - 4096;   // opt-in ceiling minus the static shared memory of the kernels
 
 void init_once() {
@@ -1148,7 +1159,7 @@ int sa_tc_favor_featmap_bwd(const sa_favor_desc* d, const void* x, const float* 
   int rc;
   if ((rc = feat_map(&P.map_a, feat, d)) != SA_OK) return rc;
   if ((rc = feat_map(&P.map_b, dfeat, d)) != SA_OK) return rc;
-  P.tmem_cols = 64;
+  P.tmem_cols = 128;
   const int total = P.nchunks * d->batch * d->heads;
   tc_featmap_bwd_kernel<<<dim3((unsigned)(total < sa_sm_count() ? total : sa_sm_count())), F_THREADS, smem_fbwd(d->mp), st>>>(P);
   SA_LAUNCH_CHECK();
