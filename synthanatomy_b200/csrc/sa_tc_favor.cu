@@ -795,19 +795,22 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
     __nv_bfloat16* dst = P.df_out + ((long long)bh * P.N + n) * P.mp;
     for (int cb = 0; cb < P.nblk; ++cb) {
       const int ncols = (cb == P.nblk - 1) ? P.tail : 64;
+      const int c0 = cb * 64 + hf * 32;
+      const int nv = hf * 32 < ncols ? (min(32, ncols - hf * 32) >> 3) : 0;      // 16-byte output vectors (8 columns each)
+      uint4 vr[4];                           // the "1" row of this block: fetched before the accumulator is waited for
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vr[i] = i < nv ? __ldg(reinterpret_cast<const uint4*>(vecrow + c0) + i) : make_uint4(0, 0, 0, 0);
       mbar_wait(&acc_full[cb & 1], (uint32_t)((cb >> 1) & 1));
       tc_fence_after();
       if (hf * 32 < ncols) {                 // warp-uniform
         uint32_t v[32];
         tmem_ld_32x32(tD + tlane + (uint32_t)((cb & 1) * 64 + hf * 32), v);
         tmem_ld_wait();
-        const int c0 = cb * 64 + hf * 32;
-        const int nv = min(32, ncols - hf * 32) >> 3;      // 16-byte output vectors (8 columns each)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i < nv) {
             float sv[8], f[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(vecrow + c0) + i), sv);
+            unpack8(vr[i], sv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float acc = __uint_as_float(v[i * 8 + j]);
@@ -908,6 +911,11 @@ tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
       const bool row_ok = n < P.N;
       int am = -1;
       if (P.is_query && row_ok) am = P.argmax[(long long)bh * P.N + n];
+      // the x row of the final epilogue is fetched now: its latency hides behind the feature blocks
+      const long long xo = ((long long)b * P.N + n) * P.ld + h * 64 + hf * 32;
+      uint4 xr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xr[i] = row_ok ? __ldg(reinterpret_cast<const uint4*>(P.x + xo) + i) : make_uint4(0, 0, 0, 0);
       float part = 0.f;
       for (int cb = 0; cb < P.nblk; ++cb) {
         mbar_wait(&full[stage], phase);
@@ -952,15 +960,13 @@ tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
       tc_fence_before();
       mbar_arrive(&d_empty[bsel]);
       if (row_ok) {
-        const long long xo = ((long long)b * P.N + n) * P.ld + h * 64 + hf * 32;
-        const uint4* px = reinterpret_cast<const uint4*>(P.x + xo);
         uint4* dst = reinterpret_cast<uint4*>(P.o_out + xo);
         const float c2s = P.c * P.c * ssum;
         const uint8_t* prow = am >= 0 ? sw_row(Ps, am) : nullptr;     // bf16 P row of the arg-max feature (64 columns)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float xv[8], f[8], pv[8];
-          unpack8(__ldg(px + i), xv);
+          unpack8(xr[i], xv);
           if (prow) {
             unpack8(*reinterpret_cast<const uint4*>(prow + (((hf * 4 + i) ^ (am & 7)) << 4)), pv);
           } else {
