@@ -26,6 +26,7 @@ constexpr int G_THREADS = 320;
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
 constexpr int G_STAGES = 4;
+constexpr int G_STAGES_MAX = 6;               // CTA-pair kernel: 32 KB stages
 
 struct NtParams {
   CUtensorMap amap, bmap;
@@ -155,11 +156,16 @@ __device__ __forceinline__ float fast_gelu_grad(float x) {
   return fmaf(x, p, c);
 }
 
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile -- CTA r stages
+// rows r * 128 .. of the A tile and rows r * BN/2 .. of the B tile, the even CTA issues the 256-row MMAs, and each CTA
+// drains its own 128 accumulator rows.  Per k block an SM then pulls 16 KB + BN/2 * 128 B from L2 instead of
+// 16 KB + BN * 128 B for the same flops, which is what bounds the single-CTA kernel.
+template <int CG>
 __global__ void __launch_bounds__(G_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[G_STAGES];
-  __shared__ uint64_t empty_bar[G_STAGES];
+  __shared__ uint64_t full_bar[G_STAGES_MAX];
+  __shared__ uint64_t empty_bar[G_STAGES_MAX];
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t in_bar[8];            // one per epilogue warp: TMA loads of epilogue inputs
@@ -168,21 +174,24 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t a_bytes = G_BM * 128;
-  const uint32_t b_bytes = (uint32_t)P.BN * 128;
+  const uint32_t b_bytes = (uint32_t)(P.BN / CG) * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int total_tiles = P.m_tiles * P.n_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < P.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8 * CG); }
     for (int i = 0; i < 8; ++i) mbar_init(&in_bar[i], 1);
     fence_mbar_init();
     fence_proxy_async();
   }
+  if (CG == 2) cluster_sync_all();            // the peer's barriers exist before anything is signalled across the pair
   if (warp == 1) {
-    tmem_alloc(&tmem_base_slot, 512);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_pair(&tmem_base_slot, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(&tmem_base_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -194,24 +203,34 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
       prefetch_tmap(&P.amap);
       prefetch_tmap(&P.bmap);
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int arow = (mt * CG + (int)rank) * G_BM;
+        const int brow = nt * P.BN + (int)rank * (P.BN / CG);
         for (int kb = 0; kb < P.kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          tma_load_2d(sa, &P.amap, &full_bar[stage], kb * G_BK, mt * G_BM);
-          tma_load_2d(sa + a_bytes, &P.bmap, &full_bar[stage], kb * G_BK, nt * P.BN);
+          if (CG == 2) {
+            // both CTAs' bytes are credited to the leader's barrier (it may see the peer's bytes before its own expect_tx)
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+            const uint32_t lbar = mapa_u32(&full_bar[stage], 0);
+            tma_load_2d_pair(sa, &P.amap, lbar, kb * G_BK, arow);
+            tma_load_2d_pair(sa + a_bytes, &P.bmap, lbar, kb * G_BK, brow);
+          } else {
+            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            tma_load_2d(sa, &P.amap, &full_bar[stage], kb * G_BK, arow);
+            tma_load_2d(sa + a_bytes, &P.bmap, &full_bar[stage], kb * G_BK, brow);
+          }
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(G_BM, P.BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(G_BM * CG, P.BN, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
@@ -224,12 +243,13 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
           for (int k = 0; k < G_BK / 16; ++k) {
             const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024, 2);
             const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024, 2);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          if (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == P.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if (CG == 2) umma_commit_pair(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -247,10 +267,10 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
     float dot = 0.f;
     uint32_t in_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
-      const long long row = (long long)mt * G_BM + quad * 32 + lane;
-      const int row0 = mt * G_BM + quad * 32;
+      const int row0 = (mt * CG + (int)rank) * G_BM + quad * 32;
+      const long long row = (long long)row0 + lane;
       const bool row_ok = row < P.m;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -412,7 +432,10 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {                       // the accumulator stage is free once BOTH CTAs have drained their rows
+        if (CG == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(&tmem_empty_bar[acc], 0));
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (e.dot_out) {
@@ -423,8 +446,13 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (CG == 2) {
+    cluster_sync_all();                       // neither CTA leaves (or frees TMEM) while the other may still signal it
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ TN (wgrad)
@@ -555,7 +583,8 @@ void init_once() {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 2048);
+    cudaFuncSetAttribute(tc_gemm_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 2048);
+    cudaFuncSetAttribute(tc_gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 2048);
     cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 2048);
   });
 }
@@ -586,7 +615,12 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
   static thread_local NtParams P;
   P.m = m; P.n = n; P.k = k;
   P.BN = n >= 256 ? 256 : (int)sa_cdiv(n, 16) * 16;
-  P.m_tiles = (int)sa_cdiv(m, G_BM);
+  // CTA pairs for the big launches (256-row tiles); SA_GEMM_PAIR=0 keeps the single-CTA kernel
+  // (measured at m = 84 000: +6 % at k = 1024 / 2048, -5 % at k = 512, where the tile count per CTA matters more)
+  bool pair = m >= 1024 && k >= 1024 && P.BN % 32 == 0 && g_sms >= 2;
+  if (const char* env = getenv("SA_GEMM_PAIR")) { pair = env[0] != '0' && m >= 1024 && P.BN % 32 == 0 && g_sms >= 2; }
+  const int cg = pair ? 2 : 1;
+  P.m_tiles = (int)sa_cdiv(m, G_BM * cg);
   P.n_tiles = (int)sa_cdiv(n, P.BN);
   P.kblocks = (int)sa_cdiv(k, G_BK);
   P.e = e;
@@ -596,14 +630,14 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
   P.vec = vec ? 1 : 0;
   int rc = make_2d(&P.amap, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, G_BK, G_BM);
   if (rc != SA_OK) return rc;
-  rc = make_2d(&P.bmap, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, G_BK, (uint32_t)P.BN);
+  rc = make_2d(&P.bmap, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, G_BK, (uint32_t)(P.BN / cg));
   if (rc != SA_OK) return rc;
   // TMA-store epilogue: whole 64-column blocks per warp, at most one "second" output (pre or out_f32)
   P.tma_out = (vec && P.BN % 128 == 0 && n % 64 == 0 && (e.out_act || e.out_f32) &&
                !(e.out_f32 && e.act == SA_ACT_GELU_FWD)) ? 1 : 0;
   if (const char* env = getenv("SA_GEMM_TMA_OUT")) { if (env[0] == '0') P.tma_out = 0; }
-  const size_t stage_bytes = G_BM * 128 + (size_t)P.BN * 128;
-  P.stages = G_STAGES;
+  const size_t stage_bytes = G_BM * 128 + (size_t)(P.BN / cg) * 128;
+  P.stages = pair ? G_STAGES_MAX : G_STAGES;
   const size_t stg_bytes = P.tma_out ? 8 * 8192 : 0;
   while (P.stages > 2 && (size_t)P.stages * stage_bytes + stg_bytes + 1024 > (size_t)g_max_smem - 2048) --P.stages;
   if (P.tma_out) {
@@ -642,8 +676,23 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
   }
   const size_t smem = (size_t)P.stages * stage_bytes + stg_bytes + 1024;
   const int total = P.m_tiles * P.n_tiles;
-  const unsigned grid = (unsigned)(total < g_sms ? total : g_sms);
-  tc_gemm_nt_kernel<<<grid, G_THREADS, smem, st>>>(P);
+  if (pair) {
+    const int pairs = g_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs)));
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, tc_gemm_nt_kernel<2>, P);
+    if (err != cudaSuccess) { sa_set_error("tc_gemm_nt (CTA pairs): %s", cudaGetErrorString(err)); return SA_ERR_CUDA; }
+  } else {
+    const unsigned grid = (unsigned)(total < g_sms ? total : g_sms);
+    tc_gemm_nt_kernel<1><<<grid, G_THREADS, smem, st>>>(P);
+  }
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

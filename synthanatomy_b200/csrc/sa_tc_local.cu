@@ -15,6 +15,7 @@
 // Replaces local_attention.LocalAttention.forward (+ autograd) called by performer-pytorch SelfAttention for the local
 // heads, reached from /root/reference/src/networks/transformers/performer.py:270 (ctor args :199-200).
 #include <mutex>
+#include <stdlib.h>
 
 #include "sa_pf_common.cuh"
 #include "sa_tc_common.cuh"
@@ -32,6 +33,7 @@ struct LcParams {
   CUtensorMap qmap, kmap, vmap, domap;   // 2-D maps over the [rows][ld] buffers, based at head 0 of each block
   int B, N, H, W;
   int ld, out_ld;
+  int fast;                  // 1: warp-uniform interior-tile fast path (SA_LOCAL_FASTMASK=0 turns it off)
   float scale;
   const __nv_bfloat16* out;
   const __nv_bfloat16* dout;
@@ -187,6 +189,8 @@ tc_local_fwd_kernel(const __grid_constant__ LcParams P) {
     const int lo = lc_lo(p, P.W);
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
     const float c2 = P.scale * LOG2E;
+    const int w_p0 = i0 + warp * 32;                      // first row of this warp; lo() is non-decreasing in the row
+    const int w_lo_max = lc_lo(w_p0 + 31, P.W);
     float o[64];
 #pragma unroll
     for (int e = 0; e < 64; ++e) o[e] = 0.f;
@@ -196,8 +200,9 @@ tc_local_fwd_kernel(const __grid_constant__ LcParams P) {
       mbar_wait(&s_full[t & 1], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       const uint32_t ts = tS0 + lane_addr + (uint32_t)((t & 1) * 64);
-      // interior tiles (every key of the tile is visible to this row) skip the per-score mask arithmetic
-      const bool full = (j0 + 63 <= p) && (j0 >= lo) && (p < P.N);
+      // interior tiles (every key of the tile visible to every row of this warp: a warp-uniform test, so no divergence)
+      // skip the per-score mask arithmetic
+      const bool full = P.fast && (j0 + 63 <= w_p0) && (j0 >= w_lo_max) && (w_p0 + 31 < P.N);
       // pass 1 over the S row: running maximum (TMEM reads are cheap; keeps the register footprint at 2 CTAs / SM)
       float mt = -INFINITY;
 #pragma unroll
@@ -376,10 +381,14 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
       delta = row_delta(P.out + ro, P.dout + ro);
       if (P.delta_ws) P.delta_ws[(long long)bh * P.N + p] = delta;
     }
+    const int w_p0 = i0 + warp * 32;
+    const int w_lo_max = lc_lo(w_p0 + 31, P.W);
     for (int t = 0; t < ntiles; ++t) {
       const int j0 = j_beg + t * 64;
       mbar_wait(&sdp_full, (uint32_t)(t & 1));
       tc_fence_after();
+      // interior tile for the whole warp (uniform): no mask arithmetic
+      const bool full = P.fast && (j0 + 63 <= w_p0) && (j0 >= w_lo_max) && (w_p0 + 31 < P.N);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t vs[32], vd[32];
@@ -387,12 +396,18 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
         tmem_ld_32x32(tdP + lane_addr + (uint32_t)(hh * 32), vd);
         tmem_ld_wait();
         float f[32];
+        if (full) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int j = j0 + hh * 32 + c;
-          const bool ok = row_ok && (j <= p) && (j >= lo);
-          const float pr = ok ? ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) : 0.f;
-          f[c] = pr * (__uint_as_float(vd[c]) - delta) * P.scale;
+          for (int c = 0; c < 32; ++c)
+            f[c] = ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) * (__uint_as_float(vd[c]) - delta) * P.scale;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int j = j0 + hh * 32 + c;
+            const bool ok = row_ok && (j <= p) && (j >= lo);
+            const float pr = ok ? ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) : 0.f;
+            f[c] = pr * (__uint_as_float(vd[c]) - delta) * P.scale;
+          }
         }
         st_sw128_32(dSs, r, hh * 32, f);
       }
@@ -517,6 +532,8 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
         }
       }
     };
+    const int w_j0 = j0 + warp * 32;                       // first key of this warp; p_hi is non-decreasing in the key
+    const int w_p_hi_min = min(P.N - 1, (w_j0 / P.W + 2) * P.W - 1);
     float nl2, ndl;
     load_stats(0, nl2, ndl);
     for (int t = 0; t < ntiles; ++t) {
@@ -527,6 +544,8 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
       bar_softmax();
       mbar_wait(&sdp_full, (uint32_t)(t & 1));
       tc_fence_after();
+      // every (key of this warp, query of this tile) pair visible (warp-uniform): no mask arithmetic
+      const bool full = P.fast && (w_j0 + 31 <= q0) && (q0 + 63 <= w_p_hi_min) && (w_j0 + 31 < P.N);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t vs[32], vd[32];
@@ -534,13 +553,22 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
         tmem_ld_32x32(tdPT + lane_addr + (uint32_t)(hh * 32), vd);
         tmem_ld_wait();
         float fp[32], fd[32];
+        if (full) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int p = q0 + hh * 32 + c;
-          const bool ok = (j <= p) && (p <= p_hi);
-          const float pr = ok ? ex2(fmaf(__uint_as_float(vs[c]), c2, -s_lse2[buf][hh * 32 + c])) : 0.f;
-          fp[c] = pr;
-          fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
+          for (int c = 0; c < 32; ++c) {
+            const float pr = ex2(fmaf(__uint_as_float(vs[c]), c2, -s_lse2[buf][hh * 32 + c]));
+            fp[c] = pr;
+            fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int p = q0 + hh * 32 + c;
+            const bool ok = (j <= p) && (p <= p_hi);
+            const float pr = ok ? ex2(fmaf(__uint_as_float(vs[c]), c2, -s_lse2[buf][hh * 32 + c])) : 0.f;
+            fp[c] = pr;
+            fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
+          }
         }
         st_sw128_32(PTs, r, hh * 32, fp);
         st_sw128_32(dSTs, r, hh * 32, fd);
@@ -684,6 +712,7 @@ int make_map(CUtensorMap* m, const void* base, const sa_local_desc* d, int ld, u
 void fill_common(LcParams& P, const sa_local_desc* d) {
   P.B = d->batch; P.N = d->seq; P.H = d->heads; P.W = d->window; P.ld = d->ld; P.out_ld = d->out_ld;
   P.scale = 1.0f / sqrtf((float)d->dim_head);
+  { const char* env = getenv("SA_LOCAL_FASTMASK"); P.fast = (env && env[0] == '0') ? 0 : 1; }
   P.out = nullptr; P.dout = nullptr; P.o_out = nullptr; P.lse = nullptr; P.dq = P.dk = P.dv = nullptr;
   P.delta_ws = nullptr;
 }

@@ -81,8 +81,12 @@ def _bf(t):
 
 
 @pytest.mark.parametrize("m,n,k,ldo_pad", [(300, 512, 128, 0), (1000, 256, 512, 0), (257, 80, 64, 0), (130, 2049, 192, 0),
-                                           (128, 64, 1024, 64), (4099, 1024, 256, 0)])
-def test_tcgen05_gemm_nt_bf16(m, n, k, ldo_pad):
+                                           (128, 64, 1024, 64), (4099, 1024, 256, 0),
+                                           # m >= 1024: CTA-pair kernel (256-row tiles, cta_group::2)
+                                           (2500, 2049, 192, 0), (1500, 96, 128, 0), (3000, 512, 512, 64),
+                                           (1024, 160, 64, 0), (2000, 512, 1024, 0)])
+def test_tcgen05_gemm_nt_bf16(m, n, k, ldo_pad, monkeypatch):
+    monkeypatch.setenv("SA_GEMM_PAIR", "1")      # pairs whenever the shape allows (default: only for k >= 1024)
     """bf16 operands / fp32 accumulation on tcgen05; reference = fp32 matmul of the same bf16-rounded operands.
     Tolerance: bf16 output rounding (2^-8 relative) + fp32 accumulation-order slack."""
     ops, pf = _mods()
