@@ -209,6 +209,22 @@ int sa_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* target, int64_
                   const float* grad_scale_dev, float* loss_sum, float* dlogits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Token plumbing between the two models (integer gathers; all pointers are device pointers)
+ * ---------------------------------------------------------------------------------------------- */
+/* element type of a latent index grid: uint16 is what the extraction mode stores per subject (run_vqvae.py:484-498),
+ * int64 what index_quantize returns (baseline.py:343-346) */
+typedef enum sa_tok_dtype { SA_TOK_U16 = 0, SA_TOK_I32 = 1, SA_TOK_I64 = 2 } sa_tok_dtype;
+/* prepare_batch (src/utils/transformer.py:259-282) in one launch:
+ *   y[b][i] = grid[b][order[i]]   x_in[b][0] = bos   x_in[b][i] = y[b][i - 1]      grid [batch][n_src], order [n] (n <= n_src) */
+int sa_tokens_prepare(const void* grid, int tok_dtype, int batch, int64_t n_src, const int64_t* order, int64_t n, int64_t bos,
+                      int64_t* x_in, int64_t* y, void* stream);
+/* out[b][i] = src[b][index[i]]  -- e.g. sampled sequence -> grid with the reverted ordering (src/inferer/transformer.py:63-71) */
+int sa_tokens_gather(const void* src, int tok_dtype, int batch, int64_t n_src, const int64_t* index, int64_t n, int64_t* out,
+                     void* stream);
+/* out[i] = (uint16) src[i]; out_of_range[0] is set to 1 if any value is outside [0, 65535] (zeroed by the caller) */
+int sa_tokens_narrow(const int64_t* src, int64_t n, uint16_t* out, int* out_of_range, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Small helpers
  * ---------------------------------------------------------------------------------------------- */
 /* dst[r][c] = (dst dtype) src[r][c] for c < cols; columns [cols, dst_ld) of dst are zero-filled (pads the logits

@@ -139,6 +139,9 @@ SIGNATURES = {
                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sa_embed_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_void_p, c_int, c_void_p]),
+    "sa_tokens_prepare": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "sa_tokens_gather": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "sa_tokens_narrow": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "sa_rotary_qk": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "sa_rotary": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "sa_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p,

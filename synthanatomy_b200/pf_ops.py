@@ -237,6 +237,53 @@ def local_attn_bwd(d, buf, qcol, kcol, vcol, inv_freq, out, dout, ocol, lse, dbu
 
 
 # ------------------------------------------------------------------------------------------------
+# token plumbing between the two models
+# ------------------------------------------------------------------------------------------------
+_TOK_DTYPES = {torch.uint16: 0, torch.int16: 0, torch.int32: 1, torch.int64: 2}     # sa_tok_dtype (int16 storage read as uint16)
+
+
+def tokens_prepare(grid: torch.Tensor, order: torch.Tensor, bos: int):
+    """(x_in, y) int64 [B, N] from a latent index grid [B, ...] in its stored type (uint16 / int32 / int64), one launch"""
+    assert grid.is_contiguous() and order.dtype == torch.int64 and order.is_contiguous()
+    B = grid.shape[0]
+    n_src = grid.numel() // max(B, 1)
+    n = order.numel()
+    x_in = torch.empty(B, n, dtype=torch.int64, device=grid.device)
+    y = torch.empty(B, n, dtype=torch.int64, device=grid.device)
+    if B == 0 or n == 0:
+        return x_in, y
+    _lib.check(lib().sa_tokens_prepare(_ptr(grid), _TOK_DTYPES[grid.dtype], B, n_src, _ptr(order), n, int(bos), _ptr(x_in),
+                                       _ptr(y), _stream()), "sa_tokens_prepare")
+    return x_in, y
+
+
+def tokens_gather(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """out[b][i] = src[b][index[i]] (int64 out); src [B, n_src] in uint16 / int32 / int64"""
+    assert src.is_contiguous() and index.dtype == torch.int64 and index.is_contiguous()
+    B = src.shape[0]
+    n_src = src.numel() // max(B, 1)
+    out = torch.empty(B, index.numel(), dtype=torch.int64, device=src.device)
+    if out.numel() == 0:
+        return out
+    _lib.check(lib().sa_tokens_gather(_ptr(src), _TOK_DTYPES[src.dtype], B, n_src, _ptr(index), index.numel(), _ptr(out),
+                                      _stream()), "sa_tokens_gather")
+    return out
+
+
+def tokens_narrow(idx: torch.Tensor) -> torch.Tensor:
+    """int64 indices -> uint16 (the on-disk token type); raises if a value does not fit"""
+    assert idx.dtype == torch.int64 and idx.is_contiguous()
+    out = torch.empty(idx.shape, dtype=torch.uint16, device=idx.device)
+    if idx.numel() == 0:
+        return out
+    bad = torch.zeros(1, dtype=torch.int32, device=idx.device)
+    _lib.check(lib().sa_tokens_narrow(_ptr(idx), idx.numel(), _ptr(out), _ptr(bad), _stream()), "sa_tokens_narrow")
+    if int(bad.item()):
+        raise ValueError("token index outside [0, 65535] cannot be stored as uint16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # optional per-launch CUDA-event timing (bench.py: roofline of the dominant kernel, per-kernel breakdown)
 # ------------------------------------------------------------------------------------------------
 class KernelTimer:
