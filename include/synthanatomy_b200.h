@@ -165,6 +165,31 @@ int sa_vq_embed(const int64_t* idx, const float* codebook, int64_t rows, int dim
                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * PatchGAN discriminator blocks (src/networks/discriminator/baseline.py:43-79): nn.BatchNorm3d + nn.LeakyReLU over
+ * channels-last activations [rows = B*D*H*W][channels] (act dtype fp32 / bf16, statistics and parameters fp32).
+ * `workspace`: sa_bn_workspace(channels) bytes of device memory.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sa_bn_workspace(int channels);
+/* training-mode statistics: mean[c], rstd[c] = 1/sqrt(biased var + eps); running_mean / running_var (may be NULL)
+ * are updated as nn.BatchNorm3d does: r <- (1 - momentum) r + momentum * (mean | unbiased var) */
+int sa_bn_stats(const void* x, int dtype, int64_t rows, int channels, void* workspace, float eps, float momentum, float* mean,
+                float* rstd, float* running_mean, float* running_var, void* stream);
+/* eval-mode statistics: mean = running_mean, rstd = 1/sqrt(running_var + eps) */
+int sa_bn_eval_stats(const float* running_mean, const float* running_var, int channels, float eps, float* mean, float* rstd,
+                     void* stream);
+/* y = leaky_relu(gamma * (x - mean) * rstd + beta, slope)   (slope = 1: plain BatchNorm) */
+int sa_bn_lrelu_fwd(const void* x, int dtype, int64_t rows, int channels, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, float slope, void* y, void* stream);
+/* training-mode backward of the pair: g = dL/dy, x = BatchNorm input, y = the forward's output.
+ *   dgamma, dbeta [channels];  dx (may be NULL) = gamma rstd (g' - mean(g') - xhat mean(g' xhat)),  g' = g lrelu'(y) */
+int sa_bn_lrelu_bwd(const void* g, const void* x, const void* y, int dtype, int64_t rows, int channels, const float* mean,
+                    const float* rstd, const float* gamma, float slope, void* workspace, float* dgamma, float* dbeta, void* dx,
+                    void* stream);
+/* in place: x <- leaky_relu(x, slope);   g <- g * leaky_relu'(y) */
+int sa_lrelu_fwd(void* x, int dtype, int64_t n, float slope, void* stream);
+int sa_lrelu_bwd(void* g, const void* y, int dtype, int64_t n, float slope, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Elementwise / layout helpers
  * ---------------------------------------------------------------------------------------------- */
 /* dst[b][s][c] = src[b][c][s]  (NCDHW -> NDHWC, `spatial` = D*H*W) and back; dtypes are sa_dtype */

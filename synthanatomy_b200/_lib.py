@@ -93,6 +93,16 @@ SIGNATURES = {
     "sa_nchw_to_nhwc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
     "sa_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
     "sa_cast": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
+    "sa_bn_workspace": (C.c_size_t, [c_int]),
+    "sa_bn_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p]),
+    "sa_bn_eval_stats": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "sa_bn_lrelu_fwd": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                c_void_p]),
+    "sa_bn_lrelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sa_lrelu_fwd": (c_int, [c_void_p, c_int, c_int64, c_float, c_void_p]),
+    "sa_lrelu_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_float, c_void_p]),
     "sa_mse_fwd_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sa_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int,
                              c_void_p]),

@@ -249,6 +249,64 @@ def bias_grad(dy: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# BatchNorm3d + LeakyReLU (PatchGAN discriminator blocks), channels-last activations
+# ------------------------------------------------------------------------------------------------
+def _bn_ws(c: int, device) -> torch.Tensor:
+    return torch.empty(int(lib().sa_bn_workspace(c)), dtype=torch.uint8, device=device)
+
+
+def bn_stats(x: torch.Tensor, eps: float, momentum: float, running_mean: Optional[torch.Tensor],
+             running_var: Optional[torch.Tensor]):
+    """training-mode statistics of x [..., C]: (mean, rstd) fp32 [C]; the running buffers are updated in place"""
+    c = x.shape[-1]
+    rows = x.numel() // c
+    mean = torch.empty(c, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(c, device=x.device, dtype=torch.float32)
+    _lib.check(lib().sa_bn_stats(_p(x), _dt(x.dtype), rows, c, _p(_bn_ws(c, x.device)), float(eps), float(momentum), _p(mean),
+                                 _p(rstd), _p(running_mean), _p(running_var), _stream()), "sa_bn_stats")
+    return mean, rstd
+
+
+def bn_eval_stats(running_mean: torch.Tensor, running_var: torch.Tensor, eps: float):
+    c = running_mean.numel()
+    mean = torch.empty_like(running_mean)
+    rstd = torch.empty_like(running_mean)
+    _lib.check(lib().sa_bn_eval_stats(_p(running_mean), _p(running_var), c, float(eps), _p(mean), _p(rstd), _stream()),
+               "sa_bn_eval_stats")
+    return mean, rstd
+
+
+def bn_lrelu_fwd(x, mean, rstd, gamma, beta, slope: float) -> torch.Tensor:
+    c = x.shape[-1]
+    y = torch.empty_like(x)
+    _lib.check(lib().sa_bn_lrelu_fwd(_p(x), _dt(x.dtype), x.numel() // c, c, _p(mean), _p(rstd), _p(gamma), _p(beta),
+                                     float(slope), _p(y), _stream()), "sa_bn_lrelu_fwd")
+    return y
+
+
+def bn_lrelu_bwd(g, x, y, mean, rstd, gamma, slope: float, need_dx: bool = True):
+    """(dx | None, dgamma, dbeta) of y = lrelu(bn(x)) in training mode"""
+    c = x.shape[-1]
+    dgamma = torch.empty(c, device=x.device, dtype=torch.float32)
+    dbeta = torch.empty(c, device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x) if need_dx else None
+    _lib.check(lib().sa_bn_lrelu_bwd(_p(g), _p(x), _p(y), _dt(x.dtype), x.numel() // c, c, _p(mean), _p(rstd), _p(gamma),
+                                     float(slope), _p(_bn_ws(c, x.device)), _p(dgamma), _p(dbeta), _p(dx), _stream()),
+               "sa_bn_lrelu_bwd")
+    return dx, dgamma, dbeta
+
+
+def lrelu_fwd_(x: torch.Tensor, slope: float) -> torch.Tensor:
+    _lib.check(lib().sa_lrelu_fwd(_p(x), _dt(x.dtype), x.numel(), float(slope), _stream()), "sa_lrelu_fwd")
+    return x
+
+
+def lrelu_bwd_(g: torch.Tensor, y: torch.Tensor, slope: float) -> torch.Tensor:
+    _lib.check(lib().sa_lrelu_bwd(_p(g), _p(y), _dt(g.dtype), g.numel(), float(slope), _stream()), "sa_lrelu_bwd")
+    return g
+
+
+# ------------------------------------------------------------------------------------------------
 # layout
 # ------------------------------------------------------------------------------------------------
 def ncdhw_to_ndhwc(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
