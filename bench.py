@@ -493,7 +493,11 @@ def performer_b200(args, world, rank, local, dev):
     if summ:
         ach = summ["flop"] / (summ["ms"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "tc_gemm_nt_kernel (all dense-layer forward / data-gradient launches)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                # dram read + write per launch, mean over the 8 launches of one layer + the output head in the committed
+                # `ncu --set full` capture; algorithmic = bf16 operands once + the outputs of the fused epilogue
+                "traffic": 7.243e8 if (grid == (20, 28, 25) and B == 6) else None,
+                "traffic_source": "profiles/r1_performer_ncu_gemm.txt (ncu, same kernel and shapes; not measured in this run)",
                 "launches_timed": summ["launches"], "avg_ms": summ["ms"] / summ["launches"],
                 "flop_per_launch": summ["flop"] / summ["launches"], "share_of_step": summ["ms"] / ms,
                 "peak_source": peak_src}
