@@ -97,3 +97,71 @@ class CELoss(_Loss):
 
     def get_summaries(self) -> Dict[str, torch.Tensor]:
         return self.summaries
+
+
+# ------------------------------------------------------------------------------------------------
+# adversarial criteria on the discriminator's patch map (/root/reference/src/losses/adversarial/adversarial.py:11-122).
+# The map is ~7e4 values at the README size: a handful of elementwise torch ops, device-agnostic host logic.
+# ------------------------------------------------------------------------------------------------
+ADVERSARIAL_CRITERIA = ("vanilla", "hinge", "least_square")          # src/losses/adversarial/utils.py
+
+
+def adversarial_criterion(name: str):
+    """per-element loss(logits, is_real); note the reference's naming: "vanilla" is the relu hinge, "hinge" the softplus
+    form (adversarial.py:85-120)"""
+    sign = lambda is_real: -1.0 if is_real else 1.0                   # noqa: E731
+    if name == "vanilla":
+        return lambda logits, is_real: torch.relu(1.0 + sign(is_real) * logits)
+    if name == "hinge":
+        return lambda logits, is_real: torch.nn.functional.softplus(sign(is_real) * logits)
+    if name == "least_square":
+        return lambda logits, is_real: (logits - (1.0 if is_real else 0.0)) ** 2
+    raise ValueError(f"Unknown adversarial loss. Available losses are {list(ADVERSARIAL_CRITERIA)} but received {name}")
+
+
+class AdversarialLoss(_Loss):
+    """generator side (is_discriminator=False): weight * mean(criterion(D(fake), real=True));
+    discriminator side: weight * 0.5 * (mean(criterion(D(fake), False)) + mean(criterion(D(real), True)))"""
+
+    def __init__(self, criterion: str = "least_square", is_discriminator: bool = True, weight=None, size_average: bool = None,
+                 reduce: bool = None, reduction: str = "mean"):
+        super().__init__(size_average, reduce, reduction)
+        if reduction not in ("sum", "mean"):
+            raise ValueError("Reduction must be either 'sum' or 'mean'")
+        self.criterion = criterion
+        self.is_discriminator = is_discriminator
+        self.criterion_function = adversarial_criterion(criterion)
+        self._weight = weight
+        self.summaries: Dict = {"scalar": dict()}
+
+    def forward(self, logits_fake: torch.Tensor, logits_real: torch.Tensor = None) -> torch.Tensor:
+        side = "Discriminator" if self.is_discriminator else "Generator"
+        loss = torch.mean(self.criterion_function(logits_fake.float(), not self.is_discriminator))
+        self.summaries["scalar"][f"Loss-Adversarial_{side}-Reconstruction"] = loss
+        if self.is_discriminator:
+            loss_real = torch.mean(self.criterion_function(logits_real.float(), True))
+            self.summaries["scalar"]["Loss-Adversarial_Discriminator-Originals"] = loss_real
+            loss = 0.5 * (loss + loss_real)
+        return self._weight * loss
+
+    def get_summaries(self) -> Dict[str, torch.Tensor]:
+        return self.summaries
+
+    def get_weight(self) -> float:
+        return self._weight
+
+    def set_weight(self, weight: float) -> float:
+        self._weight = weight
+        return self.get_weight()
+
+
+def get_discriminator_loss(config: dict) -> AdversarialLoss:
+    """src/losses/adversarial/configure.py:10-22"""
+    adversarial_criterion(config["discriminator_loss"])
+    return AdversarialLoss(criterion=config["discriminator_loss"], is_discriminator=True, weight=0.005)
+
+
+def get_generator_loss(config: dict) -> AdversarialLoss:
+    """src/losses/adversarial/configure.py:25-37"""
+    adversarial_criterion(config["generator_loss"])
+    return AdversarialLoss(criterion=config["generator_loss"], is_discriminator=False, weight=0.005)

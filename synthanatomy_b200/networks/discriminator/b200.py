@@ -94,14 +94,14 @@ class _DiscFunction(torch.autograd.Function):
                 y = z
                 saved.append((h, None, None, None, None))
             h = y
-        ctx.net, ctx.saved, ctx.params, ctx.was_training = net, saved, params, training
+        ctx.net, ctx.saved, ctx.params, ctx.was_training, ctx.dt = net, saved, params, training, dt
         ctx.in_dhw = tuple(x.shape[2:])
         return ops.ndhwc_to_ncdhw(h, torch.float32)
 
     @staticmethod
     def backward(ctx, gout: torch.Tensor):
         net, params = ctx.net, ctx.params
-        dt = net._dtype()
+        dt = ctx.dt          # the forward's activation type (autocast may no longer be active when backward runs)
         if not ctx.was_training and any(b.bn is not None for b in net._blocks):
             raise RuntimeError("B200Discriminator: backward through eval-mode BatchNorm is not implemented")
         g = ops.ncdhw_to_ndhwc(gout.contiguous(), dt)

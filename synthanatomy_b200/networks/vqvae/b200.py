@@ -206,6 +206,24 @@ def _stack_backward(ops_list, saved, params, g, in_is_relu: bool, need_dx: bool)
     return g, grads
 
 
+# The backward of a stack drops its saved activations as soon as it has run (the decoder's 40 GB are gone before the
+# encoder's backward starts).  A caller that differentiates the same graph more than once -- the adaptive adversarial
+# weight, /root/reference/src/engines/trainer.py:264-289: two autograd.grad(..., retain_graph=True) before backward() --
+# wraps the iteration in `retain_activations()`.
+_RETAIN_ACTIVATIONS = [False]
+
+
+class retain_activations:
+    def __enter__(self):
+        self.prev = _RETAIN_ACTIVATIONS[0]
+        _RETAIN_ACTIVATIONS[0] = True
+        return self
+
+    def __exit__(self, *exc):
+        _RETAIN_ACTIVATIONS[0] = self.prev
+        return False
+
+
 class _StackFn(torch.autograd.Function):
     """One encoder / decoder stack.  Input and output are NCDHW fp32 (what the reference's callers see)."""
 
@@ -229,8 +247,12 @@ class _StackFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         g = ops.ncdhw_to_ndhwc(gout.float().contiguous(), ctx.compute_dtype)
+        if ctx.saved is None:
+            raise RuntimeError("B200VQVAE: second backward through a stack whose activations were released; wrap the "
+                               "iteration in synthanatomy_b200.networks.vqvae.b200.retain_activations()")
         dx, grads = _stack_backward(ctx.ops_list, ctx.saved, ctx.pdet, g, False, ctx.need_dx)
-        ctx.saved = None
+        if not _RETAIN_ACTIVATIONS[0]:
+            ctx.saved = None
         gx = ops.ndhwc_to_ncdhw(dx, torch.float32) if dx is not None else None
         return (gx, None, None, *grads)
 

@@ -129,3 +129,36 @@ def test_discriminator_generator_side_gradient_only():
     (-net(xd).mean()).backward()
     assert _rel(xd.grad.cpu(), xr.grad) <= 2e-4
     assert all(p.grad is None for p in net.parameters())
+
+
+@pytest.mark.parametrize("adaptive,amp", [(True, False), (False, True)])
+def test_adversarial_iteration_with_the_dropin_networks(adaptive, amp):
+    """one AdversarialTrainer iteration (trainer.py:122-262) over the drop-in VQ-VAE and discriminator: the adaptive weight
+    differentiates the generator's graph three times (retain_activations), autocast selects the bf16 kernels"""
+    from synthanatomy_b200 import engines
+    from synthanatomy_b200.losses import MSELoss, get_discriminator_loss, get_generator_loss
+    from synthanatomy_b200.networks.discriminator import B200Discriminator
+    from synthanatomy_b200.networks.vqvae import B200VQVAE
+    torch.manual_seed(9)
+    G = B200VQVAE(n_levels=1, downsample_parameters=((4, 2, 1, 1),), upsample_parameters=((4, 2, 1, 0, 1),), n_embed=64,
+                  embed_dim=8, n_channels=32, n_res_channels=32, n_res_layers=1, vq_decay=0.5, commitment_cost=0.25).cuda()
+    D = B200Discriminator(input_nc=1, ndf=8, n_layers=2).cuda()
+    og, od = torch.optim.Adam(G.parameters(), lr=1e-3), torch.optim.Adam(D.parameters(), lr=1e-3)
+    g0 = [p.detach().clone() for p in G.parameters()]
+    d0 = [p.detach().clone() for p in D.parameters()]
+    x = torch.rand(2, 1, 16, 16, 16, device="cuda")
+    out = engines.adversarial_iteration(x, x, G, D, og, od, MSELoss(), get_generator_loss({"generator_loss": "least_square"}),
+                                        get_discriminator_loss({"discriminator_loss": "least_square"}), epoch=1,
+                                        use_adversarial_adaptive_weight=adaptive, amp=amp)
+    assert all(np.isfinite(out[k]) for k in ("loss", "g_loss", "d_loss"))
+    assert out["g_loss"] >= out["loss"] - 1e-6                      # reconstruction + w * (non-negative adversarial term)
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(g0, G.parameters()))
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(d0, D.parameters()))
+    assert all(torch.isfinite(p).all() for p in list(G.parameters()) + list(D.parameters()))
+    if not adaptive:
+        # without retain_activations a second differentiation of the generator's graph is refused, not silently wrong
+        pred = G(x)
+        loss = pred["reconstruction"][0].mean()
+        torch.autograd.grad(loss, G.get_last_layer(), retain_graph=True)
+        with pytest.raises(RuntimeError, match="retain_activations"):
+            loss.backward()
