@@ -27,6 +27,8 @@ class Adam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                if torch.is_tensor(st["step"]):     # state restored from a torch.optim.Adam checkpoint (tensor step)
+                    st["step"] = int(st["step"].item())
                 st["step"] += 1
                 ops.adam_step(p.data, p.grad.contiguous(), st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2,
                               group["eps"], st["step"])
