@@ -29,6 +29,10 @@ ORDER_CASES = [
     ("reflect_3x4x5", "raster_scan", (1, 3, 4, 5), (True, False, True), ((1, 0, 2),), ((1, 2),),
      ("transpose", "rotate_90", "reflect")),
     ("s_curve_2d_4x5", "s_curve", (1, 4, 5), (False, True), ((1, 0),), ((0, 1),), ("transpose", "rotate_90", "reflect")),
+    ("hilbert_10x14x10", "hilbert_curve", (1, 10, 14, 10), (False,) * 3, ((2, 0, 1),), ((0, 1),), ("rotate_90", "transpose")),
+    ("hilbert_odd_3x7x5", "hilbert_curve", (1, 3, 7, 5), (False, True, False), ((0, 2, 1),), ((0, 2),),
+     ("reflect", "transpose", "rotate_90")),
+    ("hilbert_2d_5x12", "hilbert_curve", (1, 5, 12), (True, False), ((1, 0),), ((0, 1),), ("transpose", "rotate_90", "reflect")),
 ]
 
 

@@ -112,7 +112,82 @@ def ordering_restated(ordering_type: str, dimensions: Sequence[int], reflected: 
                 else:
                     out.append(template[r, c])
         return np.array(out)
+    if ordering_type == "hilbert_curve":                                              # :196-201
+        coords = list(gilbert_curve(template.shape))
+        return np.array([template[c] for c in coords])
     raise NotImplementedError(ordering_type)
+
+
+def gilbert_curve(shape: Sequence[int]):
+    """Generalised Hilbert curve over a rectangle / cuboid: the visiting order the reference obtains from the vendored
+    third-party generators gilbert2d / gilbert3d (J. Cerveny, BSD-2-Clause; img2seq_ordering.py:7-8,196-201), restated as
+    ONE recursion on tuples for both ranks.  A box = corner + axis vectors (major first).  Pinned by the golden sequences
+    of oracle/make_golden_performer.py, which come from the vendored generators through the reference's Ordering class."""
+    def add(*vs):
+        return tuple(sum(c) for c in zip(*vs))
+
+    def neg(v):
+        return tuple(-c for c in v)
+
+    def sub(u, v):
+        return add(u, neg(v))
+
+    def unit(v):
+        return tuple((c > 0) - (c < 0) for c in v)
+
+    def size(v):
+        return abs(sum(v))
+
+    def half(v, even_above_2):
+        h = tuple(c // 2 for c in v)                       # floor, also for negative components
+        if size(h) % 2 and even_above_2:
+            h = add(h, unit(v))
+        return h
+
+    def rec(p, vs):
+        n = [size(v) for v in vs]
+        thick = [i for i, k in enumerate(n) if k != 1]
+        if len(thick) <= 1:
+            i = thick[0] if thick else 0
+            for _ in range(n[i]):
+                yield p
+                p = add(p, unit(vs[i]))
+            return
+        if len(vs) == 2:
+            a, b = vs
+            w, h = n
+            if 2 * w > 3 * h:
+                a2 = half(a, w > 2)
+                parts = [(p, (a2, b)), (add(p, a2), (sub(a, a2), b))]
+            else:
+                a2, b2 = tuple(c // 2 for c in a), half(b, h > 2)
+                parts = [(p, (b2, a2)), (add(p, b2), (a, sub(b, b2))),
+                         (add(p, sub(a, unit(a)), sub(b2, unit(b))), (neg(b2), neg(sub(a, a2))))]
+        else:
+            a, b, c = vs
+            w, h, d = n
+            a2, b2, c2 = half(a, w > 2), half(b, h > 2), half(c, d > 2)
+            ea, eb, ec = sub(a, unit(a)), sub(b2, unit(b)), sub(c, unit(c))
+            if 2 * w > 3 * h and 2 * w > 3 * d:
+                parts = [(p, (a2, b, c)), (add(p, a2), (sub(a, a2), b, c))]
+            elif 3 * h > 4 * d:
+                parts = [(p, (b2, c, a2)), (add(p, b2), (a, sub(b, b2), c)), (add(p, ea, eb), (neg(b2), c, neg(sub(a, a2))))]
+            elif 3 * d > 4 * h:
+                parts = [(p, (c2, a2, b)), (add(p, c2), (a, b, sub(c, c2))),
+                         (add(p, ea, sub(c2, unit(c))), (neg(c2), neg(sub(a, a2)), b))]
+            else:
+                parts = [(p, (b2, c2, a2)), (add(p, b2), (c, a2, sub(b, b2))),
+                         (add(p, eb, ec), (a, neg(b2), neg(sub(c, c2)))),
+                         (add(p, ea, b2, ec), (neg(c), neg(sub(a, a2)), sub(b, b2))),
+                         (add(p, ea, eb), (neg(b2), c2, neg(sub(a, a2))))]
+        for q, sub_vs in parts:
+            yield from rec(q, sub_vs)
+
+    rank = len(shape)
+    lead = max(range(rank), key=lambda i: (shape[i], -i))
+    order = [lead] + [i for i in range(rank) if i != lead]
+    vecs = tuple(tuple(shape[i] if j == i else 0 for j in range(rank)) for i in order)
+    yield from rec((0,) * rank, vecs)
 
 
 def prepare_batch(quantization: np.ndarray, index_sequence: np.ndarray, vocab_size: int):

@@ -76,8 +76,9 @@ class Ordering:
             idx = np.indices(template.shape).reshape(template.ndim, -1).T.copy()
             np.random.shuffle(idx)
             return np.array([template[tuple(e)] for e in idx])
-        raise NotImplementedError("hilbert_curve ordering needs the reference's vendored `gilbert` package; pass the "
-                                  "reference's own Ordering object instead")
+        from .hilbert import hilbert_curve_indices          # generalised Hilbert curve (img2seq_ordering.py:196-201)
+        idx = hilbert_curve_indices(*template.shape)
+        return template[tuple(idx.T)].copy()
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         return x[self._sequence_ordering]
