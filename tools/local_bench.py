@@ -24,4 +24,4 @@ lse = torch.empty(B * H, N, device="cuda")
 desc = pf.local_desc(B, N, H, d, W, 3 * H * d, H * d, torch.bfloat16)
 tf = timeit(lambda: pf.local_attn_fwd(desc, buf, 0, H * d, 2 * H * d, None, out, 0, lse))
 tb = timeit(lambda: pf.local_attn_bwd(desc, buf, 0, H * d, 2 * H * d, None, out, dout, 0, lse, dbuf))
-print(f"local attention B={B} N={N} H={H} W={W} fast={os.environ.get('SA_LOCAL_FASTMASK', '1')} v2={os.environ.get('SA_LOCAL_V2', '11')}: fwd {tf:.3f} ms  bwd {tb:.3f} ms", flush=True)
+print(f"local attention B={B} N={N} H={H} W={W} fast={os.environ.get('SA_LOCAL_FASTMASK', '1')}: fwd {tf:.3f} ms  bwd {tb:.3f} ms", flush=True)
