@@ -1,0 +1,29 @@
+"""The spectral-loss oracle against golden values of the unmodified reference class (no GPU; the CUDA path for SURVEY
+section 8(f) rank 2 does not exist yet -- this pins the checker it will be held to)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import losses_oracle as lo
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "jukebox.npz")
+
+
+def test_jukebox_loss_oracle_matches_reference_value_and_gradient():
+    g = np.load(GOLD)
+    y, q = torch.from_numpy(g["y"]), torch.from_numpy(g["q"])
+    for name, kw in (("default", {}), ("no_pixel_f2", {"include_pixel_loss": False, "fft_factor": 2.0})):
+        pred = torch.from_numpy(g["pred"].copy()).requires_grad_(True)
+        loss = lo.jukebox_loss(pred, y, [q], **kw)
+        assert abs(loss.item() - float(g[f"{name}/loss"])) <= 1e-7
+        loss.backward()
+        torch.testing.assert_close(pred.grad, torch.from_numpy(g[f"{name}/grad"]), rtol=1e-5, atol=1e-9)
+
+
+def test_amplitude_is_parseval_consistent_and_shift_invariant():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 1, 6, 8, 10, generator=g)
+    amp = lo.fft_amplitude(x)
+    torch.testing.assert_close((amp ** 2).sum(dim=(1, 2, 3, 4)), (x ** 2).sum(dim=(1, 2, 3, 4)), rtol=1e-5, atol=1e-5)   # ortho norm
+    torch.testing.assert_close(lo.fft_amplitude(torch.roll(x, (2, 3), dims=(2, 4))), amp, rtol=1e-4, atol=1e-5)      # |F| ignores shifts
