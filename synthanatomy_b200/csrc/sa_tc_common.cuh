@@ -110,6 +110,31 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// ---------------------------------------------------------------- A operand in TMEM (TS form)
+// Not used by a shipped kernel yet (local attention with Q, dO, P and dS resident in TMEM).
+// registers -> TMEM: thread i of the warp writes 16 / 32 consecutive 32-bit columns of lane (lane_base + i); a row of
+// packed bf16 pairs written this way is the K-major A operand of a kind::f16 MMA (K = 16 elements = 8 columns per step).
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x K packed bf16 columns at `tmem_a`, issued by ONE thread
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2): two CTAs of a cluster of 2
 // on the SMs of one TPC run ONE 256-row MMA; each stages its own 128 rows of A and half of the B rows, so the bytes
 // an SM pulls from L2 per flop drop by a third against a single-CTA 128 x 256 tile.  Only the even CTA issues MMAs.
