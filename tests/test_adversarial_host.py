@@ -98,3 +98,39 @@ def test_adaptive_weight_threshold_and_disabled():
     assert engines.adaptive_adversarial_weight(G, rec, gl, 2, enabled=True, threshold=5, value=0.25) == 0.25
     w = engines.adaptive_adversarial_weight(G, rec, gl, 7, enabled=True, threshold=5, value=0.25)
     assert torch.is_tensor(w) and not w.requires_grad and 0.0 <= float(w) <= 1e4
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/src"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("criterion", ["vanilla", "hinge", "least_square"])
+def test_adversarial_loss_against_the_imported_reference_class(criterion):
+    """the unmodified AdversarialLoss (src/losses/adversarial/adversarial.py); only its TensorBoard enum import is stubbed"""
+    import enum
+    import sys
+    import types
+    hg = types.ModuleType("src.handlers.general")
+    hg.TBSummaryTypes = enum.Enum("TBSummaryTypes", {"SCALAR": "scalar"})
+    saved = {k: sys.modules.get(k) for k in ("src.handlers", "src.handlers.general")}
+    sys.path.insert(0, "/root/reference")
+    try:
+        import src  # noqa: F401
+        sys.modules["src.handlers"] = types.ModuleType("src.handlers")
+        sys.modules["src.handlers.general"] = hg
+        from src.losses.adversarial.adversarial import AdversarialLoss as Ref
+    finally:
+        sys.path.pop(0)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    g = torch.Generator().manual_seed(3)
+    fake = torch.randn(2, 1, 3, 3, 3, generator=g).requires_grad_(True)
+    real = torch.randn(2, 1, 3, 3, 3, generator=g)
+    for is_d in (True, False):
+        mine, ref = AdversarialLoss(criterion, is_d, weight=0.005), Ref(criterion=criterion, is_discriminator=is_d, weight=0.005)
+        a = mine(fake, real if is_d else None)
+        b = ref(fake, real if is_d else None)
+        assert torch.equal(a, b)
+        ga, = torch.autograd.grad(a, fake)
+        gb, = torch.autograd.grad(b, fake)
+        assert torch.equal(ga, gb)
