@@ -209,6 +209,11 @@ int sa_mse_fwd_bwd(const void* a, int a_dtype, const float* b, int64_t n, float 
 int sa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, int step, void* stream);
 
+/* The same update for `count` parameter tensors at once (host arrays of device pointers / element counts; all tensors
+ * share lr / betas / eps / step): 64 tensors per launch instead of one launch per tensor. */
+int sa_adam_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v,
+                  const int64_t* n, float lr, float beta1, float beta2, float eps, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,8 @@ SIGNATURES = {
     "sa_mse_fwd_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sa_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int,
                              c_void_p]),
+    "sa_adam_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
+                              c_int, c_void_p]),
     # ---- Performer path (include/synthanatomy_b200_performer.h)
     "sa_gemm_nt": (c_int, [c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, C.POINTER(GemmEpilogue),
                            c_int64, c_void_p]),
@@ -178,6 +180,12 @@ def load(build_if_missing: bool = True) -> C.CDLL:
             if not build_if_missing:
                 raise RuntimeError(f"{path} is missing: run `python -m synthanatomy_b200.build` (needs nvcc). "
                                    "synthanatomy_b200 has no CPU / eager fallback.")
+            path = _build.build_library()
+        elif not _build.is_current():
+            # the sources (csrc/, include/) changed since this .so was built: rebuild (under the cross-process build
+            # lock) rather than run stale kernels against new headers
+            if not build_if_missing:
+                raise RuntimeError(f"{path} is stale (sources changed): run `python -m synthanatomy_b200.build`")
             path = _build.build_library()
         lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():

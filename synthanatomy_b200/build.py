@@ -5,6 +5,8 @@
 from __future__ import annotations
 
 import concurrent.futures as cf
+import contextlib
+import fcntl
 import hashlib
 import os
 import shutil
@@ -36,52 +38,84 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _digest(paths) -> str:
+def library_path() -> str:
+    return os.path.join(LIBDIR, LIBNAME)
+
+
+def stamp_path() -> str:
+    """digest of the sources the .so was built from; lives next to the .so so that it travels with it"""
+    return library_path() + ".digest"
+
+
+def source_digest() -> str:
+    root = os.path.dirname(HERE)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers += [os.path.join(root, "include", f) for f in sorted(os.listdir(os.path.join(root, "include")))
+                if f.endswith(".h")]
+    srcs = [os.path.join(CSRC, f) for f in _sources()]
+    # paths enter the digest relative to the repo root: the same tree hashes the same wherever it is checked out
     h = hashlib.sha1()
-    for p in sorted(paths):
+    for p in sorted(srcs + headers):
         with open(p, "rb") as f:
-            h.update(p.encode()); h.update(f.read())
+            h.update(os.path.relpath(p, root).encode()); h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
-def library_path() -> str:
-    return os.path.join(LIBDIR, LIBNAME)
+def is_current() -> bool:
+    out, stamp = library_path(), stamp_path()
+    return os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == source_digest()
+
+
+@contextlib.contextmanager
+def _build_lock():
+    """one builder at a time across processes (every rank of a torchrun job calls load() at once)"""
+    os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lf:
+        fcntl.flock(lf, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(lf, fcntl.LOCK_UN)
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
-    nvcc = _nvcc()
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers.append(os.path.join(os.path.dirname(HERE), "include", "synthanatomy_b200.h"))
-    srcs = [os.path.join(CSRC, f) for f in _sources()]
-    stamp = os.path.join(OBJDIR, "stamp")
-    digest = _digest(srcs + headers)
     out = library_path()
-    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == digest:
+    if not force and is_current():
         return out
+    with _build_lock():
+        if not force and is_current():          # another process built it while this one waited for the lock
+            return out
+        nvcc = _nvcc()
+        srcs = [os.path.join(CSRC, f) for f in _sources()]
+        digest = source_digest()
+        tag = f".{os.getpid()}.tmp"
 
-    def compile_one(src):
-        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
-        if verbose:
-            cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
+        def compile_one(src):
+            obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+            cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj + tag]
+            if verbose:
+                cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+            if verbose:
+                sys.stderr.write(r.stderr)
+            os.replace(obj + tag, obj)
+            return obj
+
+        with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+            objs = list(ex.map(compile_one, srcs))
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out + tag, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
-        if verbose:
-            sys.stderr.write(r.stderr)
-        return obj
-
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as f:
-        f.write(digest)
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(out + tag, out)              # a concurrent loader sees the old library or the new one, never half
+        with open(stamp_path() + tag, "w") as f:
+            f.write(digest)
+        os.replace(stamp_path() + tag, stamp_path())
     return out
 
 

@@ -211,6 +211,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// multi-tensor form: one launch updates up to ADAM_BATCH parameter tensors (blockIdx.y = tensor, grid-stride over its
+// elements), so that an optimiser step over the 155 (VQ-VAE) / 249 (Performer) parameter tensors is 3-4 launches
+constexpr int ADAM_BATCH = 64;
+struct AdamBatch {
+  float* p[ADAM_BATCH];
+  const float* g[ADAM_BATCH];
+  float* m[ADAM_BATCH];
+  float* v[ADAM_BATCH];
+  long long n[ADAM_BATCH];
+};
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamBatch B, float beta1, float beta2, float eps, float step_size,
+                  float inv_sqrt_bc2) {
+  const int t = blockIdx.y;
+  float* __restrict__ p = B.p[t];
+  const float* __restrict__ g = B.g[t];
+  float* __restrict__ m = B.m[t];
+  float* __restrict__ v = B.v[t];
+  const long long n = B.n[t];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
 // cols[b, o, t] = x[b, o*s - p + t]  (single-channel x), t = (td*k + th)*k + tw.  One thread per (o, td, th):
 // the k taps along w are contiguous in x and in cols, a position's k^3 taps form one contiguous row.
 template <typename T>
@@ -396,6 +425,31 @@ extern "C" int sa_adam_step(float* p, const float* g, float* m, float* v, int64_
   adam_kernel<<<ew_grid(n, 4), EW_THREADS, 0, sa_stream(stream)>>>(p, g, m, v, n, beta1, beta2, eps,
                                                                    (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)));
   SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_adam_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v,
+                             const int64_t* n, float lr, float beta1, float beta2, float eps, int step, void* stream) {
+  SA_CHECK_ARG(count >= 0 && (count == 0 || (p && g && m && v && n)) && step >= 1, "bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  cudaStream_t st = sa_stream(stream);
+  for (int base = 0; base < count; base += ADAM_BATCH) {
+    AdamBatch B;
+    const int nb = count - base < ADAM_BATCH ? count - base : ADAM_BATCH;
+    long long nmax = 0;
+    for (int i = 0; i < nb; ++i) {
+      SA_CHECK_ARG(p[base + i] && g[base + i] && m[base + i] && v[base + i] && n[base + i] >= 0, "null tensor");
+      B.p[i] = p[base + i]; B.g[i] = g[base + i]; B.m[i] = m[base + i]; B.v[i] = v[base + i]; B.n[i] = n[base + i];
+      if (B.n[i] > nmax) nmax = B.n[i];
+    }
+    if (nmax == 0) continue;
+    long long bx = sa_cdiv(nmax, 256 * 4);
+    if (bx > 148) bx = 148;
+    adam_multi_kernel<<<dim3((unsigned)bx, (unsigned)nb), 256, 0, st>>>(B, beta1, beta2, eps, (float)((double)lr / bc1),
+                                                                       (float)(1.0 / sqrt(bc2)));
+    SA_LAUNCH_CHECK();
+  }
   return SA_OK;
 }
 

@@ -38,8 +38,11 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ cb, int
     x2 = __fadd_rn(x2, __fmul_rn(x[c], x[c]));            // (flat ** 2).sum(1)   baseline.py:50
   }
 
+  // best_k starts at a VALID code: a row of NaNs (a diverged step) compares false everywhere and must still index
+  // inside the codebook (torch.max over an all-NaN row also returns an in-range index); lanes start at their own
+  // first code so that the lane merge below keeps "lowest index on ties" for ordinary rows.
   float best = INFINITY;
-  int best_k = 0x7fffffff;
+  int best_k = sub < n_embed ? sub : 0;
   for (int k0 = 0; k0 < n_embed; k0 += VQ_CODE_CHUNK) {
     const int nk = min(VQ_CODE_CHUNK, n_embed - k0);
     __syncthreads();

@@ -57,7 +57,9 @@ def adversarial_iteration(inputs: torch.Tensor, targets: torch.Tensor, g_network
                                                              adaptive_adversarial_weight_threshold,
                                                              adaptive_adversarial_weight_value)
             generator_loss = reconstruction_loss + generator_loss * adversarial_weight
-        generator_loss.backward()
+    # outside `retain`: this last differentiation releases the stacks' saved activations (tens of GB at README size)
+    # as the reference's backward() does, instead of keeping them alive through the discriminator step
+    generator_loss.backward()
     g_optimizer.step()
 
     # ---- discriminator (trainer.py:215-251): gradients the generator pass left on it are dropped first

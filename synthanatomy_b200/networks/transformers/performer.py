@@ -181,6 +181,11 @@ class ProjectionUpdater(nn.Module):
     def fix_projections_(self):
         self.feature_redraw_interval = None
 
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        # resume the redraw phase where the checkpoint left it (one .item() at load time, none on the hot path)
+        self._calls = int(self.calls_since_last_redraw.item())
+
     def __getstate__(self):      # the prefetch thread / pinned buffers are rebuilt on demand (deepcopy, pickling)
         st = dict(self.__dict__)
         for k in ("_pins", "_pin_events", "_gen", "_pool", "_next"):
@@ -808,10 +813,11 @@ class Performer(TransformerBase):
         O(N^2) layer evaluations).  With one attention layer the result is the reference's; with deeper stacks it
         agrees up to the reference's own non-causal coupling through the prefix-dependent key stabiliser (see
         ``_Decoder`` and tests/test_gpu_performer.py::test_recurrent_decoder_matches_prefix_forward).
-        ``recurrent=False`` (default taken from ``self.recurrent_sampling``; also used for conditioning / a CPU
-        module) runs the reference's loop of full forwards."""
+        The recurrent evaluator is OPT-IN (``recurrent=True`` or ``self.recurrent_sampling = True``): the default, like
+        the reference, is the loop of full forwards over the growing prefix, so that a drop-in samples from exactly the
+        reference's distribution (also used for conditioning / a CPU module)."""
         if recurrent is None:
-            recurrent = getattr(self, "recurrent_sampling", True)
+            recurrent = getattr(self, "recurrent_sampling", False)
         if not recurrent or conditioning is not None or not prefix.is_cuda:
             return super().sample(prefix, conditioning=conditioning, temperature=temperature, sample=sample, top_k=top_k)
         self.eval()

@@ -391,6 +391,10 @@ class B200VQVAE(VQVAEBase, nn.Module):
         for prm in tuple(downsample_parameters) + tuple(upsample_parameters):
             if prm[-1] != 1:
                 raise NotImplementedError("dilation != 1 is not implemented; no fallback")
+        if embed_dim not in (8, 16, 32, 64):
+            # the fused quantiser kernel keeps one latent row in registers (csrc/sa_vq.cu); README.md:83 uses 32
+            raise NotImplementedError(f"embed_dim={embed_dim} is not implemented (the quantiser kernel takes 8, 16, 32 or "
+                                      f"64; README.md:83 uses 32); no fallback")
         self.n_levels = n_levels
         self.downsample_parameters = downsample_parameters
         self.upsample_parameters = upsample_parameters

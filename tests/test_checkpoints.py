@@ -69,3 +69,33 @@ def test_ddp_style_wrappers_are_unwrapped():
     objs = _objects(3)
     wrapped = torch.nn.DataParallel(objs["network"])
     assert list(ck._unwrap(wrapped).state_dict()) == list(objs["network"].state_dict())
+
+
+def test_optimizer_state_round_trips_into_torch_adam_and_steps():
+    """a run saved with this library's Adam is resumed by the reference's entry points with torch.optim.Adam
+    (run_vqvae.py:82, :312-344): the param_groups must carry every key torch's step() reads"""
+    torch.manual_seed(5)
+    src = torch.nn.Linear(3, 2)
+    mine = Adam(src.parameters(), lr=5e-4)
+    for p in src.parameters():            # the state a few steps of the CUDA kernel would have left
+        mine.state[p] = {"step": torch.tensor(3.0), "exp_avg": torch.randn_like(p), "exp_avg_sq": torch.rand_like(p)}
+    sd = mine.state_dict()
+    ref_keys = set(torch.optim.Adam(torch.nn.Linear(1, 1).parameters()).param_groups[0])
+    assert ref_keys <= set(sd["param_groups"][0]), ref_keys - set(sd["param_groups"][0])
+    dst = torch.nn.Linear(3, 2)
+    dst.load_state_dict(src.state_dict())
+    theirs = torch.optim.Adam(dst.parameters(), lr=1.0)
+    theirs.load_state_dict(sd)
+    before = [p.detach().clone() for p in dst.parameters()]
+    for p in dst.parameters():
+        p.grad = torch.ones_like(p)
+    theirs.step()                                                        # raised KeyError('weight_decay') before
+    assert theirs.param_groups[0]["lr"] == 5e-4
+    assert all(float(theirs.state[p]["step"]) == 4.0 for p in dst.parameters())
+    assert all(not torch.equal(a, p) for a, p in zip(before, dst.parameters()))
+    # and back: a torch checkpoint with a setting the kernel does not implement is refused, not ignored
+    wd = torch.optim.Adam(torch.nn.Linear(3, 2).parameters(), lr=1e-3, weight_decay=0.1)
+    with pytest.raises(NotImplementedError):
+        Adam(torch.nn.Linear(3, 2).parameters()).load_state_dict(wd.state_dict())
+    with pytest.raises(NotImplementedError):
+        Adam(torch.nn.Linear(3, 2).parameters(), amsgrad=True)

@@ -1,0 +1,332 @@
+"""Oracle parity of the BENCHMARKED path (bf16 operands on tcgen05, fp32 accumulation) at BASELINE.json's full shapes.
+
+The CPU oracle cannot run config 2 at batch 8 in seconds, but it can at batch 1 (the bench's own `cpu_baseline` leg
+runs one 160 x 224 x 160 volume in ~9 s).  So:
+
+  * every conv of the 4-level / 256-channel VQ-VAE at its true 160 x 224 x 160 shape, TEACHER-FORCED: the fp32 oracle
+    (oracle/vqvae_oracle.py, pinned to the reference) walks the network once; each layer of the product then runs on the
+    oracle's own input of that layer and is held to the oracle's output of that layer evaluated on the SAME bf16-rounded
+    operands (fp32 accumulation) -- the kernel's exact arithmetic model -- to 2 bf16 ulp per element;
+  * the data / weight / bias gradients of the layers that dominate the step (level-1 ResidualLayer, the 4/2/1 strided
+    conv and transposed conv, both 1-channel ends) against autograd of the oracle's functional layer on the same
+    operands;
+  * the whole model, forward + backward at 160 x 224 x 160 (batch 1) against ``vo.train_step_grads`` in fp32;
+  * the Performer at N = 14 000 (grid 20 x 28 x 25, dim 512, 16 heads of which 8 local, window 420), depth 2, against
+    ``po.train_step_grads``.
+
+Tolerances are stated as bf16 ulps (2^-8 relative) of the quantity compared, not as an end-to-end constant.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+ULP = 2.0 ** -8        # bf16: 8 significand bits => relative rounding error <= 2^-9, spacing 2^-8
+
+KW = dict(n_levels=4, downsample_parameters=((4, 2, 1, 1),) * 4, upsample_parameters=((4, 2, 1, 0, 1),) * 4,
+          n_embed=2048, embed_dim=32, n_channels=256, n_res_channels=256, n_res_layers=3, vq_decay=0.5,
+          commitment_cost=0.25)
+VOL = (160, 224, 160)
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _ndhwc(x, dtype=torch.bfloat16):
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(dtype).cuda()
+
+
+def _ncdhw(y):
+    return y.float().cpu().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def _assert_ulps(got, want, ulps, what):
+    """|got - want| <= ulps * 2^-8 * max(|want|, rms(want)) elementwise"""
+    got, want = got.float(), want.float()
+    rms = float(want.pow(2).mean().sqrt())
+    bound = ulps * ULP * torch.maximum(want.abs(), torch.full_like(want, rms))
+    excess = (got - want).abs() - bound
+    worst = float(excess.max())
+    assert worst <= 0, (f"{what}: exceeds {ulps} bf16 ulp by {worst:.3e} (rms {rms:.3e}, max |want| "
+                        f"{float(want.abs().max()):.3e})")
+
+
+def _model():
+    from oracle import vqvae_oracle as vo
+    from synthanatomy_b200.networks.vqvae import B200VQVAE
+    torch.manual_seed(4)
+    net = B200VQVAE(**KW, compute_dtype=torch.bfloat16)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    return vo, vo.VQVAEConfig(**KW), net, sd
+
+
+def _layer_walk(vo, cfg, sd, x):
+    """fp32 oracle walk: yields (stack, op_index, kind, params-prefix, meta, input, output) per programme op"""
+    out = []
+    with torch.no_grad():
+        h = x
+        for kind, i, m in vo.encoder_program(cfg):
+            p = f"encoder.0.{i}"
+            y = _oracle_op(vo, sd, p, kind, m, h)
+            out.append(("enc", kind, p, m, h, y))
+            h = y
+        q_st, _, _, _ = vo.quantize(sd, cfg, h, True)
+        h = q_st
+        for kind, i, m in vo.decoder_program(cfg):
+            p = f"decoder.0.{i}"
+            y = _oracle_op(vo, sd, p, kind, m, h)
+            out.append(("dec", kind, p, m, h, y))
+            h = y
+    return out
+
+
+def _oracle_op(vo, sd, p, kind, m, x, rounded=False):
+    """one programme op of the oracle (baseline.py:150-160, 218-228, 242-244, 258, 283-297); rounded=True evaluates it
+    in the bf16 kernels' arithmetic model: bf16 operands, fp32 accumulation, bf16 activations between convs"""
+    r = _bf if rounded else (lambda t: t)
+    if kind == "conv":
+        y = F.conv3d(r(x), r(sd[f"{p}.weight"]), sd[f"{p}.bias"], stride=m["s"], padding=m["p"])
+        return F.relu(y) if m["relu"] else y
+    if kind == "deconv":
+        y = F.conv_transpose3d(r(x), r(sd[f"{p}.weight"]), sd[f"{p}.bias"], stride=m["s"], padding=m["p"])
+        return F.relu(y) if m["relu"] else y
+    h = r(x)
+    for j in range(m["n"]):
+        t = F.relu(F.conv3d(h, r(sd[f"{p}.{j}.0.weight"]), sd[f"{p}.{j}.0.bias"], padding=1))
+        t = F.conv3d(r(t), r(sd[f"{p}.{j}.3.weight"]), sd[f"{p}.{j}.3.bias"])
+        h = r(F.relu(h + t))
+    return h
+
+
+def test_vqvae_config2_every_layer_teacher_forced_against_oracle():
+    """58 convs (20 programme ops) of BASELINE config 2 at 1 x 160 x 224 x 160, bf16 tcgen05 path, each on the oracle's
+    own layer input.  A ResidualLayer group is 3 x (3x3x3 -> ReLU -> 1x1x1 -> +x -> ReLU) with bf16 activations in
+    between: an element of h that sits on a rounding boundary may land one ulp apart between the two accumulation
+    orders, so groups are held to 4 ulp, single convs to 2."""
+    from synthanatomy_b200 import ops
+    from synthanatomy_b200.networks.vqvae import b200
+    vo, cfg, net, sd = _model()
+    x = torch.rand(1, 1, *VOL, generator=torch.Generator().manual_seed(7))
+    walk = _layer_walk(vo, cfg, sd, x)
+    net = net.cuda()
+    progs = {"enc": net._enc_ops, "dec": net._dec_ops}
+    cursor = {"enc": 0, "dec": 0}
+    tc_ops = 0
+    for stack, kind, p, m, xin, _y32 in walk:
+        prog = progs[stack]
+        n_ops = m["n"] if kind == "res" else 1
+        sub = prog[cursor[stack]: cursor[stack] + n_ops]
+        cursor[stack] += n_ops
+        params = [t.detach().float().contiguous() for op in sub for t in op.params()]
+        with torch.no_grad():
+            want = _oracle_op(vo, sd, p, kind, m, xin, rounded=True)
+            got, _ = b200._stack_forward(sub, _ndhwc(xin), params, save=False)
+        tc_ops += int(ops.last_path() == 2)
+        ulps = 4 if kind == "res" else 2
+        if kind == "deconv" and m["cout"] == 1:
+            # last ConvTranspose3d 128 -> 1: the per-tap products r[pos][tap] are a bf16 tensor before the col2im gather
+            # sums 8 of them (one more rounding, of terms that may be larger than their sum)
+            ulps = 16
+        _assert_ulps(_ncdhw(got), _bf(want) if kind != "res" else want, ulps, f"{p} ({kind})")
+    assert cursor["enc"] == len(net._enc_ops) and cursor["dec"] == len(net._dec_ops)
+    assert tc_ops >= 16, "the tcgen05 kernels were not the ones exercised"
+
+
+def _grad_case(vo, sd, p, kind, m, xin, seed):
+    """autograd of the oracle's functional layer on bf16-rounded operands; returns tensors for the GPU side"""
+    g = torch.Generator().manual_seed(seed)
+    xr = _bf(xin).requires_grad_(True)
+    leaves = {}
+
+    def leaf(k, rounded=True):
+        t = sd[k]
+        leaves[k] = (_bf(t) if rounded else t.clone()).requires_grad_(True)
+        return leaves[k]
+
+    if kind == "res":
+        h = F.relu(F.conv3d(xr, leaf(f"{p}.0.0.weight"), leaf(f"{p}.0.0.bias", False), padding=1))
+        hb = h + (_bf(h.detach()) - h.detach())                 # bf16 activation between the two convs (straight-through)
+        pre = xr + F.conv3d(hb, leaf(f"{p}.0.3.weight"), leaf(f"{p}.0.3.bias", False))
+        y = F.relu(pre)
+        aux = (hb.detach(), y.detach())
+    elif kind == "conv":
+        y = F.conv3d(xr, leaf(f"{p}.weight"), leaf(f"{p}.bias", False), stride=m["s"], padding=m["p"])
+        aux = ()
+    else:
+        y = F.conv_transpose3d(xr, leaf(f"{p}.weight"), leaf(f"{p}.bias", False), stride=m["s"], padding=m["p"])
+        aux = ()
+    gy = _bf(torch.randn(y.shape, generator=g))
+    if kind == "res":
+        gy = gy * (y.detach() > 0)                              # the product's backward receives g already ReLU-masked
+        pre.backward(gy)
+    else:
+        y.backward(gy)
+    return xr, gy, leaves, aux
+
+
+def _close_rel(got, want, tol, what):
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    err = float((got - want).abs().max())
+    scale = float(want.abs().max())
+    assert err <= tol * scale, f"{what}: max abs err {err:.3e} > {tol:.1e} * max |want| {scale:.3e}"
+
+
+def test_vqvae_config2_dominant_layer_gradients_against_oracle():
+    """dgrad / wgrad / bias-grad kernels at the true level-1 shapes (1 x 80 x 112 x 80 x 128) and at the 1-channel ends,
+    bf16 operands.  dx is a bf16 tensor (2 ulp); dW / db are fp32 sums over 7e5 - 5.7e6 positions (1e-3 of max |dW|:
+    fp32 accumulation order on both sides)."""
+    from synthanatomy_b200 import ops
+    from synthanatomy_b200.ops import ConvSpec
+    vo, cfg, net, sd = _model()
+    x = torch.rand(1, 1, *VOL, generator=torch.Generator().manual_seed(8))
+    walk = _layer_walk(vo, cfg, sd, x)
+    pick = {"encoder.0.0": None, "encoder.0.2": None, "encoder.0.3": None, "decoder.0.8": None, "decoder.0.10": None,
+            "decoder.0.11": None}
+    for stack, kind, p, m, xin, y in walk:
+        if p in pick:
+            pick[p] = (kind, m, xin)
+    assert all(v is not None for v in pick.values()), [k for k, v in pick.items() if v is None]
+    bf = torch.bfloat16
+    for seed, (p, (kind, m, xin)) in enumerate(pick.items()):
+        xr, gy, leaves, aux = _grad_case(vo, sd, p, kind, m, xin, 100 + seed)
+        gd = _ndhwc(gy)
+        xd = _ndhwc(xr.detach())
+        in_dhw = tuple(xin.shape[2:])
+        if kind == "res":
+            hb, _y = aux
+            w3, w1 = leaves[f"{p}.0.0.weight"], leaves[f"{p}.0.3.weight"]
+            c = m["c"]
+            s3, s1 = ConvSpec("conv", c, c, 3, 1, 1), ConvSpec("conv", c, c, 1, 1, 0)
+            hd = _ndhwc(hb)
+            wp1_t = ops.pack_weight(w1.detach().cuda(), True, bf)
+            assert ops.conv1x1_bwd_fused_supported(s1, gd)
+            dh, dw1, db1 = ops.conv1x1_bwd_fused(s1, gd, hd, wp1_t, w1.detach().cuda())
+            dw3 = ops.conv_wgrad(s3, xd, dh, w3.detach().cuda())
+            db3 = ops.bias_grad(dh)
+            wp3_t = ops.pack_weight(w3.detach().cuda(), True, bf)
+            dx = ops.conv_dgrad(s3, dh, wp3_t, in_dhw, gd, None)              # (+ g): the residual branch
+            assert ops.last_path() == 2
+            _close_rel(dw1, w1.grad, 1e-3, f"{p} dW1"); _close_rel(db1, leaves[f"{p}.0.3.bias"].grad, 1e-3, f"{p} db1")
+            # dW3 / db3 / dx see dh rounded to bf16 (one more rounding than the oracle's fp32 chain)
+            _close_rel(dw3, w3.grad, ULP, f"{p} dW3"); _close_rel(db3, leaves[f"{p}.0.0.bias"].grad, ULP, f"{p} db3")
+            _assert_ulps(_ncdhw(dx), xr.grad, 6, f"{p} dx")
+            continue
+        w = leaves[f"{p}.weight"]
+        op = [o for o in (net._enc_ops + net._dec_ops) if isinstance(o, type(net._enc_ops[0])) and o.module.weight.shape ==
+              w.shape and o.spec.kind == kind][0]
+        sp = op.spec
+        if op.single_channel_gemm(bf):
+            # the product's own path for the 1-channel ends: im2col / col2im + a tcgen05 GEMM over the 64 taps
+            from synthanatomy_b200.networks.vqvae import b200
+            params = [w.detach().cuda().contiguous(), leaves[f"{p}.bias"].detach().cuda().contiguous()]
+            with torch.no_grad():
+                _yd, saved = b200._stack_forward([op], xd, params, save=True)
+                # _stack_backward refuses stacks that end in a ReLU; these two ops are evaluated without it here
+                relu, op.relu = op.relu, False
+                try:
+                    dx, grads = b200._stack_backward([op], saved, params, gd, False, need_dx=(kind == "deconv"))
+                finally:
+                    op.relu = relu
+            _close_rel(grads[0], w.grad, 1e-3, f"{p} dW"); _close_rel(grads[1], leaves[f"{p}.bias"].grad, 1e-3, f"{p} db")
+            if dx is not None:
+                _assert_ulps(_ncdhw(dx), xr.grad, 2, f"{p} dx")
+            continue
+        dw = ops.conv_wgrad(sp, xd, gd, w.detach().cuda())
+        db = ops.bias_grad(gd)
+        wp_t = ops.pack_weight(w.detach().cuda(), transpose=(kind == "conv"), dtype=bf)
+        dx = ops.conv_dgrad(sp, gd, wp_t, in_dhw)
+        assert ops.last_path() == 2
+        _close_rel(dw, w.grad, 1e-3, f"{p} dW"); _close_rel(db, leaves[f"{p}.bias"].grad, 1e-3, f"{p} db")
+        _assert_ulps(_ncdhw(dx), xr.grad, 2, f"{p} dx")
+
+
+def test_vqvae_config2_full_model_step_against_oracle():
+    """BASELINE config 2 (4 levels, 256 channels, codebook 2048 x 32) at 1 x 160 x 224 x 160, training mode: forward,
+    loss, perplexity, code indices, EMA codebook and every parameter gradient, bf16 tcgen05 path vs the fp32 oracle.
+    End-to-end bound: the encoder is 29 convs deep, so the latents carry ~sqrt(29) * 2^-9 = 1e-2 relative noise; a
+    latent within that distance of a Voronoi face may pick the neighbouring code (counted, bounded), after which the
+    decoder sees a different input at that position.  Stated bounds: >= 90 % of the 1400 indices identical,
+    reconstruction within 3e-2 of its range in relative L2, loss within 3e-2, every gradient cosine >= 0.97."""
+    from synthanatomy_b200.networks.vqvae import B200VQVAE  # noqa: F401
+    vo, cfg, net, sd = _model()
+    with torch.no_grad():       # a codebook on the scale of the latents, so that the quantiser is not degenerate
+        z = vo.encode(sd, cfg, torch.rand(1, 1, *VOL, generator=torch.Generator().manual_seed(9)))
+        cb = z.permute(0, 2, 3, 4, 1).reshape(-1, 32)
+        pick = torch.randint(0, cb.shape[0], (2048,), generator=torch.Generator().manual_seed(10))
+        cbw = cb[pick] + 0.05 * cb.std() * torch.randn(2048, 32, generator=torch.Generator().manual_seed(11))
+        for k in ("quantizer.0.impl.weight", "quantizer.0.impl.embedding.weight", "quantizer.0.impl.embed_avg"):
+            sd[k] = cbw.clone()
+    net.load_state_dict(sd)
+    x = torch.rand(1, 1, *VOL, generator=torch.Generator().manual_seed(9))
+    loss_ref, grads_ref, out_ref = vo.train_step_grads(sd, cfg, x)
+    net = net.cuda().train()
+    out = net(x.cuda())
+    rec = out["reconstruction"][0]
+    loss = F.mse_loss(rec.float(), x.cuda()) + out["quantization_losses"][0]
+    loss.backward()
+    idx = net.index_quantize  # noqa: F841  (API presence)
+    rec_ref = out_ref["reconstruction"][0]
+    rel = float((rec.cpu() - rec_ref).norm() / rec_ref.norm())
+    assert rel <= 3e-2, f"reconstruction relative L2 error {rel:.3e}"
+    assert abs(float(loss) - float(loss_ref)) <= 3e-2 * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    ppl = float(net.get_perplexity()[0])
+    ppl_ref = float(vo.perplexity(out_ref["indices"], cfg.n_embed))
+    assert abs(ppl - ppl_ref) <= 0.1 * ppl_ref, (ppl, ppl_ref)
+    worst = 1.0
+    for k, p in net.named_parameters():
+        if not p.requires_grad:
+            continue
+        a, b = p.grad.cpu().flatten().double(), grads_ref[k].flatten().double()
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        worst = min(worst, cos)
+        assert cos >= 0.97, f"{k}: gradient cosine {cos:.4f}"
+    # EMA statistics: the codebook rows the oracle updated are the rows this path updated (same argmin up to near-ties)
+    n_ref = out_ref["new_state"]["N"]
+    n_got = net.quantizer[0].impl.N.cpu()
+    agree = float(((n_ref > 0) == (n_got > 0)).float().mean())
+    assert agree >= 0.9, f"EMA cluster-usage pattern agreement {agree:.3f}"
+
+
+def test_performer_config4_depth2_against_oracle_at_14000_tokens():
+    """Performer of BASELINE config 4 at its full sequence length (grid 20 x 28 x 25 = 14 000 tokens, 34 local windows,
+    110 scan chunks), two layers, batch 1, gates opened: fp32 CUDA-core path at 1e-4 (2e-4 of max |grad|), then the
+    benchmarked bf16 tcgen05 path at a stated bound -- logits within 8 bf16 ulp of their range (2 layers x (attention +
+    FFN) roundings on a residual stream kept in fp32), loss within 1e-2, gradient cosines >= 0.99."""
+    from oracle import performer_oracle as po
+    from synthanatomy_b200.losses import CELoss
+    from tests.test_gpu_performer import _build, _close
+    kw = dict(num_tokens=2049, dim=512, depth=2, heads=16, dim_head=64, local_attn_heads=8, local_window_size=420)
+    grid = (20, 28, 25)
+    ref = None
+    for dt in (None, torch.bfloat16):
+        cfg, sd, net, seqs, x_in, y = _build(kw, grid, 31, compute_dtype=dt)      # deterministic in the seed
+        x_in, y = x_in[:1], y[:1]
+        if ref is None:
+            ref = po.train_step_grads(sd, cfg, x_in, y, seqs)
+        loss_ref, grads_ref, logits_ref = ref
+        net = net.cuda().train()
+        logits = net(x_in.cuda())
+        loss = CELoss()(logits.transpose(1, 2), y.cuda())
+        loss.backward()
+        named = dict(net.named_parameters())
+        if dt is None:
+            _close(logits, logits_ref, 1e-4, "fp32 logits @ N=14000")
+            assert abs(float(loss) - float(loss_ref)) <= 1e-4 * max(1.0, abs(float(loss_ref)))
+            for k, gref in grads_ref.items():
+                err = float((named[k].grad.cpu() - gref).abs().max()) / max(float(gref.abs().max()), 1e-3)
+                assert err <= 2e-4, f"fp32 grad {k}: {err:.3e}"
+        else:
+            err = float((logits.cpu() - logits_ref).abs().max()) / float(logits_ref.abs().max())
+            assert err <= 8 * ULP, f"bf16 logits: {err:.3e} of max |logit|"
+            assert abs(float(loss) - float(loss_ref)) <= 1e-2 * abs(float(loss_ref))
+            for k, gref in grads_ref.items():
+                if float(gref.abs().max()) < 1e-7:
+                    continue
+                a, b = named[k].grad.cpu().flatten().double(), gref.flatten().double()
+                cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+                assert cos >= 0.99, f"bf16 grad {k}: cosine {cos:.4f}"
+        del net
+        torch.cuda.empty_cache()

@@ -508,7 +508,7 @@ def test_recurrent_sampling_equals_full_forward_sampling():
     cfg, sd, net, seqs, x_in, y = _build(kw, grid, 23)
     net = net.cuda().eval()
     prefix = torch.full((2, 1), cfg.num_tokens - 1, dtype=torch.long, device="cuda")
-    a = net.sample(prefix, sample=False)
-    b = net.sample(prefix, sample=False, recurrent=False)
+    a = net.sample(prefix, sample=False, recurrent=True)
+    b = net.sample(prefix, sample=False)          # default = the reference's loop of full forwards
     assert tuple(a.shape) == (2, *grid)
     assert torch.equal(a, b)
