@@ -19,6 +19,7 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -38,6 +39,50 @@ KW = dict(n_levels=4, downsample_parameters=((4, 2, 1, 1),) * 4, upsample_parame
           commitment_cost=0.25)
 
 
+def vq_config(vol, batch, world):
+    """the `config` object of the VQ-VAE line; the reference arm prints the SAME object (it measures that workload)"""
+    full = tuple(vol) == (160, 224, 160)
+    return {"workload": f"baseline_vqvae 4-level 256ch {vol[0]}x{vol[1]}x{vol[2]} codebook 2048x32 "
+                        f"batch {batch}/GPU, fwd+bwd+Adam" + ("" if full else " (REDUCED volume: not the headline)"),
+            "parallelism": f"dp{world}", "global_batch": batch * world,
+            "l2_policy": "inputs and activations (>= 1.4 GB per tensor) exceed the 126 MB L2; no flush needed"}
+
+
+def pf_config(grid, batch, depth, world):
+    n = grid[0] * grid[1] * grid[2]
+    full = tuple(grid) == (20, 28, 25) and depth == 24 and batch == 6
+    return {"workload": f"Performer dim512 L{depth} h16 (8 local, w420) m266 vocab2049, grid "
+                        f"{grid[0]}x{grid[1]}x{grid[2]} = {n} tokens, batch {batch}/GPU, fwd+CE+bwd+Adam, feature "
+                        f"redraw every 2nd step" + ("" if full else " (REDUCED: not the headline)"),
+            "parallelism": f"dp{world}", "global_batch": batch * world,
+            "l2_policy": "per-layer activations (>= 86 MB each, 2.6 GB per layer) exceed the 126 MB L2; no flush needed"}
+
+
+def git_blob_hash(path):
+    data = open(path, "rb").read()
+    return hashlib.sha1(b"blob %d\0" % len(data) + data).hexdigest()
+
+
+def measured_traffic(kernel):
+    """(bytes per launch | None, provenance): the committed ncu figure of profiles/traffic.json, valid only while the
+    kernel's source file is byte-identical to the one that was profiled"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        if git_blob_hash(os.path.join(ROOT, t["file"])) != t["blob"]:
+            return None, f"stale: {t['file']} changed since {t['source']} was captured"
+        return float(t["dram_bytes_per_launch"]), (f"{t['source']} (ncu --set full, same kernel source [git blob "
+                                                   f"{t['blob'][:10]}] and shape; not measured in this run)")
+    except Exception as e:      # noqa: BLE001
+        return None, f"no committed capture ({type(e).__name__})"
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:       # noqa: BLE001
+        return {}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -54,6 +99,9 @@ def parse():
     ap.add_argument("--pf-grid", type=int, nargs=3, default=[20, 28, 25])
     ap.add_argument("--pf-depth", type=int, default=24)
     ap.add_argument("--pf-breakdown", action="store_true", help="add a per-kernel time breakdown of one extra step")
+    ap.add_argument("--no-vendor", action="store_true", help="skip the cuDNN / cuBLAS comparator legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the bf16x3 (fp32-class tensor-core) arms")
+    ap.add_argument("--no-extra", action="store_true", help="skip the VQ-kernel (config 3) and N = 1400 Performer arms")
     return ap.parse_args()
 
 
@@ -177,7 +225,7 @@ def vqvae_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "baseline_vqvae 4-level 256ch 160x224x160 codebook 2048x32 (CPU sample, see cpu_baseline)"},
+        "config": vq_config(tuple(args.vol), args.batch, args.gpus),   # the b200 arm's workload; the sample is in cpu_baseline
         "cpu_baseline": cb,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -262,19 +310,16 @@ def vqvae_b200(args, world, rank, local, dev):
     # ---- end-to-end through the public module API with host buffers
     ms_e2e, _ = (ms, None) if args.no_e2e else timed(args.steps, e2e=True)
 
+    hbm_peak = torch.cuda.max_memory_allocated() / 2 ** 30
     del model, net, opt
     torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
     if rank != 0:
         return None
     vols = B * world * args.steps
     value = vols / (ms / 1e3)
     e2e_value = vols / (ms_e2e / 1e3)
-    full = vol == (160, 224, 160)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)     # kernel timed inside a long step -> sustained figure
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
     dt = timer.elapsed_ms()
@@ -284,35 +329,182 @@ def vqvae_b200(args, world, rank, local, dev):
         flop = 2.0 * pos * 27 * 128 * 128                    # algorithmic FLOPs of one 3x3x3 128->128 launch
         avg_ms = sum(dt) / len(dt)
         ach = flop / (avg_ms * 1e-3) / 1e12
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one level-1 launch from the committed
-        # `ncu --set full` capture (profiles/r1_vqvae_ncu_conv3.txt); algorithmic bytes = bf16 NDHWC in + out
-        traffic = 2.894e9 if (full and B == 8) else None
+        traffic, traffic_src = measured_traffic("tc_conv3_kernel")
+        if not (vol == (160, 224, 160) and B == 8):
+            traffic, traffic_src = None, "the committed capture is of the batch-8 160x224x160 launch"
         roof = {"bound": "tensor", "kernel": "tc_conv3_kernel (3x3x3 128->128 @ level 1, fwd + dgrad launches)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
-                "traffic_source": "profiles/r1_vqvae_ncu_conv3.txt (ncu, same kernel and shape; not measured in this run)",
-                "algorithmic_bytes_per_launch": 2.0 * pos * 128 * 2,
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": 2.0 * pos * 128 * 2,     # bf16 NDHWC activation in + out, once each
                 "launches_timed": len(dt), "avg_ms": avg_ms, "flop_per_launch": flop, "peak_source": peak_src}
     step_flop = 3 * FLOP_PER_VOL_FWD * B * (vol[0] * vol[1] * vol[2]) / (160 * 224 * 160)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"baseline_vqvae 4-level 256ch {vol[0]}x{vol[1]}x{vol[2]} codebook 2048x32 "
-                               f"batch {B}/GPU, fwd+bwd+Adam" + ("" if full else " (REDUCED volume: not the headline)"),
-                   "parallelism": f"dp{world}", "global_batch": B * world,
-                   "l2_policy": "inputs and activations (>= 1.4 GB per tensor) exceed the 126 MB L2; no flush needed"},
+        "config": vq_config(vol, B, world),
         "step_tflops": step_flop / (ms / args.steps * 1e-3) / 1e12,
         "loss": loss,
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": roof,
+        "hbm_peak_gb": hbm_peak,
     }
+    if world == 1 and not args.no_extra:
+        out["vq_kernel"] = vq_kernel_arm(dev)
+    if world == 1 and not args.no_parity:
+        out["parity_arm"] = vq_parity_arm(args, dev, value)
+    if world == 1 and not args.no_vendor:
+        out["vendor_baseline"] = vendor_vqvae(args, value)
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(args.cpu_budget_s)
         out["cpu_baseline"] = cb
     return out
+
+
+X3_DTYPE = "bf16x3 (fp32 tensors; products on the bf16 tensor cores as hi.hi + lo.hi + hi.lo of split operands, fp32 accumulation)"
+
+
+def vq_parity_arm(args, dev, bf16_value):
+    """The SAME workload in the tensor-core parity mode (compute_dtype = BF16X3, csrc/sa_x3.cu): the arithmetic that meets
+    1e-4 against the fp32 oracle (tests/test_gpu_x3.py, tests/test_gpu_parity_fullsize.py) at tensor-core speed; the
+    256-output-channel layers and the two 1-channel ends run on the CUDA-core fp32 kernels."""
+    import torch
+    from synthanatomy_b200 import ops
+    from synthanatomy_b200.losses import MSELoss
+    from synthanatomy_b200.networks.vqvae import B200VQVAE
+    from synthanatomy_b200.optim import Adam
+    vol = tuple(args.vol)
+    B = args.batch
+    while B >= 1:
+        net = opt = x = None
+        try:
+            torch.manual_seed(4)
+            net = B200VQVAE(**KW, compute_dtype=ops.BF16X3).to(dev).train()
+            opt = Adam(net.parameters(), lr=1.65e-4)
+            crit = MSELoss()
+            x = torch.rand(B, 1, *vol, device=dev)
+
+            def step():
+                loss = crit(net(x), x)
+                loss.backward()
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+                return loss
+
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            steps = max(2, min(args.steps, 3))
+            ops.reset_launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            val = B / (ms / 1e3)
+            return {"dtype": X3_DTYPE, "value": val, "unit": UNIT, "ms_per_step": ms, "batch": B, "steps": steps,
+                    "loss": float(loss.detach()), "gpu_launches": int(ops.launch_count()),
+                    "tolerance": "1e-4 against the fp32 oracle (north_star): tests/test_gpu_x3.py",
+                    "vs_bf16_arm": val / bf16_value,
+                    "hbm_peak_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        except torch.OutOfMemoryError:
+            B //= 2
+        except Exception as e:      # noqa: BLE001  -- a secondary arm must not take the headline line down
+            return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+        finally:
+            del net, opt, x
+            ops._X3_WS.clear()
+            torch.cuda.empty_cache()
+    return {"unavailable": "out of memory at batch 1"}
+
+
+def pf_parity_arm(args, dev, bf16_value):
+    """The Performer workload at the reference's own precision class (fp32 storage, TF32-or-better products;
+    run_transformer.py:165 amp=False): dense layers in bf16x3 on the tensor cores, attention on the exact fp32 CUDA-core
+    kernels.  1e-4 against the fp32 oracle (tests/test_gpu_x3.py)."""
+    import torch
+    from synthanatomy_b200 import ops
+    grid = tuple(args.pf_grid)
+    B = args.pf_batch
+    while B >= 1:
+        S = None
+        try:
+            S = _pf_setup(args, grid, 1, 0, 0, dev, ops.BF16X3, batch=B)
+            S["step"](S["x_dev"], S["y_dev"])
+            steps = 2
+            ops.reset_launch_count()
+            ms, loss = _pf_timed(S, 1, dev, steps, e2e=False)
+            val = B * S["n"] * steps / (ms / 1e3)
+            return {"dtype": X3_DTYPE + "; attention kernels in fp32 on CUDA cores", "value": val, "unit": PF_UNIT,
+                    "ms_per_step": ms / steps, "batch": B, "steps": steps, "loss": loss,
+                    "gpu_launches": int(ops.launch_count()),
+                    "tolerance": "1e-4 against the fp32 oracle (north_star): tests/test_gpu_x3.py",
+                    "vs_bf16_arm": val / bf16_value, "hbm_peak_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        except torch.OutOfMemoryError:
+            B //= 2
+        except Exception as e:      # noqa: BLE001
+            return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+        finally:
+            if S is not None:
+                S.clear()
+            ops._X3_WS.clear()
+            torch.cuda.empty_cache()
+    return {"unavailable": "out of memory at batch 1"}
+
+
+def vq_kernel_arm(dev):
+    """BASELINE.json configs[2] / SURVEY.md 8(d) config 3: the fused quantiser kernel alone, 10x14x10x32 latents of a
+    batch of 8 (11 200 rows) against the 2048 x 32 codebook.  Latency-bound (1.4 MB in): reported as microseconds per
+    launch and algorithmic GB/s, not as a roofline fraction.  Inputs are L2-resident, as in the training step (the
+    encoder's last conv has just written them)."""
+    import torch
+    from synthanatomy_b200 import ops
+    rows, dim, K = 8 * 10 * 14 * 10, 32, 2048
+    z = torch.randn(8, 32, 10, 14, 10, generator=torch.Generator().manual_seed(0))
+    flat = z.permute(0, 2, 3, 4, 1).reshape(rows, dim).contiguous().to(dev)
+    cb = torch.randn(K, dim, generator=torch.Generator().manual_seed(1)).to(dev)
+    stats = torch.zeros(K + K * dim + 1, device=dev)
+    for _ in range(5):
+        ops.vq_forward(flat, cb, stats, True)
+    torch.cuda.synchronize()
+    n = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        ops.vq_forward(flat, cb, stats, True)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n
+    # z in + codebook in + idx (int64) + q out + the statistics buffer read-modify-written
+    by = rows * dim * 4 + K * dim * 4 + rows * 8 + rows * dim * 4 + 2 * (K + K * dim + 1) * 4
+    return {"kernel": "vq_forward_kernel (distance + argmin + gather + STE + histogram + per-code sums + SSE)",
+            "rows": rows, "codebook": [K, dim], "us_per_launch": us, "algorithmic_bytes": by,
+            "achieved_gbs": by / (us * 1e-6) / 1e9, "flop": 2.0 * rows * K * dim,
+            "achieved_gflops": 2.0 * rows * K * dim / (us * 1e-6) / 1e9,
+            "note": "back-to-back launches incl. launch overhead; includes the allocation of idx / q by the wrapper"}
+
+
+def vendor_vqvae(args, value):
+    """The vendor-library comparator: the reference's layer list as stock nn.Conv3d / nn.ConvTranspose3d
+    under bf16 autocast, channels_last_3d, cudnn.benchmark = True, torch.optim.Adam -- cuDNN 9 / cuBLAS sm_100 kernels."""
+    import torch
+    from tools import vendor_baseline as vb
+    kw = dict(n_levels=4, n_embed=2048, embed_dim=32, n_channels=256, n_res_layers=3)
+    try:
+        r = vb.time_vendor_vqvae(args.batch, tuple(args.vol), max(2, min(args.steps, 5)), 2, torch.bfloat16, kw)
+    except Exception as e:      # noqa: BLE001  -- a comparator failure must not take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+    r.update({"unit": UNIT, "kind": "torch nn.Conv3d / ConvTranspose3d stack (cuDNN, cudnn.benchmark=True, bf16 autocast, "
+                                    "channels_last_3d) + torch.optim.Adam, same layer list and batch unless it did not fit",
+              "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()})
+    if "value" in r:
+        r["vs_vendor"] = value / r["value"]
+    return r
 
 
 # ------------------------------------------------------------------------------------------------
@@ -377,30 +569,29 @@ def performer_reference(args):
     return {"impl": "reference", "metric": PF_METRIC, "value": cb["value"], "unit": PF_UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Performer dim512 L24 h16 (8 local, w420) m266 vocab2049 (CPU sample, see cpu_baseline)"},
+            "config": pf_config(tuple(args.pf_grid), args.pf_batch, args.pf_depth, args.gpus),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": PF_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
 
 
-def performer_b200(args, world, rank, local, dev):
+def _pf_setup(args, grid, world, rank, local, dev, compute_dtype, batch=None):
+    """model + optimiser + one synthetic batch (device-resident and as pinned host uint16 grid) + the step closure"""
     import numpy as np
     import torch
-    import torch.distributed as dist
-    from synthanatomy_b200 import ops, pf_ops
     from synthanatomy_b200.losses import CELoss
     from synthanatomy_b200.networks.transformers import Ordering, Performer
     from synthanatomy_b200.optim import Adam
+    from synthanatomy_b200.utils import tokens as tk
     from synthanatomy_b200.utils.transformer import prepare_batch
 
-    grid = tuple(args.pf_grid)
     n = int(np.prod(grid))
-    B = args.pf_batch
+    B = batch or args.pf_batch
     torch.manual_seed(4)
     order = Ordering("raster_scan", 3, (1, *grid), (False,) * 3, ((2, 0, 1),), ((0, 1),), ("rotate_90", "transpose"))
     net = Performer(max_seq_len=n + 1, depth=args.pf_depth, ordering=order, causal=True, feature_redraw_interval=1,
                     generalized_attention=False, use_rezero=True, spatial_position_emb="absolute", spatial_shape=grid,
-                    compute_dtype=torch.bfloat16, **PF_KW).to(dev).train()
+                    compute_dtype=compute_dtype, **PF_KW).to(dev).train()
     model = net
     if world > 1:
         # the reference wraps with broadcast_buffers=True so that every rank sees rank 0's projection matrices
@@ -412,11 +603,8 @@ def performer_b200(args, world, rank, local, dev):
     quant = torch.randint(0, 2048, (B, *grid), generator=g)
     seq = order.get_sequence_ordering()
     (x_host, _), y_host = prepare_batch({"quantization": quant}, seq, 2048)
-    x_host, y_host = x_host.contiguous().pin_memory(), y_host.contiguous().pin_memory()
-    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    x_dev, y_dev = x_host.contiguous().to(dev), y_host.contiguous().to(dev)
     # end-to-end leg: the token grid crosses PCIe as stored on disk (uint16) and one gather kernel forms both sequences
-    from synthanatomy_b200.utils import tokens as tk
     dev_order = tk.DeviceOrdering(order, dev)
     quant_host = torch.from_numpy(quant.numpy().astype(np.uint16)).pin_memory()
 
@@ -428,101 +616,163 @@ def performer_b200(args, world, rank, local, dev):
         opt.zero_grad(set_to_none=True)
         return loss
 
+    def e2e_batch():
+        (x, _), y = tk.prepare_batch_device({"quantization": quant_host}, dev_order, 2048)
+        return x, y
+
+    return dict(n=n, B=B, net=net, model=model, opt=opt, step=step, x_dev=x_dev, y_dev=y_dev, e2e_batch=e2e_batch,
+                h2d_bytes=quant_host.numel() * 2)
+
+
+def _pf_timed(S, world, dev, nsteps, e2e):
+    import torch
+    import torch.distributed as dist
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, e2e):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(nsteps):
-            if e2e:
-                (x, _), y = tk.prepare_batch_device({"quantization": quant_host}, dev_order, 2048)
-                loss = step(x, y)
-                loss_host.copy_(loss.detach(), non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-            else:
-                loss = step(x_dev, y_dev)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, float(loss.detach().item())
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(nsteps):
+        if e2e:
+            x, y = S["e2e_batch"]()
+            loss = S["step"](x, y)
+            loss_host.copy_(loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            loss = S["step"](S["x_dev"], S["y_dev"])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, float(loss.detach().item())
 
+
+def performer_b200(args, world, rank, local, dev):
+    import torch
+    from synthanatomy_b200 import ops, pf_ops
+
+    grid = tuple(args.pf_grid)
+    S = _pf_setup(args, grid, world, rank, local, dev, torch.bfloat16)
+    n, B = S["n"], S["B"]
     for _ in range(args.warmup):
-        step(x_dev, y_dev)
+        S["step"](S["x_dev"], S["y_dev"])
     timer = pf_ops.KernelTimer(lambda name: name == "gemm_nt")
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     ops.reset_launch_count()
     pf_ops.set_timer(timer)
-    ms, loss = timed(args.steps, e2e=False)
+    ms, loss = _pf_timed(S, world, dev, args.steps, e2e=False)
     pf_ops.set_timer(None)
     launches = ops.launch_count()
     clk = clocks.stop() if rank == 0 else None
-    ms_e2e, _ = (ms, None) if args.no_e2e else timed(args.steps, e2e=True)
+    ms_e2e, _ = (ms, None) if args.no_e2e else _pf_timed(S, world, dev, args.steps, e2e=True)
     breakdown = None
     if args.pf_breakdown and rank == 0:
         t_all = pf_ops.KernelTimer()
         pf_ops.set_timer(t_all)
-        step(x_dev, y_dev)
+        S["step"](S["x_dev"], S["y_dev"])
         torch.cuda.synchronize()
         pf_ops.set_timer(None)
         breakdown = {k: {"ms": round(v["ms"], 3), "launches": v["launches"]} for k, v in
                      sorted(t_all.summary().items(), key=lambda kv: -kv[1]["ms"])}
-    del model, net, opt
+    h2d = S["h2d_bytes"]
+    hbm_peak = torch.cuda.max_memory_allocated() / 2 ** 30
+    S.clear()
     torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
     if rank != 0:
         return None
     toks = B * n * world * args.steps
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
     summ = timer.summary().get("gemm_nt")
     roof = None
     if summ:
         ach = summ["flop"] / (summ["ms"] * 1e-3) / 1e12
+        traffic, traffic_src = measured_traffic("tc_gemm_nt_kernel")
+        if not (grid == (20, 28, 25) and B == 6):
+            traffic, traffic_src = None, "the committed capture is of the batch-6 N = 14 000 launches"
         roof = {"bound": "tensor", "kernel": "tc_gemm_nt_kernel (all dense-layer forward / data-gradient launches)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                # dram read + write per launch, mean over the 8 launches of one layer + the output head in the committed
-                # `ncu --set full` capture; algorithmic = bf16 operands once + the outputs of the fused epilogue
-                "traffic": 7.243e8 if (grid == (20, 28, 25) and B == 6) else None,
-                "traffic_source": "profiles/r1_performer_ncu_gemm.txt (ncu, same kernel and shapes; not measured in this run)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                # operands read once + every epilogue tensor the launch names read / written once, mean over launches
+                "algorithmic_bytes_per_launch": summ["bytes"] / summ["launches"],
                 "launches_timed": summ["launches"], "avg_ms": summ["ms"] / summ["launches"],
                 "flop_per_launch": summ["flop"] / summ["launches"], "share_of_step": summ["ms"] / ms,
                 "peak_source": peak_src}
-    full = grid == (20, 28, 25) and args.pf_depth == 24 and B == 6
     step_flop = pf_flop_per_token(args.pf_depth, n) * B * n
+    value = toks / (ms / 1e3)
     out = {
-        "metric": PF_METRIC, "value": toks / (ms / 1e3), "unit": PF_UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": PF_METRIC, "value": value, "unit": PF_UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"Performer dim512 L{args.pf_depth} h16 (8 local, w420) m266 vocab2049, grid "
-                               f"{grid[0]}x{grid[1]}x{grid[2]} = {n} tokens, batch {B}/GPU, fwd+CE+bwd+Adam, feature "
-                               f"redraw every 2nd step" + ("" if full else " (REDUCED: not the headline)"),
-                   "parallelism": f"dp{world}", "global_batch": B * world,
-                   "l2_policy": "per-layer activations (>= 86 MB each, 2.6 GB per layer) exceed the 126 MB L2; no flush needed"},
+        "config": pf_config(grid, B, args.pf_depth, world),
         "step_tflops": step_flop / (ms / args.steps * 1e-3) / 1e12,
         "loss": loss, "clocks": clk,
-        "e2e": {"value": toks / (ms_e2e / 1e3), "unit": PF_UNIT, "h2d_bytes_per_step": quant_host.numel() * 2,
+        "e2e": {"value": toks / (ms_e2e / 1e3), "unit": PF_UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "roofline": roof,
+        "gpu_launches": int(launches), "roofline": roof, "hbm_peak_gb": hbm_peak,
     }
     if breakdown:
         out["breakdown_ms"] = breakdown
+    if world == 1 and not args.no_extra and grid != (10, 14, 10):
+        out["n1400"] = performer_n1400(args, dev)
+    if world == 1 and not args.no_parity:
+        out["parity_arm"] = pf_parity_arm(args, dev, value)
+    if world == 1 and not args.no_vendor:
+        out["vendor_baseline"] = vendor_performer(args, value)
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = pf_cpu_baseline(depth=args.pf_depth)
         out["cpu_baseline"] = cb
+    return out
+
+
+def performer_n1400(args, dev):
+    """SURVEY.md 8(a) note / 8(d) config 4, second size: the README-faithful latent grid 10 x 14 x 10 = 1400 tokens (local
+    attention pads to 1680), same network and batch, device-resident inputs"""
+    import torch
+    grid = (10, 14, 10)
+    S = _pf_setup(args, grid, 1, 0, 0, dev, torch.bfloat16)
+    for _ in range(max(3, args.warmup)):
+        S["step"](S["x_dev"], S["y_dev"])
+    steps = max(args.steps, 5)
+    ms, loss = _pf_timed(S, 1, dev, steps, e2e=False)
+    n, B = S["n"], S["B"]
+    S.clear()
+    torch.cuda.empty_cache()
+    return {"value": B * n * steps / (ms / 1e3), "unit": PF_UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "config": pf_config(grid, B, args.pf_depth, 1), "loss": loss,
+            "step_tflops": pf_flop_per_token(args.pf_depth, n) * B * n / (ms / steps * 1e-3) / 1e12,
+            "l2_note": "per-layer activations at this size (8.6 MB per [8400 x 512] bf16 tensor) fit the 126 MB L2 and "
+                       "stay there between consecutive kernels, exactly as they do in training; no flush"}
+
+
+def vendor_performer(args, value):
+    """The vendor-library comparator: the same layer stack in stock torch ops (cuBLAS TF32 matmuls on fp32 storage, the
+    reference's effective mode -- run_transformer.py:165 amp=False on an NGC image with TF32 on -- and bf16 autocast)."""
+    import torch
+    from tools import vendor_baseline as vb
+    out = {"unit": PF_UNIT, "kind": "stock torch ops (F.linear / einsum / softmax -> cuBLAS, ATen), torch.optim.Adam; the "
+                                    "causal numerator as chunked einsums (the fast-transformers CUDA extension is absent); "
+                                    "batch halves until autograd's saved feature / score tensors fit",
+           "torch": torch.__version__}
+    for name, dt in (("tf32", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            out[name] = vb.time_vendor_performer(args.pf_batch, tuple(args.pf_grid), args.pf_depth, 2, 1, dt, PF_KW)
+        except Exception as e:      # noqa: BLE001
+            out[name] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+        if "value" in out[name]:
+            out[name]["vs_vendor"] = value / out[name]["value"]
     return out
 
 

@@ -85,6 +85,24 @@ int sa_conv3d_fwd(const sa_conv_desc* d, const void* x, const void* wp, const fl
 int sa_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void* q, float* dwp, int accumulate,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * bf16x3 "parity" arithmetic of the two entry points above: fp32 tensors in and out, products on the bf16 tensor cores
+ * with each fp32 operand split into hi + lo bf16 parts (x ~= hi + lo to 16 significand bits) and the three cross terms
+ * hi.hi + lo.hi + hi.lo evaluated as ONE contraction three times as long (input channels concatenated for the forward /
+ * data-gradient form, the batch concatenated for the weight gradient), fp32 accumulation.  Error ~1e-5 of the operand
+ * scale: this is the tensor-core path that meets the reference's fp32 results to 1e-4 (the reference itself runs these
+ * convs in fp16 autocast or TF32).  x / y / addend / mask / p / q are fp32 NDHWC, wp is the PACKED fp32 weight
+ * (sa_pack_weight with dst_dtype SA_F32), d->act_dtype must be SA_F32.  `workspace`: sa_conv3d_x3_workspace(d, wgrad)
+ * bytes, 256-byte aligned.  sa_conv3d_x3_supported tells whether the tensor-core kernels take the shape (otherwise the
+ * caller uses sa_conv3d_fwd / sa_conv3d_wgrad with SA_F32, the CUDA-core fp32 kernels).
+ * ---------------------------------------------------------------------------------------------- */
+int sa_conv3d_x3_supported(const sa_conv_desc* d, int wgrad);
+size_t sa_conv3d_x3_workspace(const sa_conv_desc* d, int wgrad);
+int sa_conv3d_fwd_x3(const sa_conv_desc* d, const float* x, const float* wp, const float* bias, const float* addend,
+                     const float* mask, int relu, float* y, void* workspace, size_t ws_bytes, void* stream);
+int sa_conv3d_wgrad_x3(const sa_conv_desc* d, const float* p, const float* q, float* dwp, int accumulate,
+                       void* workspace, size_t ws_bytes, void* stream);
+
 /* Fused backward of the pointwise (1x1x1, 128 -> 128 channels) convolution of a ResidualLayer
  * (/root/reference/src/networks/vqvae/baseline.py:153-160: y = relu(x + conv1x1(h)), h = relu(conv3x3x3(x))).
  * g [m][c_out] = gradient w.r.t. the pre-activation of y, h [m][c_in] the saved activation (bf16, NDHWC flattened to

@@ -63,6 +63,19 @@ int sa_gemm_nt(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, c
 int sa_gemm_tn(int64_t m, int na, int nb, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
                const float* scale_dev, float scale, float* d, int accumulate, void* stream);
 
+/* bf16x3 "parity" arithmetic of the two dense entry points (see sa_conv3d_fwd_x3 in synthanatomy_b200.h): fp32 operands
+ * and fp32 epilogue tensors (every `void*` of the epilogue is fp32 here), products on the bf16 tensor cores as
+ * hi.hi + lo.hi + hi.lo with fp32 accumulation.  The reference runs these layers in fp32 storage with TF32 matmuls
+ * (run_transformer.py:165 amp=False); this path is closer to fp32 than TF32 is.  `workspace`: 256-byte aligned,
+ * sa_gemm_nt_x3_workspace / sa_gemm_tn_x3_workspace bytes. */
+size_t sa_gemm_nt_x3_workspace(int64_t m, int n, int k);
+int sa_gemm_nt_x3(int64_t m, int n, int k, const float* a, int64_t lda, const float* b, int64_t ldb,
+                  const sa_gemm_epilogue* epi, int64_t ldo, void* workspace, size_t ws_bytes, void* stream);
+size_t sa_gemm_tn_x3_workspace(int64_t m, int na, int nb);
+int sa_gemm_tn_x3(int64_t m, int na, int nb, const float* a, int64_t lda, const float* b, int64_t ldb,
+                  const float* scale_dev, float scale, float* d, int accumulate, void* workspace, size_t ws_bytes,
+                  void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Embedding front end, performer.py:241-268 (conditioning off, dropout 0):
  *   x[b][n] = tok_w[tokens[b][n]] + sum_a (sp_idx[a][n] >= 0 ? sp_w[a][sp_idx[a][n]] : 0) + pos_w[n]

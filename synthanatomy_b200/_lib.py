@@ -108,7 +108,18 @@ SIGNATURES = {
                              c_void_p]),
     "sa_adam_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
                               c_int, c_void_p]),
+    "sa_conv3d_x3_supported": (c_int, [C.POINTER(ConvDesc), c_int]),
+    "sa_conv3d_x3_workspace": (C.c_size_t, [C.POINTER(ConvDesc), c_int]),
+    "sa_conv3d_fwd_x3": (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_void_p, C.c_size_t, c_void_p]),
+    "sa_conv3d_wgrad_x3": (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p, C.c_size_t, c_void_p]),
     # ---- Performer path (include/synthanatomy_b200_performer.h)
+    "sa_gemm_nt_x3_workspace": (C.c_size_t, [c_int64, c_int, c_int]),
+    "sa_gemm_nt_x3": (c_int, [c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, C.POINTER(GemmEpilogue), c_int64,
+                              c_void_p, C.c_size_t, c_void_p]),
+    "sa_gemm_tn_x3_workspace": (C.c_size_t, [c_int64, c_int, c_int]),
+    "sa_gemm_tn_x3": (c_int, [c_int64, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_float, c_void_p,
+                              c_int, c_void_p, C.c_size_t, c_void_p]),
     "sa_gemm_nt": (c_int, [c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, C.POINTER(GemmEpilogue),
                            c_int64, c_void_p]),
     "sa_gemm_tn": (c_int, [c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_float, c_void_p,

@@ -49,11 +49,15 @@ struct C3Params {
   int oD, oH, oW, os, oqd, oqh, oqw;                   // output position = g * os + oq
   int relu;
   const float* bias;
-  const __nv_bfloat16* addend;
-  const __nv_bfloat16* mask;
-  __nv_bfloat16* y;
+  const void* addend;          // OutT
+  const void* mask;            // OutT
+  void* y;                     // OutT
 };
 
+// OutT = __nv_bfloat16: the bf16 training path.  OutT = float: the bf16x3 "parity" path (sa_x3.cu) -- the operands are
+// hi / lo bf16 splits of fp32 tensors concatenated along the channel axis, the accumulator (= the fp32-class result)
+// leaves as fp32 and the epilogue tensors are fp32.
+template <typename OutT>
 __global__ void __launch_bounds__(C3_THREADS, 1)
 tc_conv3_kernel(const __grid_constant__ C3Params P) {
   extern __shared__ uint8_t smem_raw[];
@@ -177,8 +181,43 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
               }
             }
           }
+          if constexpr (sizeof(OutT) == 4) {
+            // ---- fp32 epilogue tensors (bf16x3 path)
+            if (P.addend) {
+              const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.addend) + obase + c0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (q * 4 < nc) {
+                  const float4 u = __ldg(ap + q);
+                  f[q * 4 + 0] += u.x; f[q * 4 + 1] += u.y; f[q * 4 + 2] += u.z; f[q * 4 + 3] += u.w;
+                }
+              }
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (P.mask) {
+              const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.mask) + obase + c0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (q * 4 < nc) {
+                  const float4 u = __ldg(mp + q);
+                  if (!(u.x > 0.f)) f[q * 4 + 0] = 0.f;
+                  if (!(u.y > 0.f)) f[q * 4 + 1] = 0.f;
+                  if (!(u.z > 0.f)) f[q * 4 + 2] = 0.f;
+                  if (!(u.w > 0.f)) f[q * 4 + 3] = 0.f;
+                }
+              }
+            }
+            float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(P.y) + obase + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (q * 4 < nc) yp[q] = make_float4(f[q * 4 + 0], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+            }
+          } else {
           if (P.addend) {
-            const uint4* ap = reinterpret_cast<const uint4*>(P.addend + obase + c0);
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(P.addend) + obase + c0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (q * 8 < nc) {
@@ -195,7 +234,7 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           if (P.mask) {
-            const uint4* mp = reinterpret_cast<const uint4*>(P.mask + obase + c0);
+            const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(P.mask) + obase + c0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (q * 8 < nc) {
@@ -209,7 +248,7 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
               }
             }
           }
-          uint4* yp = reinterpret_cast<uint4*>(P.y + obase + c0);
+          uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(P.y) + obase + c0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             if (q * 8 < nc) {
@@ -220,6 +259,7 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
               u.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
               yp[q] = u;
             }
+          }
           }
         }
       }
@@ -253,7 +293,7 @@ int c3_act_map(CUtensorMap* m, const void* base, int C, int D, int H, int W, int
   return sa_make_tmap_bf16(m, p, 5, dims, strides, box);
 }
 
-int c3_launch(C3Params& P, int batch, cudaStream_t st) {
+int c3_launch(C3Params& P, int batch, bool out_f32, cudaStream_t st) {
   P.ntd = (int)sa_cdiv(P.gD, C3_TD); P.nth = (int)sa_cdiv(P.gH, C3_TH); P.ntw = (int)sa_cdiv(P.gW, C3_TW);
   P.batch = batch;
   const int64_t total = (int64_t)P.ntd * P.nth * P.ntw * batch;
@@ -267,7 +307,8 @@ int c3_launch(C3Params& P, int batch, cudaStream_t st) {
   P.stages = stages;
   const size_t smem = stages * stage_bytes + 1024;
   const unsigned grid = (unsigned)(P.total_tiles < g_c3_sms ? P.total_tiles : g_c3_sms);
-  tc_conv3_kernel<<<grid, C3_THREADS, smem, st>>>(P);
+  if (out_f32) tc_conv3_kernel<float><<<grid, C3_THREADS, smem, st>>>(P);
+  else tc_conv3_kernel<__nv_bfloat16><<<grid, C3_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -299,13 +340,23 @@ bool sa_tc_conv3_supported(const sa_conv_desc* d) {
   return false;
 }
 
+int sa_tc_conv3_fwd_ex(const sa_conv_desc* d, const void* x, const void* wp, const float* bias, const void* addend,
+                       const void* mask, int relu, void* y, bool out_f32, cudaStream_t st);
+
 int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const float* bias, const void* addend,
                     const void* mask, int relu, void* y, cudaStream_t st) {
+  return sa_tc_conv3_fwd_ex(d, x, wp, bias, addend, mask, relu, y, false, st);
+}
+
+// out_f32: y / addend / mask are fp32 tensors (x and wp stay bf16): the bf16x3 path of sa_x3.cu
+int sa_tc_conv3_fwd_ex(const sa_conv_desc* d, const void* x, const void* wp, const float* bias, const void* addend,
+                       const void* mask, int relu, void* y, bool out_f32, cudaStream_t st) {
   std::call_once(g_c3_once, [] {
     int dev = 0, v = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) g_c3_sms = v;
-    cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    cudaFuncSetAttribute(tc_conv3_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    cudaFuncSetAttribute(tc_conv3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   });
   sa_note_path(SA_PATH_TCGEN05);
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) { sa_set_error("tc_conv3: bias not 16-byte aligned"); return SA_ERR_INVALID; }
@@ -316,7 +367,7 @@ int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const 
   P.cchunks = d->c_in / 64;
   P.oD = d->out_dhw[0]; P.oH = d->out_dhw[1]; P.oW = d->out_dhw[2];
   P.relu = relu; P.bias = bias;
-  P.addend = (const __nv_bfloat16*)addend; P.mask = (const __nv_bfloat16*)mask; P.y = (__nv_bfloat16*)y;
+  P.addend = addend; P.mask = mask; P.y = y;
   {
     const uint64_t dims[2] = {(uint64_t)d->c_in, (uint64_t)taps * d->c_out};
     const uint64_t strides[2] = {2, (uint64_t)d->c_in * 2};
@@ -341,7 +392,7 @@ int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const 
           g.wrow[dd] = (d->transposed ? taps - 1 - t : t) * d->c_out;    // flipped taps: transposed form
         }
       }
-    return c3_launch(P, d->batch, st);
+    return c3_launch(P, d->batch, out_f32, st);
   }
   // ---- 4/2/1: per dimension tap t <-> (parity view, offset):  0: (odd, -1)  1: (even, 0)  2: (odd, 0)  3: (even, +1)
   auto par = [](int t) { return (t & 1) ? 0 : 1; };
@@ -367,7 +418,7 @@ int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const 
           g.wrow[2] = 0;
         }
     P.ngroups = gi;
-    return c3_launch(P, d->batch, st);
+    return c3_launch(P, d->batch, out_f32, st);
   }
   // transposed 4/2/1: output parity phase q -> two taps per dim:  q=0: (t=3, off -1), (t=1, off 0)   q=1: (t=2, off 0), (t=0, off +1)
   P.gD = iD; P.gH = iH; P.gW = iW;
@@ -387,7 +438,7 @@ int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const 
         g.wrow[dd] = ((tap_of[qd][dd] * 4 + tap_of[qh][jh]) * 4 + tap_of[qw][jw]) * d->c_out;
       g.wrow[2] = 0;
     }
-    if ((rc = c3_launch(P, d->batch, st)) != SA_OK) return rc;
+    if ((rc = c3_launch(P, d->batch, out_f32, st)) != SA_OK) return rc;
   }
   return SA_OK;
 }

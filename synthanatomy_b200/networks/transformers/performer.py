@@ -8,8 +8,11 @@ Same keyword-only constructor, same module tree (=> same ``state_dict`` keys), s
 one hand-scheduled forward / backward programme over the C ABI in ``include/synthanatomy_b200_performer.h``.
 
 Precision: ``compute_dtype=None`` follows the caller like the reference (fp32 normally = CUDA-core fp32 "parity"
-path; bf16 operands + fp32 accumulation on tcgen05 under ``torch.autocast``).  The residual stream, LayerNorm
-statistics, softmax / feature-map statistics, logits and all gradients of parameters are fp32 in both modes.
+path; bf16 operands + fp32 accumulation on tcgen05 under ``torch.autocast``).  ``compute_dtype=ops.BF16X3`` keeps fp32
+tensors and runs every dense layer (75 % of the FLOPs) on the bf16 tensor cores as hi.hi + lo.hi + hi.lo of split
+operands (csrc/sa_x3.cu; the attention kernels stay on the exact fp32 CUDA-core path): the reference's own precision
+class (fp32 storage, TF32-or-better products; run_transformer.py:165 amp=False).  The residual stream, LayerNorm
+statistics, softmax / feature-map statistics, logits and all gradients of parameters are fp32 in every mode.
 """
 from __future__ import annotations
 
@@ -325,6 +328,13 @@ class _PerformerFn(torch.autograd.Function):
     def forward(ctx, tokens, net, dt, return_encodings, *params):
         if not tokens.is_cuda:
             raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
+        dt, x3 = ops.resolve_dtype(dt)       # BF16X3: fp32 tensors, dense layers as split-bf16 tensor-core products
+        ctx.x3 = x3
+        with ops.x3_mode(x3):
+            return _PerformerFn._forward(ctx, tokens, net, dt, return_encodings, *params)
+
+    @staticmethod
+    def _forward(ctx, tokens, net, dt, return_encodings, *params):
         dev = tokens.device
         B, N = tokens.shape
         D = _Dims(net, B, N, dt)
@@ -429,6 +439,11 @@ class _PerformerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        with ops.x3_mode(ctx.x3):
+            return _PerformerFn._backward(ctx, gout)
+
+    @staticmethod
+    def _backward(ctx, gout):
         D, net, p = ctx.D, ctx.net, ctx.p
         dt, M, B, N = D.dt, D.M, D.B, D.N
         f32 = torch.float32
@@ -713,7 +728,7 @@ class Performer(TransformerBase):
         conditioning_num_tokens: Optional[Tuple[int, ...]] = None,
         conditioning_type: str = _NONE,
         # ---- extensions (not in the reference signature)
-        compute_dtype: Optional[torch.dtype] = None,
+        compute_dtype: Union[torch.dtype, str, None] = None,
         local_rel_pos: str = "rotary",
     ):
         super().__init__()
@@ -803,7 +818,7 @@ class Performer(TransformerBase):
 
     def make_decoder(self, batch: int, max_len: int) -> _Decoder:
         """recurrent-state evaluator for sampling: ``decoder.step(tokens_t, t) -> logits [batch, num_tokens]``"""
-        return _Decoder(self, batch, max_len, self._dtype())
+        return _Decoder(self, batch, max_len, ops.resolve_dtype(self._dtype())[0])
 
     @torch.no_grad()
     def sample(self, prefix: torch.Tensor, conditioning: torch.Tensor = None, temperature: float = 1.0,

@@ -9,7 +9,9 @@ dgrad epilogues), the quantiser is one fused kernel.
 
 Precision: ``compute_dtype=None`` (default) follows the caller like the reference does -- fp32 activations
 normally ("parity" path, CUDA-core fp32 FMA), bf16 activations + fp32 accumulation on tcgen05 tensor cores
-when called under ``torch.autocast`` (the reference trains with ``--amp=True``, README.md:52).  The quantiser
+when called under ``torch.autocast`` (the reference trains with ``--amp=True``, README.md:52).
+``compute_dtype=ops.BF16X3`` is the tensor-core parity mode: fp32 activations, every product on the bf16 tensor
+cores as hi.hi + lo.hi + hi.lo of split operands (csrc/sa_x3.cu), 1e-4 against the reference in fp32.  The quantiser
 is always fp32 (baseline.py:38,43).
 """
 from __future__ import annotations
@@ -232,15 +234,18 @@ class _StackFn(torch.autograd.Function):
         if not x.is_cuda:
             raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
         need_grad = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward)
+        compute_dtype, x3 = ops.resolve_dtype(compute_dtype)     # BF16X3: fp32 tensors, split-bf16 tensor-core products
         xin = ops.ncdhw_to_ndhwc(x.detach().float().contiguous(), compute_dtype)
         pdet = [p.detach().float().contiguous() for p in params]
-        y, saved = _stack_forward(ops_list, xin, pdet, need_grad)
+        with ops.x3_mode(x3):
+            y, saved = _stack_forward(ops_list, xin, pdet, need_grad)
         out = ops.ndhwc_to_ncdhw(y, torch.float32)
         if need_grad:
             ctx.ops_list = ops_list
             ctx.saved = saved
             ctx.pdet = pdet
             ctx.compute_dtype = compute_dtype
+            ctx.x3 = x3
             ctx.need_dx = x.requires_grad
         return out
 
@@ -250,7 +255,8 @@ class _StackFn(torch.autograd.Function):
         if ctx.saved is None:
             raise RuntimeError("B200VQVAE: second backward through a stack whose activations were released; wrap the "
                                "iteration in synthanatomy_b200.networks.vqvae.b200.retain_activations()")
-        dx, grads = _stack_backward(ctx.ops_list, ctx.saved, ctx.pdet, g, False, ctx.need_dx)
+        with ops.x3_mode(ctx.x3):
+            dx, grads = _stack_backward(ctx.ops_list, ctx.saved, ctx.pdet, g, False, ctx.need_dx)
         if not _RETAIN_ACTIVATIONS[0]:
             ctx.saved = None
         gx = ops.ndhwc_to_ncdhw(dx, torch.float32) if dx is not None else None
@@ -377,7 +383,7 @@ class B200VQVAE(VQVAEBase, nn.Module):
         commitment_cost: float = 0.25,
         vq_decay: float = 0.5,
         use_subpixel_conv: bool = False,
-        compute_dtype: Optional[torch.dtype] = None,
+        compute_dtype: Union[torch.dtype, str, None] = None,
     ):
         super().__init__()
         assert n_levels == len(downsample_parameters) and n_levels == len(upsample_parameters), (

@@ -64,6 +64,54 @@ def set_force_simt(on: bool) -> None:
 
 
 # ------------------------------------------------------------------------------------------------
+# bf16x3 "parity" arithmetic (csrc/sa_x3.cu): fp32 tensors, products on the bf16 tensor cores as hi.hi + lo.hi + hi.lo.
+# `compute_dtype=BF16X3` on the two networks selects it; while the mode is on, every fp32 conv / dense call whose shape
+# the tcgen05 kernels take goes through the *_x3 entry points (the rest stays on the CUDA-core fp32 kernels).
+# ------------------------------------------------------------------------------------------------
+BF16X3 = "bf16x3"
+_X3 = [False]
+_X3_WS = {}
+
+
+class x3_mode:
+    def __init__(self, on: bool):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = _X3[0]
+        _X3[0] = self.on
+        return self
+
+    def __exit__(self, *exc):
+        _X3[0] = self.prev
+        return False
+
+
+def x3_enabled() -> bool:
+    return _X3[0] and not _FORCE_SIMT
+
+
+def x3_workspace(nbytes: int, device) -> torch.Tensor:
+    """grow-only scratch buffer for the split operands (all launches are on one stream, so one buffer is enough)"""
+    key = device.index
+    buf = _X3_WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _X3_WS.pop(key, None)
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _X3_WS[key] = buf
+    return buf
+
+
+def resolve_dtype(compute_dtype):
+    """(tensor dtype, x3 flag) of a `compute_dtype` argument (a torch dtype or BF16X3)"""
+    if isinstance(compute_dtype, str):
+        if compute_dtype != BF16X3:
+            raise ValueError(f"compute_dtype must be a torch dtype or {BF16X3!r}, got {compute_dtype!r}")
+        return torch.float32, True
+    return compute_dtype, False
+
+
+# ------------------------------------------------------------------------------------------------
 # conv geometry
 # ------------------------------------------------------------------------------------------------
 @dataclass(frozen=True)
@@ -142,8 +190,14 @@ def _run_fwd(d: ConvDesc, x, wp, bias, addend, mask, relu, out_shape):
     if timed:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(lib().sa_conv3d_fwd(C.byref(d), _p(x), _p(wp), _p(bias), _p(addend), _p(mask), int(relu), _p(y),
-                                   _stream()), "sa_conv3d_fwd")
+    if x3_enabled() and x.dtype == torch.float32 and lib().sa_conv3d_x3_supported(C.byref(d), 0):
+        nb = int(lib().sa_conv3d_x3_workspace(C.byref(d), 0))
+        ws = x3_workspace(nb, x.device)
+        _lib.check(lib().sa_conv3d_fwd_x3(C.byref(d), _p(x), _p(wp), _p(bias), _p(addend), _p(mask), int(relu), _p(y),
+                                          _p(ws), nb, _stream()), "sa_conv3d_fwd_x3")
+    else:
+        _lib.check(lib().sa_conv3d_fwd(C.byref(d), _p(x), _p(wp), _p(bias), _p(addend), _p(mask), int(relu), _p(y),
+                                       _stream()), "sa_conv3d_fwd")
     if timed:
         e1.record()
         _TIMER.events.append((e0, e1))
@@ -185,7 +239,13 @@ def conv_wgrad(spec: ConvSpec, x: torch.Tensor, dy: torch.Tensor, weight_like: t
         d = _desc(B, out_dhw, in_dhw, spec.cout, spec.cin, spec.k, spec.s, spec.p, 0, x.dtype)
         pp, qq = x, dy
     dwp = torch.empty((taps, d.c_out, d.c_in), device=x.device, dtype=torch.float32)
-    _lib.check(lib().sa_conv3d_wgrad(C.byref(d), _p(pp), _p(qq), _p(dwp), 0, _stream()), "sa_conv3d_wgrad")
+    if x3_enabled() and x.dtype == torch.float32 and lib().sa_conv3d_x3_supported(C.byref(d), 1):
+        nb = int(lib().sa_conv3d_x3_workspace(C.byref(d), 1))
+        ws = x3_workspace(nb, x.device)
+        _lib.check(lib().sa_conv3d_wgrad_x3(C.byref(d), _p(pp), _p(qq), _p(dwp), 0, _p(ws), nb, _stream()),
+                   "sa_conv3d_wgrad_x3")
+    else:
+        _lib.check(lib().sa_conv3d_wgrad(C.byref(d), _p(pp), _p(qq), _p(dwp), 0, _stream()), "sa_conv3d_wgrad")
     return unpack_wgrad(dwp, weight_like, transpose=False)
 
 

@@ -11,6 +11,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
+from . import ops as _ops
 from ._lib import FavorDesc, GemmEpilogue, LocalDesc, SA_ACT_GELU_BWD, SA_ACT_GELU_FWD, SA_ACT_NONE  # noqa: F401
 from .ops import _dt, _p, _stream, lib
 
@@ -55,6 +56,13 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, bias=None, dot_with=None, dot_o
     e.bias = _ptr(bias); e.dot_with = _ptr(dot_with); e.dot_out = _ptr(dot_out); e.scale_dev = _ptr(scale_dev)
     e.scale = float(scale); e.act = int(act); e.pre = _ptr(pre); e.resid = _ptr(resid)
     e.out_f32 = _ptr(out_f32); e.out_act = _ptr(out_act)
+    if _ops.x3_enabled() and a.dtype == torch.float32 and m > 8 and n >= 8 and k >= 8:
+        # bf16x3 parity arithmetic (csrc/sa_x3.cu); m <= 8 rows (one decoding position) stay on the weight-streaming kernel
+        nb = int(lib().sa_gemm_nt_x3_workspace(m, n, k))
+        ws = _ops.x3_workspace(nb, a.device)
+        _lib.check(lib().sa_gemm_nt_x3(m, n, k, _ptr(a), _rowmajor(a), _ptr(b), _rowmajor(b), C.byref(e), ldo, _p(ws), nb,
+                                       _stream()), "sa_gemm_nt_x3")
+        return
     _lib.check(lib().sa_gemm_nt(m, n, k, _dt(a.dtype), _ptr(a), _rowmajor(a), _ptr(b), _rowmajor(b), C.byref(e), ldo,
                                 _stream()), "sa_gemm_nt")
 
@@ -66,6 +74,12 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, scale_dev=None
     nb = b.shape[1]
     assert b.shape[0] == m and a.dtype == b.dtype
     assert d.dtype == torch.float32 and d.is_contiguous() and tuple(d.shape) == (na, nb)
+    if _ops.x3_enabled() and a.dtype == torch.float32 and m >= 64 and na >= 8 and nb >= 8:
+        nbytes = int(lib().sa_gemm_tn_x3_workspace(m, na, nb))
+        ws = _ops.x3_workspace(nbytes, a.device)
+        _lib.check(lib().sa_gemm_tn_x3(m, na, nb, _ptr(a), _rowmajor(a), _ptr(b), _rowmajor(b), _ptr(scale_dev), float(scale),
+                                       _p(d), int(accumulate), _p(ws), nbytes, _stream()), "sa_gemm_tn_x3")
+        return
     _lib.check(lib().sa_gemm_tn(m, na, nb, _dt(a.dtype), _ptr(a), _rowmajor(a), _ptr(b), _rowmajor(b), _ptr(scale_dev),
                                 float(scale), _p(d), int(accumulate), _stream()), "sa_gemm_tn")
 
@@ -298,8 +312,8 @@ class KernelTimer:
         out = {}
         for name, e0, e1, meta in self.records:
             ms = e0.elapsed_time(e1)
-            d = out.setdefault(name, {"ms": 0.0, "launches": 0, "flop": 0.0})
-            d["ms"] += ms; d["launches"] += 1; d["flop"] += meta
+            d = out.setdefault(name, {"ms": 0.0, "launches": 0, "flop": 0.0, "bytes": 0.0})
+            d["ms"] += ms; d["launches"] += 1; d["flop"] += meta[0]; d["bytes"] += meta[1]
         return out
 
 
@@ -311,14 +325,25 @@ def set_timer(timer: Optional[KernelTimer]) -> None:
     _TIMER = timer
 
 
-def _flops(name, args):
+def _meta(name, args, kwargs):
+    """(algorithmic FLOPs, algorithmic HBM bytes) of one call: operands read once + every epilogue tensor the call
+    names read / written once"""
     if name == "gemm_nt":
         a, b = args[0], args[1]
-        return 2.0 * a.shape[0] * a.shape[1] * b.shape[0]
+        m, k, n = a.shape[0], a.shape[1], b.shape[0]
+        by = (m * k + n * k) * a.element_size()
+        for key in ("dot_with", "pre", "resid", "out_f32", "out_act"):
+            t = kwargs.get(key)
+            if t is not None:
+                by += m * n * t.element_size()
+        if kwargs.get("bias") is not None:
+            by += n * 4
+        return 2.0 * m * k * n, float(by)
     if name == "gemm_tn":
         a, b = args[0], args[1]
-        return 2.0 * a.shape[0] * a.shape[1] * b.shape[1]
-    return 0.0
+        m, na, nb = a.shape[0], a.shape[1], b.shape[1]
+        return 2.0 * m * na * nb, float(m * (na + nb) * a.element_size() + na * nb * 4)
+    return 0.0, 0.0
 
 
 def _instrument(name, fn):
@@ -330,7 +355,7 @@ def _instrument(name, fn):
         e0.record()
         r = fn(*args, **kwargs)
         e1.record()
-        t.records.append((name, e0, e1, _flops(name, args)))
+        t.records.append((name, e0, e1, _meta(name, args, kwargs)))
         return r
     wrapper.__name__ = fn.__name__
     wrapper.__doc__ = fn.__doc__

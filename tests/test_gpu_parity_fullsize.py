@@ -64,28 +64,34 @@ def _model():
 
 
 def _layer_walk(vo, cfg, sd, x):
-    """fp32 oracle walk: yields (stack, op_index, kind, params-prefix, meta, input, output) per programme op"""
+    """fp32 oracle walk: one entry (stack, kind, params-prefix, meta, input, output) per conv / ResidualLayer, i.e. per op
+    of the product's stack programme; kind is 'conv' | 'deconv' | 'res' (ONE residual layer, prefix '<group>.<j>')"""
     out = []
+
+    def run(stack, prog, prefix, h):
+        for kind, i, m in prog:
+            p = f"{prefix}.{i}"
+            if kind == "res":
+                for j in range(m["n"]):
+                    y = _oracle_op(sd, f"{p}.{j}", "res", m, h)
+                    out.append((stack, "res", f"{p}.{j}", m, h, y))
+                    h = y
+            else:
+                y = _oracle_op(sd, p, kind, m, h)
+                out.append((stack, kind, p, m, h, y))
+                h = y
+        return h
+
     with torch.no_grad():
-        h = x
-        for kind, i, m in vo.encoder_program(cfg):
-            p = f"encoder.0.{i}"
-            y = _oracle_op(vo, sd, p, kind, m, h)
-            out.append(("enc", kind, p, m, h, y))
-            h = y
-        q_st, _, _, _ = vo.quantize(sd, cfg, h, True)
-        h = q_st
-        for kind, i, m in vo.decoder_program(cfg):
-            p = f"decoder.0.{i}"
-            y = _oracle_op(vo, sd, p, kind, m, h)
-            out.append(("dec", kind, p, m, h, y))
-            h = y
+        z = run("enc", vo.encoder_program(cfg), "encoder.0", x)
+        q_st, _, _, _ = vo.quantize(sd, cfg, z, True)
+        run("dec", vo.decoder_program(cfg), "decoder.0", q_st)
     return out
 
 
-def _oracle_op(vo, sd, p, kind, m, x, rounded=False):
-    """one programme op of the oracle (baseline.py:150-160, 218-228, 242-244, 258, 283-297); rounded=True evaluates it
-    in the bf16 kernels' arithmetic model: bf16 operands, fp32 accumulation, bf16 activations between convs"""
+def _oracle_op(sd, p, kind, m, x, rounded=False):
+    """one conv / ResidualLayer of the oracle (baseline.py:150-160, 218-228, 242-244, 258, 283-297); rounded=True evaluates
+    it in the bf16 kernels' arithmetic model: bf16 operands, fp32 accumulation, bf16 activation between the two convs"""
     r = _bf if rounded else (lambda t: t)
     if kind == "conv":
         y = F.conv3d(r(x), r(sd[f"{p}.weight"]), sd[f"{p}.bias"], stride=m["s"], padding=m["p"])
@@ -94,18 +100,17 @@ def _oracle_op(vo, sd, p, kind, m, x, rounded=False):
         y = F.conv_transpose3d(r(x), r(sd[f"{p}.weight"]), sd[f"{p}.bias"], stride=m["s"], padding=m["p"])
         return F.relu(y) if m["relu"] else y
     h = r(x)
-    for j in range(m["n"]):
-        t = F.relu(F.conv3d(h, r(sd[f"{p}.{j}.0.weight"]), sd[f"{p}.{j}.0.bias"], padding=1))
-        t = F.conv3d(r(t), r(sd[f"{p}.{j}.3.weight"]), sd[f"{p}.{j}.3.bias"])
-        h = r(F.relu(h + t))
-    return h
+    t = F.relu(F.conv3d(h, r(sd[f"{p}.0.weight"]), sd[f"{p}.0.bias"], padding=1))
+    t = F.conv3d(r(t), r(sd[f"{p}.3.weight"]), sd[f"{p}.3.bias"])
+    return F.relu(h + t)
 
 
 def test_vqvae_config2_every_layer_teacher_forced_against_oracle():
-    """58 convs (20 programme ops) of BASELINE config 2 at 1 x 160 x 224 x 160, bf16 tcgen05 path, each on the oracle's
-    own layer input.  A ResidualLayer group is 3 x (3x3x3 -> ReLU -> 1x1x1 -> +x -> ReLU) with bf16 activations in
-    between: an element of h that sits on a rounding boundary may land one ulp apart between the two accumulation
-    orders, so groups are held to 4 ulp, single convs to 2."""
+    """all 58 convs (34 programme ops: 10 convs + 24 ResidualLayers) of BASELINE config 2 at 1 x 160 x 224 x 160, bf16
+    tcgen05 path, each on the oracle's own layer input.  Single convs: 2 ulp.  A ResidualLayer is 3x3x3 -> ReLU -> [bf16]
+    -> 1x1x1 -> +x -> ReLU: an element of the intermediate h that sits on a rounding boundary may land one bf16 step
+    apart between the two fp32 accumulation orders, which the 1x1x1 conv then spreads over the output channels, so a
+    layer is held to 4 ulp."""
     from synthanatomy_b200 import ops
     from synthanatomy_b200.networks.vqvae import b200
     vo, cfg, net, sd = _model()
@@ -115,14 +120,14 @@ def test_vqvae_config2_every_layer_teacher_forced_against_oracle():
     progs = {"enc": net._enc_ops, "dec": net._dec_ops}
     cursor = {"enc": 0, "dec": 0}
     tc_ops = 0
+    report = []
     for stack, kind, p, m, xin, _y32 in walk:
-        prog = progs[stack]
-        n_ops = m["n"] if kind == "res" else 1
-        sub = prog[cursor[stack]: cursor[stack] + n_ops]
-        cursor[stack] += n_ops
-        params = [t.detach().float().contiguous() for op in sub for t in op.params()]
+        sub = progs[stack][cursor[stack]: cursor[stack] + 1]
+        cursor[stack] += 1
+        assert isinstance(sub[0], b200._ResOp) == (kind == "res"), p
+        params = [t.detach().float().contiguous() for t in sub[0].params()]
         with torch.no_grad():
-            want = _oracle_op(vo, sd, p, kind, m, xin, rounded=True)
+            want = _bf(_oracle_op(sd, p, kind, m, xin, rounded=True))
             got, _ = b200._stack_forward(sub, _ndhwc(xin), params, save=False)
         tc_ops += int(ops.last_path() == 2)
         ulps = 4 if kind == "res" else 2
@@ -130,12 +135,16 @@ def test_vqvae_config2_every_layer_teacher_forced_against_oracle():
             # last ConvTranspose3d 128 -> 1: the per-tap products r[pos][tap] are a bf16 tensor before the col2im gather
             # sums 8 of them (one more rounding, of terms that may be larger than their sum)
             ulps = 16
-        _assert_ulps(_ncdhw(got), _bf(want) if kind != "res" else want, ulps, f"{p} ({kind})")
+        try:
+            _assert_ulps(_ncdhw(got), want, ulps, f"{p} ({kind})")
+        except AssertionError as e:
+            report.append(str(e))
+    assert not report, "\n".join(report)
     assert cursor["enc"] == len(net._enc_ops) and cursor["dec"] == len(net._dec_ops)
-    assert tc_ops >= 16, "the tcgen05 kernels were not the ones exercised"
+    assert tc_ops >= 28, "the tcgen05 kernels were not the ones exercised"
 
 
-def _grad_case(vo, sd, p, kind, m, xin, seed):
+def _grad_case(sd, p, kind, m, xin, seed):
     """autograd of the oracle's functional layer on bf16-rounded operands; returns tensors for the GPU side"""
     g = torch.Generator().manual_seed(seed)
     xr = _bf(xin).requires_grad_(True)
@@ -147,9 +156,9 @@ def _grad_case(vo, sd, p, kind, m, xin, seed):
         return leaves[k]
 
     if kind == "res":
-        h = F.relu(F.conv3d(xr, leaf(f"{p}.0.0.weight"), leaf(f"{p}.0.0.bias", False), padding=1))
+        h = F.relu(F.conv3d(xr, leaf(f"{p}.0.weight"), leaf(f"{p}.0.bias", False), padding=1))
         hb = h + (_bf(h.detach()) - h.detach())                 # bf16 activation between the two convs (straight-through)
-        pre = xr + F.conv3d(hb, leaf(f"{p}.0.3.weight"), leaf(f"{p}.0.3.bias", False))
+        pre = xr + F.conv3d(hb, leaf(f"{p}.3.weight"), leaf(f"{p}.3.bias", False))
         y = F.relu(pre)
         aux = (hb.detach(), y.detach())
     elif kind == "conv":
@@ -183,7 +192,7 @@ def test_vqvae_config2_dominant_layer_gradients_against_oracle():
     vo, cfg, net, sd = _model()
     x = torch.rand(1, 1, *VOL, generator=torch.Generator().manual_seed(8))
     walk = _layer_walk(vo, cfg, sd, x)
-    pick = {"encoder.0.0": None, "encoder.0.2": None, "encoder.0.3": None, "decoder.0.8": None, "decoder.0.10": None,
+    pick = {"encoder.0.0": None, "encoder.0.2.0": None, "encoder.0.3": None, "decoder.0.8": None, "decoder.0.10.2": None,
             "decoder.0.11": None}
     for stack, kind, p, m, xin, y in walk:
         if p in pick:
@@ -191,13 +200,13 @@ def test_vqvae_config2_dominant_layer_gradients_against_oracle():
     assert all(v is not None for v in pick.values()), [k for k, v in pick.items() if v is None]
     bf = torch.bfloat16
     for seed, (p, (kind, m, xin)) in enumerate(pick.items()):
-        xr, gy, leaves, aux = _grad_case(vo, sd, p, kind, m, xin, 100 + seed)
+        xr, gy, leaves, aux = _grad_case(sd, p, kind, m, xin, 100 + seed)
         gd = _ndhwc(gy)
         xd = _ndhwc(xr.detach())
         in_dhw = tuple(xin.shape[2:])
         if kind == "res":
             hb, _y = aux
-            w3, w1 = leaves[f"{p}.0.0.weight"], leaves[f"{p}.0.3.weight"]
+            w3, w1 = leaves[f"{p}.0.weight"], leaves[f"{p}.3.weight"]
             c = m["c"]
             s3, s1 = ConvSpec("conv", c, c, 3, 1, 1), ConvSpec("conv", c, c, 1, 1, 0)
             hd = _ndhwc(hb)
@@ -209,9 +218,9 @@ def test_vqvae_config2_dominant_layer_gradients_against_oracle():
             wp3_t = ops.pack_weight(w3.detach().cuda(), True, bf)
             dx = ops.conv_dgrad(s3, dh, wp3_t, in_dhw, gd, None)              # (+ g): the residual branch
             assert ops.last_path() == 2
-            _close_rel(dw1, w1.grad, 1e-3, f"{p} dW1"); _close_rel(db1, leaves[f"{p}.0.3.bias"].grad, 1e-3, f"{p} db1")
+            _close_rel(dw1, w1.grad, 1e-3, f"{p} dW1"); _close_rel(db1, leaves[f"{p}.3.bias"].grad, 1e-3, f"{p} db1")
             # dW3 / db3 / dx see dh rounded to bf16 (one more rounding than the oracle's fp32 chain)
-            _close_rel(dw3, w3.grad, ULP, f"{p} dW3"); _close_rel(db3, leaves[f"{p}.0.0.bias"].grad, ULP, f"{p} db3")
+            _close_rel(dw3, w3.grad, ULP, f"{p} dW3"); _close_rel(db3, leaves[f"{p}.0.bias"].grad, ULP, f"{p} db3")
             _assert_ulps(_ncdhw(dx), xr.grad, 6, f"{p} dx")
             continue
         w = leaves[f"{p}.weight"]
@@ -246,48 +255,57 @@ def test_vqvae_config2_dominant_layer_gradients_against_oracle():
 def test_vqvae_config2_full_model_step_against_oracle():
     """BASELINE config 2 (4 levels, 256 channels, codebook 2048 x 32) at 1 x 160 x 224 x 160, training mode: forward,
     loss, perplexity, code indices, EMA codebook and every parameter gradient, bf16 tcgen05 path vs the fp32 oracle.
-    End-to-end bound: the encoder is 29 convs deep, so the latents carry ~sqrt(29) * 2^-9 = 1e-2 relative noise; a
-    latent within that distance of a Voronoi face may pick the neighbouring code (counted, bounded), after which the
-    decoder sees a different input at that position.  Stated bounds: >= 90 % of the 1400 indices identical,
-    reconstruction within 3e-2 of its range in relative L2, loss within 3e-2, every gradient cosine >= 0.97."""
-    from synthanatomy_b200.networks.vqvae import B200VQVAE  # noqa: F401
+    The encoder is 29 bf16 convs deep, so the latents carry ~sqrt(29) * 2^-9 = 1e-2 relative noise; a latent that close to
+    a Voronoi face picks the neighbouring code, after which the decoder sees a different input at that position (a
+    discrete event, not a rounding error).  The codebook is built so that such faces are rare (half the codes sit on
+    latents of this very volume), the remaining flips are counted, and the bounds are stated for what is left:
+    >= 97 % identical indices, reconstruction within 2e-2 relative L2, loss within 2e-2, every gradient cosine >= 0.97."""
     vo, cfg, net, sd = _model()
-    with torch.no_grad():       # a codebook on the scale of the latents, so that the quantiser is not degenerate
-        z = vo.encode(sd, cfg, torch.rand(1, 1, *VOL, generator=torch.Generator().manual_seed(9)))
-        cb = z.permute(0, 2, 3, 4, 1).reshape(-1, 32)
-        pick = torch.randint(0, cb.shape[0], (2048,), generator=torch.Generator().manual_seed(10))
-        cbw = cb[pick] + 0.05 * cb.std() * torch.randn(2048, 32, generator=torch.Generator().manual_seed(11))
+    x = torch.rand(1, 1, *VOL, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        z = vo.encode(sd, cfg, x)
+        lat = z.permute(0, 2, 3, 4, 1).reshape(-1, 32)                      # 1400 latents
+        g = torch.Generator().manual_seed(10)
+        own = lat[torch.randperm(lat.shape[0], generator=g)[:1024]]
+        cbw = torch.cat((own + 0.02 * lat.std() * torch.randn(1024, 32, generator=g),
+                         lat.mean(0) + lat.std(0) * torch.randn(1024, 32, generator=g)))
         for k in ("quantizer.0.impl.weight", "quantizer.0.impl.embedding.weight", "quantizer.0.impl.embed_avg"):
             sd[k] = cbw.clone()
     net.load_state_dict(sd)
-    x = torch.rand(1, 1, *VOL, generator=torch.Generator().manual_seed(9))
     loss_ref, grads_ref, out_ref = vo.train_step_grads(sd, cfg, x)
     net = net.cuda().train()
+    with torch.no_grad():
+        net.eval()
+        idx = net.index_quantize(x.cuda())[0].cpu()
+        net.train()
+    same = float((idx == out_ref["indices"]).float().mean())
     out = net(x.cuda())
     rec = out["reconstruction"][0]
     loss = F.mse_loss(rec.float(), x.cuda()) + out["quantization_losses"][0]
     loss.backward()
-    idx = net.index_quantize  # noqa: F841  (API presence)
     rec_ref = out_ref["reconstruction"][0]
-    rel = float((rec.cpu() - rec_ref).norm() / rec_ref.norm())
-    assert rel <= 3e-2, f"reconstruction relative L2 error {rel:.3e}"
-    assert abs(float(loss) - float(loss_ref)) <= 3e-2 * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    rel = float((rec.detach().cpu() - rec_ref).norm() / rec_ref.norm())
+    cosines = {}
+    for k, p in net.named_parameters():
+        if p.requires_grad:
+            a, b = p.grad.cpu().flatten().double(), grads_ref[k].flatten().double()
+            cosines[k] = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+    worst = min(cosines, key=cosines.get)
+    summary = (f"indices equal {same:.4f}; recon rel L2 {rel:.3e}; loss {float(loss):.6f} vs {float(loss_ref):.6f}; "
+               f"min grad cosine {cosines[worst]:.4f} ({worst})")
+    print(summary)
+    assert same >= 0.97, summary
+    assert rel <= 2e-2, summary
+    assert abs(float(loss) - float(loss_ref)) <= 2e-2 * abs(float(loss_ref)), summary
     ppl = float(net.get_perplexity()[0])
     ppl_ref = float(vo.perplexity(out_ref["indices"], cfg.n_embed))
-    assert abs(ppl - ppl_ref) <= 0.1 * ppl_ref, (ppl, ppl_ref)
-    worst = 1.0
-    for k, p in net.named_parameters():
-        if not p.requires_grad:
-            continue
-        a, b = p.grad.cpu().flatten().double(), grads_ref[k].flatten().double()
-        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
-        worst = min(worst, cos)
-        assert cos >= 0.97, f"{k}: gradient cosine {cos:.4f}"
+    assert abs(ppl - ppl_ref) <= 0.05 * ppl_ref, (ppl, ppl_ref)
+    assert cosines[worst] >= 0.97, summary
     # EMA statistics: the codebook rows the oracle updated are the rows this path updated (same argmin up to near-ties)
     n_ref = out_ref["new_state"]["N"]
     n_got = net.quantizer[0].impl.N.cpu()
     agree = float(((n_ref > 0) == (n_got > 0)).float().mean())
-    assert agree >= 0.9, f"EMA cluster-usage pattern agreement {agree:.3f}"
+    assert agree >= 0.97, f"EMA cluster-usage pattern agreement {agree:.3f}"
 
 
 def test_performer_config4_depth2_against_oracle_at_14000_tokens():
