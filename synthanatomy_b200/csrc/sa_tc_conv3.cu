@@ -44,7 +44,8 @@ struct C3Params {
   CUtensorMap wmap;
   C3Group groups[32];
   int ngroups, ndd;
-  int N, cchunks, stages;
+  int N, cchunks, stages;                              // N: output channels of THIS launch (<= 128)
+  int ldy;                                             // channel stride of y / addend / mask (the layer's c_out)
   int gD, gH, gW, ntd, nth, ntw, batch, total_tiles;   // tile grid
   int oD, oH, oW, os, oqd, oqh, oqw;                   // output position = g * os + oq
   int relu;
@@ -160,7 +161,7 @@ tc_conv3_kernel(const __grid_constant__ C3Params P) {
       const int gd = td_i * C3_TD + dz, gh = th_i * C3_TH + hy, gw = tw_i * C3_TW + wx;
       const bool valid = gd < P.gD && gh < P.gH && gw < P.gW;
       const int64_t obase = ((((int64_t)b * P.oD + (gd * P.os + P.oqd)) * P.oH + (gh * P.os + P.oqh)) * P.oW +
-                             (gw * P.os + P.oqw)) * P.N;
+                             (gw * P.os + P.oqw)) * P.ldy;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       for (int c0 = 0; c0 < P.N; c0 += 32) {
@@ -318,8 +319,10 @@ int c3_launch(C3Params& P, int batch, bool out_f32, cudaStream_t st) {
 // stride-1 k = 3 / k = 1 convs (and their transposed forms), 4/2/1 strided convs and 4/2/1 transposed convs
 bool sa_tc_conv3_supported(const sa_conv_desc* d) {
   if (d->act_dtype != SA_BF16) return false;
-  if (d->c_in % 64 != 0 || d->c_out % 16 != 0 || d->c_out < 16 || d->c_out > 128) return false;
+  // up to 128 output channels per launch; 256 = two launches over the two halves of the output channels
+  if (d->c_in % 64 != 0 || d->c_out % 16 != 0 || d->c_out < 16 || (d->c_out > 128 && d->c_out != 256)) return false;
   if (const char* e = getenv("SA_TC_CONV3")) { if (e[0] == '0') return false; }   // A/B switch for benchmarking
+  if (d->c_out == 256) { if (const char* e = getenv("SA_TC_CONV3_N256")) { if (e[0] == '0') return false; } }
   if (!sa_get_tmap_encode()) return false;
   const int k = d->ksize;
   if (d->stride == 1 && (k == 3 || k == 1)) {
@@ -348,9 +351,24 @@ int sa_tc_conv3_fwd(const sa_conv_desc* d, const void* x, const void* wp, const 
   return sa_tc_conv3_fwd_ex(d, x, wp, bias, addend, mask, relu, y, false, st);
 }
 
+static int c3_fwd_part(const sa_conv_desc* d, const void* x, const void* wp, const float* bias, const void* addend,
+                       const void* mask, int relu, void* y, bool out_f32, int n0, int N, cudaStream_t st);
+
 // out_f32: y / addend / mask are fp32 tensors (x and wp stay bf16): the bf16x3 path of sa_x3.cu
 int sa_tc_conv3_fwd_ex(const sa_conv_desc* d, const void* x, const void* wp, const float* bias, const void* addend,
                        const void* mask, int relu, void* y, bool out_f32, cudaStream_t st) {
+  const int parts = d->c_out > 128 ? 2 : 1;
+  const int N = d->c_out / parts;
+  for (int h = 0; h < parts; ++h) {
+    const int rc = c3_fwd_part(d, x, wp, bias, addend, mask, relu, y, out_f32, h * N, N, st);
+    if (rc != SA_OK) return rc;
+  }
+  return SA_OK;
+}
+
+// output channels [n0, n0 + N) of the layer
+static int c3_fwd_part(const sa_conv_desc* d, const void* x, const void* wp, const float* bias, const void* addend,
+                       const void* mask, int relu, void* y, bool out_f32, int n0, int N, cudaStream_t st) {
   std::call_once(g_c3_once, [] {
     int dev = 0, v = 0;
     cudaGetDevice(&dev);
@@ -363,15 +381,19 @@ int sa_tc_conv3_fwd_ex(const sa_conv_desc* d, const void* x, const void* wp, con
   static thread_local C3Params P;
   const int iD = d->in_dhw[0], iH = d->in_dhw[1], iW = d->in_dhw[2];
   const int k = d->ksize, taps = k * k * k;
-  P.N = d->c_out;
+  P.N = N;
+  P.ldy = d->c_out;
   P.cchunks = d->c_in / 64;
   P.oD = d->out_dhw[0]; P.oH = d->out_dhw[1]; P.oW = d->out_dhw[2];
-  P.relu = relu; P.bias = bias;
-  P.addend = addend; P.mask = mask; P.y = y;
+  const size_t es = out_f32 ? 4 : 2;
+  P.relu = relu; P.bias = bias ? bias + n0 : nullptr;
+  P.addend = addend ? (const uint8_t*)addend + (size_t)n0 * es : nullptr;
+  P.mask = mask ? (const uint8_t*)mask + (size_t)n0 * es : nullptr;
+  P.y = (uint8_t*)y + (size_t)n0 * es;
   {
     const uint64_t dims[2] = {(uint64_t)d->c_in, (uint64_t)taps * d->c_out};
     const uint64_t strides[2] = {2, (uint64_t)d->c_in * 2};
-    const uint32_t box[2] = {64, (uint32_t)d->c_out};
+    const uint32_t box[2] = {64, (uint32_t)N};
     int rc = sa_make_tmap_bf16(&P.wmap, wp, 2, dims, strides, box);
     if (rc != SA_OK) return rc;
   }
@@ -389,7 +411,7 @@ int sa_tc_conv3_fwd_ex(const sa_conv_desc* d, const void* x, const void* wp, con
         g.map = 0; g.od = (int8_t)(-pe); g.oh = (int8_t)(dh - pe); g.ow = (int8_t)(dw - pe);
         for (int dd = 0; dd < k; ++dd) {
           const int t = (dd * k + dh) * k + dw;
-          g.wrow[dd] = (d->transposed ? taps - 1 - t : t) * d->c_out;    // flipped taps: transposed form
+          g.wrow[dd] = (d->transposed ? taps - 1 - t : t) * d->c_out + n0;    // flipped taps: transposed form
         }
       }
     return c3_launch(P, d->batch, out_f32, st);
@@ -413,8 +435,8 @@ int sa_tc_conv3_fwd_ex(const sa_conv_desc* d, const void* x, const void* wp, con
           const int td0 = pd ? 0 : 1, td1 = pd ? 2 : 3;       // odd-parity view: taps 0, 2   even: taps 1, 3
           g.map = (int8_t)((pd << 2) | (par(th) << 1) | par(tw));
           g.od = (int8_t)off(td0); g.oh = (int8_t)off(th); g.ow = (int8_t)off(tw);
-          g.wrow[0] = ((td0 * 4 + th) * 4 + tw) * d->c_out;
-          g.wrow[1] = ((td1 * 4 + th) * 4 + tw) * d->c_out;
+          g.wrow[0] = ((td0 * 4 + th) * 4 + tw) * d->c_out + n0;
+          g.wrow[1] = ((td1 * 4 + th) * 4 + tw) * d->c_out + n0;
           g.wrow[2] = 0;
         }
     P.ngroups = gi;
@@ -435,7 +457,7 @@ int sa_tc_conv3_fwd_ex(const sa_conv_desc* d, const void* x, const void* wp, con
       C3Group& g = P.groups[j];
       g.map = 0; g.od = (int8_t)off_of[qd][0]; g.oh = (int8_t)off_of[qh][jh]; g.ow = (int8_t)off_of[qw][jw];
       for (int dd = 0; dd < 2; ++dd)
-        g.wrow[dd] = ((tap_of[qd][dd] * 4 + tap_of[qh][jh]) * 4 + tap_of[qw][jw]) * d->c_out;
+        g.wrow[dd] = ((tap_of[qd][dd] * 4 + tap_of[qh][jh]) * 4 + tap_of[qw][jw]) * d->c_out + n0;
       g.wrow[2] = 0;
     }
     if ((rc = c3_launch(P, d->batch, out_f32, st)) != SA_OK) return rc;

@@ -68,10 +68,11 @@ class _ConvOp:
         return [self.module.weight, self.module.bias]
 
     def single_channel_gemm(self, dt: torch.dtype) -> bool:
-        """bf16 path only: the 1-channel ends of the network (first Conv3d 1->C, last ConvTranspose3d C->1) run as
-        im2col / col2im + a 1x1x1 tensor-core GEMM over the k^3 = 64 taps."""
+        """tensor-core paths only (bf16, or fp32 tensors in the bf16x3 mode): the 1-channel ends of the network (first
+        Conv3d 1->C, last ConvTranspose3d C->1) run as im2col / col2im + a 1x1x1 tensor-core GEMM over the k^3 = 64 taps."""
         sp = self.spec
-        if dt != torch.bfloat16 or sp.k ** 3 != 64:
+        tensor_core = dt == torch.bfloat16 or (dt == torch.float32 and ops.x3_enabled())
+        if not tensor_core or sp.k ** 3 != 64:
             return False
         if sp.kind == "conv":
             return sp.cin == 1 and sp.cout % 16 == 0
