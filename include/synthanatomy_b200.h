@@ -227,6 +227,18 @@ int sa_mse_fwd_bwd(const void* a, int a_dtype, const float* b, int64_t n, float 
 int sa_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, int step, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Spectral (Jukebox) reconstruction loss, src/losses/vqvae/vqvae.py:522-640 (torch.fft.fftn, norm="ortho", amplitude,
+ * F.mse_loss).  The axis transforms are dense DFT-matrix products through sa_gemm_nt_x3 (bf16x3 on the tensor cores);
+ * a complex tensor is stored as [..][2 = re, im][axis].  These two entry points are the non-GEMM parts:
+ *   sa_swap_outer_inner:  dst[b][c][m][a] = src[b][a][m][c]  (fp32) -- brings the next axis to the contraction position
+ *   sa_spectral_amp_loss: spectra [rows][2][L]; sse[0] += sum (|P| - |T|)^2 (may be NULL);
+ *                         grad (may be NULL) = coef * coef_dev[0] * (|P| - |T|) * P / |P|   (coef_dev may be NULL = 1)
+ * ---------------------------------------------------------------------------------------------- */
+int sa_swap_outer_inner(const float* src, float* dst, int64_t batch, int A, int M, int C, void* stream);
+int sa_spectral_amp_loss(const float* pred_spec, const float* target_spec, int64_t rows, int L, float coef,
+                         const float* coef_dev, float* sse, float* grad, void* stream);
+
 /* The same update for `count` parameter tensors at once (host arrays of device pointers / element counts; all tensors
  * share lr / betas / eps / step): 64 tensors per launch instead of one launch per tensor. */
 int sa_adam_multi(int count, float* const* p, const float* const* g, float* const* m, float* const* v,

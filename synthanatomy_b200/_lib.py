@@ -106,6 +106,8 @@ SIGNATURES = {
     "sa_mse_fwd_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sa_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int,
                              c_void_p]),
+    "sa_swap_outer_inner": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "sa_spectral_amp_loss": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sa_adam_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
                               c_int, c_void_p]),
     "sa_conv3d_x3_supported": (c_int, [C.POINTER(ConvDesc), c_int]),
