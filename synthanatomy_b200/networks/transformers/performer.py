@@ -320,104 +320,221 @@ def _as(t: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
     return out
 
 
-class _PerformerFn(torch.autograd.Function):
-    """params: token_emb, pos_emb, spatial tables..., then per layer (g_a, Wq, Wk, Wv, Wo, g_f, W1, b1, W2, b2),
-    then norm.weight, norm.bias, to_out.weight, to_out.bias."""
+class _Ctx:
+    """what every piece of the programme shares for one forward / backward pass"""
+
+    def __init__(self, net: "Performer", B: int, N: int, dt: torch.dtype, x3: bool, dev):
+        self.net, self.x3, self.dev = net, x3, dev
+        self.D = D = _Dims(net, B, N, dt)
+        self.fd = pf_ops.favor_desc(B, N, D.gh, D.dh, D.m, D.mp, 3 * D.inner, dt) if D.gh > 0 else None
+        self.ld = pf_ops.local_desc(B, N, D.lh, D.dh, D.W, 3 * D.inner, D.inner, dt) if D.lh > 0 else None
+
+    def ws(self, backward: bool):
+        return _workspace(pf_ops.favor_scan_workspace(self.fd, backward), self.dev) if self.fd is not None else None
+
+
+# The bf16 copy of a gradient that the GEMM epilogue of one piece's backward writes next to the fp32 gradient it returns:
+# the next piece's backward (the layer below) looks it up by the storage of the gradient autograd hands it, and casts
+# only if it is not there (a hook or an accumulation in between made a new tensor).
+_GRAD_COPY = {}
+
+
+def _grad_copy(g: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+    hit = _GRAD_COPY.pop("last", None)
+    if hit is not None and hit[0] == g.data_ptr() and hit[1].dtype == dt and hit[1].shape == g.shape:
+        return hit[1]
+    return _as(g, dt)
+
+
+class _EmbedFn(torch.autograd.Function):
+    """performer.py:241-268: token + spatial + absolute position embeddings -> (x fp32, x in the activation dtype)"""
 
     @staticmethod
-    def forward(ctx, tokens, net, dt, return_encodings, *params):
-        if not tokens.is_cuda:
-            raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
-        dt, x3 = ops.resolve_dtype(dt)       # BF16X3: fp32 tensors, dense layers as split-bf16 tensor-core products
-        ctx.x3 = x3
-        with ops.x3_mode(x3):
-            return _PerformerFn._forward(ctx, tokens, net, dt, return_encodings, *params)
+    def forward(ctx, tokens, C, *tables):
+        D = C.D
+        f32 = torch.float32
+        p = [t.detach() for t in tables]
+        tokens = tokens.long().contiguous()
+        x32 = torch.empty((D.M, D.dim), device=C.dev, dtype=f32)
+        xa = x32 if D.dt == f32 else torch.empty((D.M, D.dim), device=C.dev, dtype=D.dt)
+        sp_idx = C.net._sp_idx(D.N, C.dev)
+        pf_ops.embed_fwd(tokens, sp_idx, p[0], p[2:], p[1], x32, None if D.dt == f32 else xa)
+        ctx.C, ctx.tokens, ctx.sp_idx, ctx.shapes = C, tokens, sp_idx, [t.shape for t in p]
+        if D.dt == f32:
+            return x32, None              # fp32: the residual stream itself is the operand
+        ctx.mark_non_differentiable(xa)
+        return x32, xa
 
     @staticmethod
-    def _forward(ctx, tokens, net, dt, return_encodings, *params):
-        dev = tokens.device
-        B, N = tokens.shape
-        D = _Dims(net, B, N, dt)
-        need_grad = any(ctx.needs_input_grad)
+    def backward(ctx, dx32, _dxa):
+        C = ctx.C
+        _GRAD_COPY.pop("last", None)
+        dev = dx32.device
+        d_tabs = [torch.zeros(s, device=dev, dtype=torch.float32) for s in ctx.shapes]
+        pf_ops.embed_bwd(dx32.contiguous(), ctx.tokens, ctx.sp_idx, d_tabs[0], d_tabs[2:], d_tabs[1])
+        return (None, None, *d_tabs)
+
+
+class _LayerFn(torch.autograd.Function):
+    """one performer-pytorch layer: x + g_a * SelfAttention(x), then x + g_f * FeedForward(x) (ReZero, no LayerNorm).
+    params: g_a, Wq, Wk, Wv, Wo, g_f, W1, b1, W2, b2.  Returning the gradients layer by layer lets DistributedDataParallel
+    start reducing a layer's bucket while the layers below are still in their backward pass."""
+
+    @staticmethod
+    def forward(ctx, x32, xa, C, li, *params):
+        with ops.x3_mode(C.x3):
+            return _LayerFn._forward(ctx, x32, xa, C, li, *params)
+
+    @staticmethod
+    def _forward(ctx, x32, xa, C, li, *params):
+        D, net, dev = C.D, C.net, C.dev
+        dt, M, B, N = D.dt, D.M, D.B, D.N
         f32 = torch.float32
         is32 = dt == f32
-        p = [q.detach() for q in params]
-        tok_w, pos_w = p[0], p[1]
-        sp_ws = p[2:2 + D.n_axes]
-        base = 2 + D.n_axes
-        tokens = tokens.long().contiguous()
-        M = D.M
-
-        # ---- embeddings (performer.py:241-268)
-        x32 = torch.empty((M, D.dim), device=dev, dtype=f32)
-        xa = x32 if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
-        sp_idx = net._sp_idx(N, dev)
-        pf_ops.embed_fwd(tokens, sp_idx, tok_w, sp_ws, pos_w, x32, None if is32 else xa)
-
-        ws = None
+        need_grad = any(ctx.needs_input_grad)
+        g_a, Wq, Wk, Wv, Wo, g_f, W1, b1, W2, b2 = [q.detach() for q in params]
+        x32 = x32.detach()
+        xa = x32 if (is32 or xa is None) else xa.detach()
+        attn_mod = net.performer.net.layers[li][0].fn
+        Wqkv = _as(torch.cat((Wq, Wk, Wv), dim=0), dt)
+        Wo_, W1_, W2_ = _as(Wo, dt), _as(W1, dt), _as(W2, dt)
+        # ---- attention sub-layer
+        xa_attn = xa
+        qkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
+        pf_ops.gemm_nt(xa, Wqkv, out_act=qkv)
+        attn = torch.empty((M, D.inner), device=dev, dtype=dt)
+        qf = kf = argq = kmax = den = lse = proj = inv_freq = states = None
         if D.gh > 0:
-            fd = pf_ops.favor_desc(B, N, D.gh, D.dh, D.m, D.mp, 3 * D.inner, dt)
-            ws = _workspace(pf_ops.favor_scan_workspace(fd, need_grad), dev)
+            fd = C.fd
+            proj = attn_mod.fast_attention.projection_matrix
+            kmax = torch.zeros((1,), device=dev, dtype=torch.int64)
+            pf_ops.favor_kmax(fd, qkv, D.inner, proj, kmax)
+            qf = torch.empty((B, D.gh, N, D.mp), device=dev, dtype=dt)
+            kf = torch.empty((B, D.gh, N, D.mp), device=dev, dtype=dt)
+            argq = torch.empty((B, D.gh, N), device=dev, dtype=torch.int32)
+            pf_ops.favor_featmap_fwd(fd, qkv, 0, proj, True, None, net.eps_feature, qf, argq)
+            pf_ops.favor_featmap_fwd(fd, qkv, D.inner, proj, False, kmax, net.eps_feature, kf, None)
+            den = torch.empty((B, D.gh, N), device=dev, dtype=f32)
+            # the tcgen05 path can keep its per-chunk prefix states for the backward scan (no recomputation)
+            nst = pf_ops.favor_scan_states_bytes(fd) if need_grad else 0
+            states = torch.empty((nst,), device=dev, dtype=torch.uint8) if nst else None
+            pf_ops.favor_scan_fwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, 0, den, C.ws(need_grad), states)
         if D.lh > 0:
-            ld_ = pf_ops.local_desc(B, N, D.lh, D.dh, D.W, 3 * D.inner, D.inner, dt)
-        saved = []
-        weights = []
-        for li in range(D.depth):
-            g_a, Wq, Wk, Wv, Wo, g_f, W1, b1, W2, b2 = p[base + 10 * li: base + 10 * li + 10]
-            attn_mod = net.performer.net.layers[li][0].fn
-            Wqkv = _as(torch.cat((Wq, Wk, Wv), dim=0), dt)
-            Wo_, W1_, W2_ = _as(Wo, dt), _as(W1, dt), _as(W2, dt)
-            # ---- attention sub-layer
-            xa_attn = xa
-            qkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
-            pf_ops.gemm_nt(xa, Wqkv, out_act=qkv)
-            attn = torch.empty((M, D.inner), device=dev, dtype=dt)
-            qf = kf = argq = kmax = den = lse = proj = inv_freq = states = None
-            if D.gh > 0:
-                proj = attn_mod.fast_attention.projection_matrix
-                kmax = torch.zeros((1,), device=dev, dtype=torch.int64)
-                pf_ops.favor_kmax(fd, qkv, D.inner, proj, kmax)
-                qf = torch.empty((B, D.gh, N, D.mp), device=dev, dtype=dt)
-                kf = torch.empty((B, D.gh, N, D.mp), device=dev, dtype=dt)
-                argq = torch.empty((B, D.gh, N), device=dev, dtype=torch.int32)
-                pf_ops.favor_featmap_fwd(fd, qkv, 0, proj, True, None, net.eps_feature, qf, argq)
-                pf_ops.favor_featmap_fwd(fd, qkv, D.inner, proj, False, kmax, net.eps_feature, kf, None)
-                den = torch.empty((B, D.gh, N), device=dev, dtype=f32)
-                # the tcgen05 path can keep its per-chunk prefix states for the backward scan (no recomputation)
-                nst = pf_ops.favor_scan_states_bytes(fd) if need_grad else 0
-                states = torch.empty((nst,), device=dev, dtype=torch.uint8) if nst else None
-                pf_ops.favor_scan_fwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, 0, den, ws, states)
-            if D.lh > 0:
-                inv_freq = attn_mod.local_attn.rel_pos.inv_freq if attn_mod.local_attn.rel_pos is not None else None
-                lse = torch.empty((B, D.lh, N), device=dev, dtype=f32)
-                c0 = D.gh * D.dh
-                if inv_freq is not None:       # rotary position term, in place: the saved q / k of the local heads are rotated
-                    pf_ops.rotary_qk(qkv, c0, D.inner + c0, B, N, D.lh, D.dh, inv_freq, False)
-                pf_ops.local_attn_fwd(ld_, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, c0, lse)
-            if is32:
-                xn_ = torch.empty((M, D.dim), device=dev, dtype=f32)
-                pf_ops.gemm_nt(attn, Wo_, scale_dev=g_a, resid=x32, out_f32=xn_)
-                x32 = xa = xn_
-            else:
-                xa = torch.empty((M, D.dim), device=dev, dtype=dt)
-                pf_ops.gemm_nt(attn, Wo_, scale_dev=g_a, resid=x32, out_f32=x32, out_act=xa)
-            # ---- feed-forward sub-layer
-            xa_ffn = xa
-            u = torch.empty((M, D.ff), device=dev, dtype=dt)
-            h = torch.empty((M, D.ff), device=dev, dtype=dt)
-            pf_ops.gemm_nt(xa, W1_, bias=b1, act=SA_ACT_GELU_FWD, pre=u, out_act=h)
-            if is32:
-                xn_ = torch.empty((M, D.dim), device=dev, dtype=f32)
-                pf_ops.gemm_nt(h, W2_, bias=b2, scale_dev=g_f, resid=x32, out_f32=xn_)
-                x32 = xa = xn_
-            else:
-                xa = torch.empty((M, D.dim), device=dev, dtype=dt)
-                pf_ops.gemm_nt(h, W2_, bias=b2, scale_dev=g_f, resid=x32, out_f32=x32, out_act=xa)
-            if need_grad:
-                saved.append((xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq, states))
-                weights.append((Wqkv, Wo_, W1_, W2_))
-        # ---- final LayerNorm + logits (performer.py:273-286)
-        nw, nb, Wout, bout = p[base + 10 * D.depth: base + 10 * D.depth + 4]
+            inv_freq = attn_mod.local_attn.rel_pos.inv_freq if attn_mod.local_attn.rel_pos is not None else None
+            lse = torch.empty((B, D.lh, N), device=dev, dtype=f32)
+            c0 = D.gh * D.dh
+            if inv_freq is not None:       # rotary position term, in place: the saved q / k of the local heads are rotated
+                pf_ops.rotary_qk(qkv, c0, D.inner + c0, B, N, D.lh, D.dh, inv_freq, False)
+            pf_ops.local_attn_fwd(C.ld, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, c0, lse)
+        x_mid = torch.empty((M, D.dim), device=dev, dtype=f32)
+        xa_mid = x_mid if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
+        pf_ops.gemm_nt(attn, Wo_, scale_dev=g_a, resid=x32, out_f32=x_mid, out_act=None if is32 else xa_mid)
+        # ---- feed-forward sub-layer
+        u = torch.empty((M, D.ff), device=dev, dtype=dt)
+        h = torch.empty((M, D.ff), device=dev, dtype=dt)
+        pf_ops.gemm_nt(xa_mid, W1_, bias=b1, act=SA_ACT_GELU_FWD, pre=u, out_act=h)
+        x_out = torch.empty((M, D.dim), device=dev, dtype=f32)
+        xa_out = None if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
+        pf_ops.gemm_nt(h, W2_, bias=b2, scale_dev=g_f, resid=x_mid, out_f32=x_out, out_act=xa_out)
+        if need_grad:
+            ctx.C = C
+            ctx.saved = (xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_mid, u, h, proj, inv_freq, states)
+            ctx.weights = (Wqkv, Wo_, W1_, W2_)
+            ctx.scalars = (g_a, g_f, b1, b2)
+        if is32:
+            return x_out, None
+        ctx.mark_non_differentiable(xa_out)
+        return x_out, xa_out
+
+    @staticmethod
+    def backward(ctx, g32, _gxa):
+        with ops.x3_mode(ctx.C.x3):
+            return _LayerFn._backward(ctx, g32)
+
+    @staticmethod
+    def _backward(ctx, g32):
+        C = ctx.C
+        D, net, dev = C.D, C.net, C.dev
+        dt, M, B, N = D.dt, D.M, D.B, D.N
+        f32 = torch.float32
+        is32 = dt == f32
+        if ctx.saved is None:
+            raise RuntimeError("Performer: second backward through a layer whose activations were released")
+        xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq, states = ctx.saved
+        Wqkv, Wo_, W1_, W2_ = ctx.weights
+        g_a, g_f, b1, b2 = ctx.scalars
+        ctx.saved = ctx.weights = None
+        g32 = g32.contiguous()
+        dxa = g32 if is32 else _grad_copy(g32, dt)
+        # ---- feed-forward sub-layer: x_out = x + g_f * (gelu(x W1^T + b1) W2^T + b2)
+        dot = torch.zeros((1,), device=dev, dtype=f32)
+        du = torch.empty((M, D.ff), device=dev, dtype=dt)
+        pf_ops.gemm_nt(dxa, W2_.t().contiguous(), dot_with=h, dot_out=dot, scale_dev=g_f, act=SA_ACT_GELU_BWD, pre=u, out_act=du)
+        colsum = ops.bias_grad(dxa)
+        db2 = torch.empty_like(b2)
+        dg_f = torch.empty((), device=dev, dtype=f32)
+        pf_ops.rezero_finish(colsum, b2, g_f, dot, db2, dg_f)
+        dW2 = torch.empty((D.dim, D.ff), device=dev, dtype=f32)
+        pf_ops.gemm_tn(dxa, h, dW2, scale_dev=g_f)
+        dW1 = torch.empty((D.ff, D.dim), device=dev, dtype=f32)
+        pf_ops.gemm_tn(du, xa_ffn, dW1)
+        db1 = ops.bias_grad(du)
+        d_mid = torch.empty((M, D.dim), device=dev, dtype=f32)
+        dxa_mid = d_mid if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
+        pf_ops.gemm_nt(du, W1_.t().contiguous(), resid=g32, out_f32=d_mid, out_act=None if is32 else dxa_mid)
+        del du, u, h
+        # ---- attention sub-layer: x_mid = x + g_a * (attn Wo^T)
+        dot = torch.zeros((1,), device=dev, dtype=f32)
+        dattn = torch.empty((M, D.inner), device=dev, dtype=dt)
+        pf_ops.gemm_nt(dxa_mid, Wo_.t().contiguous(), dot_with=attn, dot_out=dot, scale_dev=g_a, out_act=dattn)
+        dWo = torch.empty((D.dim, D.inner), device=dev, dtype=f32)
+        pf_ops.gemm_tn(dxa_mid, attn, dWo, scale_dev=g_a)
+        dqkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
+        if D.lh > 0:
+            c0 = D.gh * D.dh
+            pf_ops.local_attn_bwd(C.ld, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, dattn, c0, lse, dqkv)
+            if inv_freq is not None:       # transpose of the rotary map on the gradients of the rotated q / k
+                pf_ops.rotary_qk(dqkv, c0, D.inner + c0, B, N, D.lh, D.dh, inv_freq, True)
+        if D.gh > 0:
+            fd = C.fd
+            dqf = torch.empty_like(qf)
+            dkf = torch.empty_like(kf)
+            if states is not None and pf_ops.favor_scan_states_bytes(fd) == 0:
+                states = None          # the dispatch changed since the forward pass: recompute
+            pf_ops.favor_scan_bwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, dattn, 0, den, dqf, dkf, dqkv,
+                                  2 * D.inner, C.ws(True), states)
+            gsum = torch.zeros((1,), device=dev, dtype=f32)
+            pf_ops.favor_featmap_bwd(fd, qkv, 0, proj, True, net.eps_feature, qf, dqf, argq, dqkv, 0, None)
+            pf_ops.favor_featmap_bwd(fd, qkv, D.inner, proj, False, net.eps_feature, kf, dkf, None, dqkv, D.inner, gsum)
+            pf_ops.favor_kmax_fixup(fd, proj, kmax, gsum, dqkv, D.inner)
+            del dqf, dkf
+        dWqkv = torch.empty((3 * D.inner, D.dim), device=dev, dtype=f32)
+        pf_ops.gemm_tn(dqkv, xa_attn, dWqkv)
+        dx = torch.empty((M, D.dim), device=dev, dtype=f32)
+        dxa_in = None if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
+        pf_ops.gemm_nt(dqkv, Wqkv.t().contiguous(), resid=d_mid, out_f32=dx, out_act=dxa_in)
+        if dxa_in is not None:
+            _GRAD_COPY["last"] = (dx.data_ptr(), dxa_in)
+        return (dx, None, None, None, dot.view(()), dWqkv[:D.inner], dWqkv[D.inner:2 * D.inner], dWqkv[2 * D.inner:], dWo,
+                dg_f, dW1, db1, dW2, db2)
+
+
+class _HeadFn(torch.autograd.Function):
+    """performer.py:273-286: final LayerNorm (+ to_out).  params: norm.weight, norm.bias, to_out.weight, to_out.bias"""
+
+    @staticmethod
+    def forward(ctx, x32, C, return_encodings, *params):
+        with ops.x3_mode(C.x3):
+            return _HeadFn._forward(ctx, x32, C, return_encodings, *params)
+
+    @staticmethod
+    def _forward(ctx, x32, C, return_encodings, *params):
+        D, dev = C.D, C.dev
+        dt, M, B, N = D.dt, D.M, D.B, D.N
+        f32 = torch.float32
+        is32 = dt == f32
+        nw, nb, Wout, bout = [q.detach() for q in params]
+        x32 = x32.detach()
         mean = torch.empty((M,), device=dev, dtype=f32)
         rstd = torch.empty((M,), device=dev, dtype=f32)
         enc32 = torch.empty((M, D.dim), device=dev, dtype=f32) if (return_encodings or is32) else None
@@ -426,41 +543,34 @@ class _PerformerFn(torch.autograd.Function):
         if return_encodings:
             out = enc32.view(B, N, D.dim)
         else:
-            Wout_ = _as(Wout, dt)
             logits = torch.empty((M, D.V), device=dev, dtype=f32)
-            pf_ops.gemm_nt(xn, Wout_, bias=bout, out_f32=logits)
+            pf_ops.gemm_nt(xn, _as(Wout, dt), bias=bout, out_f32=logits)
             out = logits.view(B, N, D.V)
-        if need_grad:
-            ctx.D, ctx.net = D, net
-            ctx.saved, ctx.weights = saved, weights
-            ctx.tail = (tokens, sp_idx, x32, xn, mean, rstd, return_encodings)
-            ctx.p = p
+        if any(ctx.needs_input_grad):
+            ctx.C, ctx.return_encodings = C, return_encodings
+            ctx.saved = (x32, xn, mean, rstd, nw, nb, Wout)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        with ops.x3_mode(ctx.x3):
-            return _PerformerFn._backward(ctx, gout)
+        with ops.x3_mode(ctx.C.x3):
+            return _HeadFn._backward(ctx, gout)
 
     @staticmethod
     def _backward(ctx, gout):
-        D, net, p = ctx.D, ctx.net, ctx.p
-        dt, M, B, N = D.dt, D.M, D.B, D.N
+        C = ctx.C
+        D, dev = C.D, C.dev
+        dt, M = D.dt, D.M
         f32 = torch.float32
         is32 = dt == f32
-        dev = gout.device
-        tokens, sp_idx, x32, xn, mean, rstd, return_encodings = ctx.tail
-        base = 2 + D.n_axes
-        nw, nb, Wout, bout = p[base + 10 * D.depth: base + 10 * D.depth + 4]
-        grads: List[Optional[torch.Tensor]] = [None] * len(p)
-        gi = base + 10 * D.depth
-
-        # ---- logits + LayerNorm
-        if return_encodings:
+        x32, xn, mean, rstd, nw, nb, Wout = ctx.saved
+        ctx.saved = None
+        dWout = dbout = None
+        if ctx.return_encodings:
             dxn = gout.float().contiguous().view(M, D.dim)
         else:
             dl = gout.float().contiguous().view(M, D.V)
-            grads[gi + 3] = ops.bias_grad(dl)
+            dbout = ops.bias_grad(dl)
             if is32:
                 dlb, Wout_t = dl, Wout.t().contiguous()
             else:
@@ -473,88 +583,28 @@ class _PerformerFn(torch.autograd.Function):
             pf_ops.gemm_nt(dlb, Wout_t, out_f32=dxn)
             dWout = torch.empty((D.V, D.dim), device=dev, dtype=f32)
             pf_ops.gemm_tn(dlb[:, :D.V], xn, dWout)
-            grads[gi + 2] = dWout
             del dl, dlb
         dx32 = torch.empty((M, D.dim), device=dev, dtype=f32)
         dnw = torch.zeros_like(nw)
         dnb = torch.zeros_like(nb)
         pf_ops.layernorm_bwd(dxn, x32, nw, mean, rstd, dx32, dnw, dnb)
-        grads[gi], grads[gi + 1] = dnw, dnb
-        del dxn
-        dxa = dx32 if is32 else _as(dx32, dt)
+        _GRAD_COPY.pop("last", None)
+        return (dx32, None, None, dnw, dnb, dWout, dbout)
 
-        ws = None
-        if D.gh > 0:
-            fd = pf_ops.favor_desc(B, N, D.gh, D.dh, D.m, D.mp, 3 * D.inner, dt)
-            ws = _workspace(pf_ops.favor_scan_workspace(fd, True), dev)
-        if D.lh > 0:
-            ld_ = pf_ops.local_desc(B, N, D.lh, D.dh, D.W, 3 * D.inner, D.inner, dt)
 
-        for li in range(D.depth - 1, -1, -1):
-            o = base + 10 * li
-            g_a, _Wq, _Wk, _Wv, _Wo, g_f, _W1, b1, _W2, b2 = p[o:o + 10]
-            xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq, states = ctx.saved[li]
-            Wqkv, Wo_, W1_, W2_ = ctx.weights[li]
-            ctx.saved[li] = None
-            # ---- feed-forward sub-layer: x_out = x + g_f * (gelu(x W1^T + b1) W2^T + b2)
-            dot = torch.zeros((1,), device=dev, dtype=f32)
-            du = torch.empty((M, D.ff), device=dev, dtype=dt)
-            pf_ops.gemm_nt(dxa, W2_.t().contiguous(), dot_with=h, dot_out=dot, scale_dev=g_f, act=SA_ACT_GELU_BWD, pre=u,
-                           out_act=du)
-            colsum = ops.bias_grad(dxa)
-            db2 = torch.empty_like(b2)
-            dg_f = torch.empty((), device=dev, dtype=f32)
-            pf_ops.rezero_finish(colsum, b2, g_f, dot, db2, dg_f)
-            dW2 = torch.empty((D.dim, D.ff), device=dev, dtype=f32)
-            pf_ops.gemm_tn(dxa, h, dW2, scale_dev=g_f)
-            dW1 = torch.empty((D.ff, D.dim), device=dev, dtype=f32)
-            pf_ops.gemm_tn(du, xa_ffn, dW1)
-            db1 = ops.bias_grad(du)
-            pf_ops.gemm_nt(du, W1_.t().contiguous(), resid=dx32, out_f32=dx32, out_act=None if is32 else dxa)
-            grads[o + 5], grads[o + 6], grads[o + 7], grads[o + 8], grads[o + 9] = dg_f, dW1, db1, dW2, db2
-            del du, u, h
-            # ---- attention sub-layer: x_out = x + g_a * (attn Wo^T)
-            dot = torch.zeros((1,), device=dev, dtype=f32)
-            dattn = torch.empty((M, D.inner), device=dev, dtype=dt)
-            pf_ops.gemm_nt(dxa, Wo_.t().contiguous(), dot_with=attn, dot_out=dot, scale_dev=g_a, out_act=dattn)
-            dWo = torch.empty((D.dim, D.inner), device=dev, dtype=f32)
-            pf_ops.gemm_tn(dxa, attn, dWo, scale_dev=g_a)
-            dqkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
-            if D.lh > 0:
-                c0 = D.gh * D.dh
-                pf_ops.local_attn_bwd(ld_, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, dattn, c0, lse, dqkv)
-                if inv_freq is not None:       # transpose of the rotary map on the gradients of the rotated q / k
-                    pf_ops.rotary_qk(dqkv, c0, D.inner + c0, B, N, D.lh, D.dh, inv_freq, True)
-            if D.gh > 0:
-                dqf = torch.empty_like(qf)
-                dkf = torch.empty_like(kf)
-                if states is not None and pf_ops.favor_scan_states_bytes(fd) == 0:
-                    states = None          # the dispatch changed since the forward pass: recompute
-                pf_ops.favor_scan_bwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, dattn, 0, den, dqf, dkf, dqkv,
-                                      2 * D.inner, ws, states)
-                gsum = torch.zeros((1,), device=dev, dtype=f32)
-                pf_ops.favor_featmap_bwd(fd, qkv, 0, proj, True, net.eps_feature, qf, dqf, argq, dqkv, 0, None)
-                pf_ops.favor_featmap_bwd(fd, qkv, D.inner, proj, False, net.eps_feature, kf, dkf, None, dqkv, D.inner, gsum)
-                pf_ops.favor_kmax_fixup(fd, proj, kmax, gsum, dqkv, D.inner)
-                del dqf, dkf
-            dWqkv = torch.empty((3 * D.inner, D.dim), device=dev, dtype=f32)
-            pf_ops.gemm_tn(dqkv, xa_attn, dWqkv)
-            pf_ops.gemm_nt(dqkv, Wqkv.t().contiguous(), resid=dx32, out_f32=dx32, out_act=None if is32 else dxa)
-            grads[o] = dot.view(())
-            grads[o + 1], grads[o + 2], grads[o + 3] = dWqkv[:D.inner], dWqkv[D.inner:2 * D.inner], dWqkv[2 * D.inner:]
-            grads[o + 4] = dWo
-            del dqkv, dattn, attn, qkv, qf, kf
-
-        # ---- embeddings
-        d_tok = torch.zeros_like(p[0])
-        d_pos = torch.zeros_like(p[1])
-        d_sps = [torch.zeros_like(t) for t in p[2:2 + D.n_axes]]
-        pf_ops.embed_bwd(dx32, tokens, sp_idx, d_tok, d_sps, d_pos)
-        grads[0], grads[1] = d_tok, d_pos
-        for a, g in enumerate(d_sps):
-            grads[2 + a] = g
-        ctx.saved = ctx.weights = None
-        return (None, None, None, None, *grads)
+def _run_programme(net: "Performer", tokens: torch.Tensor, dt, return_encodings: bool):
+    """embeddings -> depth x layer -> LayerNorm / logits, one autograd node per piece"""
+    if not tokens.is_cuda:
+        raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
+    dt, x3 = ops.resolve_dtype(dt)       # BF16X3: fp32 tensors, dense layers as split-bf16 tensor-core products
+    B, N = tokens.shape
+    C = _Ctx(net, B, N, dt, x3, tokens.device)
+    ps = net._params()
+    n_tab = 2 + C.D.n_axes
+    x32, xa = _EmbedFn.apply(tokens, C, *ps[:n_tab])
+    for li in range(C.D.depth):
+        x32, xa = _LayerFn.apply(x32, xa, C, li, *ps[n_tab + 10 * li: n_tab + 10 * li + 10])
+    return _HeadFn.apply(x32, C, return_encodings, *ps[n_tab + 10 * C.D.depth:])
 
 
 class _Decoder:
@@ -869,4 +919,4 @@ class Performer(TransformerBase):
             raise NotImplementedError("conditioning is not implemented (README configuration has none); no fallback")
         if self.performer.auto_check_redraw:
             self.performer.proj_updater.redraw_projections()
-        return _PerformerFn.apply(x, self, self._dtype(), return_encodings, *self._params())
+        return _run_programme(self, x, self._dtype(), return_encodings)

@@ -131,8 +131,9 @@ def _stack_forward(ops_list, x: torch.Tensor, params: Sequence[torch.Tensor], sa
     return x, saved
 
 
-def _stack_backward(ops_list, saved, params, g, in_is_relu: bool, need_dx: bool):
-    """g: gradient w.r.t. the stack output (NDHWC).  Returns (dx | None, grads)."""
+def _stack_backward(ops_list, saved, params, g, in_is_relu: bool, need_dx: bool, allow_relu_tail: bool = False):
+    """g: gradient w.r.t. the stack output (NDHWC).  Returns (dx | None, grads).  If the last op ends in a ReLU, g must
+    already carry that ReLU's mask (allow_relu_tail: the consumer's data-gradient epilogue applied it)."""
     grads: List[Optional[torch.Tensor]] = [None] * len(params)
     n = len(ops_list)
     # offsets of each op's params
@@ -146,7 +147,7 @@ def _stack_backward(ops_list, saved, params, g, in_is_relu: bool, need_dx: bool)
         relu_in.append(True if isinstance(op, _ResOp) else op.relu)
 
     last = ops_list[-1]
-    if isinstance(last, _ResOp) or last.relu:
+    if not allow_relu_tail and (isinstance(last, _ResOp) or last.relu):
         # the stacks of this model never end in a ReLU (encoder: 3x3x3 projection, decoder: last transposed conv)
         raise RuntimeError("synthanatomy_b200: stack ending in ReLU is not supported")
 
@@ -227,41 +228,60 @@ class retain_activations:
         return False
 
 
-class _StackFn(torch.autograd.Function):
-    """One encoder / decoder stack.  Input and output are NCDHW fp32 (what the reference's callers see)."""
+class _InFn(torch.autograd.Function):
+    """NCDHW fp32 (what the reference's callers hand over) -> channels-last NDHWC in the activation dtype"""
 
     @staticmethod
-    def forward(ctx, x, ops_list, compute_dtype, *params):
+    def forward(ctx, x, dt):
         if not x.is_cuda:
             raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
-        need_grad = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward)
-        compute_dtype, x3 = ops.resolve_dtype(compute_dtype)     # BF16X3: fp32 tensors, split-bf16 tensor-core products
-        xin = ops.ncdhw_to_ndhwc(x.detach().float().contiguous(), compute_dtype)
-        pdet = [p.detach().float().contiguous() for p in params]
-        with ops.x3_mode(x3):
-            y, saved = _stack_forward(ops_list, xin, pdet, need_grad)
-        out = ops.ndhwc_to_ncdhw(y, torch.float32)
-        if need_grad:
-            ctx.ops_list = ops_list
-            ctx.saved = saved
-            ctx.pdet = pdet
-            ctx.compute_dtype = compute_dtype
-            ctx.x3 = x3
-            ctx.need_dx = x.requires_grad
-        return out
+        return ops.ncdhw_to_ndhwc(x.detach().float().contiguous(), dt)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.ndhwc_to_ncdhw(g.contiguous(), torch.float32), None
+
+
+class _OutFn(torch.autograd.Function):
+    """NDHWC activation -> NCDHW fp32"""
+
+    @staticmethod
+    def forward(ctx, y, dt):
+        ctx.dt = dt
+        return ops.ndhwc_to_ncdhw(y.detach(), torch.float32)
 
     @staticmethod
     def backward(ctx, gout):
-        g = ops.ncdhw_to_ndhwc(gout.float().contiguous(), ctx.compute_dtype)
+        return ops.ncdhw_to_ndhwc(gout.float().contiguous(), ctx.dt), None
+
+
+class _OpFn(torch.autograd.Function):
+    """One op of a stack programme (a conv / transposed conv, or a whole ResidualLayer) on NDHWC activations.  One
+    autograd node per op: a layer's parameter gradients exist as soon as ITS backward has run, so DistributedDataParallel
+    reduces the buckets of the upper layers while the lower layers are still in their backward pass, and a layer's saved
+    activations are released right after use."""
+
+    @staticmethod
+    def forward(ctx, x, op, relu_in, x3, *params):
+        need_grad = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward)
+        pdet = [p.detach().float().contiguous() for p in params]
+        with ops.x3_mode(x3):
+            y, saved = _stack_forward([op], x.detach(), pdet, need_grad)
+        if need_grad:
+            ctx.op, ctx.saved, ctx.pdet, ctx.relu_in, ctx.x3 = op, saved, pdet, relu_in, x3
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
         if ctx.saved is None:
-            raise RuntimeError("B200VQVAE: second backward through a stack whose activations were released; wrap the "
+            raise RuntimeError("B200VQVAE: second backward through a layer whose activations were released; wrap the "
                                "iteration in synthanatomy_b200.networks.vqvae.b200.retain_activations()")
         with ops.x3_mode(ctx.x3):
-            dx, grads = _stack_backward(ctx.ops_list, ctx.saved, ctx.pdet, g, False, ctx.need_dx)
+            dx, grads = _stack_backward([ctx.op], ctx.saved, ctx.pdet, g.contiguous(), ctx.relu_in,
+                                        ctx.needs_input_grad[0], allow_relu_tail=True)
         if not _RETAIN_ACTIVATIONS[0]:
             ctx.saved = None
-        gx = ops.ndhwc_to_ncdhw(dx, torch.float32) if dx is not None else None
-        return (gx, None, None, *grads)
+        return (dx, None, None, None, *grads)
 
 
 class _QuantizeFn(torch.autograd.Function):
@@ -480,8 +500,13 @@ class B200VQVAE(VQVAEBase, nn.Module):
         return torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
 
     def _run(self, prog, x):
-        params = [p for op in prog for p in op.params()]
-        return _StackFn.apply(x, prog, self._dtype(), *params)
+        dt, x3 = ops.resolve_dtype(self._dtype())     # BF16X3: fp32 tensors, split-bf16 tensor-core products
+        h = _InFn.apply(x, dt)
+        relu_in = False                               # is the op's input a post-ReLU tensor?  (mask fused into its dgrad)
+        for op in prog:
+            h = _OpFn.apply(h, op, relu_in, x3, *op.params())
+            relu_in = True if isinstance(op, _ResOp) else op.relu
+        return _OutFn.apply(h, dt)
 
     # ---- VQVAEBase API (baseline.py:301-362) ----
     def get_ema_decay(self) -> Sequence[float]:
