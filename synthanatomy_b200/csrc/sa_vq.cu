@@ -8,8 +8,11 @@
 
 namespace {
 
-constexpr int VQ_ROWS_PER_BLOCK = 64;   // 4 lanes cooperate on one latent row
-constexpr int VQ_LANES_PER_ROW = 4;
+// 16 lanes cooperate on one latent row (each scans every 16th code, in ascending order): 11 200 rows (config 2 / 3) are
+// 700 blocks, ~5 per SM, and a thread's serial chain is 128 codes x 32 FMAs.  (With 4 lanes per row the same launch was
+// 175 blocks -- barely one 8-warp block per SM -- and took 171 us; the arithmetic and its order are unchanged.)
+constexpr int VQ_ROWS_PER_BLOCK = 16;
+constexpr int VQ_LANES_PER_ROW = 16;
 constexpr int VQ_THREADS = VQ_ROWS_PER_BLOCK * VQ_LANES_PER_ROW;
 constexpr int VQ_CODE_CHUNK = 256;      // codes staged in shared memory per pass
 

@@ -320,6 +320,12 @@ def _as(t: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
     return out
 
 
+def _t(w: torch.Tensor) -> torch.Tensor:
+    """contiguous transpose of a 2-D weight (same dtype), one launch of the library's tiled transpose kernel"""
+    n, k = w.shape
+    return ops.ncdhw_to_ndhwc(w.contiguous().view(1, n, k), w.dtype).view(k, n)
+
+
 class _Ctx:
     """what every piece of the programme shares for one forward / backward pass"""
 
@@ -360,6 +366,7 @@ class _EmbedFn(torch.autograd.Function):
         sp_idx = C.net._sp_idx(D.N, C.dev)
         pf_ops.embed_fwd(tokens, sp_idx, p[0], p[2:], p[1], x32, None if D.dt == f32 else xa)
         ctx.C, ctx.tokens, ctx.sp_idx, ctx.shapes = C, tokens, sp_idx, [t.shape for t in p]
+        ctx.set_materialize_grads(False)      # no zero tensor for the (non-differentiable) activation-dtype copy
         if D.dt == f32:
             return x32, None              # fp32: the residual stream itself is the operand
         ctx.mark_non_differentiable(xa)
@@ -392,6 +399,7 @@ class _LayerFn(torch.autograd.Function):
         f32 = torch.float32
         is32 = dt == f32
         need_grad = any(ctx.needs_input_grad)
+        ctx.set_materialize_grads(False)      # no zero tensor for the (non-differentiable) activation-dtype copy
         g_a, Wq, Wk, Wv, Wo, g_f, W1, b1, W2, b2 = [q.detach() for q in params]
         x32 = x32.detach()
         xa = x32 if (is32 or xa is None) else xa.detach()
@@ -469,7 +477,7 @@ class _LayerFn(torch.autograd.Function):
         # ---- feed-forward sub-layer: x_out = x + g_f * (gelu(x W1^T + b1) W2^T + b2)
         dot = torch.zeros((1,), device=dev, dtype=f32)
         du = torch.empty((M, D.ff), device=dev, dtype=dt)
-        pf_ops.gemm_nt(dxa, W2_.t().contiguous(), dot_with=h, dot_out=dot, scale_dev=g_f, act=SA_ACT_GELU_BWD, pre=u, out_act=du)
+        pf_ops.gemm_nt(dxa, _t(W2_), dot_with=h, dot_out=dot, scale_dev=g_f, act=SA_ACT_GELU_BWD, pre=u, out_act=du)
         colsum = ops.bias_grad(dxa)
         db2 = torch.empty_like(b2)
         dg_f = torch.empty((), device=dev, dtype=f32)
@@ -481,12 +489,12 @@ class _LayerFn(torch.autograd.Function):
         db1 = ops.bias_grad(du)
         d_mid = torch.empty((M, D.dim), device=dev, dtype=f32)
         dxa_mid = d_mid if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
-        pf_ops.gemm_nt(du, W1_.t().contiguous(), resid=g32, out_f32=d_mid, out_act=None if is32 else dxa_mid)
+        pf_ops.gemm_nt(du, _t(W1_), resid=g32, out_f32=d_mid, out_act=None if is32 else dxa_mid)
         del du, u, h
         # ---- attention sub-layer: x_mid = x + g_a * (attn Wo^T)
         dot = torch.zeros((1,), device=dev, dtype=f32)
         dattn = torch.empty((M, D.inner), device=dev, dtype=dt)
-        pf_ops.gemm_nt(dxa_mid, Wo_.t().contiguous(), dot_with=attn, dot_out=dot, scale_dev=g_a, out_act=dattn)
+        pf_ops.gemm_nt(dxa_mid, _t(Wo_), dot_with=attn, dot_out=dot, scale_dev=g_a, out_act=dattn)
         dWo = torch.empty((D.dim, D.inner), device=dev, dtype=f32)
         pf_ops.gemm_tn(dxa_mid, attn, dWo, scale_dev=g_a)
         dqkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
@@ -512,7 +520,7 @@ class _LayerFn(torch.autograd.Function):
         pf_ops.gemm_tn(dqkv, xa_attn, dWqkv)
         dx = torch.empty((M, D.dim), device=dev, dtype=f32)
         dxa_in = None if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
-        pf_ops.gemm_nt(dqkv, Wqkv.t().contiguous(), resid=d_mid, out_f32=dx, out_act=dxa_in)
+        pf_ops.gemm_nt(dqkv, _t(Wqkv), resid=d_mid, out_f32=dx, out_act=dxa_in)
         if dxa_in is not None:
             _GRAD_COPY["last"] = (dx.data_ptr(), dxa_in)
         return (dx, None, None, None, dot.view(()), dWqkv[:D.inner], dWqkv[D.inner:2 * D.inner], dWqkv[2 * D.inner:], dWo,
