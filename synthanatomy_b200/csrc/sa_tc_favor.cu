@@ -182,6 +182,7 @@ struct FvParams {
   __nv_bfloat16* df_out;             // dqk: dq' / dk'
   float* sums;                       // chunk_state output
   const __nv_bfloat16* st_vec;       // dqk: the bf16 states (their row 64 is read directly)
+  __nv_bfloat16* st_out;             // state_scan: the bf16 prefix / suffix states it writes
   const float2* dinv;                // backward: per (batch, head, position) {delta = dout . out, 1 / den}
 };
 
@@ -509,6 +510,168 @@ tc_chunk_state_kernel(const __grid_constant__ FvParams P) {
                             __uint_as_float(v[i * 4 + 3]));
         }
       }
+    }
+  }
+  FV_EPILOGUE();
+}
+
+// ------------------------------------------------------------------------------------------------ running state
+// The chunk sums AND their exclusive prefix (suffix) in one kernel: a CTA owns (batch, head, up to two 64-column feature
+// blocks) and walks the chunks of the sequence in order with the running state  S[e'][f] = sum_{earlier chunks}
+// sum_tok W_aug[tok][e'] F[tok][f]  as ONE fp32 accumulator in TMEM (the MMAs of chunk c accumulate onto chunks < c).
+// Before chunk c is added the accumulator IS the exclusive prefix: the epilogue warps read it, round it to bf16 and write
+// states[bh][c] (the tensor the scan / dqk kernels consume and the backward pass keeps), then release the tensor core.
+// Replaces tc_chunk_state_kernel + fv_prefix_kernel: no fp32 chunk sums in HBM (373 MB per layer and direction) and one
+// dependent pass instead of two.  MODE / W_aug as in tc_chunk_state_kernel; MODE 1 walks the chunks backwards (suffix).
+// Roles: warps 0-7 build the W operand (MODE 1) and drain TMEM, warp 8 issues MMAs, warp 9 drives TMA (2-stage ring).
+template <int MODE>
+__global__ void __launch_bounds__(F_THREADS, 1)
+tc_state_scan_kernel(const __grid_constant__ FvParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ uint64_t f_full[2], f_empty[2], w_ready[2], d_full, rd_done;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
+  const int cb_beg = blockIdx.x * 2;
+  const int cb_end = min(cb_beg + 2, P.nblk);
+  const int nb = cb_end - cb_beg;
+  const int ncols = min(P.mp, cb_end * 64) - cb_beg * 64;     // feature columns of this CTA: a multiple of 16, <= 128
+  const uint32_t stage_bytes = (uint32_t)(2 + nb) * BLK;      // W | aug | F blocks
+  const int nch = P.nchunks;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&f_full[i], 1); mbar_init(&f_empty[i], 1); mbar_init(&w_ready[i], 256); }
+    mbar_init(&d_full, 1); mbar_init(&rd_done, 256);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp < 8) {
+    // aug blocks of both stages: all zero; MODE 0: column 0 = 1 (constant), MODE 1: column 0 is rewritten per chunk
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    for (int s = 0; s < 2; ++s) {
+      uint8_t* aug = smem + s * stage_bytes + BLK;
+      uint8_t* row = aug + (r >> 3) * 1024 + (r & 7) * 128 + hf * 64;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(row + i * 16) = make_uint4(0, 0, 0, 0);
+    }
+    bar_epi();
+    if (MODE == 0 && hf == 0) {
+      for (int s = 0; s < 2; ++s) {
+        __nv_bfloat16* p0 = reinterpret_cast<__nv_bfloat16*>(sw_row(smem + s * stage_bytes + BLK, r) + ((0 ^ (r & 7)) << 4));
+        *p0 = __float2bfloat16_rn(1.0f);
+      }
+    }
+    fence_proxy_async();
+  }
+  __syncthreads();
+  FV_ALLOC();
+
+  if (warp == 9) {
+    // ------------------------------------------------------------ TMA producer (the last chunk in walking order is never added)
+    if (lane == 0) {
+      prefetch_tmap(&P.map_a);
+      if (MODE == 0) prefetch_tmap(&P.map_b);
+      for (int it = 0; it + 1 < nch; ++it) {
+        const int s = it & 1;
+        const int chunk = MODE ? nch - 1 - it : it;
+        mbar_wait(&f_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1));
+        mbar_expect_tx(&f_full[s], (uint32_t)nb * BLK + (MODE == 0 ? BLK : 0u));
+        uint8_t* st = smem + s * stage_bytes;
+        for (int cb = 0; cb < nb; ++cb) tma_load_3d(st + (2 + cb) * BLK, &P.map_a, &f_full[s], (cb_beg + cb) * 64, chunk * FC, bh);
+        if (MODE == 0) tma_load_3d(st, &P.map_b, &f_full[s], h * 64, chunk * FC, b);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      for (int it = 0; it + 1 < nch; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&f_full[s], ph);
+        if (MODE == 1) mbar_wait(&w_ready[s], ph);
+        mbar_wait(&rd_done, (uint32_t)(it & 1));            // the exclusive state of this chunk has left TMEM
+        tc_fence_after();
+        const uint32_t wa = smem_u32(smem + s * stage_bytes), fa = wa + 2 * BLK;
+#pragma unroll
+        for (int k = 0; k < FC / 16; ++k)
+          mma_cols(tmem_base, make_smem_desc(wa + k * 2048, BLK, 1024, 2), fa + k * 2048, false, BLK, ncols, 1,
+                   (uint32_t)((it | k) != 0));
+        umma_commit(&f_empty[s]);
+        umma_commit(&d_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ W operand (MODE 1) + state drain
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int U = ncols >> 4, U0 = U >> 1;
+    const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
+
+    auto prep = [&](int it) {      // MODE 1: W = dout / den (64 columns) | aug = -delta / den, for the chunk walked at `it`
+      const int s = it & 1;
+      const int chunk = nch - 1 - it;
+      const int n = chunk * FC + r;
+      uint8_t* Ws = smem + s * stage_bytes;
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = 0.f;
+      float aug = 0.f;
+      if (n < P.N) {
+        const long long ro = ((long long)b * P.N + n) * P.out_ld + h * 64;
+        const float2 di = __ldg(P.dinv + (long long)bh * P.N + n);
+        const float inv = di.y;
+        aug = -di.x * inv;
+        const uint4* pd = reinterpret_cast<const uint4*>(P.dout + ro + hf * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          unpack8(__ldg(pd + i), f + i * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[i * 8 + j] *= inv;
+        }
+      }
+      st_sw_32(Ws, r, hf * 32, f);
+      if (hf == 0) {
+        __nv_bfloat16* p0 = reinterpret_cast<__nv_bfloat16*>(sw_row(Ws + BLK, r) + ((0 ^ (r & 7)) << 4));
+        *p0 = __float2bfloat16_rn(aug);
+      }
+      fence_proxy_async();
+      mbar_arrive(&w_ready[s]);
+    };
+
+    if (MODE == 1 && nch > 1) prep(0);
+    for (int it = 0; it < nch; ++it) {
+      const int chunk = MODE ? nch - 1 - it : it;
+      if (it > 0) {
+        mbar_wait(&d_full, (uint32_t)((it - 1) & 1));       // chunks walked so far are in the accumulator
+        tc_fence_after();
+      }
+      if (q * 32 < ST_ROWS) {                               // warp-uniform: quadrants 0..2 hold rows < 80
+        __nv_bfloat16* dst = P.st_out + (((long long)bh * nch + chunk) * ST_ROWS + r) * P.mp + cb_beg * 64;
+        for (int u = u_beg; u < u_end; ++u) {
+          uint32_t v[16];
+          if (it > 0) {
+            tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0u;
+          }
+          if (r < ST_ROWS) {
+            float f[16];
+            const float seed = (MODE == 0 && r == 64) ? P.eps : 0.f;      // forward: k_cumsum + eps
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = (r < SUM_ROWS) ? __uint_as_float(v[j]) + seed : 0.f;
+            uint4* d4 = reinterpret_cast<uint4*>(dst + u * 16);
+            d4[0] = pack8(f);
+            d4[1] = pack8(f + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&rd_done);
+      if (MODE == 1 && it + 2 < nch) prep(it + 1);          // (stage (it + 1) & 1 was last read by the MMAs of chunk it - 1)
     }
   }
   FV_EPILOGUE();
@@ -1017,6 +1180,8 @@ void init_once() {
     cudaFuncSetAttribute(tc_featmap_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(tc_chunk_state_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(tc_chunk_state_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_state_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_state_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(tc_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SCAN);
     cudaFuncSetAttribute(tc_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SCAN);
     cudaFuncSetAttribute(tc_dqk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQK);
@@ -1041,6 +1206,7 @@ void fill_common(FvParams& P, const sa_favor_desc* d, int out_ld, float eps) {
   P.proj = nullptr; P.kmax_in = nullptr; P.kmax_out = nullptr; P.x = nullptr; P.feat = nullptr; P.dfeat = nullptr;
   P.argmax = nullptr; P.gsum = nullptr; P.is_query = 0; P.out = nullptr; P.dout = nullptr; P.den_in = nullptr;
   P.den_out = nullptr; P.o_out = nullptr; P.df_out = nullptr; P.sums = nullptr; P.st_vec = nullptr; P.dinv = nullptr;
+  P.st_out = nullptr;
 }
 
 // [bh][n][mp] feature tensor: box = 64 columns x 128 tokens of one (batch, head)
@@ -1084,6 +1250,19 @@ int launch_states(const sa_favor_desc* d, int mode, const void* feat, const void
   if ((rc = feat_map(&P.map_a, feat, d)) != SA_OK) return rc;
   if (mode == 0 && (rc = head_map(&P.map_b, w, d, d->ld)) != SA_OK) return rc;
   P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.sums = sums; P.dinv = dinv;
+  bool serial = true;                                  // SA_FAVOR_STATE_SCAN=0: the two-kernel form (chunk sums, then prefix)
+  if (const char* e = getenv("SA_FAVOR_STATE_SCAN")) serial = e[0] != '0';
+  if (serial) {
+    P.st_out = (__nv_bfloat16*)states;
+    const int nb = P.nblk < 2 ? P.nblk : 2;
+    const dim3 sgrid((unsigned)((P.nblk + 1) / 2), (unsigned)(d->batch * d->heads));
+    const size_t ssmem = (size_t)2 * (2 + nb) * BLK + 1024;
+    P.tmem_cols = tmem_cols_for(d->mp < 128 ? d->mp : 128);
+    if (mode == 0) tc_state_scan_kernel<0><<<sgrid, F_THREADS, ssmem, st>>>(P);
+    else tc_state_scan_kernel<1><<<sgrid, F_THREADS, ssmem, st>>>(P);
+    SA_LAUNCH_CHECK();
+    return SA_OK;
+  }
   dim3 grid = fv_grid(d);
   size_t smem = smem_state(d->mp);
   P.tmem_cols = tmem_cols_for(d->mp);
