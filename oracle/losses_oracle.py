@@ -1,5 +1,6 @@
 """CPU oracle for the spectral reconstruction loss of the README run (TEST INFRASTRUCTURE -- never imported by the
-product; SURVEY.md section 8(f) rank 2, for which no CUDA path exists yet).
+product; the CUDA path it checks is synthanatomy_b200.losses.JukeboxLoss,
+tests/test_gpu_losses.py).
 
 ``jukebox_loss`` restates ``JukeboxLoss.forward`` (/root/reference/src/losses/vqvae/vqvae.py:522-640): orthonormal FFT
 over the channel and spatial axes, amplitude ``sqrt(re^2 + im^2)``, mean squared amplitude difference times

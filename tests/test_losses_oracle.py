@@ -1,5 +1,5 @@
-"""The spectral-loss oracle against golden values of the unmodified reference class (no GPU; the CUDA path for SURVEY
-section 8(f) rank 2 does not exist yet -- this pins the checker it will be held to)."""
+"""The spectral-loss oracle against golden values of the unmodified reference class (no GPU; this pins the checker the
+CUDA path of SURVEY section 8(f) rank 2 -- tests/test_gpu_losses.py -- is held to)."""
 import os
 
 import numpy as np

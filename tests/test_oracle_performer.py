@@ -142,3 +142,31 @@ def test_readme_parameter_count():
     assert per_layer == 4196866
     total = 24 * per_layer + 2049 * 512 + 1401 * 512 + 3 * 1399 * 512 + 2 * 512 + 2049 * 512 + 2049
     assert abs(total - 105.7e6) < 0.1e6
+
+
+def test_restatement_against_installed_packages():
+    """the third-party arithmetic of the Performer oracle (performer-pytorch 1.0.11, local-attention)
+    is restated from the published source, not executed -- neither package is in this image, in /opt/wheelhouse or on the
+    GPU box, so this test SKIPS there.  Wherever the packages can be imported it pins the restatement to them:
+    softmax_kernel (query / key forms), the non-CUDA causal linear attention, the local window attention."""
+    import pytest
+    pp = pytest.importorskip("performer_pytorch.performer_pytorch")
+    g = torch.Generator().manual_seed(0)
+    data = torch.randn(2, 3, 37, 64, generator=g)
+    proj = torch.randn(40, 64, generator=g)
+    for is_query in (True, False):
+        want = pp.softmax_kernel(data, projection_matrix=proj, is_query=is_query)
+        torch.testing.assert_close(po.softmax_kernel(data, proj, is_query), want, rtol=1e-5, atol=1e-7)
+    q = po.softmax_kernel(data, proj, True)
+    k = po.softmax_kernel(data, proj, False)
+    v = torch.randn(2, 3, 37, 64, generator=g)
+    if hasattr(pp, "causal_linear_attention_noncuda"):
+        want = pp.causal_linear_attention_noncuda(q, k, v)
+        torch.testing.assert_close(po.causal_linear_attention(q, k, v), want, rtol=1e-4, atol=1e-6)
+    la = pytest.importorskip("local_attention")
+    attn = la.LocalAttention(window_size=8, causal=True, autopad=True, look_backward=1, look_forward=0, dropout=0.0,
+                             rel_pos_emb_config=(64, 3))
+    x = [torch.randn(2, 3, 37, 64, generator=g) for _ in range(3)]
+    want = attn(*x)
+    rel = "rotary" if any("rel_pos" in n or "inv_freq" in n for n, _ in attn.named_buffers()) else "none"
+    torch.testing.assert_close(po.local_attention(*x, 8, rel), want, rtol=1e-4, atol=1e-6)
