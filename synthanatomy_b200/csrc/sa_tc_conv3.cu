@@ -320,7 +320,10 @@ int c3_launch(C3Params& P, int batch, bool out_f32, cudaStream_t st) {
 bool sa_tc_conv3_supported(const sa_conv_desc* d) {
   if (d->act_dtype != SA_BF16) return false;
   // up to 128 output channels per launch; 256 = two launches over the two halves of the output channels
-  if (d->c_in % 64 != 0 || d->c_out % 16 != 0 || d->c_out < 16 || (d->c_out > 128 && d->c_out != 256)) return false;
+  // input channels: whole 64-channel TMA boxes, or ONE partial box (c_in = 16 / 32 / 48: the box is 64 wide, the
+  // channels past c_in are zero-filled by the TMA unit on both operands) -- the 32-channel quantiser projections
+  if ((d->c_in % 64 != 0 && !(d->c_in < 64 && d->c_in % 16 == 0)) || d->c_in < 16) return false;
+  if (d->c_out % 16 != 0 || d->c_out < 16 || (d->c_out > 128 && d->c_out != 256)) return false;
   if (const char* e = getenv("SA_TC_CONV3")) { if (e[0] == '0') return false; }   // A/B switch for benchmarking
   if (d->c_out == 256) { if (const char* e = getenv("SA_TC_CONV3_N256")) { if (e[0] == '0') return false; } }
   if (!sa_get_tmap_encode()) return false;
@@ -383,7 +386,7 @@ static int c3_fwd_part(const sa_conv_desc* d, const void* x, const void* wp, con
   const int k = d->ksize, taps = k * k * k;
   P.N = N;
   P.ldy = d->c_out;
-  P.cchunks = d->c_in / 64;
+  P.cchunks = (d->c_in + 63) / 64;
   P.oD = d->out_dhw[0]; P.oH = d->out_dhw[1]; P.oW = d->out_dhw[2];
   const size_t es = out_f32 ? 4 : 2;
   P.relu = relu; P.bias = bias ? bias + n0 : nullptr;

@@ -145,3 +145,35 @@ def test_bf16_grads_close_to_oracle():
         cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
         assert cos > 0.99, f"{k}: cosine {cos:.4f}"
         assert float((a - b).abs().max()) < 0.1 * float(b.abs().max()) + 1e-7, k
+
+
+def test_amp_gradscaler_iteration_as_the_reference_trainer_runs_it():
+    """the generator half of AdversarialTrainer._iteration (/root/reference/src/engines/trainer.py:157-190) /
+    MONAI's SupervisedTrainer with amp=True: forward under torch.cuda.amp.autocast() (fp16 autocast in the reference; the
+    drop-in answers any autocast with its bf16 tensor-core path), GradScaler.scale(loss).backward(), scaler.step,
+    scaler.update -- with stock torch.optim.Adam as run_vqvae.py:82 builds it."""
+    from synthanatomy_b200.networks.vqvae import B200VQVAE
+    from synthanatomy_b200 import ops
+    kw = dict(n_levels=1, downsample_parameters=((4, 2, 1, 1),), upsample_parameters=((4, 2, 1, 0, 1),),
+              n_embed=64, embed_dim=16, n_channels=128, n_res_channels=128, n_res_layers=2, vq_decay=0.5,
+              commitment_cost=0.25)
+    torch.manual_seed(0)
+    net = B200VQVAE(**kw).cuda().train()
+    opt = torch.optim.Adam(net.parameters(), 1.65e-4)
+    scaler = torch.amp.GradScaler("cuda")
+    x = torch.rand(2, 1, 16, 16, 32, device="cuda")
+    before = [p.detach().clone() for p in net.parameters()]
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        with torch.autocast("cuda"):                      # default dtype of CUDA autocast = float16, as in the reference
+            out = net(x)
+            loss = F.mse_loss(out["reconstruction"][0].float(), x) + out["quantization_losses"][0]
+        assert ops.last_path() == 2, "the tensor-core path did not answer the autocast region"
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        losses.append(float(loss))
+    assert all(torch.isfinite(p).all() for p in net.parameters())
+    assert sum(int(not torch.equal(a, p)) for a, p in zip(before, net.parameters())) >= len(before) - 2   # codebook: EMA
+    assert scaler.get_scale() > 0 and losses[-1] < losses[0]
