@@ -39,7 +39,8 @@ typedef enum sa_path { SA_PATH_NONE = 0, SA_PATH_SIMT = 1, SA_PATH_TCGEN05 = 2 }
 const char* sa_last_error(void);
 int sa_version(void);
 int sa_last_path(void);
-/* number of kernels launched by this library on the calling thread since the last reset */
+/* number of kernels launched by this library (all threads of the process: autograd runs backward passes on its own
+ * device thread) since the last reset */
 int64_t sa_launch_count(void);
 void sa_launch_count_reset(void);
 /* 0: dispatch normally; 1: force the CUDA-core (SIMT) kernels even where a tcgen05 kernel exists */

@@ -2,6 +2,7 @@
 // thread-local status plumbing.  See include/synthanatomy_b200.h for the contract.
 #include <stdarg.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "sa_tc_common.cuh"
@@ -24,7 +25,9 @@ int sa_tc_conv3d_wgrad(const sa_conv_desc*, const void*, const void*, float*, cu
 namespace {
 thread_local char g_err[512] = "";
 thread_local int g_path = SA_PATH_NONE;
-thread_local int64_t g_launches = 0;
+// process-wide (not per thread): autograd runs the backward pass of CUDA graphs on its own device thread, and a step's
+// launch count must include it
+std::atomic<int64_t> g_launches{0};
 int g_force_simt = 0;
 }  // namespace
 
@@ -34,15 +37,15 @@ void sa_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void sa_note_launch(int n) { g_launches += n; }
+void sa_note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void sa_note_path(int path) { g_path = path; }
 bool sa_force_simt() { return g_force_simt != 0; }
 
 extern "C" const char* sa_last_error(void) { return g_err; }
 extern "C" int sa_version(void) { return 100; }
 extern "C" int sa_last_path(void) { return g_path; }
-extern "C" int64_t sa_launch_count(void) { return g_launches; }
-extern "C" void sa_launch_count_reset(void) { g_launches = 0; }
+extern "C" int64_t sa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void sa_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); }
 extern "C" void sa_set_force_simt(int on) { g_force_simt = on; }
 
 // ------------------------------------------------------------------------------------------------
