@@ -62,6 +62,9 @@ class PerformerConfig:
     key_stabiliser: str = "global"          # 1.0.11: torch.max over the whole key tensor; "per_head" = later 1.1.x
     eps_feature: float = 1e-4               # softmax_kernel eps
     eps_cumsum: float = 1e-6                # causal_linear_attention eps
+    fixed_position_emb: bool = False        # performer.py:136-138: sinusoidal pos_emb (performer-pytorch FixedPositionalEmbedding)
+    conditioning_num_tokens: Optional[Tuple[int, ...]] = None     # performer.py:183-187
+    conditioning_type: str = "none"         # "none" | "bos_replacement" | "prepending" (src/utils/transformer.py:21-24)
 
     @property
     def inner(self) -> int:
@@ -363,11 +366,17 @@ def init_state_dict(cfg: PerformerConfig, seed: int = 0) -> Dict[str, torch.Tens
             sd[name + ".bias"] = (torch.rand(out_f, generator=g) * 2 - 1) * bound
 
     n_seq = cfg.max_seq_len - 1                       # = prod(spatial_shape); the wrapper is built with max_seq_len = N + 1
+    n_cond = len(cfg.conditioning_num_tokens) if (cfg.conditioning_num_tokens and cfg.conditioning_type == "prepending") else 0
     sd["token_emb.weight"] = torch.randn(cfg.num_tokens, cfg.dim, generator=g)
-    sd["pos_emb.emb.weight"] = torch.randn(cfg.max_seq_len, cfg.dim, generator=g)
+    if cfg.fixed_position_emb:
+        sd["pos_emb.emb"] = sinusoid_table(torch.arange(0, cfg.max_seq_len + n_cond), cfg.dim)
+    else:
+        sd["pos_emb.emb.weight"] = torch.randn(cfg.max_seq_len + n_cond, cfg.dim, generator=g)     # performer.py:119-125
     if cfg.spatial_position_emb == "absolute":
         for a in range(len(cfg.spatial_shape)):
             sd[f"spatial_position_emb.{a}.emb.weight"] = torch.randn(n_seq - 1, cfg.dim, generator=g)  # performer.py:27-33
+    for i, cnt in enumerate(cfg.conditioning_num_tokens or ()):
+        sd[f"conditioning_emb.{i}.weight"] = torch.randn(cnt, cfg.dim, generator=g)
     for i in range(cfg.depth):
         p = layer_prefix(i)
         sd[p + "0.g"] = torch.tensor(1e-3)
@@ -386,7 +395,7 @@ def init_state_dict(cfg: PerformerConfig, seed: int = 0) -> Dict[str, torch.Tens
     return sd
 
 
-BUFFER_SUFFIXES = ("projection_matrix",)
+BUFFER_SUFFIXES = ("projection_matrix", "pos_emb.emb")
 
 
 def trainable_keys(sd: Dict[str, torch.Tensor]) -> List[str]:
@@ -419,9 +428,16 @@ def feed_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], p: str) -> torch.
     return F.linear(F.gelu(F.linear(x, sd[p + "w1.weight"], sd[p + "w1.bias"])), sd[p + "w2.weight"], sd[p + "w2.bias"])
 
 
+def sinusoid_table(positions: torch.Tensor, dim: int) -> torch.Tensor:
+    """performer.py:46-57 / performer-pytorch FixedPositionalEmbedding: cat(sin(p f), cos(p f)), f = 10000^(-2i/dim)"""
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim))
+    sinusoid_inp = torch.einsum("i,j->ij", positions.float(), inv_freq)
+    return torch.cat((sinusoid_inp.sin(), sinusoid_inp.cos()), dim=-1)
+
+
 def embed(sd: Dict[str, torch.Tensor], cfg: PerformerConfig, tokens: torch.Tensor,
-          spatial_seqs: Optional[Sequence[torch.Tensor]]) -> torch.Tensor:
-    """performer.py:241-268 (conditioning off, dropout 0)."""
+          spatial_seqs: Optional[Sequence[torch.Tensor]], conditionings: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+    """performer.py:241-268 (dropout 0)."""
     n = tokens.shape[1]
     x = F.embedding(tokens, sd["token_emb.weight"])                                  # :241
     if cfg.spatial_position_emb == "absolute":
@@ -430,20 +446,39 @@ def embed(sd: Dict[str, torch.Tensor], cfg: PerformerConfig, tokens: torch.Tenso
             sc = sc[None, : n - 1, :]                                                # :37
             sc = F.pad(sc, (0, 0, 1, 0, 0, 0), "constant", 0)                        # :31, 38 (zero BOS row)
             x = x + sc
-    x = x + sd["pos_emb.emb.weight"][:n]                                             # :266 AbsolutePositionalEmbedding
+    elif cfg.spatial_position_emb == "fixed":
+        for seq in spatial_seqs:                                                     # :43-67
+            table = sinusoid_table(torch.arange(0, int(seq.max()) + 1), cfg.dim)     # :48-53
+            sc = table[seq.long(), :][:-1]                                           # :54-58
+            sc = F.pad(sc[None, : n - 1, :], (0, 0, 1, 0, 0, 0), "constant", 0)      # :63-66
+            x = x + sc
+    if conditionings and cfg.conditioning_type != "none":                            # :248-264
+        if cfg.conditioning_type == "bos_replacement":
+            c = torch.zeros_like(x[:, 0, :]).unsqueeze(1)
+            for i, cond in enumerate(conditionings):
+                c = c + F.embedding(cond, sd[f"conditioning_emb.{i}.weight"])
+            x = torch.cat((c[:, :1, :], x[:, 1:, :]), dim=1)                         # x[:, 0, :] = c[:, 0, :]
+        else:
+            for i, cond in enumerate(conditionings):
+                x = torch.cat((F.embedding(cond, sd[f"conditioning_emb.{i}.weight"]), x), dim=1)
+    pos = sd["pos_emb.emb"] if cfg.fixed_position_emb else sd["pos_emb.emb.weight"]
+    x = x + pos[: x.shape[1]]                                                        # :266 (Absolute | Fixed)PositionalEmbedding
     return x
 
 
 def forward(sd: Dict[str, torch.Tensor], cfg: PerformerConfig, tokens: torch.Tensor,
-            spatial_seqs: Optional[Sequence[torch.Tensor]] = None, return_encodings: bool = False) -> torch.Tensor:
+            spatial_seqs: Optional[Sequence[torch.Tensor]] = None, return_encodings: bool = False,
+            conditionings: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
     """Performer.forward, performer.py:229-288 -> logits [B, N, num_tokens]."""
     assert tokens.shape[1] <= cfg.max_seq_len                                        # :237-239
-    x = embed(sd, cfg, tokens, spatial_seqs)
+    x = embed(sd, cfg, tokens, spatial_seqs, conditionings)
     for i in range(cfg.depth):                                                       # SequentialSequence
         p = layer_prefix(i)
         x = x + self_attention(x, sd, p + "0.fn.", cfg) * sd[p + "0.g"]              # ReZero(SelfAttention)
         x = x + feed_forward(x, sd, p + "1.fn.fn.") * sd[p + "1.g"]                  # ReZero(Chunk(FeedForward))
     x = F.layer_norm(x, (cfg.dim,), sd["norm.weight"], sd["norm.bias"], 1e-5)        # :273
+    if conditionings and cfg.conditioning_type == "prepending":                      # :275-280
+        x = x[:, len(conditionings):, :]
     if return_encodings:
         return x
     return F.linear(x, sd["to_out.weight"], sd["to_out.bias"])                       # :286
@@ -455,10 +490,11 @@ def ce_loss(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
 
 
 def train_step_grads(sd: Dict[str, torch.Tensor], cfg: PerformerConfig, x_in: torch.Tensor, y: torch.Tensor,
-                     spatial_seqs: Optional[Sequence[torch.Tensor]] = None):
+                     spatial_seqs: Optional[Sequence[torch.Tensor]] = None,
+                     conditionings: Optional[Sequence[torch.Tensor]] = None):
     """-> (loss, {key: grad}, logits) with torch autograd over the restatement."""
     leaves = {k: (v.clone().requires_grad_(True) if k in set(trainable_keys(sd)) else v) for k, v in sd.items()}
-    logits = forward(leaves, cfg, x_in, spatial_seqs)
+    logits = forward(leaves, cfg, x_in, spatial_seqs, conditionings=conditionings)
     loss = ce_loss(logits, y)
     keys = [k for k in trainable_keys(sd)]
     grads = torch.autograd.grad(loss, [leaves[k] for k in keys], allow_unused=True)

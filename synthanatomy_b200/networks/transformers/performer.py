@@ -27,7 +27,8 @@ from ... import ops, pf_ops
 from ...pf_ops import SA_ACT_GELU_BWD, SA_ACT_GELU_FWD
 from .transformer import TransformerBase
 
-_NONE = "none"   # TransformerConditioningType.NONE.value (src/utils/transformer.py)
+# TransformerConditioningType values (src/utils/transformer.py:21-24)
+_NONE, _BOS_REPLACEMENT, _PREPENDING = "none", "bos_replacement", "prepending"
 
 
 def _no_exec(*_a, **_k):
@@ -55,6 +56,36 @@ class AbsoluteSpatialPositionalEmbedding(nn.Module):
         self.register_buffer("spatial_indices_sequence", spatial_indices_sequence)
         self.spatial_indices_sequence = self.spatial_indices_sequence[:-1]     # the last element is the predicted one
         self.emb = nn.Embedding(len(self.spatial_indices_sequence), dim)
+
+    forward = _no_exec
+
+
+def _sinusoid_table(positions: torch.Tensor, dim: int) -> torch.Tensor:
+    """[len(positions), dim] = cat(sin(p f), cos(p f)), f = 10000^(-2i / dim)"""
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim))
+    sinusoid_inp = torch.einsum("i,j->ij", positions.float(), inv_freq)
+    return torch.cat((sinusoid_inp.sin(), sinusoid_inp.cos()), dim=-1)
+
+
+class FixedPositionalEmbedding(nn.Module):
+    """performer-pytorch: sinusoidal table over the sequence positions (buffer ``emb``), emb[:n]"""
+
+    def __init__(self, dim, max_seq_len):
+        super().__init__()
+        self.register_buffer("emb", _sinusoid_table(torch.arange(0, max_seq_len), dim))
+
+    forward = _no_exec
+
+
+class FixedSpatialPositionalEmbedding(nn.Module):
+    """performer.py:43-67: sinusoidal code of the COORDINATE of each sequence position (buffer ``emb``, one row per
+    position, last one dropped: it is the predicted position)"""
+
+    def __init__(self, dim: int, spatial_indices_sequence: torch.Tensor):
+        super().__init__()
+        max_position = int(torch.max(spatial_indices_sequence))
+        table = _sinusoid_table(torch.arange(0, max_position + 1), dim)
+        self.register_buffer("emb", table[spatial_indices_sequence.long(), :][:-1])
 
     forward = _no_exec
 
@@ -331,6 +362,7 @@ class _Ctx:
 
     def __init__(self, net: "Performer", B: int, N: int, dt: torch.dtype, x3: bool, dev):
         self.net, self.x3, self.dev = net, x3, dev
+        self.lead = 0
         self.D = D = _Dims(net, B, N, dt)
         self.fd = pf_ops.favor_desc(B, N, D.gh, D.dh, D.m, D.mp, 3 * D.inner, dt) if D.gh > 0 else None
         self.ld = pf_ops.local_desc(B, N, D.lh, D.dh, D.W, 3 * D.inner, D.inner, dt) if D.lh > 0 else None
@@ -363,7 +395,7 @@ class _EmbedFn(torch.autograd.Function):
         tokens = tokens.long().contiguous()
         x32 = torch.empty((D.M, D.dim), device=C.dev, dtype=f32)
         xa = x32 if D.dt == f32 else torch.empty((D.M, D.dim), device=C.dev, dtype=D.dt)
-        sp_idx = C.net._sp_idx(D.N, C.dev)
+        sp_idx = C.net._sp_idx(D.N - C.lead, C.dev, C.lead)
         pf_ops.embed_fwd(tokens, sp_idx, p[0], p[2:], p[1], x32, None if D.dt == f32 else xa)
         ctx.C, ctx.tokens, ctx.sp_idx, ctx.shapes = C, tokens, sp_idx, [t.shape for t in p]
         ctx.set_materialize_grads(False)      # no zero tensor for the (non-differentiable) activation-dtype copy
@@ -600,14 +632,18 @@ class _HeadFn(torch.autograd.Function):
         return (dx32, None, None, dnw, dnb, dWout, dbout)
 
 
-def _run_programme(net: "Performer", tokens: torch.Tensor, dt, return_encodings: bool):
-    """embeddings -> depth x layer -> LayerNorm / logits, one autograd node per piece"""
+def _run_programme(net: "Performer", tokens: torch.Tensor, dt, return_encodings: bool, tok_table=None, lead: int = 0):
+    """embeddings -> depth x layer -> LayerNorm / logits, one autograd node per piece.  tok_table: the token table with
+    conditioning rows appended (None: the plain one); lead: number of prepended conditioning positions"""
     if not tokens.is_cuda:
         raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
     dt, x3 = ops.resolve_dtype(dt)       # BF16X3: fp32 tensors, dense layers as split-bf16 tensor-core products
     B, N = tokens.shape
     C = _Ctx(net, B, N, dt, x3, tokens.device)
+    C.lead = lead
     ps = net._params()
+    if tok_table is not None:
+        ps[0] = tok_table
     n_tab = 2 + C.D.n_axes
     x32, xa = _EmbedFn.apply(tokens, C, *ps[:n_tab])
     for li in range(C.D.depth):
@@ -671,8 +707,9 @@ class _Decoder:
         self.xn = torch.empty((batch, D.dim), device=dev, dtype=f32 if is32 else dt)
         self.logits = torch.empty((batch, D.V), device=dev, dtype=f32)
         self.tok_w = net.token_emb.weight.detach()
-        self.sp_ws = [m.emb.weight.detach() for m in net.spatial_position_emb]
-        self.pos_w = net.pos_emb.emb.weight.detach()
+        self.sp_ws = [(m.emb if isinstance(m, FixedSpatialPositionalEmbedding) else m.emb.weight).detach()
+                      for m in net.spatial_position_emb]
+        self.pos_w = net._pos_table().detach()
         self.graph = None
         self.calls = 0
         import os
@@ -795,10 +832,8 @@ class Performer(TransformerBase):
             "dropout > 0": (emb_dropout, ff_dropout, attn_dropout) != (0.0, 0.0, 0.0),
             "generalized_attention": generalized_attention, "use_scalenorm": use_scalenorm,
             "use_rezero=False": not use_rezero, "cross_attend": cross_attend, "no_projection": no_projection,
-            "tie_embed": tie_embed, "rotary/fixed/axial position_emb": rotary_position_emb or fixed_position_emb or
-            axial_position_emb, "qkv_bias / attn_out_bias": qkv_bias or attn_out_bias,
-            "spatial_position_emb='fixed'": spatial_position_emb == "fixed",
-            "conditioning": bool(conditioning_num_tokens) and conditioning_type != _NONE,
+            "tie_embed": tie_embed, "rotary / axial position_emb": rotary_position_emb or axial_position_emb,
+            "qkv_bias / attn_out_bias": qkv_bias or attn_out_bias,
         }
         bad = [k for k, v in unsupported.items() if v]
         if bad:
@@ -808,6 +843,10 @@ class Performer(TransformerBase):
             assert len(local_attn_heads) == 1, "per-layer local head counts are not implemented"
             local_attn_heads = local_attn_heads[0]
         assert local_rel_pos in ("rotary", "none")
+        assert conditioning_type in (_NONE, _BOS_REPLACEMENT, _PREPENDING), conditioning_type
+        # accounting for the number of prepended conditionings (performer.py:119-125)
+        max_seq_len = max_seq_len + (len(conditioning_num_tokens)
+                                     if conditioning_num_tokens and conditioning_type == _PREPENDING else 0)
         self.num_tokens, self.max_seq_len = num_tokens, max_seq_len
         self.dim, self.depth, self.heads, self.dim_head = dim, depth, heads, dim_head
         self.local_attn_heads, self.local_window_size, self.ff_mult = local_attn_heads, local_window_size, ff_mult
@@ -817,7 +856,8 @@ class Performer(TransformerBase):
         self.conditioning_type = conditioning_type
 
         self.token_emb = nn.Embedding(num_tokens, dim)
-        self.pos_emb = AbsolutePositionalEmbedding(dim, self.max_seq_len)
+        self.pos_emb = (FixedPositionalEmbedding(dim, self.max_seq_len) if fixed_position_emb
+                        else AbsolutePositionalEmbedding(dim, self.max_seq_len))
         self.ordering = ordering
         self.spatial_position_emb = nn.ModuleList()
         if spatial_position_emb:
@@ -829,8 +869,12 @@ class Performer(TransformerBase):
             for i in axis:
                 seq = torch.from_numpy(coord_channels[i, ...].flatten())
                 seq = self.ordering(seq)
-                self.spatial_position_emb.append(AbsoluteSpatialPositionalEmbedding(dim=dim, spatial_indices_sequence=seq))
+                cls = FixedSpatialPositionalEmbedding if spatial_position_emb == "fixed" else AbsoluteSpatialPositionalEmbedding
+                self.spatial_position_emb.append(cls(dim=dim, spatial_indices_sequence=seq))
         self.conditioning_emb = nn.ModuleList()
+        if conditioning_num_tokens:
+            for cnt in conditioning_num_tokens:
+                self.conditioning_emb.append(nn.Embedding(cnt, dim))
         self.dropout = nn.Dropout(emb_dropout)
         self.performer = PerformerStack(dim, depth, heads, dim_head, local_attn_heads, local_window_size, ff_mult,
                                         nb_features, feature_redraw_interval, auto_check_redraw,
@@ -846,22 +890,31 @@ class Performer(TransformerBase):
     def fix_projection_matrices_(self):
         self.performer.fix_projection_matrices_()
 
-    def _sp_idx(self, n: int, device) -> Optional[torch.Tensor]:
-        """[n_axes, n] int32: coordinate of sequence position n - 1 along each axis, -1 at the BOS position."""
+    def _sp_idx(self, n: int, device, lead: int = 0) -> Optional[torch.Tensor]:
+        """[n_axes, lead + n] int32 row of each axis' table that sequence position j adds (-1: none): nothing at the
+        `lead` prepended conditioning positions and at the BOS position; then, for an absolute table (one row per
+        coordinate VALUE, performer.py:27-33) the coordinate of position j - 1, for a fixed table (one row per sequence
+        position, performer.py:43-57) j - 1 itself."""
         if len(self.spatial_position_emb) == 0:
             return None
-        key = (n, str(device))
+        key = (n, lead, str(device))
         if key not in self._sp_cache:
             rows = []
             for mod in self.spatial_position_emb:
-                seq = mod.spatial_indices_sequence[: n - 1].to(torch.int32).cpu()
-                rows.append(torch.cat((torch.full((1,), -1, dtype=torch.int32), seq)))
+                if isinstance(mod, FixedSpatialPositionalEmbedding):
+                    seq = torch.arange(0, n - 1, dtype=torch.int32)
+                else:
+                    seq = mod.spatial_indices_sequence[: n - 1].to(torch.int32).cpu()
+                rows.append(torch.cat((torch.full((lead + 1,), -1, dtype=torch.int32), seq)))
             self._sp_cache = {key: torch.stack(rows).contiguous().to(device)}
         return self._sp_cache[key]
 
+    def _pos_table(self) -> torch.Tensor:
+        return self.pos_emb.emb if isinstance(self.pos_emb, FixedPositionalEmbedding) else self.pos_emb.emb.weight
+
     def _params(self) -> List[torch.Tensor]:
-        ps = [self.token_emb.weight, self.pos_emb.emb.weight]
-        ps += [m.emb.weight for m in self.spatial_position_emb]
+        ps = [self.token_emb.weight, self._pos_table()]
+        ps += [m.emb if isinstance(m, FixedSpatialPositionalEmbedding) else m.emb.weight for m in self.spatial_position_emb]
         for layer in self.performer.net.layers:
             a, f = layer[0], layer[1]
             ps += [a.g, a.fn.to_q.weight, a.fn.to_k.weight, a.fn.to_v.weight, a.fn.to_out.weight,
@@ -923,8 +976,29 @@ class Performer(TransformerBase):
         b, n = x.shape
         assert n <= self.max_seq_len, \
             f"sequence length {n} must be less than the max sequence length {self.max_seq_len}"
-        if conditionings and self.conditioning_type != _NONE:
-            raise NotImplementedError("conditioning is not implemented (README configuration has none); no fallback")
         if self.performer.auto_check_redraw:
             self.performer.proj_updater.redraw_projections()
-        return _run_programme(self, x, self._dtype(), return_encodings)
+        tok_table, lead = None, 0
+        if conditionings and self.conditioning_type != _NONE:
+            # performer.py:248-264.  Both forms become rows appended to the token table, so that the fused embedding
+            # kernel (and its scatter backward) serve them unchanged; torch only concatenates / indexes [B, dim]-sized
+            # pieces here and its autograd routes their gradients to the conditioning tables.
+            V = self.token_emb.weight.shape[0]
+            if self.conditioning_type == _BOS_REPLACEMENT:
+                # x[:, 0] = sum_i conditioning_emb_i(c_i)   (replaces the BOS token embedding; position term still added)
+                c = sum(emb(conditionings[i].long().view(b)) for i, emb in enumerate(self.conditioning_emb))
+                tok_table = torch.cat((self.token_emb.weight, c), dim=0)
+                x = torch.cat((V + torch.arange(b, device=x.device, dtype=x.dtype).view(b, 1), x[:, 1:]), dim=1)
+            else:
+                # x = cat(conditioning_emb_i(c_i), x) for i = 0, 1, ...: the LAST conditioning ends up first
+                tok_table = torch.cat([self.token_emb.weight] + [emb.weight for emb in self.conditioning_emb], dim=0)
+                offs, cols = V, []
+                for i, emb in enumerate(self.conditioning_emb):
+                    cols.append(offs + conditionings[i].long().view(b, 1))
+                    offs += emb.weight.shape[0]
+                x = torch.cat(cols[::-1] + [x], dim=1)
+                lead = len(cols)
+        out = _run_programme(self, x, self._dtype(), return_encodings, tok_table, lead)
+        if lead:
+            out = out[:, lead:, :]                    # performer.py:275-280
+        return out

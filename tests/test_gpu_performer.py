@@ -512,3 +512,65 @@ def test_recurrent_sampling_equals_full_forward_sampling():
     b = net.sample(prefix, sample=False)          # default = the reference's loop of full forwards
     assert tuple(a.shape) == (2, *grid)
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ wrapper options
+def _build_opts(seed, **opts):
+    """tiny network with the wrapper options of performer.py:43-67 (fixed spatial code), :136-138 (fixed position code)
+    and :183-187 / :248-280 (conditioning)"""
+    from synthanatomy_b200.networks.transformers import Ordering, Performer
+    kw, grid = CASES["tiny"]
+    order = Ordering("raster_scan", 3, (1, *grid), (False,) * 3, ((2, 0, 1),), ((0, 1),), ("rotate_90", "transpose"))
+    n = int(np.prod(grid))
+    cfg = po.PerformerConfig(max_seq_len=n + 1, spatial_shape=tuple(grid), **kw, **opts)
+    sd = po.init_state_dict(cfg, seed)
+    for i in range(cfg.depth):
+        sd[po.layer_prefix(i) + "0.g"] = torch.tensor(0.7); sd[po.layer_prefix(i) + "1.g"] = torch.tensor(-0.4)
+    net = Performer(num_tokens=cfg.num_tokens, max_seq_len=n + 1, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads,
+                    ordering=order, dim_head=cfg.dim_head, local_attn_heads=cfg.local_attn_heads,
+                    local_window_size=cfg.local_window_size, feature_redraw_interval=1, use_rezero=True,
+                    spatial_position_emb=cfg.spatial_position_emb, spatial_shape=tuple(grid),
+                    fixed_position_emb=cfg.fixed_position_emb, conditioning_num_tokens=cfg.conditioning_num_tokens,
+                    conditioning_type=cfg.conditioning_type)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(("proj_updater" in k) or k.endswith(("inv_freq", "spatial_indices_sequence", ".emb")) for k in missing), missing
+    net.fix_projection_matrices_()
+    seqs = [torch.from_numpy(s.copy()) for s in po.spatial_index_sequences(grid, order.get_sequence_ordering())]
+    g = torch.Generator().manual_seed(seed + 1)
+    q = torch.randint(0, cfg.num_tokens - 1, (2, *grid), generator=g)
+    x_in, y = po.prepare_batch(q.numpy(), order.get_sequence_ordering(), cfg.num_tokens - 1)
+    return cfg, sd, net, seqs, torch.from_numpy(x_in), torch.from_numpy(y)
+
+
+@pytest.mark.parametrize("opts", [
+    dict(spatial_position_emb="fixed"),
+    dict(fixed_position_emb=True),
+    dict(conditioning_num_tokens=(5, 3), conditioning_type="bos_replacement"),
+    dict(conditioning_num_tokens=(5, 3), conditioning_type="prepending"),
+], ids=["fixed_spatial", "fixed_position", "bos_replacement", "prepending"])
+def test_wrapper_options_match_oracle_fp32(opts):
+    from synthanatomy_b200.losses import CELoss
+    cfg, sd, net, seqs, x_in, y = _build_opts(41, **opts)
+    conds = None
+    if cfg.conditioning_num_tokens:
+        g = torch.Generator().manual_seed(7)
+        conds = [torch.randint(0, cnt, (2, 1), generator=g) for cnt in cfg.conditioning_num_tokens]
+    if cfg.fixed_position_emb or cfg.spatial_position_emb == "fixed":      # the drop-in's own buffers = the formula
+        for k, v in net.state_dict().items():
+            if k.endswith(".emb") and k in sd:
+                torch.testing.assert_close(v, sd[k])
+    loss_ref, grads_ref, logits_ref = po.train_step_grads(sd, cfg, x_in, y, seqs, conditionings=conds)
+    net = net.cuda().train()
+    logits = net(x_in.cuda(), [c.cuda() for c in conds] if conds else None)
+    assert tuple(logits.shape) == tuple(logits_ref.shape)
+    _close(logits, logits_ref, 1e-4, "logits")
+    loss = CELoss()(logits.transpose(1, 2), y.cuda())
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * max(1.0, abs(float(loss_ref)))
+    loss.backward()
+    named = dict(net.named_parameters())
+    for k, gref in grads_ref.items():
+        got = named[k].grad
+        assert got is not None, k
+        err = float((got.cpu() - gref).abs().max()) / max(float(gref.abs().max()), 1e-3)
+        assert err <= 2e-4, f"grad {k}: {err:.3e}"
