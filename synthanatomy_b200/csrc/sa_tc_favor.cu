@@ -649,23 +649,34 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
       }
       if (q * 32 < ST_ROWS) {                               // warp-uniform: quadrants 0..2 hold rows < 80
         __nv_bfloat16* dst = P.st_out + (((long long)bh * nch + chunk) * ST_ROWS + r) * P.mp + cb_beg * 64;
-        for (int u = u_beg; u < u_end; ++u) {
-          uint32_t v[16];
-          if (it > 0) {
-            tmem_ld_32x16(tbase + (uint32_t)(u * 16), v);
-            tmem_ld_wait();
-          } else {
+        // this warp's (at most four) 16-column units: all TMEM loads in flight before the one wait -- the drain sits on
+        // the chunk-to-chunk critical path
+        const int nu = u_end - u_beg;
+        uint32_t v[4][16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0u;
+        for (int i = 0; i < 4; ++i) {
+          if (i < nu) {
+            if (it > 0) {
+              tmem_ld_32x16(tbase + (uint32_t)((u_beg + i) * 16), v[i]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[i][j] = 0u;
+            }
           }
-          if (r < ST_ROWS) {
-            float f[16];
-            const float seed = (MODE == 0 && r == 64) ? P.eps : 0.f;      // forward: k_cumsum + eps
+        }
+        if (it > 0) tmem_ld_wait();
+        if (r < ST_ROWS) {
+          const float seed = (MODE == 0 && r == 64) ? P.eps : 0.f;        // forward: k_cumsum + eps
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = (r < SUM_ROWS) ? __uint_as_float(v[j]) + seed : 0.f;
-            uint4* d4 = reinterpret_cast<uint4*>(dst + u * 16);
-            d4[0] = pack8(f);
-            d4[1] = pack8(f + 8);
+          for (int i = 0; i < 4; ++i) {
+            if (i < nu) {
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = (r < SUM_ROWS) ? __uint_as_float(v[i][j]) + seed : 0.f;
+              uint4* d4 = reinterpret_cast<uint4*>(dst + (u_beg + i) * 16);
+              d4[0] = pack8(f);
+              d4[1] = pack8(f + 8);
+            }
           }
         }
       }
