@@ -517,19 +517,22 @@ tc_chunk_state_kernel(const __grid_constant__ FvParams P) {
 
 // ------------------------------------------------------------------------------------------------ running state
 // The chunk sums AND their exclusive prefix (suffix) in one kernel: a CTA owns (batch, head, up to two 64-column feature
-// blocks) and walks the chunks of the sequence in order with the running state  S[e'][f] = sum_{earlier chunks}
-// sum_tok W_aug[tok][e'] F[tok][f]  as ONE fp32 accumulator in TMEM (the MMAs of chunk c accumulate onto chunks < c).
-// Before chunk c is added the accumulator IS the exclusive prefix: the epilogue warps read it, round it to bf16 and write
-// states[bh][c] (the tensor the scan / dqk kernels consume and the backward pass keeps), then release the tensor core.
-// Replaces tc_chunk_state_kernel + fv_prefix_kernel: no fp32 chunk sums in HBM (373 MB per layer and direction) and one
-// dependent pass instead of two.  MODE / W_aug as in tc_chunk_state_kernel; MODE 1 walks the chunks backwards (suffix).
-// Roles: warps 0-7 build the W operand (MODE 1) and drain TMEM, warp 8 issues MMAs, warp 9 drives TMA (2-stage ring).
+// blocks) and walks the chunks of the sequence in order.  The tensor core computes the chunk sums
+//   Z_c[e'][f] = sum_tok W_aug[tok][e'] F[tok][f]
+// into two alternating TMEM accumulators (no dependency between chunks: TMA, MMA and the drain are pipelined), the
+// epilogue warps keep the running state  S = sum_{earlier chunks} Z  in fp32 REGISTERS (thread = row e', 64 columns each):
+// per chunk they write the state before the chunk is added -- the exclusive prefix, rounded to bf16, the tensor the
+// scan / dqk kernels consume and the backward pass keeps -- and then add the chunk's sums out of TMEM.
+// Replaces tc_chunk_state_kernel + fv_prefix_kernel: no fp32 chunk sums in HBM (373 MB per layer and direction), one
+// pass instead of two, bound by the feature reads + state writes.  MODE / W_aug as in tc_chunk_state_kernel; MODE 1 walks
+// the chunks backwards (suffix).  Roles: warps 0-7 build the W operand (MODE 1), drain TMEM and own the running state,
+// warp 8 issues MMAs, warp 9 drives TMA (2-stage ring).
 template <int MODE>
 __global__ void __launch_bounds__(F_THREADS, 1)
 tc_state_scan_kernel(const __grid_constant__ FvParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ uint64_t f_full[2], f_empty[2], w_ready[2], d_full, rd_done;
+  __shared__ uint64_t f_full[2], f_empty[2], w_ready[2], acc_full[2], acc_empty[2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
@@ -540,8 +543,10 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
   const uint32_t stage_bytes = (uint32_t)(2 + nb) * BLK;      // W | aug | F blocks
   const int nch = P.nchunks;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&f_full[i], 1); mbar_init(&f_empty[i], 1); mbar_init(&w_ready[i], 256); }
-    mbar_init(&d_full, 1); mbar_init(&rd_done, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&f_full[i], 1); mbar_init(&f_empty[i], 1); mbar_init(&w_ready[i], 256);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256);
+    }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -583,31 +588,32 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
       }
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------ MMA issuer: chunk sums into accumulator it & 1
     if (lane == 0) {
       for (int it = 0; it + 1 < nch; ++it) {
         const int s = it & 1;
         const uint32_t ph = (uint32_t)((it >> 1) & 1);
         mbar_wait(&f_full[s], ph);
         if (MODE == 1) mbar_wait(&w_ready[s], ph);
-        mbar_wait(&rd_done, (uint32_t)(it & 1));            // the exclusive state of this chunk has left TMEM
+        mbar_wait(&acc_empty[s], ph ^ 1);                   // the drain of chunk it - 2 has left this accumulator
         tc_fence_after();
         const uint32_t wa = smem_u32(smem + s * stage_bytes), fa = wa + 2 * BLK;
+        const uint32_t td = tmem_base + (uint32_t)(s * 128);
 #pragma unroll
         for (int k = 0; k < FC / 16; ++k)
-          mma_cols(tmem_base, make_smem_desc(wa + k * 2048, BLK, 1024, 2), fa + k * 2048, false, BLK, ncols, 1,
-                   (uint32_t)((it | k) != 0));
+          mma_cols(td, make_smem_desc(wa + k * 2048, BLK, 1024, 2), fa + k * 2048, false, BLK, ncols, 1, (uint32_t)(k != 0));
         umma_commit(&f_empty[s]);
-        umma_commit(&d_full);
+        umma_commit(&acc_full[s]);
       }
     }
   } else {
-    // ------------------------------------------------------------ W operand (MODE 1) + state drain
+    // ------------------------------------------------------------ W operand (MODE 1) + running state
     const int q = warp & 3, hf = warp >> 2;
     const int r = q * 32 + lane;
-    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
     const int U = ncols >> 4, U0 = U >> 1;
     const int u_beg = hf ? U0 : 0, u_end = hf ? U : U0;
+    const int nu = u_end - u_beg;                           // this thread's 16-column units (<= 4)
+    const bool active = q * 32 < ST_ROWS;                   // warp-uniform: quadrants 0..2 hold rows < 80
 
     auto prep = [&](int it) {      // MODE 1: W = dout / den (64 columns) | aug = -delta / den, for the chunk walked at `it`
       const int s = it & 1;
@@ -640,49 +646,55 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
       mbar_arrive(&w_ready[s]);
     };
 
+    float run[4][16];                                       // the running state of this thread's row and columns (fp32)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) run[i][j] = 0.f;
+    const float seed = (MODE == 0 && r == 64) ? P.eps : 0.f;              // forward: k_cumsum + eps
+
     if (MODE == 1 && nch > 1) prep(0);
     for (int it = 0; it < nch; ++it) {
       const int chunk = MODE ? nch - 1 - it : it;
-      if (it > 0) {
-        mbar_wait(&d_full, (uint32_t)((it - 1) & 1));       // chunks walked so far are in the accumulator
-        tc_fence_after();
-      }
-      if (q * 32 < ST_ROWS) {                               // warp-uniform: quadrants 0..2 hold rows < 80
+      // (1) the exclusive prefix of this chunk
+      if (active && r < ST_ROWS) {
         __nv_bfloat16* dst = P.st_out + (((long long)bh * nch + chunk) * ST_ROWS + r) * P.mp + cb_beg * 64;
-        // this warp's (at most four) 16-column units: all TMEM loads in flight before the one wait -- the drain sits on
-        // the chunk-to-chunk critical path
-        const int nu = u_end - u_beg;
-        uint32_t v[4][16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i < nu) {
-            if (it > 0) {
-              tmem_ld_32x16(tbase + (uint32_t)((u_beg + i) * 16), v[i]);
-            } else {
+            float f[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[i][j] = 0u;
-            }
-          }
-        }
-        if (it > 0) tmem_ld_wait();
-        if (r < ST_ROWS) {
-          const float seed = (MODE == 0 && r == 64) ? P.eps : 0.f;        // forward: k_cumsum + eps
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < nu) {
-              float f[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = (r < SUM_ROWS) ? __uint_as_float(v[i][j]) + seed : 0.f;
-              uint4* d4 = reinterpret_cast<uint4*>(dst + (u_beg + i) * 16);
-              d4[0] = pack8(f);
-              d4[1] = pack8(f + 8);
-            }
+            for (int j = 0; j < 16; ++j) f[j] = (r < SUM_ROWS) ? run[i][j] + seed : 0.f;
+            uint4* d4 = reinterpret_cast<uint4*>(dst + (u_beg + i) * 16);
+            d4[0] = pack8(f);
+            d4[1] = pack8(f + 8);
           }
         }
       }
+      if (it + 1 >= nch) break;
+      // (2) MODE 1: the W operand of the next chunk (its stage was last read by the MMAs of chunk it - 1, whose
+      //     accumulator this thread drained in the previous iteration)
+      if (MODE == 1 && it + 2 < nch) prep(it + 1);
+      // (3) add this chunk's sums
+      const int s = it & 1;
+      mbar_wait(&acc_full[s], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      if (active) {
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 128);
+        uint32_t v[4][16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nu) tmem_ld_32x16(tbase + (uint32_t)((u_beg + i) * 16), v[i]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) run[i][j] += __uint_as_float(v[i][j]);
+          }
+      }
       tc_fence_before();
-      mbar_arrive(&rd_done);
-      if (MODE == 1 && it + 2 < nch) prep(it + 1);          // (stage (it + 1) & 1 was last read by the MMAs of chunk it - 1)
+      mbar_arrive(&acc_empty[s]);
     }
   }
   FV_EPILOGUE();
@@ -1268,7 +1280,7 @@ int launch_states(const sa_favor_desc* d, int mode, const void* feat, const void
     const int nb = P.nblk < 2 ? P.nblk : 2;
     const dim3 sgrid((unsigned)((P.nblk + 1) / 2), (unsigned)(d->batch * d->heads));
     const size_t ssmem = (size_t)2 * (2 + nb) * BLK + 1024;
-    P.tmem_cols = tmem_cols_for(d->mp < 128 ? d->mp : 128);
+    P.tmem_cols = 256;                                 // two chunk-sum accumulators of up to 128 columns
     if (mode == 0) tc_state_scan_kernel<0><<<sgrid, F_THREADS, ssmem, st>>>(P);
     else tc_state_scan_kernel<1><<<sgrid, F_THREADS, ssmem, st>>>(P);
     SA_LAUNCH_CHECK();
