@@ -527,12 +527,14 @@ tc_chunk_state_kernel(const __grid_constant__ FvParams P) {
 // pass instead of two, bound by the feature reads + state writes.  MODE / W_aug as in tc_chunk_state_kernel; MODE 1 walks
 // the chunks backwards (suffix).  Roles: warps 0-7 build the W operand (MODE 1), drain TMEM and own the running state,
 // warp 8 issues MMAs, warp 9 drives TMA (2-stage ring).
+constexpr int SS_STAGES = 3;        // shared-memory ring (W | aug | F blocks per stage); the TMEM accumulators alternate
+
 template <int MODE>
 __global__ void __launch_bounds__(F_THREADS, 1)
 tc_state_scan_kernel(const __grid_constant__ FvParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ uint64_t f_full[2], f_empty[2], w_ready[2], acc_full[2], acc_empty[2];
+  __shared__ uint64_t f_full[SS_STAGES], f_empty[SS_STAGES], w_ready[SS_STAGES], acc_full[2], acc_empty[2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
@@ -543,18 +545,16 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
   const uint32_t stage_bytes = (uint32_t)(2 + nb) * BLK;      // W | aug | F blocks
   const int nch = P.nchunks;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&f_full[i], 1); mbar_init(&f_empty[i], 1); mbar_init(&w_ready[i], 256);
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256);
-    }
+    for (int i = 0; i < SS_STAGES; ++i) { mbar_init(&f_full[i], 1); mbar_init(&f_empty[i], 1); mbar_init(&w_ready[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
     fence_mbar_init();
     fence_proxy_async();
   }
   if (warp < 8) {
-    // aug blocks of both stages: all zero; MODE 0: column 0 = 1 (constant), MODE 1: column 0 is rewritten per chunk
+    // aug blocks of every stage: all zero; MODE 0: column 0 = 1 (constant), MODE 1: column 0 is rewritten per chunk
     const int q = warp & 3, hf = warp >> 2;
     const int r = q * 32 + lane;
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < SS_STAGES; ++s) {
       uint8_t* aug = smem + s * stage_bytes + BLK;
       uint8_t* row = aug + (r >> 3) * 1024 + (r & 7) * 128 + hf * 64;
 #pragma unroll
@@ -562,7 +562,7 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
     }
     bar_epi();
     if (MODE == 0 && hf == 0) {
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < SS_STAGES; ++s) {
         __nv_bfloat16* p0 = reinterpret_cast<__nv_bfloat16*>(sw_row(smem + s * stage_bytes + BLK, r) + ((0 ^ (r & 7)) << 4));
         *p0 = __float2bfloat16_rn(1.0f);
       }
@@ -578,9 +578,9 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
       prefetch_tmap(&P.map_a);
       if (MODE == 0) prefetch_tmap(&P.map_b);
       for (int it = 0; it + 1 < nch; ++it) {
-        const int s = it & 1;
+        const int s = it % SS_STAGES;
         const int chunk = MODE ? nch - 1 - it : it;
-        mbar_wait(&f_empty[s], (uint32_t)(((it >> 1) & 1) ^ 1));
+        mbar_wait(&f_empty[s], (uint32_t)(((it / SS_STAGES) & 1) ^ 1));
         mbar_expect_tx(&f_full[s], (uint32_t)nb * BLK + (MODE == 0 ? BLK : 0u));
         uint8_t* st = smem + s * stage_bytes;
         for (int cb = 0; cb < nb; ++cb) tma_load_3d(st + (2 + cb) * BLK, &P.map_a, &f_full[s], (cb_beg + cb) * 64, chunk * FC, bh);
@@ -591,19 +591,19 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
     // ------------------------------------------------------------ MMA issuer: chunk sums into accumulator it & 1
     if (lane == 0) {
       for (int it = 0; it + 1 < nch; ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        const int s = it % SS_STAGES, a = it & 1;
+        const uint32_t ph = (uint32_t)((it / SS_STAGES) & 1);
         mbar_wait(&f_full[s], ph);
         if (MODE == 1) mbar_wait(&w_ready[s], ph);
-        mbar_wait(&acc_empty[s], ph ^ 1);                   // the drain of chunk it - 2 has left this accumulator
+        mbar_wait(&acc_empty[a], (uint32_t)(((it >> 1) & 1) ^ 1));   // the drain of chunk it - 2 has left this accumulator
         tc_fence_after();
         const uint32_t wa = smem_u32(smem + s * stage_bytes), fa = wa + 2 * BLK;
-        const uint32_t td = tmem_base + (uint32_t)(s * 128);
+        const uint32_t td = tmem_base + (uint32_t)(a * 128);
 #pragma unroll
         for (int k = 0; k < FC / 16; ++k)
           mma_cols(td, make_smem_desc(wa + k * 2048, BLK, 1024, 2), fa + k * 2048, false, BLK, ncols, 1, (uint32_t)(k != 0));
         umma_commit(&f_empty[s]);
-        umma_commit(&acc_full[s]);
+        umma_commit(&acc_full[a]);
       }
     }
   } else {
@@ -616,7 +616,7 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
     const bool active = q * 32 < ST_ROWS;                   // warp-uniform: quadrants 0..2 hold rows < 80
 
     auto prep = [&](int it) {      // MODE 1: W = dout / den (64 columns) | aug = -delta / den, for the chunk walked at `it`
-      const int s = it & 1;
+      const int s = it % SS_STAGES;
       const int chunk = nch - 1 - it;
       const int n = chunk * FC + r;
       uint8_t* Ws = smem + s * stage_bytes;
@@ -653,7 +653,9 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
       for (int j = 0; j < 16; ++j) run[i][j] = 0.f;
     const float seed = (MODE == 0 && r == 64) ? P.eps : 0.f;              // forward: k_cumsum + eps
 
-    if (MODE == 1 && nch > 1) prep(0);
+    if (MODE == 1) {
+      for (int i = 0; i < SS_STAGES - 1 && i + 1 < nch; ++i) prep(i);
+    }
     for (int it = 0; it < nch; ++it) {
       const int chunk = MODE ? nch - 1 - it : it;
       // (1) the exclusive prefix of this chunk
@@ -672,11 +674,11 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
         }
       }
       if (it + 1 >= nch) break;
-      // (2) MODE 1: the W operand of the next chunk (its stage was last read by the MMAs of chunk it - 1, whose
-      //     accumulator this thread drained in the previous iteration)
-      if (MODE == 1 && it + 2 < nch) prep(it + 1);
+      // (2) MODE 1: the W operand of the chunk SS_STAGES - 1 ahead (its stage was last read by the MMAs of chunk it - 1,
+      //     whose accumulator this thread drained in the previous iteration)
+      if (MODE == 1 && it + SS_STAGES < nch) prep(it + SS_STAGES - 1);
       // (3) add this chunk's sums
-      const int s = it & 1;
+      const int s = it & 1;                                 // accumulator of this chunk
       mbar_wait(&acc_full[s], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       if (active) {
@@ -1279,7 +1281,7 @@ int launch_states(const sa_favor_desc* d, int mode, const void* feat, const void
     P.st_out = (__nv_bfloat16*)states;
     const int nb = P.nblk < 2 ? P.nblk : 2;
     const dim3 sgrid((unsigned)((P.nblk + 1) / 2), (unsigned)(d->batch * d->heads));
-    const size_t ssmem = (size_t)2 * (2 + nb) * BLK + 1024;
+    const size_t ssmem = (size_t)SS_STAGES * (2 + nb) * BLK + 1024;
     P.tmem_cols = 256;                                 // two chunk-sum accumulators of up to 128 columns
     if (mode == 0) tc_state_scan_kernel<0><<<sgrid, F_THREADS, ssmem, st>>>(P);
     else tc_state_scan_kernel<1><<<sgrid, F_THREADS, ssmem, st>>>(P);
