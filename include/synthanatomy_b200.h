@@ -112,6 +112,10 @@ int sa_conv3d_wgrad_x3(const sa_conv_desc* d, const float* p, const float* q, fl
  * (dwp / dbias are accumulated into: zero them first).  Replaces three launches of the general entry points. */
 int sa_conv1x1_bwd_fused(int64_t m, int c_out, int c_in, const void* g, const void* h, const void* wp_t, void* dh,
                          float* dwp, float* dbias, void* stream);
+/* The same pass with one more output: dbias_h[c_in] += column sums of dh (may be NULL) -- the bias gradient of the 3x3x3
+ * conv that produced h (baseline.py:153), so that no separate reduction has to stream dh again. */
+int sa_conv1x1_bwd_fused_dbh(int64_t m, int c_out, int c_in, const void* g, const void* h, const void* wp_t, void* dh,
+                             float* dwp, float* dbias, float* dbias_h, void* stream);
 /* Streaming forward twin: y[m][c_out] = relu?(x W^T + bias + addend), wp = sa_pack_weight(w, transpose = 0)
  * (128 -> 128 channels; the residual `addend` is required). */
 int sa_conv1x1_fwd_fused(int64_t m, int c_out, int c_in, const void* x, const void* wp, const float* bias,

@@ -34,6 +34,7 @@ struct PwParams {
   int tiles;
   float* dwp;
   float* dbias;
+  float* dbias_h;        // MODE 0, optional: column sums of dh (the bias gradient of the conv that produced h)
   const float* bias;     // forward mode
   int relu;
 };
@@ -149,6 +150,11 @@ tc_pw_kernel(const __grid_constant__ PwParams P) {
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
     int stage = 0;
     int it = 0;
+    // column sums of this thread's rows of dh over all tiles of the CTA (its 64 columns), reduced over the warp at the end
+    float colsum[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) colsum[j] = 0.f;
+    const bool want_dbh = MODE == 0 && P.dbias_h != nullptr;
     for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
       const int bsel = it & 1;
       mbar_wait(&full_bar[stage], (uint32_t)((it >> 1) & 1));       // the h tile (mask) is in shared memory
@@ -196,6 +202,14 @@ tc_pw_kernel(const __grid_constant__ PwParams P) {
           u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
           u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
           *reinterpret_cast<uint4*>(orow + ((ch ^ (r & 7)) << 4)) = u;
+          if (want_dbh) {          // the bf16-rounded values, i.e. exactly what a reduction over the stored dh would add
+            const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              colsum[ch * 8 + 2 * e] += bf16lo(ww[e]);
+              colsum[ch * 8 + 2 * e + 1] += bf16hi(ww[e]);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -211,6 +225,15 @@ tc_pw_kernel(const __grid_constant__ PwParams P) {
       if (++stage == PW_STAGES) stage = 0;
     }
     if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (want_dbh && my_tiles > 0) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        float v = colsum[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(P.dbias_h + half * 64 + j, v);
+      }
+    }
     if (MODE == 0 && my_tiles > 0) {
       // dW1 / db1 partials of this CTA: lane = n
       mbar_wait(&final_full, 0);
@@ -252,8 +275,18 @@ int pw_map(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint3
 
 // g [m][128], h [m][128], wp_t [128 (c)][128 (n)] bf16 (pack_weight(w1, transpose = 1)); dh [m][128] bf16;
 // dwp [128 (n)][128 (c)] fp32 and dbias [128] fp32 are ACCUMULATED into (zero them first).
+extern "C" int sa_conv1x1_bwd_fused_dbh(int64_t m, int c_out, int c_in, const void* g, const void* h, const void* wp_t,
+                                        void* dh, float* dwp, float* dbias, float* dbias_h, void* stream);
+
 extern "C" int sa_conv1x1_bwd_fused(int64_t m, int c_out, int c_in, const void* g, const void* h, const void* wp_t, void* dh,
                                     float* dwp, float* dbias, void* stream) {
+  return sa_conv1x1_bwd_fused_dbh(m, c_out, c_in, g, h, wp_t, dh, dwp, dbias, nullptr, stream);
+}
+
+// the same pass with one more product: dbias_h[c] += sum_pos dh[pos][c] (may be NULL), the bias gradient of the 3x3x3 conv
+// that produced h -- saves a separate streaming reduction over dh
+extern "C" int sa_conv1x1_bwd_fused_dbh(int64_t m, int c_out, int c_in, const void* g, const void* h, const void* wp_t,
+                                        void* dh, float* dwp, float* dbias, float* dbias_h, void* stream) {
   SA_CHECK_ARG(g && h && wp_t && dh && dwp && dbias, "null pointer");
   SA_CHECK_ARG(m > 0, "bad sizes");
   SA_UNSUPPORTED(c_out != 128 || c_in != 128, "the fused pointwise backward is built for 128 -> 128 channels");
@@ -270,7 +303,7 @@ extern "C" int sa_conv1x1_bwd_fused(int64_t m, int c_out, int c_in, const void* 
   static thread_local PwParams P;
   P.m = m;
   P.tiles = (int)sa_cdiv(m, PW_M);
-  P.dwp = dwp; P.dbias = dbias;
+  P.dwp = dwp; P.dbias = dbias; P.dbias_h = dbias_h;
   int rc;
   if ((rc = pw_map(&P.gmap, g, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;
   if ((rc = pw_map(&P.hmap, h, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;
@@ -305,7 +338,7 @@ extern "C" int sa_conv1x1_fwd_fused(int64_t m, int c_out, int c_in, const void* 
   static thread_local PwParams P;
   P.m = m;
   P.tiles = (int)sa_cdiv(m, PW_M);
-  P.dwp = nullptr; P.dbias = nullptr; P.bias = bias; P.relu = relu;
+  P.dwp = nullptr; P.dbias = nullptr; P.dbias_h = nullptr; P.bias = bias; P.relu = relu;
   int rc;
   if ((rc = pw_map(&P.gmap, x, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;
   if ((rc = pw_map(&P.hmap, addend, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;

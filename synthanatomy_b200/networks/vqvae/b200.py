@@ -194,14 +194,15 @@ def _stack_backward(ops_list, saved, params, g, in_is_relu: bool, need_dx: bool,
             # y = relu(x + conv1(h) + b1), h = relu(conv3(x) + b3); g already carries the (y > 0) mask
             wp1_t = ops.pack_weight(w1, True, g.dtype)
             if ops.conv1x1_bwd_fused_supported(op.c1.spec, g):
-                # one pass over g and h: dh = dgrad(g) * (h > 0), dW1, db1
-                dh, grads[o + 2], grads[o + 3] = ops.conv1x1_bwd_fused(op.c1.spec, g, h, wp1_t, w1)
+                # one pass over g and h: dh = dgrad(g) * (h > 0), dW1, db1 and db3 = the column sums of dh
+                dh, grads[o + 2], grads[o + 3], grads[o + 1] = ops.conv1x1_bwd_fused(op.c1.spec, g, h, wp1_t, w1,
+                                                                                      with_dbh=True)
             else:
                 grads[o + 2] = ops.conv_wgrad(op.c1.spec, h, g, w1)
                 grads[o + 3] = ops.bias_grad(g)
                 dh = ops.conv_dgrad(op.c1.spec, g, wp1_t, h.shape[1:4], None, h)        # * (h > 0)
+                grads[o + 1] = ops.bias_grad(dh)
             grads[o] = ops.conv_wgrad(op.c3.spec, x, dh, w3)
-            grads[o + 1] = ops.bias_grad(dh)
             if want_dx:
                 wp3_t = ops.pack_weight(w3, True, g.dtype)
                 g = ops.conv_dgrad(op.c3.spec, dh, wp3_t, x.shape[1:4], g, x if relu_in[i] else None)  # (+ g) * (x > 0)

@@ -254,15 +254,21 @@ def conv1x1_bwd_fused_supported(spec: ConvSpec, g: torch.Tensor) -> bool:
             and g.dtype == torch.bfloat16 and not _FORCE_SIMT)
 
 
-def conv1x1_bwd_fused(spec: ConvSpec, g: torch.Tensor, h: torch.Tensor, wp_t: torch.Tensor, weight_like: torch.Tensor):
-    """One pass over g and h: dh = dgrad(g) * (h > 0), dW (torch layout of `weight_like`, fp32) and db."""
+def conv1x1_bwd_fused(spec: ConvSpec, g: torch.Tensor, h: torch.Tensor, wp_t: torch.Tensor, weight_like: torch.Tensor,
+                      with_dbh: bool = False):
+    """One pass over g and h: dh = dgrad(g) * (h > 0), dW (torch layout of `weight_like`, fp32) and db; with_dbh: also the
+    column sums of dh (the bias gradient of the conv that produced h) as a fourth result."""
     m = g.numel() // spec.cout
     dh = torch.empty_like(h)
-    dwp = torch.zeros((1, spec.cout, spec.cin), device=g.device, dtype=torch.float32)
-    db = torch.zeros((spec.cout,), device=g.device, dtype=torch.float32)
-    _lib.check(lib().sa_conv1x1_bwd_fused(m, spec.cout, spec.cin, _p(g), _p(h), _p(wp_t), _p(dh), _p(dwp), _p(db),
-                                          _stream()), "sa_conv1x1_bwd_fused")
-    return dh, unpack_wgrad(dwp, weight_like, transpose=False), db
+    # one zeroed buffer: dW | db | dbh
+    acc = torch.zeros((spec.cout * spec.cin + spec.cout + spec.cin,), device=g.device, dtype=torch.float32)
+    dwp = acc[: spec.cout * spec.cin].view(1, spec.cout, spec.cin)
+    db = acc[spec.cout * spec.cin: spec.cout * spec.cin + spec.cout]
+    dbh = acc[spec.cout * spec.cin + spec.cout:]
+    _lib.check(lib().sa_conv1x1_bwd_fused_dbh(m, spec.cout, spec.cin, _p(g), _p(h), _p(wp_t), _p(dh), _p(dwp), _p(db),
+                                              _p(dbh) if with_dbh else None, _stream()), "sa_conv1x1_bwd_fused")
+    dw = unpack_wgrad(dwp, weight_like, transpose=False)
+    return (dh, dw, db, dbh) if with_dbh else (dh, dw, db)
 
 
 def conv1x1_fwd_fused(spec: ConvSpec, x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor],

@@ -72,8 +72,10 @@ def test_pointwise_backward_fused_equals_general_kernels_full_size():
     w = (torch.randn(C, C, 1, 1, 1, device="cuda", generator=g) * 0.05).to(torch.bfloat16).float()
     spec = ops.ConvSpec("conv", C, C, 1, 1, 0)
     wp_t = ops.pack_weight(w, True, torch.bfloat16)
-    dh, dw, db = ops.conv1x1_bwd_fused(spec, gy, h, wp_t, w)
+    dh, dw, db, dbh = ops.conv1x1_bwd_fused(spec, gy, h, wp_t, w, with_dbh=True)
     assert torch.equal(dh, ops.conv_dgrad(spec, gy, wp_t, (D, H, W), None, h))
+    dbh2 = ops.bias_grad(dh)             # the separate streaming reduction the fused column sums replace
+    torch.testing.assert_close(dbh, dbh2, rtol=1e-3, atol=1e-3 * float(dbh2.abs().max()))
     dw2, db2 = ops.conv_wgrad(spec, h, gy, w), ops.bias_grad(gy)
     torch.testing.assert_close(dw, dw2, rtol=1e-3, atol=1e-3 * float(dw2.abs().max()))
     torch.testing.assert_close(db, db2, rtol=1e-3, atol=1e-3 * float(db2.abs().max()))
