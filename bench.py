@@ -363,6 +363,7 @@ def vqvae_b200(args, world, rank, local, dev):
     }
     if world == 1 and not args.no_extra:
         out["vq_kernel"] = vq_kernel_arm(dev)
+        out["jukebox_loss"] = jukebox_loss_arm(args, dev)
     if world == 1 and not args.no_parity:
         out["parity_arm"] = vq_parity_arm(args, dev, value)
     if world == 1 and not args.no_vendor:
@@ -496,6 +497,56 @@ def vq_kernel_arm(dev):
             "achieved_gbs": by / (us * 1e-6) / 1e9, "flop": 2.0 * rows * K * dim,
             "achieved_gflops": 2.0 * rows * K * dim / (us * 1e-6) / 1e9,
             "note": "back-to-back launches incl. launch overhead; includes the allocation of idx / q by the wrapper"}
+
+
+def jukebox_loss_arm(args, dev):
+    """the spectral (Jukebox) reconstruction loss of the README run on a batch of reconstructions --
+    3-D orthonormal DFT as DFT-matrix products on the tensor cores (bf16x3), amplitude MSE + pixel MSE, forward + backward;
+    beside it torch.fft.fftn (cuFFT) doing what the reference's JukeboxLoss does."""
+    import torch
+    from synthanatomy_b200.losses import JukeboxLoss
+    B, vol = args.batch, tuple(args.vol)
+    g = torch.Generator(device=dev).manual_seed(11)
+    y = torch.rand(B, 1, *vol, device=dev, generator=g)
+    pred = (y + 0.1 * torch.randn(B, 1, *vol, device=dev, generator=g)).requires_grad_(True)
+    q = torch.zeros((), device=dev)
+    crit = JukeboxLoss(dimensions=3)
+
+    def ours():
+        pred.grad = None
+        loss = crit({"reconstruction": [pred], "quantization_losses": [q]}, y)
+        loss.backward()
+        return loss
+
+    def vendor():
+        pred.grad = None
+        dims = (1, 2, 3, 4)
+        fa = torch.fft.fftn(pred.float(), dim=dims, norm="ortho")
+        fb = torch.fft.fftn(y, dim=dims, norm="ortho")
+        loss = torch.nn.functional.mse_loss(torch.sqrt(fa.real ** 2 + fa.imag ** 2), torch.sqrt(fb.real ** 2 + fb.imag ** 2))
+        loss = loss + torch.nn.functional.mse_loss(pred, y)
+        loss.backward()
+        return loss
+
+    out = {"workload": f"JukeboxLoss fwd+bwd on {B} x 1 x {vol[0]}x{vol[1]}x{vol[2]} (fp32 in, fp32 gradient out)"}
+    for name, fn in (("ms_fwd_bwd", ours), ("vendor_cufft_ms_fwd_bwd", vendor)):
+        try:
+            for _ in range(2):
+                loss = fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                loss = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = e0.elapsed_time(e1) / 5
+            out[name.replace("ms_fwd_bwd", "loss")] = float(loss.detach())
+        except Exception as e:      # noqa: BLE001
+            out[name] = f"unavailable: {type(e).__name__}: {str(e)[:120]}"
+    del pred, y
+    torch.cuda.empty_cache()
+    return out
 
 
 def vendor_vqvae(args, value):
