@@ -1,6 +1,8 @@
 """CUDA-graph replay of the training step (synthanatomy_b200.utils.graphs.GraphedTrainStep): the replayed step is the eager
-step -- same kernels, same order -- so the parameter trajectory of a graphed run must equal the eager one (up to the
-fp32 atomics' ordering noise)."""
+step -- same kernels, same order.  Checked with the learning rate at 0 (so that Adam's sign-like first steps cannot amplify
+the fp32 atomics' ordering noise into different parameters): per batch, the replayed loss and every parameter gradient
+equal the eager ones; then, with the learning rate switched on (the optimiser runs outside the graph and reads it per
+step), the loss falls under replay."""
 import numpy as np
 import pytest
 import torch
@@ -9,10 +11,12 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-def _close_params(a, b, tol):
+def _close_grads(a, b, tol):
     for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
-        err = float((p.detach() - q.detach()).abs().max())
-        assert err <= tol * max(1.0, float(p.detach().abs().max())), f"{k}: {err:.3e}"
+        if p.grad is None and q.grad is None:
+            continue
+        err = float((p.grad - q.grad).abs().max())
+        assert err <= tol * max(float(p.grad.abs().max()), 1e-6), f"{k}: {err:.3e} of {float(p.grad.abs().max()):.3e}"
 
 
 def test_graphed_vqvae_step_equals_eager():
@@ -30,22 +34,22 @@ def test_graphed_vqvae_step_equals_eager():
     g = torch.Generator(device="cuda").manual_seed(1)
     xs = [torch.rand(2, 1, 16, 16, 32, device="cuda", generator=g) for _ in range(3)]
     crit = MSELoss()
-    # eager twin: 2 warm-up steps on xs[0] (what the constructor below runs), then one step per batch
-    opt_e = Adam(nets[0].parameters(), lr=1e-3)
-    eager_losses = []
-    for x in [xs[0], xs[0]] + xs:
+    opt_e = Adam(nets[0].parameters(), lr=0.0)
+    opt_g = Adam(nets[1].parameters(), lr=0.0)
+    step = GraphedTrainStep(nets[1], crit, opt_g, (xs[0],), xs[0], warmup=2)
+    for _ in range(2):                                   # keep the EMA codebooks in step with the constructor's warm-up
+        crit(nets[0](xs[0]), xs[0]).backward()
+    for x in xs:
         opt_e.zero_grad(set_to_none=True)
         loss = crit(nets[0](x), x)
         loss.backward()
-        opt_e.step()
-        eager_losses.append(float(loss))
-    opt_g = Adam(nets[1].parameters(), lr=1e-3)
-    step = GraphedTrainStep(nets[1], crit, opt_g, (xs[0],), xs[0], warmup=2)
-    graph_losses = [float(step(x, target=x)) for x in xs]
-    for a, b in zip(eager_losses[2:], graph_losses):
-        assert abs(a - b) <= 1e-3 * abs(a), (eager_losses, graph_losses)
-    _close_params(nets[0], nets[1], 2e-3)
+        gl = step(x, target=x)
+        assert abs(float(loss) - float(gl)) <= 1e-4 * abs(float(loss)), (float(loss), float(gl))
+        _close_grads(nets[0], nets[1], 2e-3)
     torch.testing.assert_close(nets[0].quantizer[0].impl.weight, nets[1].quantizer[0].impl.weight, rtol=1e-3, atol=1e-4)
+    opt_g.param_groups[0]["lr"] = 1e-3
+    losses = [float(step(xs[0], target=xs[0])) for _ in range(8)]
+    assert losses[-1] < losses[0], losses
 
 
 def test_graphed_performer_step_equals_eager_and_redraws_outside_the_graph():
@@ -70,20 +74,19 @@ def test_graphed_performer_step_equals_eager_and_redraws_outside_the_graph():
     tgts = [torch.randint(0, 64, (2, n), device="cuda", generator=g) for _ in range(3)]
     crit = CELoss()
     fwd = lambda m, x: m(x).transpose(1, 2)          # TransformerTrainingInferer
-    opt_e = Adam(nets[0].parameters(), lr=1e-3)
-    eager_losses = []
-    for x, y in [(toks[0], tgts[0])] * 2 + list(zip(toks, tgts)):
+    opt_e = Adam(nets[0].parameters(), lr=0.0)
+    opt_g = Adam(nets[1].parameters(), lr=0.0)
+    step = GraphedTrainStep(nets[1], crit, opt_g, (toks[0],), tgts[0], warmup=2, forward=fwd)
+    for x, y in zip(toks, tgts):
         opt_e.zero_grad(set_to_none=True)
         loss = crit(fwd(nets[0], x), y)
         loss.backward()
-        opt_e.step()
-        eager_losses.append(float(loss))
-    opt_g = Adam(nets[1].parameters(), lr=1e-3)
-    step = GraphedTrainStep(nets[1], crit, opt_g, (toks[0],), tgts[0], warmup=2, forward=fwd)
-    graph_losses = [float(step(x, target=y)) for x, y in zip(toks, tgts)]
-    for a, b in zip(eager_losses[2:], graph_losses):
-        assert abs(a - b) <= 2e-3 * abs(a), (eager_losses, graph_losses)
-    _close_params(nets[0], nets[1], 5e-3)
+        gl = step(x, target=y)
+        assert abs(float(loss) - float(gl)) <= 1e-4 * abs(float(loss)), (float(loss), float(gl))
+        _close_grads(nets[0], nets[1], 2e-3)
+    opt_g.param_groups[0]["lr"] = 1e-3
+    losses = [float(step(toks[0], target=tgts[0])) for _ in range(8)]
+    assert losses[-1] < losses[0], losses
     step.release()
     # with redraws: the projection matrices change between replays (copied into the static buffers outside the graph)
     torch.manual_seed(3)
