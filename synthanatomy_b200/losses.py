@@ -14,6 +14,9 @@ from torch.nn.modules.loss import _Loss
 
 from . import _lib, ops, pf_ops
 
+# The TensorBoard summaries hold DETACHED scalars: the handlers only read their values, and a live tensor would keep the
+# whole autograd graph of the last step (and the parameters' gradient accumulators with their stream) alive between steps.
+
 
 class _MSEFn(torch.autograd.Function):
     @staticmethod
@@ -49,10 +52,10 @@ class MSELoss(_Loss):
         y_pred = network_output["reconstruction"][0]
         q_losses = network_output["quantization_losses"]
         loss = mse_loss(y_pred, y)     # the reference ignores `reduction` here as well (F.mse_loss default)
-        self.summaries["scalar"]["Loss-MSE-Reconstruction"] = loss
+        self.summaries["scalar"]["Loss-MSE-Reconstruction"] = loss.detach()
         for idx, q_loss in enumerate(q_losses):
             q_loss = q_loss.float()
-            self.summaries["scalar"][f"Loss-MSE-VQ{idx}_Commitment_Cost"] = q_loss
+            self.summaries["scalar"][f"Loss-MSE-VQ{idx}_Commitment_Cost"] = q_loss.detach()
             loss = loss + q_loss
         return loss
 
@@ -177,15 +180,15 @@ class JukeboxLoss(_Loss):
         y_pred = network_output["reconstruction"][0]
         q_losses = network_output["quantization_losses"]
         loss = spectral_loss(y_pred, y) * self.fft_factor                                   # :599
-        self.summaries["scalar"]["Loss-Spectral-Reconstruction"] = loss
+        self.summaries["scalar"]["Loss-Spectral-Reconstruction"] = loss.detach()
         self.summaries["scalar"]["Auxiliary-FFT_Factor"] = self.fft_factor
         if self.include_pixel_loss:                                                         # :603-607
             l2_loss = mse_loss(y_pred, y)
-            self.summaries["scalar"]["Loss-MSE-Reconstruction"] = l2_loss
+            self.summaries["scalar"]["Loss-MSE-Reconstruction"] = l2_loss.detach()
             loss = loss + l2_loss
         for idx, q_loss in enumerate(q_losses):                                             # :609-616
             q_loss = q_loss.float()
-            self.summaries["scalar"][f"Loss-MSE-VQ{idx}_Commitment_Cost"] = q_loss
+            self.summaries["scalar"][f"Loss-MSE-VQ{idx}_Commitment_Cost"] = q_loss.detach()
             loss = loss + q_loss
         return loss
 
@@ -236,7 +239,7 @@ class CELoss(_Loss):
 
     def forward(self, y_pred: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         loss = _CEFn.apply(y_pred, y, self.reduction)
-        self.summaries["scalar"]["Loss-CE-Prediction"] = loss
+        self.summaries["scalar"]["Loss-CE-Prediction"] = loss.detach()
         return loss
 
     def get_summaries(self) -> Dict[str, torch.Tensor]:
@@ -281,10 +284,10 @@ class AdversarialLoss(_Loss):
     def forward(self, logits_fake: torch.Tensor, logits_real: torch.Tensor = None) -> torch.Tensor:
         side = "Discriminator" if self.is_discriminator else "Generator"
         loss = torch.mean(self.criterion_function(logits_fake.float(), not self.is_discriminator))
-        self.summaries["scalar"][f"Loss-Adversarial_{side}-Reconstruction"] = loss
+        self.summaries["scalar"][f"Loss-Adversarial_{side}-Reconstruction"] = loss.detach()
         if self.is_discriminator:
             loss_real = torch.mean(self.criterion_function(logits_real.float(), True))
-            self.summaries["scalar"]["Loss-Adversarial_Discriminator-Originals"] = loss_real
+            self.summaries["scalar"]["Loss-Adversarial_Discriminator-Originals"] = loss_real.detach()
             loss = 0.5 * (loss + loss_real)
         return self._weight * loss
 

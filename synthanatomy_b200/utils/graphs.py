@@ -40,6 +40,10 @@ class GraphedTrainStep:
         if self._stack is not None:
             self._stack.auto_check_redraw = False
         try:
+            # graphs of earlier eager steps (kept alive by a stored loss, say) would keep the parameters' gradient
+            # accumulators on the stream those steps ran on, which invalidates the capture below
+            import gc
+            gc.collect()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
