@@ -33,13 +33,17 @@ extern "C" {
  *     v += bias[j]
  *     dot_out[0] += sum_ij v * dot_with[i][j]          (act dtype, leading dimension ldo)
  *     v *= scale * scale_dev[0]
- *     act == SA_ACT_GELU_FWD: pre[i][j] = v; v = gelu(v)          (exact erf GELU = nn.GELU())
- *     act == SA_ACT_GELU_BWD: v *= gelu'(pre[i][j])
+ *     act == SA_ACT_GELU_FWD:   pre[i][j] = v; v = gelu(v)        (exact erf GELU = nn.GELU())
+ *     act == SA_ACT_GELU_BWD:   v *= gelu'(pre[i][j])
+ *     act == SA_ACT_GELU_FWD_D: pre[i][j] = gelu'(v); v = gelu(v)  (the forward pass keeps the DERIVATIVE for the backward
+ *     act == SA_ACT_MUL_PRE:    v *= pre[i][j]                      pass: one erf evaluation per element instead of two)
  *     v += resid[i][j]                                  (fp32, may alias out_f32)
  *     out_f32[i][j] = v;  out_act[i][j] = (act dtype) v
  *   pre / resid / dot_with / out_* all have leading dimension ldo.
  * ---------------------------------------------------------------------------------------------- */
-typedef enum sa_act { SA_ACT_NONE = 0, SA_ACT_GELU_FWD = 1, SA_ACT_GELU_BWD = 2 } sa_act;
+typedef enum sa_act {
+  SA_ACT_NONE = 0, SA_ACT_GELU_FWD = 1, SA_ACT_GELU_BWD = 2, SA_ACT_GELU_FWD_D = 3, SA_ACT_MUL_PRE = 4
+} sa_act;
 
 typedef struct sa_gemm_epilogue {
   const float* bias;

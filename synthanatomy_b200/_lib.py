@@ -63,7 +63,7 @@ class LocalDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("batch", "seq", "heads", "dim_head", "window", "ld", "out_ld", "act_dtype")]
 
 
-SA_ACT_NONE, SA_ACT_GELU_FWD, SA_ACT_GELU_BWD = 0, 1, 2
+SA_ACT_NONE, SA_ACT_GELU_FWD, SA_ACT_GELU_BWD, SA_ACT_GELU_FWD_D, SA_ACT_MUL_PRE = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); the single source of truth for tests/test_abi.py as well
 SIGNATURES = {

@@ -44,8 +44,13 @@ __device__ __forceinline__ float sa_epi_elem(const SaEpi& e, long long i, int j,
   if (e.act == SA_ACT_GELU_FWD) {
     sa_st(reinterpret_cast<T*>(e.pre), o, v);
     v = sa_gelu(v);
+  } else if (e.act == SA_ACT_GELU_FWD_D) {
+    sa_st(reinterpret_cast<T*>(e.pre), o, sa_gelu_grad(v));
+    v = sa_gelu(v);
   } else if (e.act == SA_ACT_GELU_BWD) {
     v *= sa_gelu_grad(sa_ld(reinterpret_cast<const T*>(e.pre), o));
+  } else if (e.act == SA_ACT_MUL_PRE) {
+    v *= sa_ld(reinterpret_cast<const T*>(e.pre), o);
   }
   if (e.resid) v += e.resid[o];
   if (e.out_f32) e.out_f32[o] = v;

@@ -155,6 +155,16 @@ __device__ __forceinline__ float fast_gelu_grad(float x) {
   fast_phi(x, c, p);
   return fmaf(x, p, c);
 }
+// gelu(x) and gelu'(x) from one evaluation of Phi / phi (SA_ACT_GELU_FWD_D: the forward pass stores the derivative, so
+// that the backward epilogue is one multiplication instead of a second erf evaluation)
+__device__ __forceinline__ float fast_gelu_with_grad(float x, float& grad) {
+  float c, p;
+  fast_phi(x, c, p);
+  grad = fmaf(x, p, c);
+  return x * c;
+}
+__host__ __device__ __forceinline__ bool act_is_fwd(int a) { return a == SA_ACT_GELU_FWD || a == SA_ACT_GELU_FWD_D; }
+__host__ __device__ __forceinline__ bool act_is_bwd(int a) { return a == SA_ACT_GELU_BWD || a == SA_ACT_MUL_PRE; }
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile -- CTA r stages
 // rows r * 128 .. of the A tile and rows r * BN/2 .. of the B tile, the even CTA issues the 256-row MMAs, and each CTA
@@ -316,8 +326,13 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
               for (int j = 0; j < 32; ++j) dot = fmaf(f[j], t[j], dot);
             }
             unstage_bf16_32(stgA, lane, (ci & 1) * 32, t);
+            if (e.act == SA_ACT_MUL_PRE) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = f[j] * st * fast_gelu_grad(t[j]);
+              for (int j = 0; j < 32; ++j) f[j] = f[j] * st * t[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = f[j] * st * fast_gelu_grad(t[j]);
+            }
             stage_bf16_32(stgA, lane, (ci & 1) * 32, f);
             if (ci & 1) {
               fence_proxy_async();
@@ -338,21 +353,34 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] *= st;
-          if (e.act == SA_ACT_GELU_FWD) {
+          if (act_is_fwd(e.act)) {
             if ((ci & 1) == 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
-            stage_bf16_32(stgB, lane, (ci & 1) * 32, f);
+            if (e.act == SA_ACT_GELU_FWD_D) {          // `pre` receives gelu'(v)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fast_gelu_with_grad(f[j], t[j]);
+              stage_bf16_32(stgB, lane, (ci & 1) * 32, t);
+            } else {
+              stage_bf16_32(stgB, lane, (ci & 1) * 32, f);
+            }
             if (ci & 1) {
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) { tma_store_2d(&P.omap_b, stgB, col - 32, row0); bulk_commit(); }
             }
+            if (e.act == SA_ACT_GELU_FWD) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fast_gelu(f[j]);
-          } else if (e.act == SA_ACT_GELU_BWD) {
+              for (int j = 0; j < 32; ++j) f[j] = fast_gelu(f[j]);
+            }
+          } else if (act_is_bwd(e.act)) {
             if (row_ok) {
               ld32_bf16(reinterpret_cast<const T*>(e.pre) + o, t);
+              if (e.act == SA_ACT_MUL_PRE) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= fast_gelu_grad(t[j]);
+                for (int j = 0; j < 32; ++j) f[j] *= t[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] *= fast_gelu_grad(t[j]);
+              }
             }
           }
           if (P.tma_in == 2) {
@@ -382,7 +410,7 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
           }
           if (e.out_act) {
             // single output: the two staging blocks alternate (wait only for the store issued two blocks ago)
-            const bool solo = !e.out_f32 && e.act != SA_ACT_GELU_FWD;
+            const bool solo = !e.out_f32 && !act_is_fwd(e.act);
             uint8_t* sbuf = (solo && (ci & 2)) ? stgB : stgA;
             if ((ci & 1) == 0 && solo) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
             stage_bf16_32(sbuf, lane, (ci & 1) * 32, f);
@@ -412,10 +440,18 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
             st32_bf16(reinterpret_cast<T*>(e.pre) + o, f);
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fast_gelu(f[j]);
+          } else if (e.act == SA_ACT_GELU_FWD_D) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fast_gelu_with_grad(f[j], t[j]);
+            st32_bf16(reinterpret_cast<T*>(e.pre) + o, t);
           } else if (e.act == SA_ACT_GELU_BWD) {
             ld32_bf16(reinterpret_cast<const T*>(e.pre) + o, t);
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= fast_gelu_grad(t[j]);
+          } else if (e.act == SA_ACT_MUL_PRE) {
+            ld32_bf16(reinterpret_cast<const T*>(e.pre) + o, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= t[j];
           }
           if (e.resid) {
             ld32_f32(e.resid + o, t);
@@ -634,7 +670,7 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
   if (rc != SA_OK) return rc;
   // TMA-store epilogue: whole 64-column blocks per warp, at most one "second" output (pre or out_f32)
   P.tma_out = (vec && P.BN % 128 == 0 && n % 64 == 0 && (e.out_act || e.out_f32) &&
-               !(e.out_f32 && e.act == SA_ACT_GELU_FWD)) ? 1 : 0;
+               !(e.out_f32 && act_is_fwd(e.act))) ? 1 : 0;
   if (const char* env = getenv("SA_GEMM_TMA_OUT")) { if (env[0] == '0') P.tma_out = 0; }
   const size_t stage_bytes = G_BM * 128 + (size_t)(P.BN / cg) * 128;
   P.stages = pair ? G_STAGES_MAX : G_STAGES;
@@ -647,7 +683,7 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
       const uint32_t box[2] = {64, 32};
       if ((rc = sa_make_tmap(&P.omap_act, SA_BF16, e.out_act, 2, dims, strides, box)) != SA_OK) return rc;
     }
-    if (e.act == SA_ACT_GELU_FWD) {
+    if (act_is_fwd(e.act)) {
       const uint64_t strides[2] = {2, (uint64_t)e.ldo * 2};
       const uint32_t box[2] = {64, 32};
       if ((rc = sa_make_tmap(&P.omap_b, SA_BF16, e.pre, 2, dims, strides, box)) != SA_OK) return rc;
@@ -661,7 +697,7 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
   if (P.tma_out) {
     const uint64_t dims[2] = {(uint64_t)n, (uint64_t)m};
     const bool want = !getenv("SA_GEMM_TMA_IN") || getenv("SA_GEMM_TMA_IN")[0] != '0';
-    if (want && e.act == SA_ACT_GELU_BWD && e.dot_with && e.out_act && !e.out_f32 && !e.resid) {
+    if (want && act_is_bwd(e.act) && e.dot_with && e.out_act && !e.out_f32 && !e.resid) {
       const uint64_t strides[2] = {2, (uint64_t)e.ldo * 2};
       const uint32_t box[2] = {64, 32};
       if ((rc = sa_make_tmap(&P.imap_a, SA_BF16, e.pre, 2, dims, strides, box)) != SA_OK) return rc;

@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from ... import ops, pf_ops
-from ...pf_ops import SA_ACT_GELU_BWD, SA_ACT_GELU_FWD
+from ...pf_ops import SA_ACT_GELU_FWD, SA_ACT_GELU_FWD_D, SA_ACT_MUL_PRE
 from .transformer import TransformerBase
 
 # TransformerConditioningType values (src/utils/transformer.py:21-24)
@@ -472,7 +472,8 @@ class _LayerFn(torch.autograd.Function):
         # ---- feed-forward sub-layer
         u = torch.empty((M, D.ff), device=dev, dtype=dt)
         h = torch.empty((M, D.ff), device=dev, dtype=dt)
-        pf_ops.gemm_nt(xa_mid, W1_, bias=b1, act=SA_ACT_GELU_FWD, pre=u, out_act=h)
+        # `u` receives gelu'(x W1^T + b1) when a backward pass will follow (it needs nothing else of the pre-activation)
+        pf_ops.gemm_nt(xa_mid, W1_, bias=b1, act=SA_ACT_GELU_FWD_D if need_grad else SA_ACT_GELU_FWD, pre=u, out_act=h)
         x_out = torch.empty((M, D.dim), device=dev, dtype=f32)
         xa_out = None if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
         pf_ops.gemm_nt(h, W2_, bias=b2, scale_dev=g_f, resid=x_mid, out_f32=x_out, out_act=xa_out)
@@ -509,7 +510,7 @@ class _LayerFn(torch.autograd.Function):
         # ---- feed-forward sub-layer: x_out = x + g_f * (gelu(x W1^T + b1) W2^T + b2)
         dot = torch.zeros((1,), device=dev, dtype=f32)
         du = torch.empty((M, D.ff), device=dev, dtype=dt)
-        pf_ops.gemm_nt(dxa, _t(W2_), dot_with=h, dot_out=dot, scale_dev=g_f, act=SA_ACT_GELU_BWD, pre=u, out_act=du)
+        pf_ops.gemm_nt(dxa, _t(W2_), dot_with=h, dot_out=dot, scale_dev=g_f, act=SA_ACT_MUL_PRE, pre=u, out_act=du)
         colsum = ops.bias_grad(dxa)
         db2 = torch.empty_like(b2)
         dg_f = torch.empty((), device=dev, dtype=f32)

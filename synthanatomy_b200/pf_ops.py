@@ -12,7 +12,8 @@ import torch
 
 from . import _lib
 from . import ops as _ops
-from ._lib import FavorDesc, GemmEpilogue, LocalDesc, SA_ACT_GELU_BWD, SA_ACT_GELU_FWD, SA_ACT_NONE  # noqa: F401
+from ._lib import (FavorDesc, GemmEpilogue, LocalDesc, SA_ACT_GELU_BWD, SA_ACT_GELU_FWD, SA_ACT_GELU_FWD_D,  # noqa: F401
+                   SA_ACT_MUL_PRE, SA_ACT_NONE)
 from .ops import _dt, _p, _stream, lib
 
 

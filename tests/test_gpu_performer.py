@@ -574,3 +574,32 @@ def test_wrapper_options_match_oracle_fp32(opts):
         assert got is not None, k
         err = float((got.cpu() - gref).abs().max()) / max(float(gref.abs().max()), 1e-3)
         assert err <= 2e-4, f"grad {k}: {err:.3e}"
+
+
+@pytest.mark.parametrize("dtype,m,n,k", [(torch.float32, 130, 70, 50), (torch.bfloat16, 300, 512, 128), (torch.bfloat16, 2500, 2048, 512),
+                                         (torch.bfloat16, 257, 80, 64)])
+def test_gemm_gelu_derivative_epilogues(dtype, m, n, k):
+    """SA_ACT_GELU_FWD_D stores gelu'(u) instead of u, SA_ACT_MUL_PRE multiplies by it: together they equal the
+    SA_ACT_GELU_FWD / SA_ACT_GELU_BWD pair (one erf evaluation per element instead of two)."""
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(m + k)
+    rnd = (lambda *s: _bf(torch.randn(*s, generator=g))) if dtype == torch.bfloat16 else (lambda *s: torch.randn(*s, generator=g))
+    a, b, a2, b2 = rnd(m, k), rnd(n, k) * 0.1, rnd(m, 64), rnd(n, 64) * 0.1
+    bias, w = torch.randn(n, generator=g), rnd(m, n)
+    s = torch.tensor([0.37])
+    A, Bm, A2, B2 = (t.cuda().to(dtype) for t in (a, b, a2, b2))
+    tol = 1e-5 if dtype == torch.float32 else 2 ** -6
+    u = a @ b.t() + bias
+    uu = u.clone().requires_grad_(True)
+    F.gelu(uu).sum().backward()
+    d, h = torch.empty(m, n, device="cuda", dtype=dtype), torch.empty(m, n, device="cuda", dtype=dtype)
+    pf.gemm_nt(A, Bm, bias=bias.cuda(), act=pf.SA_ACT_GELU_FWD_D, pre=d, out_act=h)
+    torch.testing.assert_close(h.float().cpu(), F.gelu(u), rtol=tol, atol=tol * float(u.abs().max()))
+    torch.testing.assert_close(d.float().cpu(), uu.grad, rtol=tol, atol=tol)
+    dot = torch.zeros(1, device="cuda")
+    o = torch.empty(m, n, device="cuda", dtype=dtype)
+    pf.gemm_nt(A2, B2, dot_with=w.cuda().to(dtype), dot_out=dot, scale_dev=s.cuda(), scale=2.0, act=pf.SA_ACT_MUL_PRE, pre=d, out_act=o)
+    v = a2 @ b2.t()
+    want = v * 0.74 * d.float().cpu()
+    torch.testing.assert_close(o.float().cpu(), want, rtol=tol, atol=tol * float(want.abs().max()))
+    assert abs(float(dot) - float((v * w).sum())) <= 1e-3 * float((v * w).abs().sum()) ** 0.5 * 30 + 1e-3
