@@ -248,6 +248,12 @@ int sa_tokens_narrow(const int64_t* src, int64_t n, uint16_t* out, int* out_of_r
  * gradient to a TMA-friendly leading dimension). */
 int sa_cast2d(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld, int64_t rows,
               int cols, void* stream);
+/* ReZero gate gradient read off the UNSCALED weight gradient t = dx^T a (sa_gemm_tn without scale) of a gated layer
+ * y = x + g (a W^T) (performer-pytorch ReZero):  dot[0] += sum t . w  ( = sum (dx W) . a );  t *= g[0]  (t becomes dW).
+ * w: the layer's fp32 weight, same [out][in] layout as t; n = out * in.  Saves reading the [rows][in] activation again
+ * in the data-gradient GEMM's epilogue. */
+int sa_gate_wgrad(float* t, const float* w, int64_t n, const float* g, float* dot, void* stream);
+
 /* ReZero backward bookkeeping (performer-pytorch ReZero: y = g * f(x)), f(x) = core(x) + bias:
  *   dg[0] = dot[0] + sum_c bias[c] * colsum[c];   dbias[c] = g[0] * colsum[c]
  * colsum = column sums of the incoming gradient, dot = sum(grad * core(x)) from the sa_gemm_nt epilogue.

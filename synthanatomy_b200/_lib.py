@@ -177,6 +177,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p]),
     "sa_ce_fwd_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sa_cast2d": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p]),
+    "sa_gate_wgrad": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "sa_rezero_finish": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

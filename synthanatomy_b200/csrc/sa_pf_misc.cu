@@ -221,6 +221,31 @@ __global__ void rezero_finish_kernel(const float* __restrict__ colsum, const flo
   }
 }
 
+// ReZero gate gradient from the UNSCALED weight gradient T = dx^T a of the gated layer y = x + g (a W^T):
+//   dg += sum_ij T[i][j] W[i][j]   ( = sum (dx W) . a: the same number as a dot product over the [rows x n] activations,
+//                                    read off a [n_out x n_in] matrix instead)
+//   T  *= g                        (T becomes the weight gradient)
+__global__ void __launch_bounds__(256)
+gate_wgrad_kernel(float* __restrict__ T, const float* __restrict__ W, long long n, const float* __restrict__ g,
+                  float* __restrict__ dot) {
+  __shared__ float s_red[8];
+  const float gv = g[0];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float t = T[i];
+    acc = fmaf(t, W[i], acc);
+    T[i] = t * gv;
+  }
+  acc = sa_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_red[w];
+    atomicAdd(dot, s);
+  }
+}
+
 inline unsigned ew_grid(long long n) {
   long long b = sa_cdiv(n, 256);
   if (b > 148 * 32) b = 148 * 32;
@@ -315,6 +340,16 @@ extern "C" int sa_cast2d(const void* src, int src_dtype, int64_t src_ld, void* d
   else if (src_dtype == SA_BF16 && dst_dtype == SA_BF16)
     cast2d_kernel<B, B><<<ew_grid(total), 256, 0, st>>>((const B*)src, src_ld, (B*)dst, dst_ld, rows, cols);
   else { sa_set_error("sa_cast2d: bad dtype"); return SA_ERR_INVALID; }
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+extern "C" int sa_gate_wgrad(float* t, const float* w, int64_t n, const float* g, float* dot, void* stream) {
+  SA_CHECK_ARG(t && w && g && dot && n >= 0, "bad arguments");
+  if (n == 0) return SA_OK;
+  long long blocks = sa_cdiv(n, 256 * 4);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  gate_wgrad_kernel<<<(unsigned)blocks, 256, 0, sa_stream(stream)>>>(t, w, n, g, dot);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

@@ -308,9 +308,9 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
             if ((ci & 1) == 0) {
               if (lane == 0) {
                 bulk_wait_read0();
-                mbar_expect_tx(&in_bar[ew], 8192);
+                mbar_expect_tx(&in_bar[ew], e.dot_with ? 8192u : 4096u);
                 tma_load_2d(stgA, &P.imap_a, &in_bar[ew], col, row0);
-                tma_load_2d(stgB, &P.imap_b, &in_bar[ew], col, row0);
+                if (e.dot_with) tma_load_2d(stgB, &P.imap_b, &in_bar[ew], col, row0);
               }
               mbar_wait(&in_bar[ew], in_phase);
               in_phase ^= 1;
@@ -320,10 +320,12 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] += t[j];
             }
-            unstage_bf16_32(stgB, lane, (ci & 1) * 32, t);
-            if (row_ok) {
+            if (e.dot_with) {
+              unstage_bf16_32(stgB, lane, (ci & 1) * 32, t);
+              if (row_ok) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dot = fmaf(f[j], t[j], dot);
+                for (int j = 0; j < 32; ++j) dot = fmaf(f[j], t[j], dot);
+              }
             }
             unstage_bf16_32(stgA, lane, (ci & 1) * 32, t);
             if (e.act == SA_ACT_MUL_PRE) {
@@ -697,11 +699,11 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
   if (P.tma_out) {
     const uint64_t dims[2] = {(uint64_t)n, (uint64_t)m};
     const bool want = !getenv("SA_GEMM_TMA_IN") || getenv("SA_GEMM_TMA_IN")[0] != '0';
-    if (want && act_is_bwd(e.act) && e.dot_with && e.out_act && !e.out_f32 && !e.resid) {
+    if (want && act_is_bwd(e.act) && e.out_act && !e.out_f32 && !e.resid) {
       const uint64_t strides[2] = {2, (uint64_t)e.ldo * 2};
       const uint32_t box[2] = {64, 32};
       if ((rc = sa_make_tmap(&P.imap_a, SA_BF16, e.pre, 2, dims, strides, box)) != SA_OK) return rc;
-      if ((rc = sa_make_tmap(&P.imap_b, SA_BF16, e.dot_with, 2, dims, strides, box)) != SA_OK) return rc;
+      if (e.dot_with && (rc = sa_make_tmap(&P.imap_b, SA_BF16, e.dot_with, 2, dims, strides, box)) != SA_OK) return rc;
       P.tma_in = 1;
     } else if (want && e.resid && e.out_f32 && e.act == SA_ACT_NONE) {
       const uint64_t strides[2] = {4, (uint64_t)e.ldo * 4};

@@ -482,6 +482,7 @@ class _LayerFn(torch.autograd.Function):
             ctx.saved = (xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_mid, u, h, proj, inv_freq, states)
             ctx.weights = (Wqkv, Wo_, W1_, W2_)
             ctx.scalars = (g_a, g_f, b1, b2)
+            ctx.masters = (Wo, W2)
         if is32:
             return x_out, None
         ctx.mark_non_differentiable(xa_out)
@@ -504,19 +505,23 @@ class _LayerFn(torch.autograd.Function):
         xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq, states = ctx.saved
         Wqkv, Wo_, W1_, W2_ = ctx.weights
         g_a, g_f, b1, b2 = ctx.scalars
-        ctx.saved = ctx.weights = None
+        Wo, W2 = ctx.masters
+        ctx.saved = ctx.weights = ctx.masters = None
         g32 = g32.contiguous()
         dxa = g32 if is32 else _grad_copy(g32, dt)
         # ---- feed-forward sub-layer: x_out = x + g_f * (gelu(x W1^T + b1) W2^T + b2)
+        # (the gate gradient sum (dx W2) . h is read off the unscaled weight gradient dx^T h below: the data-gradient
+        #  GEMM's epilogue does not have to stream h again)
         dot = torch.zeros((1,), device=dev, dtype=f32)
         du = torch.empty((M, D.ff), device=dev, dtype=dt)
-        pf_ops.gemm_nt(dxa, _t(W2_), dot_with=h, dot_out=dot, scale_dev=g_f, act=SA_ACT_MUL_PRE, pre=u, out_act=du)
+        pf_ops.gemm_nt(dxa, _t(W2_), scale_dev=g_f, act=SA_ACT_MUL_PRE, pre=u, out_act=du)
         colsum = ops.bias_grad(dxa)
+        dW2 = torch.empty((D.dim, D.ff), device=dev, dtype=f32)
+        pf_ops.gemm_tn(dxa, h, dW2)
+        pf_ops.gate_wgrad(dW2, W2, g_f, dot)               # dot = sum (dx^T h) . W2;  dW2 *= g_f
         db2 = torch.empty_like(b2)
         dg_f = torch.empty((), device=dev, dtype=f32)
         pf_ops.rezero_finish(colsum, b2, g_f, dot, db2, dg_f)
-        dW2 = torch.empty((D.dim, D.ff), device=dev, dtype=f32)
-        pf_ops.gemm_tn(dxa, h, dW2, scale_dev=g_f)
         dW1 = torch.empty((D.ff, D.dim), device=dev, dtype=f32)
         pf_ops.gemm_tn(du, xa_ffn, dW1)
         db1 = ops.bias_grad(du)
@@ -527,9 +532,10 @@ class _LayerFn(torch.autograd.Function):
         # ---- attention sub-layer: x_mid = x + g_a * (attn Wo^T)
         dot = torch.zeros((1,), device=dev, dtype=f32)
         dattn = torch.empty((M, D.inner), device=dev, dtype=dt)
-        pf_ops.gemm_nt(dxa_mid, _t(Wo_), dot_with=attn, dot_out=dot, scale_dev=g_a, out_act=dattn)
+        pf_ops.gemm_nt(dxa_mid, _t(Wo_), scale_dev=g_a, out_act=dattn)
         dWo = torch.empty((D.dim, D.inner), device=dev, dtype=f32)
-        pf_ops.gemm_tn(dxa_mid, attn, dWo, scale_dev=g_a)
+        pf_ops.gemm_tn(dxa_mid, attn, dWo)
+        pf_ops.gate_wgrad(dWo, Wo, g_a, dot)               # dg_a = sum (dx^T attn) . Wo;  dWo *= g_a
         dqkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
         if D.lh > 0:
             c0 = D.gh * D.dh

@@ -135,6 +135,12 @@ def cast2d(src, dst, cols: int) -> None:
                                cols, _stream()), "sa_cast2d")
 
 
+def gate_wgrad(t, w, g, dot) -> None:
+    """dot += sum t . w;  t *= g   (t: unscaled weight gradient of a ReZero-gated layer, w: its fp32 weight)"""
+    assert t.dtype == torch.float32 and w.dtype == torch.float32 and t.shape == w.shape and t.is_contiguous()
+    _lib.check(lib().sa_gate_wgrad(_p(t), _p(w.contiguous()), t.numel(), _p(g), _p(dot), _stream()), "sa_gate_wgrad")
+
+
 def rezero_finish(colsum, bias, g, dot, dbias, dg) -> None:
     n = 0 if colsum is None else colsum.numel()
     _lib.check(lib().sa_rezero_finish(_p(colsum), _p(bias), _p(g), _p(dot), n, _p(dbias), _p(dg), _stream()),
