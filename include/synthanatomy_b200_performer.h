@@ -67,6 +67,12 @@ int sa_gemm_nt(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, c
 int sa_gemm_tn(int64_t m, int na, int nb, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
                const float* scale_dev, float scale, float* d, int accumulate, void* stream);
 
+/* sa_gemm_tn that also returns colsum[i] = sum_r A[r][i] (fp32 [na], overwritten, never scaled): the bias gradient that
+ * goes with a dense layer's weight gradient (A = dy, B = the layer's input) without a second pass over dy.  On the
+ * tensor-core path it is one more 16-column product A^T 1 of the same staged A tiles. */
+int sa_gemm_tn_colsum(int64_t m, int na, int nb, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
+                      const float* scale_dev, float scale, float* d, int accumulate, float* colsum, void* stream);
+
 /* bf16x3 "parity" arithmetic of the two dense entry points (see sa_conv3d_fwd_x3 in synthanatomy_b200.h): fp32 operands
  * and fp32 epilogue tensors (every `void*` of the epilogue is fp32 here), products on the bf16 tensor cores as
  * hi.hi + lo.hi + hi.lo with fp32 accumulation.  The reference runs these layers in fp32 storage with TF32 matmuls

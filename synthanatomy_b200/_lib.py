@@ -126,6 +126,8 @@ SIGNATURES = {
                            c_int64, c_void_p]),
     "sa_gemm_tn": (c_int, [c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_float, c_void_p,
                            c_int, c_void_p]),
+    "sa_gemm_tn_colsum": (c_int, [c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_float,
+                                  c_void_p, c_int, c_void_p, c_void_p]),
     "sa_embed_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, C.POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_void_p]),
     "sa_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, C.POINTER(c_void_p),

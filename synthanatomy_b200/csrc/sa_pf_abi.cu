@@ -10,6 +10,8 @@ int sa_skinny_gemm_nt(int64_t, int, int, int, const void*, int64_t, const void*,
 bool sa_tc_gemm_nt_supported(int64_t m, int n, int k, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb);
 int sa_tc_gemm_nt(int64_t, int, int, const void*, int64_t, const void*, int64_t, const SaEpi&, cudaStream_t);
 bool sa_tc_gemm_tn_supported(int64_t m, int na, int nb, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb);
+int sa_tc_gemm_tn_colsum(int64_t, int, int, const void*, int64_t, const void*, int64_t, const float*, float, float*, float*,
+                         cudaStream_t);
 int sa_tc_gemm_tn(int64_t, int, int, const void*, int64_t, const void*, int64_t, const float*, float, float*,
                   cudaStream_t);
 
@@ -75,6 +77,26 @@ extern "C" int sa_gemm_tn(int64_t m, int na, int nb, int dtype, const void* a, i
   if (!sa_force_simt() && sa_tc_gemm_tn_supported(m, na, nb, dtype, a, lda, b, ldb))
     return sa_tc_gemm_tn(m, na, nb, a, lda, b, ldb, scale_dev, scale, d, st);
   return sa_simt_gemm_tn(m, na, nb, dtype, a, lda, b, ldb, scale_dev, scale, d, st);
+}
+
+extern "C" int sa_bias_grad(const void* dy, int64_t rows, int c, int dtype, float* db, int accumulate, void* stream);
+
+extern "C" int sa_gemm_tn_colsum(int64_t m, int na, int nb, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
+                                 const float* scale_dev, float scale, float* d, int accumulate, float* colsum, void* stream) {
+  SA_CHECK_ARG(a && b && d && colsum, "null pointer");
+  SA_CHECK_ARG(m > 0 && na > 0 && nb > 0 && lda >= na && ldb >= nb, "bad sizes");
+  SA_CHECK_ARG(dtype == SA_F32 || dtype == SA_BF16, "bad dtype");
+  cudaStream_t st = sa_stream(stream);
+  if (!sa_force_simt() && sa_tc_gemm_tn_supported(m, na, nb, dtype, a, lda, b, ldb)) {
+    // the column sums are one more 16-column product (A^T 1) of the CTAs that own the first column tile
+    if (!accumulate) SA_CUDA(cudaMemsetAsync(d, 0, (size_t)na * nb * sizeof(float), st));
+    SA_CUDA(cudaMemsetAsync(colsum, 0, (size_t)na * sizeof(float), st));
+    return sa_tc_gemm_tn_colsum(m, na, nb, a, lda, b, ldb, scale_dev, scale, d, colsum, st);
+  }
+  SA_CHECK_ARG(lda == na, "column sums of a column slice need the tensor-core path");
+  const int rc = sa_gemm_tn(m, na, nb, dtype, a, lda, b, ldb, scale_dev, scale, d, accumulate, stream);
+  if (rc != SA_OK) return rc;
+  return sa_bias_grad(a, m, na, dtype, colsum, 0, stream);
 }
 
 extern "C" int sa_favor_kmax(const sa_favor_desc* d, const void* k, const float* proj, unsigned long long* kmax,

@@ -510,6 +510,7 @@ struct TnParams {
   const float* scale_dev;
   float scale;
   float* d;
+  float* colsum;               // optional: colsum[i] += sum_r A[r][i] (unscaled) -- the bias gradient that goes with D
 };
 
 __global__ void __launch_bounds__(W_THREADS, 1)
@@ -532,6 +533,19 @@ tc_gemm_tn_kernel(const __grid_constant__ TnParams P) {
   const uint32_t a_bytes = 2 * W_BLOCK;
   const uint32_t b_bytes = (uint32_t)P.bblocks * W_BLOCK;
   const uint32_t stage_bytes = a_bytes + b_bytes;
+  // column sums of A ride along as one more product, A^T 1: a [64 rows x 64 cols] "ones" operand (columns 0..15 = 1)
+  // after the ring, a 16-column accumulator after the tile's; only the CTAs of the first column tile do it
+  const bool do_colsum = P.colsum != nullptr && bt == 0;
+  uint8_t* Ones = smem + (size_t)W_STAGES * stage_bytes;
+  if (do_colsum && warp >= 2) {
+    for (int idx = threadIdx.x - 64; idx < W_KP * 8; idx += W_THREADS - 64) {
+      const int r = idx >> 3, ch = idx & 7;
+      const uint32_t one2 = 0x3F803F80u;      // two bf16 ones
+      const uint4 u = ch < 2 ? make_uint4(one2, one2, one2, one2) : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Ones + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4)) = u;
+    }
+    fence_proxy_async();
+  }
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -567,6 +581,8 @@ tc_gemm_tn_kernel(const __grid_constant__ TnParams P) {
   } else if (warp == 1) {
     if (lane == 0 && nkb > 0) {
       const uint32_t idesc = make_idesc_bf16(128, P.BN, 1, 1);   // both operands MN-major
+      const uint32_t idesc_1 = make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t ones_a = smem_u32(Ones);
       int stage = 0; uint32_t phase = 0;
       for (long long kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
@@ -580,6 +596,8 @@ tc_gemm_tn_kernel(const __grid_constant__ TnParams P) {
           const uint64_t da = make_smem_desc(sa + j * 2048, W_BLOCK, 1024, 2);
           const uint64_t db = make_smem_desc(sb + j * 2048, W_BLOCK, 1024, 2);
           umma_bf16(tmem_base, da, db, idesc, (kb | j) != 0);
+          if (do_colsum)
+            umma_bf16(tmem_base + (uint32_t)P.BN, da, make_smem_desc(ones_a + j * 2048, W_BLOCK, 1024, 2), idesc_1, (kb | j) != 0);
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
@@ -743,8 +761,16 @@ bool sa_tc_gemm_tn_supported(int64_t m, int na, int nb, int dtype, const void* a
   return sa_get_tmap_encode() != nullptr;
 }
 
+int sa_tc_gemm_tn_colsum(int64_t m, int na, int nb, const void* a, int64_t lda, const void* b, int64_t ldb,
+                         const float* scale_dev, float scale, float* d, float* colsum, cudaStream_t st);
+
 int sa_tc_gemm_tn(int64_t m, int na, int nb, const void* a, int64_t lda, const void* b, int64_t ldb,
                   const float* scale_dev, float scale, float* d, cudaStream_t st) {
+  return sa_tc_gemm_tn_colsum(m, na, nb, a, lda, b, ldb, scale_dev, scale, d, nullptr, st);
+}
+
+int sa_tc_gemm_tn_colsum(int64_t m, int na, int nb, const void* a, int64_t lda, const void* b, int64_t ldb,
+                         const float* scale_dev, float scale, float* d, float* colsum, cudaStream_t st) {
   init_once();
   sa_note_path(SA_PATH_TCGEN05);
   static thread_local TnParams P;
@@ -754,8 +780,9 @@ int sa_tc_gemm_tn(int64_t m, int na, int nb, const void* a, int64_t lda, const v
   P.a_tiles = (int)sa_cdiv(na, 128);
   P.b_tiles = (int)sa_cdiv(nb, P.BN);
   P.kblocks_total = sa_cdiv(m, W_KP);
-  P.tmem_cols = P.BN <= 64 ? 64 : (P.BN <= 128 ? 128 : 256);
-  P.scale_dev = scale_dev; P.scale = scale; P.d = d;
+  const int acc_cols = P.BN + (colsum ? 32 : 0);       // the column-sum accumulator: 16 columns after the tile's
+  P.tmem_cols = acc_cols <= 64 ? 64 : (acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512));
+  P.scale_dev = scale_dev; P.scale = scale; P.d = d; P.colsum = colsum;
   const int64_t tiles = (int64_t)P.a_tiles * P.b_tiles;
   int64_t splits = g_sms / tiles;
   const int64_t max_splits = sa_cdiv(P.kblocks_total, 8);
@@ -767,7 +794,7 @@ int sa_tc_gemm_tn(int64_t m, int na, int nb, const void* a, int64_t lda, const v
   if (rc != SA_OK) return rc;
   rc = make_2d(&P.bmap, b, (uint64_t)nb, (uint64_t)m, (uint64_t)ldb, 64, W_KP);
   if (rc != SA_OK) return rc;
-  const size_t smem = (size_t)W_STAGES * (2 * W_BLOCK + (size_t)P.bblocks * W_BLOCK) + 1024;
+  const size_t smem = (size_t)W_STAGES * (2 * W_BLOCK + (size_t)P.bblocks * W_BLOCK) + W_BLOCK + 1024;
   tc_gemm_tn_kernel<<<(unsigned)(tiles * splits), W_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;

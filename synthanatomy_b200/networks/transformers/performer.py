@@ -515,16 +515,16 @@ class _LayerFn(torch.autograd.Function):
         dot = torch.zeros((1,), device=dev, dtype=f32)
         du = torch.empty((M, D.ff), device=dev, dtype=dt)
         pf_ops.gemm_nt(dxa, _t(W2_), scale_dev=g_f, act=SA_ACT_MUL_PRE, pre=u, out_act=du)
-        colsum = ops.bias_grad(dxa)
+        colsum = torch.empty((D.dim,), device=dev, dtype=f32)
         dW2 = torch.empty((D.dim, D.ff), device=dev, dtype=f32)
-        pf_ops.gemm_tn(dxa, h, dW2)
+        pf_ops.gemm_tn(dxa, h, dW2, colsum=colsum)         # + the column sums of dx (bias gradient) from the same tiles
         pf_ops.gate_wgrad(dW2, W2, g_f, dot)               # dot = sum (dx^T h) . W2;  dW2 *= g_f
         db2 = torch.empty_like(b2)
         dg_f = torch.empty((), device=dev, dtype=f32)
         pf_ops.rezero_finish(colsum, b2, g_f, dot, db2, dg_f)
         dW1 = torch.empty((D.ff, D.dim), device=dev, dtype=f32)
-        pf_ops.gemm_tn(du, xa_ffn, dW1)
-        db1 = ops.bias_grad(du)
+        db1 = torch.empty((D.ff,), device=dev, dtype=f32)
+        pf_ops.gemm_tn(du, xa_ffn, dW1, colsum=db1)
         d_mid = torch.empty((M, D.dim), device=dev, dtype=f32)
         dxa_mid = d_mid if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
         pf_ops.gemm_nt(du, _t(W1_), resid=g32, out_f32=d_mid, out_act=None if is32 else dxa_mid)

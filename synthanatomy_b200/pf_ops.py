@@ -69,12 +69,21 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, *, bias=None, dot_with=None, dot_o
 
 
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, d: torch.Tensor, *, scale_dev=None, scale: float = 1.0,
-            accumulate: bool = False) -> None:
-    """d[na, nb] (+)= scale * a.T @ b;  a [m, na], b [m, nb] row-major (column slices allowed), d fp32 dense."""
+            accumulate: bool = False, colsum: Optional[torch.Tensor] = None) -> None:
+    """d[na, nb] (+)= scale * a.T @ b;  a [m, na], b [m, nb] row-major (column slices allowed), d fp32 dense.
+    colsum (fp32 [na], optional) receives a.sum(0) -- the bias gradient that goes with the weight gradient."""
     m, na = a.shape
     nb = b.shape[1]
     assert b.shape[0] == m and a.dtype == b.dtype
     assert d.dtype == torch.float32 and d.is_contiguous() and tuple(d.shape) == (na, nb)
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == na
+        if not (_ops.x3_enabled() and a.dtype == torch.float32):
+            _lib.check(lib().sa_gemm_tn_colsum(m, na, nb, _dt(a.dtype), _ptr(a), _rowmajor(a), _ptr(b), _rowmajor(b),
+                                               _ptr(scale_dev), float(scale), _p(d), int(accumulate), _p(colsum), _stream()),
+                       "sa_gemm_tn_colsum")
+            return
+        colsum.copy_(_ops.bias_grad(a))          # split operands: the sums come from the fp32 tensor itself
     if _ops.x3_enabled() and a.dtype == torch.float32 and m >= 64 and na >= 8 and nb >= 8:
         nbytes = int(lib().sa_gemm_tn_x3_workspace(m, na, nb))
         ws = _ops.x3_workspace(nbytes, a.device)

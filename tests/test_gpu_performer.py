@@ -146,6 +146,23 @@ def test_tcgen05_gemm_tn_bf16(m, na, nb):
     _close(d, want, 2e-5 * max(1.0, m / 1000), "tc tn")
     pf.gemm_tn(A[:, 8:8 + na], Bm[:, :nb], d, accumulate=True)
     assert float(d.abs().max()) <= 1e-4 * float(want.abs().max()) * max(1.0, m / 1000)
+    # the same call with the column sums of A (the bias gradient) as one more product of the staged tiles
+    cs = torch.full((na,), 7.0, device="cuda")
+    d2 = torch.empty(na, nb, device="cuda")
+    pf.gemm_tn(A[:, 8:8 + na], Bm[:, :nb], d2, scale_dev=s, scale=2.0, colsum=cs)
+    assert ops.last_path() == 2
+    _close(d2, want, 2e-5 * max(1.0, m / 1000), "tc tn + colsum")
+    torch.testing.assert_close(cs.cpu(), a.sum(0), rtol=1e-5, atol=1e-5 * float(a.abs().sum(0).max()))
+
+
+def test_gemm_tn_colsum_cuda_core_path():
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(11)
+    a, b = torch.randn(500, 72, generator=g), torch.randn(500, 40, generator=g)
+    d, cs = torch.empty(72, 40, device="cuda"), torch.empty(72, device="cuda")
+    pf.gemm_tn(a.cuda(), b.cuda(), d, colsum=cs)
+    _close(d, a.t() @ b, 1e-5, "tn")
+    torch.testing.assert_close(cs.cpu(), a.sum(0), rtol=1e-5, atol=1e-4)
 
 
 # ------------------------------------------------------------------------------------------------ FAVOR+
