@@ -623,6 +623,12 @@ tc_gemm_tn_kernel(const __grid_constant__ TnParams P) {
           if (j < nc) atomicAdd(dst + j, st * __uint_as_float(v[j]));
       }
     }
+    if (do_colsum) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)P.BN, v);   // columns 0..15 all hold the sum
+      tmem_ld_wait();
+      if (i < P.na) atomicAdd(P.colsum + i, __uint_as_float(v[0]));
+    }
   }
 
   tc_fence_before();
