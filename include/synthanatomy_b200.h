@@ -45,6 +45,12 @@ int64_t sa_launch_count(void);
 void sa_launch_count_reset(void);
 /* 0: dispatch normally; 1: force the CUDA-core (SIMT) kernels even where a tcgen05 kernel exists */
 void sa_set_force_simt(int on);
+/* 1: every cross-CTA floating-point accumulation (split-K partials, bias / gate / loss sums, codebook statistics) is
+ * added in one fixed order (a turnstile of device counters per launch), so that a training step is bit-reproducible run
+ * to run -- the reference's `deterministic=True` (run_vqvae.py:550, run_transformer.py:417; src/utils/general.py:333).
+ * 0 (default): partials are added in arrival order with atomics. */
+void sa_set_deterministic(int on);
+int sa_get_deterministic(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Gather-GEMM convolution primitive.

@@ -73,6 +73,8 @@ SIGNATURES = {
     "sa_launch_count": (c_int64, []),
     "sa_launch_count_reset": (None, []),
     "sa_set_force_simt": (None, [c_int]),
+    "sa_set_deterministic": (None, [c_int]),
+    "sa_get_deterministic": (c_int, []),
     "sa_conv3d_fwd": (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                               c_void_p]),
     "sa_conv3d_wgrad": (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

@@ -29,7 +29,37 @@ thread_local int g_path = SA_PATH_NONE;
 // launch count must include it
 std::atomic<int64_t> g_launches{0};
 int g_force_simt = 0;
+int g_deterministic = 0;
+
+// turn counters of the deterministic mode: one zero-initialised ring per device, a fresh slot per launch
+constexpr size_t kTurnRing = 1u << 20;          // counters (4 MB)
+struct TurnPool { unsigned* base = nullptr; size_t next = 0; };
+TurnPool g_turn[64];
+std::mutex g_turn_mu;
 }  // namespace
+
+bool sa_deterministic() { return g_deterministic != 0; }
+extern "C" void sa_set_deterministic(int on) { g_deterministic = on; }
+extern "C" int sa_get_deterministic(void) { return g_deterministic; }
+
+unsigned* sa_turn_slot(int n, cudaStream_t st) {
+  if (!g_deterministic || n <= 0) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  const size_t want = ((size_t)n + 31) & ~(size_t)31;
+  if (want > kTurnRing) return nullptr;
+  std::lock_guard<std::mutex> lock(g_turn_mu);
+  TurnPool& pool = g_turn[dev];
+  if (!pool.base) {
+    if (cudaMalloc(&pool.base, kTurnRing * sizeof(unsigned)) != cudaSuccess) { pool.base = nullptr; return nullptr; }
+  }
+  if (pool.next + want > kTurnRing) pool.next = 0;
+  unsigned* slot = pool.base + pool.next;
+  pool.next += want;
+  // zeroed on the launch's own stream: a slot comes round again only after 2^20 counters' worth of later launches
+  if (cudaMemsetAsync(slot, 0, want * sizeof(unsigned), st) != cudaSuccess) return nullptr;
+  return slot;
+}
 
 void sa_set_error(const char* fmt, ...) {
   va_list ap;

@@ -15,6 +15,13 @@ void sa_set_error(const char* fmt, ...);
 void sa_note_launch(int n = 1);
 void sa_note_path(int path);
 bool sa_force_simt();
+// Deterministic mode (sa_set_deterministic): every cross-CTA floating-point accumulation (split-K partials, column sums,
+// loss sums) runs through a "turnstile" -- a zeroed device counter per output region; the CTA that holds partial number s
+// waits until the counter reads s, adds its partial, and passes the turn on -- so the additions happen in one fixed order
+// and a step is bit-reproducible run to run.  sa_turn_slot returns nullptr when the mode is off (the kernels then add in
+// arrival order with plain atomics), else `n` zeroed counters valid for ONE launch on `st`.
+bool sa_deterministic();
+unsigned* sa_turn_slot(int n, cudaStream_t st);
 
 #define SA_CHECK_ARG(cond, msg)                                   \
   do {                                                            \
@@ -65,6 +72,42 @@ __device__ __forceinline__ float sa_ld(const float* p, int64_t i) { return p[i];
 __device__ __forceinline__ float sa_ld(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
 __device__ __forceinline__ void sa_st(float* p, int64_t i, float v) { p[i] = v; }
 __device__ __forceinline__ void sa_st(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// turnstile (deterministic mode): see sa_turn_slot above.  `ctr` may be nullptr (mode off: no-ops).
+__device__ __forceinline__ void sa_turn_wait(const unsigned* ctr, unsigned my) {
+  if (ctr == nullptr) return;
+  unsigned v;
+  for (unsigned spins = 0;; ++spins) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if (v == my) break;
+    if (spins > (1u << 26)) __trap();      // seconds: a lost turn is a bug, not a wait
+    __nanosleep(40);
+  }
+}
+// a group of `nthreads` threads (named barrier `bar_id`) has finished its ordered additions: pass the turn on
+__device__ __forceinline__ void sa_group_turn_end(unsigned* ctr, unsigned my, int bar_id, int nthreads, bool leader) {
+  if (ctr == nullptr) return;
+  __threadfence();
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+  if (leader) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctr), "r"(my + 1u) : "memory");
+}
+// the caller has made the partial's additions visible (__threadfence) and joined its threads (barrier) before this
+__device__ __forceinline__ void sa_turn_pass(unsigned* ctr, unsigned my) {
+  if (ctr == nullptr) return;
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctr), "r"(my + 1u) : "memory");
+}
+// whole-block forms for the CUDA-core kernels (every thread of the block must reach them)
+__device__ __forceinline__ void sa_block_turn_begin(const unsigned* ctr, unsigned my) {
+  if (ctr == nullptr) return;
+  if (threadIdx.x == 0) sa_turn_wait(ctr, my);
+  __syncthreads();
+}
+__device__ __forceinline__ void sa_block_turn_end(unsigned* ctr, unsigned my) {
+  if (ctr == nullptr) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) sa_turn_pass(ctr, my);
+}
 
 __device__ __forceinline__ float sa_warp_sum(float v) {
 #pragma unroll

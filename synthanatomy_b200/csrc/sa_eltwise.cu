@@ -47,7 +47,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int A, int B,
 // db[c] += sum over rows; block = (C-lane, row-lane) so that global reads stay coalesced along c
 template <typename T>
 __global__ void __launch_bounds__(256)
-bias_grad_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restrict__ db, int64_t rows_per_block) {
+bias_grad_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restrict__ db, int64_t rows_per_block,
+                 unsigned* turn) {
   __shared__ float s_acc[256];
   const int cl = min(C, 256);          // threads along c
   const int rl = 256 / cl;             // row lanes (>= 1)
@@ -61,11 +62,14 @@ bias_grad_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restric
       for (int64_t r = r0 + tr; r < r1; r += rl) acc += sa_ld(dy, r * C + c);
     s_acc[threadIdx.x] = acc;
     __syncthreads();
+    const unsigned my = (unsigned)(c0 / cl) * gridDim.x + blockIdx.x;     // deterministic mode: blocks add in order
+    sa_block_turn_begin(turn, my);
     if (tr == 0 && c < C) {
       float s = 0.f;
       for (int j = 0; j < rl; ++j) s += s_acc[j * cl + tc];
       atomicAdd(db + c, s);
     }
+    sa_block_turn_end(turn, my);
     __syncthreads();
   }
 }
@@ -73,7 +77,8 @@ bias_grad_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restric
 // vectorised variant (C a multiple of the 16-byte vector, 16-byte aligned rows): 16-byte loads, 4 rows in flight
 template <typename T>
 __global__ void __launch_bounds__(256)
-bias_grad_vec_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restrict__ db, int64_t rows_per_block) {
+bias_grad_vec_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restrict__ db, int64_t rows_per_block,
+                     unsigned* turn) {
   constexpr int VEC = 16 / sizeof(T);
   __shared__ float s_acc[256 * VEC];
   const int cv = C / VEC;
@@ -127,6 +132,8 @@ bias_grad_vec_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __res
 #pragma unroll
     for (int i = 0; i < VEC; ++i) s_acc[i * 256 + threadIdx.x] = acc[i];
     __syncthreads();
+    const unsigned my = (unsigned)(v0 / cl) * gridDim.x + blockIdx.x;
+    sa_block_turn_begin(turn, my);
     if (tr == 0 && v < cv) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
@@ -135,6 +142,7 @@ bias_grad_vec_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __res
         atomicAdd(db + v * VEC + i, t);
       }
     }
+    sa_block_turn_end(turn, my);
     __syncthreads();
   }
 }
@@ -179,7 +187,7 @@ __global__ void cast_kernel(const TI* __restrict__ src, TO* __restrict__ dst, in
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS)
 mse_kernel(const T* __restrict__ a, const float* __restrict__ b, int64_t n, float scale,
-           const float* __restrict__ scale_dev, float* __restrict__ sse, T* __restrict__ grad) {
+           const float* __restrict__ scale_dev, float* __restrict__ sse, T* __restrict__ grad, unsigned* turn) {
   __shared__ float s_red[EW_THREADS / 32];
   float acc = 0.f;
   if (scale_dev) scale *= scale_dev[0];
@@ -191,11 +199,13 @@ mse_kernel(const T* __restrict__ a, const float* __restrict__ b, int64_t n, floa
   acc = sa_warp_sum(acc);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
   __syncthreads();
+  sa_block_turn_begin(turn, blockIdx.x);
   if (threadIdx.x == 0 && sse) {
     float s = 0.f;
     for (int i = 0; i < EW_THREADS / 32; ++i) s += s_red[i];
     atomicAdd(sse, s);
   }
+  sa_block_turn_end(turn, blockIdx.x);
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -334,19 +344,21 @@ extern "C" int sa_bias_grad(const void* dy, int64_t rows, int c, int dtype, floa
   if (!accumulate) SA_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * c, st));
   if (rows == 0) return SA_OK;
   int64_t blocks = sa_cdiv(rows, 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int64_t max_blocks = sa_deterministic() ? 148 * 2 : 148 * 8;      // ordered adds serialise the blocks' tails
+  if (blocks > max_blocks) blocks = max_blocks;
+  unsigned* turn = sa_turn_slot(1, st);
   const int64_t rpb = sa_cdiv(rows, blocks);
   blocks = sa_cdiv(rows, rpb);
   const int vec = dtype == SA_BF16 ? 8 : 4;
   const bool vec_ok = (c % vec == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
   if (vec_ok && dtype == SA_BF16)
-    bias_grad_vec_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, c, db, rpb);
+    bias_grad_vec_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, c, db, rpb, turn);
   else if (vec_ok)
-    bias_grad_vec_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, rows, c, db, rpb);
+    bias_grad_vec_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, rows, c, db, rpb, turn);
   else if (dtype == SA_BF16)
-    bias_grad_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, c, db, rpb);
+    bias_grad_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, c, db, rpb, turn);
   else
-    bias_grad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, rows, c, db, rpb);
+    bias_grad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, rows, c, db, rpb, turn);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -406,12 +418,14 @@ extern "C" int sa_mse_fwd_bwd(const void* a, int a_dtype, const float* b, int64_
   SA_CHECK_ARG(a && b && n >= 0, "bad arguments");
   if (n == 0) return SA_OK;
   cudaStream_t st = sa_stream(stream);
-  const unsigned g = ew_grid(n, 8);
+  unsigned g = ew_grid(n, 8);
+  if (sa_deterministic() && g > 148 * 4) g = 148 * 4;      // ordered adds serialise the blocks' tails
+  unsigned* turn = sse ? sa_turn_slot(1, st) : nullptr;
   if (a_dtype == SA_BF16)
     mse_kernel<__nv_bfloat16><<<g, EW_THREADS, 0, st>>>((const __nv_bfloat16*)a, b, n, scale, scale_dev, sse,
-                                                        (__nv_bfloat16*)grad);
+                                                        (__nv_bfloat16*)grad, turn);
   else
-    mse_kernel<float><<<g, EW_THREADS, 0, st>>>((const float*)a, b, n, scale, scale_dev, sse, (float*)grad);
+    mse_kernel<float><<<g, EW_THREADS, 0, st>>>((const float*)a, b, n, scale, scale_dev, sse, (float*)grad, turn);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

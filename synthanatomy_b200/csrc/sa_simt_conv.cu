@@ -179,7 +179,7 @@ gg_fwd_narrow_kernel(ConvGeom g, const T* __restrict__ x, const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256)
 gg_wgrad_kernel(ConvGeom g, const T* __restrict__ p, const T* __restrict__ q, float* __restrict__ dwp,
-                int64_t pos_per_split) {
+                int64_t pos_per_split, unsigned* turn) {
   __shared__ float As[TK][TM + 4];  // [pos][n]
   __shared__ float Bs[TK][TN + 4];  // [pos][j]
   const int t = threadIdx.x;
@@ -238,6 +238,9 @@ gg_wgrad_kernel(ConvGeom g, const T* __restrict__ p, const T* __restrict__ q, fl
     }
     __syncthreads();
   }
+  // deterministic mode: the position splits of one output tile add in split order
+  unsigned* my_turn = turn ? turn + blockIdx.y * gridDim.x + blockIdx.x : nullptr;
+  sa_block_turn_begin(my_turn, blockIdx.z);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int n = n0 + ty * 4 + i;
@@ -250,6 +253,7 @@ gg_wgrad_kernel(ConvGeom g, const T* __restrict__ p, const T* __restrict__ q, fl
       atomicAdd(dwp + ((int64_t)tap * g.Cout + n) * g.Cin + c, acc[i][j]);
     }
   }
+  sa_block_turn_end(my_turn, blockIdx.z);
 }
 
 template <typename T>
@@ -293,7 +297,7 @@ int launch_wgrad(const sa_conv_desc* d, const void* p, const void* q, float* dwp
   int64_t pps = sa_cdiv(sa_cdiv(M, splits), TK) * TK;
   splits = sa_cdiv(M, pps);
   dim3 grid((unsigned)sa_cdiv(g.Cout, TM), (unsigned)sa_cdiv(J, TN), (unsigned)splits);
-  gg_wgrad_kernel<T><<<grid, 256, 0, st>>>(g, (const T*)p, (const T*)q, dwp, pps);
+  gg_wgrad_kernel<T><<<grid, 256, 0, st>>>(g, (const T*)p, (const T*)q, dwp, pps, sa_turn_slot((int)tiles, st));
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

@@ -35,6 +35,7 @@ struct PwParams {
   float* dwp;
   float* dbias;
   float* dbias_h;        // MODE 0, optional: column sums of dh (the bias gradient of the conv that produced h)
+  unsigned* turn;        // deterministic mode (MODE 0): one counter, the CTAs add their partials in CTA order
   const float* bias;     // forward mode
   int relu;
 };
@@ -55,6 +56,7 @@ tc_pw_kernel(const __grid_constant__ PwParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t w_full, full_bar[PW_STAGES], empty_bar[PW_STAGES], dh_full[2], dh_empty[2], final_full;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_colsum[4][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Ws = smem;                          // W1^T: 2 blocks [128 c rows][64 n cols]                 32 KB
@@ -225,14 +227,22 @@ tc_pw_kernel(const __grid_constant__ PwParams P) {
       if (++stage == PW_STAGES) stage = 0;
     }
     if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (want_dbh && my_tiles > 0) {
+    // deterministic mode: the CTAs add their dW / db / column-sum partials in CTA order
+    if (my_tiles > 0) sa_turn_wait(P.turn, blockIdx.x);
+    if (want_dbh) {
+      // the four lane quadrants of a column half meet in shared memory and leave as ONE addition per column (a fixed
+      // order inside the CTA; across CTAs the turnstile above orders them)
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         float v = colsum[j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) atomicAdd(P.dbias_h + half * 64 + j, v);
+        if (lane == 0) s_colsum[quad][half * 64 + j] = v;
       }
+      pw_bar_epi();
+      const int c = threadIdx.x - 64;
+      if (c < 128 && my_tiles > 0)
+        atomicAdd(P.dbias_h + c, (s_colsum[0][c] + s_colsum[1][c]) + (s_colsum[2][c] + s_colsum[3][c]));
     }
     if (MODE == 0 && my_tiles > 0) {
       // dW1 / db1 partials of this CTA: lane = n
@@ -255,6 +265,7 @@ tc_pw_kernel(const __grid_constant__ PwParams P) {
         atomicAdd(P.dbias + n, __uint_as_float(v[0]));
       }
     }
+    if (my_tiles > 0) sa_group_turn_end(P.turn, blockIdx.x, 1, 256, threadIdx.x == 64);
   }
   tc_fence_before();
   __syncthreads();
@@ -296,8 +307,8 @@ extern "C" int sa_conv1x1_bwd_fused_dbh(int64_t m, int c_out, int c_in, const vo
     int dev = 0, v = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) g_pw_sms = v;
-    cudaFuncSetAttribute(tc_pw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
-    cudaFuncSetAttribute(tc_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    cudaFuncSetAttribute(tc_pw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
+    cudaFuncSetAttribute(tc_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
   });
   sa_note_path(SA_PATH_TCGEN05);
   static thread_local PwParams P;
@@ -312,6 +323,7 @@ extern "C" int sa_conv1x1_bwd_fused_dbh(int64_t m, int c_out, int c_in, const vo
   const size_t smem = (size_t)(2 + 1 + 2 + PW_STAGES * 4) * PW_BLK + 1024;
   const unsigned grid = (unsigned)(P.tiles < g_pw_sms ? P.tiles : g_pw_sms);
   P.bias = nullptr; P.relu = 0;
+  P.turn = sa_turn_slot(1, sa_stream(stream));
   tc_pw_kernel<0><<<grid, PW_THREADS, smem, sa_stream(stream)>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
@@ -331,14 +343,14 @@ extern "C" int sa_conv1x1_fwd_fused(int64_t m, int c_out, int c_in, const void* 
     int dev = 0, v = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) g_pw_sms = v;
-    cudaFuncSetAttribute(tc_pw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
-    cudaFuncSetAttribute(tc_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    cudaFuncSetAttribute(tc_pw_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
+    cudaFuncSetAttribute(tc_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
   });
   sa_note_path(SA_PATH_TCGEN05);
   static thread_local PwParams P;
   P.m = m;
   P.tiles = (int)sa_cdiv(m, PW_M);
-  P.dwp = nullptr; P.dbias = nullptr; P.dbias_h = nullptr; P.bias = bias; P.relu = relu;
+  P.dwp = nullptr; P.dbias = nullptr; P.dbias_h = nullptr; P.bias = bias; P.relu = relu; P.turn = nullptr;
   int rc;
   if ((rc = pw_map(&P.gmap, x, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;
   if ((rc = pw_map(&P.hmap, addend, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;

@@ -41,6 +41,7 @@ struct WgParams {
   int td, th, tw, ntd, nth, ntw;
   int64_t tiles_total, tiles_per_split;
   float* dwp;
+  unsigned* turn;      // deterministic mode: one counter per (group, half); the splits add in split order
 };
 
 __global__ void __launch_bounds__(WG_THREADS)
@@ -138,6 +139,8 @@ tc_wgrad_kernel(const __grid_constant__ WgParams P) {
     const int n = half * 128 + quad * 32 + lane;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    unsigned* turn = P.turn ? P.turn + half * P.ngroups + group : nullptr;
+    sa_turn_wait(turn, (unsigned)split);
     for (int t = 0; t < T; ++t) {
       float* dst = P.dwp + ((int64_t)(tap0 + t) * P.Cn + n) * P.Cc;
       for (int c0 = 0; c0 < P.Cc; c0 += 32) {
@@ -148,6 +151,7 @@ tc_wgrad_kernel(const __grid_constant__ WgParams P) {
         for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
       }
     }
+    sa_group_turn_end(turn, (unsigned)split, 1, 128, threadIdx.x == 64);
   }
 
   tc_fence_before();
@@ -271,6 +275,7 @@ int sa_tc_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void* q, floa
   P.tiles_per_split = sa_cdiv(P.tiles_total, splits);
   splits = sa_cdiv(P.tiles_total, P.tiles_per_split);
   const unsigned grid = (unsigned)(base_ctas * splits);
+  P.turn = sa_turn_slot((int)base_ctas, st);
   tc_wgrad_kernel<<<grid, WG_THREADS, stages * stage_bytes + 1024, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;

@@ -44,6 +44,7 @@ struct W3Params {
   int ntd, nth, ntw;
   int64_t tiles_total, tiles_per_split;
   float* dwp;
+  unsigned* turn;      // deterministic mode: one counter per (group, half); the splits add in split order
 };
 
 __global__ void __launch_bounds__(W3_THREADS, 1)
@@ -131,6 +132,8 @@ tc_wgrad3_kernel(const __grid_constant__ W3Params P) {
     const int n = half * 128 + quad * 32 + lane;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    unsigned* turn = P.turn ? P.turn + half * P.ngroups + gi : nullptr;
+    sa_turn_wait(turn, (unsigned)split);
     for (int dd = 0; dd < ndd; ++dd) {
       const int tap = grp.tap[dd];
       float* dst = P.dwp + ((int64_t)tap * P.Cn + n) * P.Cc;
@@ -142,6 +145,7 @@ tc_wgrad3_kernel(const __grid_constant__ W3Params P) {
         for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
       }
     }
+    sa_group_turn_end(turn, (unsigned)split, 1, 128, threadIdx.x == 64);
   }
 
   tc_fence_before();
@@ -242,6 +246,7 @@ int sa_tc_conv3d_wgrad3(const sa_conv_desc* d, const void* p, const void* q, flo
   P.tiles_per_split = sa_cdiv(P.tiles_total, splits);
   splits = sa_cdiv(P.tiles_total, P.tiles_per_split);
   const unsigned grid = (unsigned)(base_ctas * splits);
+  P.turn = sa_turn_slot((int)base_ctas, st);
   tc_wgrad3_kernel<<<grid, W3_THREADS, stages * stage_bytes + 1024, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;

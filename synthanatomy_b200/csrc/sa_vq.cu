@@ -22,7 +22,7 @@ template <int DIM>
 __global__ void __launch_bounds__(VQ_THREADS)
 vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ cb, int64_t rows, int n_embed,
                   int64_t* __restrict__ idx_out, float* __restrict__ q_out, int straight_through,
-                  float* __restrict__ counts, float* __restrict__ dw, float* __restrict__ sse) {
+                  float* __restrict__ counts, float* __restrict__ dw, float* __restrict__ sse, unsigned* turn) {
   extern __shared__ float smem[];
   float* s_cb = smem;                          // [VQ_CODE_CHUNK][DIM + 1]  (+1: conflict-free row reads)
   float* s_w2 = smem + VQ_CODE_CHUNK * (DIM + 1);  // [VQ_CODE_CHUNK]
@@ -105,11 +105,34 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ cb, int
     local_sse = sa_warp_sum(local_sse);
     if ((t & 31) == 0) s_red[t >> 5] = local_sse;
     __syncthreads();
+    sa_block_turn_begin(turn, blockIdx.x);      // deterministic mode: the blocks add in block order
     if (t == 0) {
       float s = 0.f;
       for (int i = 0; i < VQ_THREADS / 32; ++i) s += s_red[i];
       atomicAdd(sse, s);
     }
+    sa_block_turn_end(turn, blockIdx.x);
+  }
+}
+
+// deterministic mode: dw[k][c] = sum of z[row][c] over the rows quantised to code k (encodings.T @ flat, baseline.py:72),
+// one block per code, every partial sum in a fixed row order and a fixed tree across the row lanes
+template <int DIM>
+__global__ void __launch_bounds__(256)
+vq_dw_ordered_kernel(const float* __restrict__ z, const int64_t* __restrict__ idx, int64_t rows, float* __restrict__ dw) {
+  constexpr int LANES = 256 / DIM;
+  __shared__ float s_part[256];
+  const int k = blockIdx.x;
+  const int c = threadIdx.x % DIM, rl = threadIdx.x / DIM;
+  float acc = 0.f;
+  for (int64_t r = rl; r < rows; r += LANES)
+    if (idx[r] == (int64_t)k) acc += z[r * DIM + c];
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    float s = 0.f;
+    for (int j = 0; j < LANES; ++j) s += s_part[j * DIM + c];
+    dw[(int64_t)k * DIM + c] += s;
   }
 }
 
@@ -202,11 +225,17 @@ extern "C" int sa_vq_forward(const float* z, const float* codebook, int64_t rows
   cudaStream_t st = sa_stream(stream);
   const unsigned grid = (unsigned)sa_cdiv(rows, VQ_ROWS_PER_BLOCK);
   const size_t smem = (size_t)(VQ_CODE_CHUNK * (dim + 1) + VQ_CODE_CHUNK) * sizeof(float);
+  // deterministic mode: the loss sum goes through the turnstile and the per-code sums of z come from a second, ordered
+  // kernel (the counts are sums of ones: exact in fp32 below 2^24 rows per code, hence order-free)
+  unsigned* turn = sse ? sa_turn_slot(1, st) : nullptr;
+  float* dw_ordered = sa_deterministic() ? dw : nullptr;
+  if (dw_ordered) dw = nullptr;
 #define SA_VQ_LAUNCH(D)                                                                                            \
   do {                                                                                                             \
     SA_CUDA(cudaFuncSetAttribute(vq_forward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     vq_forward_kernel<D><<<grid, VQ_THREADS, smem, st>>>(z, codebook, rows, n_embed, idx, q, straight_through, counts, \
-                                                         dw, sse);                                                \
+                                                         dw, sse, turn);                                          \
+    if (dw_ordered) vq_dw_ordered_kernel<D><<<(unsigned)n_embed, 256, 0, st>>>(z, idx, rows, dw_ordered);          \
   } while (0)
   switch (dim) {
     case 8: SA_VQ_LAUNCH(8); break;

@@ -644,6 +644,7 @@ def _run_programme(net: "Performer", tokens: torch.Tensor, dt, return_encodings:
     conditioning rows appended (None: the plain one); lead: number of prepended conditioning positions"""
     if not tokens.is_cuda:
         raise RuntimeError("synthanatomy_b200: CUDA tensors only -- there is no CPU fallback")
+    ops.sync_deterministic()             # torch.backends.cudnn.deterministic -> ordered sums in the kernels
     dt, x3 = ops.resolve_dtype(dt)       # BF16X3: fp32 tensors, dense layers as split-bf16 tensor-core products
     B, N = tokens.shape
     C = _Ctx(net, B, N, dt, x3, tokens.device)

@@ -551,6 +551,7 @@ class B200VQVAE(VQVAEBase, nn.Module):
         return self.decode([samples_codes])
 
     def forward(self, images: torch.Tensor) -> Dict[str, List[torch.Tensor]]:
+        ops.sync_deterministic()          # torch.backends.cudnn.deterministic (the reference's `deterministic`) -> ordered sums
         encodings = self.encode(images)
         quantizations, quantization_losses = self.quantize(encodings)
         reconstruction = self.decode(quantizations)

@@ -63,6 +63,28 @@ def set_force_simt(on: bool) -> None:
     lib().sa_set_force_simt(1 if on else 0)
 
 
+# Deterministic mode: the reference's `deterministic=True` (run_vqvae.py:550 -> src/utils/general.py:333) sets
+# torch.backends.cudnn.deterministic; the two networks call sync_deterministic() at the top of forward, so the same
+# switch makes this library add its split-K partials / column sums / loss sums in a fixed order (csrc/sa_common.cuh).
+_DETERMINISTIC: Optional[bool] = None          # None: follow torch's flags
+
+
+def set_deterministic(on: Optional[bool]) -> None:
+    """True / False: force the mode; None: follow torch.backends.cudnn.deterministic / use_deterministic_algorithms"""
+    global _DETERMINISTIC
+    _DETERMINISTIC = on
+    sync_deterministic()
+
+
+def sync_deterministic() -> bool:
+    on = _DETERMINISTIC
+    if on is None:
+        on = bool(torch.backends.cudnn.deterministic) or torch.are_deterministic_algorithms_enabled()
+    if bool(lib().sa_get_deterministic()) != on:
+        lib().sa_set_deterministic(1 if on else 0)
+    return on
+
+
 # ------------------------------------------------------------------------------------------------
 # bf16x3 "parity" arithmetic (csrc/sa_x3.cu): fp32 tensors, products on the bf16 tensor cores as hi.hi + lo.hi + hi.lo.
 # `compute_dtype=BF16X3` on the two networks selects it; while the mode is on, every fp32 conv / dense call whose shape
