@@ -96,8 +96,11 @@ int sa_gemm_tn_x3(int64_t m, int na, int nb, const float* a, int64_t lda, const 
 int sa_embed_fwd(const int64_t* tokens, const int32_t* sp_idx, int n_axes, const float* tok_w, const float* const* sp_w,
                  const float* pos_w, int batch, int seq, int dim, int num_tokens, float* x_f32, void* x_act,
                  int act_dtype, void* stream);
+/* num_tokens / sp_rows[a]: rows of the token table / of spatial table a (the deterministic mode gathers per table row,
+ * in ascending position order, instead of scattering with atomics) */
 int sa_embed_bwd(const float* dx, const int64_t* tokens, const int32_t* sp_idx, int n_axes, int batch, int seq, int dim,
-                 float* d_tok_w, float* const* d_sp_w, float* d_pos_w, void* stream);
+                 int num_tokens, const int32_t* sp_rows, float* d_tok_w, float* const* d_sp_w, float* d_pos_w,
+                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FAVOR+ (global heads).  Replaces performer-pytorch 1.0.11 softmax_kernel + causal_linear_attention and

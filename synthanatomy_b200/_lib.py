@@ -132,8 +132,8 @@ SIGNATURES = {
                                   c_void_p, c_int, c_void_p, c_void_p]),
     "sa_embed_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, C.POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_int, c_void_p]),
-    "sa_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, C.POINTER(c_void_p),
-                             c_void_p, c_void_p]),
+    "sa_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, C.POINTER(C.c_int32), c_void_p,
+                             C.POINTER(c_void_p), c_void_p, c_void_p]),
     "sa_favor_kmax": (c_int, [C.POINTER(FavorDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sa_favor_featmap_fwd": (c_int, [C.POINTER(FavorDesc), c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p,
                                      c_void_p]),

@@ -61,6 +61,29 @@ unsigned* sa_turn_slot(int n, cudaStream_t st) {
   return slot;
 }
 
+float* sa_partial_slot(int n, cudaStream_t st) { return reinterpret_cast<float*>(sa_turn_slot(n, st)); }
+
+namespace {
+__global__ void __launch_bounds__(1024) ordered_sum_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+  __shared__ float s[1024];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) acc += part[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] += s[0];
+}
+}  // namespace
+
+int sa_ordered_sum(const float* partials, int n, float* out, cudaStream_t st) {
+  ordered_sum_kernel<<<1, 1024, 0, st>>>(partials, n, out);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
 void sa_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

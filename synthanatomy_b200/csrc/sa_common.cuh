@@ -22,6 +22,11 @@ bool sa_force_simt();
 // arrival order with plain atomics), else `n` zeroed counters valid for ONE launch on `st`.
 bool sa_deterministic();
 unsigned* sa_turn_slot(int n, cudaStream_t st);
+// scalar sums (losses, gate / stabiliser gradients) in deterministic mode: every contributor writes its partial into its
+// own word of a zeroed slot (sa_partial_slot; nullptr when the mode is off) and sa_ordered_sum adds them to out[0] in
+// index order (one CTA, fixed tree)
+float* sa_partial_slot(int n, cudaStream_t st);
+int sa_ordered_sum(const float* partials, int n, float* out, cudaStream_t st);
 
 #define SA_CHECK_ARG(cond, msg)                                   \
   do {                                                            \

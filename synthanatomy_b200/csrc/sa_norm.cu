@@ -27,7 +27,7 @@ constexpr int NB_X = 32, NB_Y = 8;
 template <typename T, int MODE>
 __global__ void colreduce_kernel(const T* __restrict__ x, const T* __restrict__ g, const T* __restrict__ y, long long rows, int C,
                                  const float* __restrict__ mean, const float* __restrict__ rstd, float slope,
-                                 double* __restrict__ out0, double* __restrict__ out1) {
+                                 double* __restrict__ out0, double* __restrict__ out1, unsigned* turn) {
   __shared__ float s0[NB_Y][NB_X + 1], s1[NB_Y][NB_X + 1];
   const int c = blockIdx.x * NB_X + threadIdx.x;
   float a0 = 0.f, a1 = 0.f;
@@ -49,6 +49,8 @@ __global__ void colreduce_kernel(const T* __restrict__ x, const T* __restrict__ 
   s0[threadIdx.y][threadIdx.x] = a0;
   s1[threadIdx.y][threadIdx.x] = a1;
   __syncthreads();
+  unsigned* my_turn = turn ? turn + blockIdx.x : nullptr;      // deterministic mode: row slabs add in slab order
+  sa_block_turn_begin(my_turn, blockIdx.y);
   if (threadIdx.y == 0 && c < C) {
     double t0 = 0.0, t1 = 0.0;
 #pragma unroll
@@ -56,6 +58,7 @@ __global__ void colreduce_kernel(const T* __restrict__ x, const T* __restrict__ 
     atomicAdd(out0 + c, t0);
     if (MODE == 2) atomicAdd(out1 + c, t1);
   }
+  sa_block_turn_end(my_turn, blockIdx.y);
 }
 
 __global__ void bn_mean_kernel(const double* __restrict__ sum, long long rows, int C, float* __restrict__ mean) {
@@ -146,11 +149,11 @@ int bn_stats_t(const T* x, long long rows, int C, double* ws, float eps, float m
                float* running_mean, float* running_var, cudaStream_t st) {
   SA_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
   const dim3 blk(NB_X, NB_Y), grd = red_grid(rows, C);
-  colreduce_kernel<T, 0><<<grd, blk, 0, st>>>(x, nullptr, nullptr, rows, C, nullptr, nullptr, 0.f, ws, nullptr);
+  colreduce_kernel<T, 0><<<grd, blk, 0, st>>>(x, nullptr, nullptr, rows, C, nullptr, nullptr, 0.f, ws, nullptr, sa_turn_slot((int)grd.x, st));
   SA_LAUNCH_CHECK();
   bn_mean_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, rows, C, mean);
   SA_LAUNCH_CHECK();
-  colreduce_kernel<T, 1><<<grd, blk, 0, st>>>(x, nullptr, nullptr, rows, C, mean, nullptr, 0.f, ws + C, nullptr);
+  colreduce_kernel<T, 1><<<grd, blk, 0, st>>>(x, nullptr, nullptr, rows, C, mean, nullptr, 0.f, ws + C, nullptr, sa_turn_slot((int)grd.x, st));
   SA_LAUNCH_CHECK();
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws + C, rows, C, eps, momentum, mean, rstd, running_mean, running_var);
   SA_LAUNCH_CHECK();
@@ -161,7 +164,9 @@ template <typename T>
 int bn_bwd_t(const T* g, const T* x, const T* y, long long rows, int C, const float* mean, const float* rstd, const float* gamma,
              float slope, double* ws, float* dgamma, float* dbeta, T* dx, cudaStream_t st) {
   SA_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
-  colreduce_kernel<T, 2><<<red_grid(rows, C), dim3(NB_X, NB_Y), 0, st>>>(x, g, y, rows, C, mean, rstd, slope, ws, ws + C);
+  const dim3 grd2 = red_grid(rows, C);
+  colreduce_kernel<T, 2><<<grd2, dim3(NB_X, NB_Y), 0, st>>>(x, g, y, rows, C, mean, rstd, slope, ws, ws + C,
+                                                            sa_turn_slot((int)grd2.x, st));
   SA_LAUNCH_CHECK();
   bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, dgamma, dbeta);
   SA_LAUNCH_CHECK();

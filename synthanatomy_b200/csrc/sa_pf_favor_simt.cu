@@ -146,7 +146,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 featmap_bwd_kernel(FmArgs a, const T* __restrict__ x, const float* __restrict__ proj, int is_query,
                    const T* __restrict__ feat, const T* __restrict__ dfeat, const int* __restrict__ argmax,
-                   T* __restrict__ dx, float* __restrict__ gsum) {
+                   T* __restrict__ dx, float* __restrict__ gsum, float* __restrict__ gpart) {
   extern __shared__ float sm[];
   float* Ps = sm;                                 // [m][65]
   float* Xs = Ps + a.m * LDA;                     // [16][65]
@@ -211,7 +211,10 @@ featmap_bwd_kernel(FmArgs a, const T* __restrict__ x, const float* __restrict__ 
     if (t < 32) {
       float s = (t < FT_TOK) ? cta_sum : 0.f;
       s = sa_warp_sum(s);
-      if (t == 0) atomicAdd(gsum, s);
+      if (t == 0) {
+        if (gpart) gpart[blockIdx.y * gridDim.x + blockIdx.x] = s;      // deterministic mode: summed in block order afterwards
+        else atomicAdd(gsum, s);
+      }
     }
   }
 }
@@ -591,17 +594,20 @@ int sa_simt_favor_featmap_bwd(const sa_favor_desc* d, const void* x, const float
   const FmArgs a = make_fm(d, eps);
   const size_t smem = fm_smem(a);
   dim3 grid((unsigned)sa_cdiv(d->seq, FT_CHUNK), (unsigned)(d->batch * d->heads));
+  const int nblocks = (int)(grid.x * grid.y);
+  float* gpart = (gsum && !is_query) ? sa_partial_slot(nblocks, st) : nullptr;
   if (d->act_dtype == SA_F32) {
     if ((rc = set_smem(featmap_bwd_kernel<float>, smem)) != SA_OK) return rc;
     featmap_bwd_kernel<float><<<grid, 256, smem, st>>>(a, (const float*)x, proj, is_query, (const float*)feat,
-                                                       (const float*)dfeat, argmax, (float*)dx, gsum);
+                                                       (const float*)dfeat, argmax, (float*)dx, gsum, gpart);
   } else {
     if ((rc = set_smem(featmap_bwd_kernel<__nv_bfloat16>, smem)) != SA_OK) return rc;
     featmap_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(a, (const __nv_bfloat16*)x, proj, is_query,
                                                                (const __nv_bfloat16*)feat, (const __nv_bfloat16*)dfeat,
-                                                               argmax, (__nv_bfloat16*)dx, gsum);
+                                                               argmax, (__nv_bfloat16*)dx, gsum, gpart);
   }
   SA_LAUNCH_CHECK();
+  if (gpart) return sa_ordered_sum(gpart, nblocks, gsum, st);
   return SA_OK;
 }
 

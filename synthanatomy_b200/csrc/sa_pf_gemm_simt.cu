@@ -77,7 +77,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gemm_tn_kernel(long long m, int na, int nb, const T* __restrict__ A, long long lda, const T* __restrict__ B,
                long long ldb, const float* __restrict__ scale_dev, float scale, float* __restrict__ D,
-               long long rows_per_split) {
+               long long rows_per_split, unsigned* turn) {
   __shared__ __align__(16) float As[GK][GP];
   __shared__ __align__(16) float Bs[GK][GP];
   const int t = threadIdx.x;
@@ -110,6 +110,8 @@ gemm_tn_kernel(long long m, int na, int nb, const T* __restrict__ A, long long l
     __syncthreads();
   }
   const float st = scale * (scale_dev ? __ldg(scale_dev) : 1.0f);
+  unsigned* my_turn = turn ? turn + blockIdx.y * gridDim.x + blockIdx.x : nullptr;     // deterministic mode: split order
+  sa_block_turn_begin(my_turn, blockIdx.z);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int gi = i0 + ty * 4 + r;
@@ -120,6 +122,7 @@ gemm_tn_kernel(long long m, int na, int nb, const T* __restrict__ A, long long l
       if (gj < nb) atomicAdd(D + (long long)gi * nb + gj, st * acc[r][s]);
     }
   }
+  sa_block_turn_end(my_turn, blockIdx.z);
 }
 
 }  // namespace
@@ -149,12 +152,13 @@ int sa_simt_gemm_tn(int64_t m, int na, int nb, int dtype, const void* a, int64_t
   int64_t rps = sa_cdiv(sa_cdiv(m, splits), GK) * GK;
   splits = sa_cdiv(m, rps);
   dim3 grid((unsigned)sa_cdiv(nb, GB), (unsigned)sa_cdiv(na, GB), (unsigned)splits);
+  unsigned* turn = sa_turn_slot((int)(grid.x * grid.y), st);
   if (dtype == SA_F32)
     gemm_tn_kernel<float><<<grid, 256, 0, st>>>(m, na, nb, (const float*)a, lda, (const float*)b, ldb, scale_dev, scale,
-                                                d, rps);
+                                                d, rps, turn);
   else
     gemm_tn_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(m, na, nb, (const __nv_bfloat16*)a, lda,
-                                                        (const __nv_bfloat16*)b, ldb, scale_dev, scale, d, rps);
+                                                        (const __nv_bfloat16*)b, ldb, scale_dev, scale, d, rps, turn);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

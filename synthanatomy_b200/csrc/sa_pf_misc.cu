@@ -42,13 +42,62 @@ __global__ void embed_bwd_kernel(const float* __restrict__ dx, const long long* 
       const long long row = (long long)b * N + n;
       const float g = dx[row * dim + c];
       sum += g;
-      atomicAdd(d_tok_w + tokens[row] * dim + c, g);
+      if (d_tok_w) atomicAdd(d_tok_w + tokens[row] * dim + c, g);
     }
     d_pos_w[i] += sum;
     for (int a = 0; a < n_axes; ++a) {
       const int s = sp_idx[a * N + n];
       if (s >= 0) atomicAdd(sp.d_sp_w[a] + (long long)s * dim + c, sum);
     }
+  }
+}
+
+// Deterministic mode: the table gradients as ordered gathers instead of scattered atomics.  One block per table row
+// `key`; the positions that index it are found 256 at a time (ballot + prefix: an ascending list) and added in that order.
+//   KIND 0: token table   -- domain = the B x N token rows, contribution dx[row]
+//   KIND 1: spatial table -- domain = the N positions of one axis, contribution sum_b dx[b * N + n] (ascending b)
+template <int KIND>
+__global__ void __launch_bounds__(256)
+embed_bwd_ordered_kernel(const float* __restrict__ dx, const long long* __restrict__ tokens, const int* __restrict__ sp_idx,
+                         int B, int N, int dim, float* __restrict__ d_w) {
+  __shared__ int s_list[256];
+  __shared__ int s_wcnt[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const long long key = blockIdx.x;
+  const long long domain = KIND == 0 ? (long long)B * N : (long long)N;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};                 // dim <= 1024: columns t, t + 256, ...
+  for (long long base = 0; base < domain; base += 256) {
+    const long long r = base + t;
+    const bool hit = r < domain && (KIND == 0 ? tokens[r] == key : (long long)sp_idx[r] == key);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_wcnt[warp] = __popc(m);
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < warp) off += s_wcnt[w]; total += s_wcnt[w]; }
+    if (hit) s_list[off + __popc(m & ((1u << lane) - 1u))] = t;
+    __syncthreads();
+    for (int j = 0; j < total; ++j) {
+      const long long rr = base + s_list[j];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = t + 256 * k;
+        if (c >= dim) break;
+        if (KIND == 0) {
+          acc[k] += dx[rr * dim + c];
+        } else {
+          float sum = 0.f;
+          for (int b = 0; b < B; ++b) sum += dx[((long long)b * N + rr) * dim + c];
+          acc[k] += sum;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = t + 256 * k;
+    if (c < dim) d_w[key * dim + c] += acc[k];
   }
 }
 
@@ -98,13 +147,12 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, int dim,
-                     float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows_per_block) {
-  extern __shared__ float sm[];     // dw partial [dim], db partial [dim]
-  float* s_dw = sm;
-  float* s_db = sm + dim;
-  for (int c = threadIdx.x; c < 2 * dim; c += blockDim.x) sm[c] = 0.f;
-  __syncthreads();
+                     float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows_per_block,
+                     unsigned* turn) {
+  extern __shared__ float sm[];     // per warp: dw partial [dim], db partial [dim]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* s_dw = sm + (size_t)warp * 2 * dim;
+  float* s_db = s_dw + dim;
   const int per = (dim + 31) / 32;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
@@ -142,16 +190,26 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   for (int i = 0; i < 32; ++i) {
     if (i >= per) break;
     const int c = lane + 32 * i;
-    if (c < dim) { atomicAdd(s_dw + c, adw[i]); atomicAdd(s_db + c, adb[i]); }
+    if (c < dim) { s_dw[c] = adw[i]; s_db[c] = adb[i]; }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < dim; c += blockDim.x) { atomicAdd(dw + c, s_dw[c]); atomicAdd(db + c, s_db[c]); }
+  // the eight warps' partials in warp order, the blocks in block order when the deterministic mode is on
+  sa_block_turn_begin(turn, blockIdx.x);
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    float tw = 0.f, tb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { tw += sm[(size_t)w * 2 * dim + c]; tb += sm[(size_t)w * 2 * dim + dim + c]; }
+    atomicAdd(dw + c, tw);
+    atomicAdd(db + c, tb);
+  }
+  sa_block_turn_end(turn, blockIdx.x);
 }
 
 // one warp per row
 __global__ void __launch_bounds__(256)
 ce_kernel(const float* logits, long long ld, const long long* __restrict__ target, long long rows, int V,
-          float grad_scale, const float* __restrict__ grad_scale_dev, float* __restrict__ loss_sum, float* dlogits) {
+          float grad_scale, const float* __restrict__ grad_scale_dev, float* __restrict__ loss_sum, float* dlogits,
+          float* __restrict__ partials) {
   __shared__ float s_loss[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * 8 + warp;
@@ -183,7 +241,8 @@ ce_kernel(const float* logits, long long ld, const long long* __restrict__ targe
   if (threadIdx.x == 0 && loss_sum) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += s_loss[w];
-    atomicAdd(loss_sum, s);
+    if (partials) partials[blockIdx.x] = s;      // deterministic mode: summed in block order by sa_ordered_sum
+    else atomicAdd(loss_sum, s);
   }
 }
 
@@ -227,7 +286,7 @@ __global__ void rezero_finish_kernel(const float* __restrict__ colsum, const flo
 //   T  *= g                        (T becomes the weight gradient)
 __global__ void __launch_bounds__(256)
 gate_wgrad_kernel(float* __restrict__ T, const float* __restrict__ W, long long n, const float* __restrict__ g,
-                  float* __restrict__ dot) {
+                  float* __restrict__ dot, float* __restrict__ partials) {
   __shared__ float s_red[8];
   const float gv = g[0];
   float acc = 0.f;
@@ -242,7 +301,8 @@ gate_wgrad_kernel(float* __restrict__ T, const float* __restrict__ W, long long 
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += s_red[w];
-    atomicAdd(dot, s);
+    if (partials) partials[blockIdx.x] = s;
+    else atomicAdd(dot, s);
   }
 }
 
@@ -275,14 +335,31 @@ extern "C" int sa_embed_fwd(const int64_t* tokens, const int32_t* sp_idx, int n_
 }
 
 extern "C" int sa_embed_bwd(const float* dx, const int64_t* tokens, const int32_t* sp_idx, int n_axes, int batch, int seq,
-                            int dim, float* d_tok_w, float* const* d_sp_w, float* d_pos_w, void* stream) {
+                            int dim, int num_tokens, const int32_t* sp_rows, float* d_tok_w, float* const* d_sp_w,
+                            float* d_pos_w, void* stream) {
   SA_CHECK_ARG(dx && tokens && d_tok_w && d_pos_w, "null pointer");
-  SA_CHECK_ARG(n_axes >= 0 && n_axes <= 3 && (n_axes == 0 || (sp_idx && d_sp_w)), "bad spatial axes");
+  SA_CHECK_ARG(n_axes >= 0 && n_axes <= 3 && (n_axes == 0 || (sp_idx && d_sp_w && sp_rows)), "bad spatial axes");
+  SA_CHECK_ARG(num_tokens > 0, "bad table size");
+  cudaStream_t st = sa_stream(stream);
   EmbPtrs sp = {};
   for (int a = 0; a < n_axes; ++a) sp.d_sp_w[a] = d_sp_w[a];
-  embed_bwd_kernel<<<ew_grid((long long)seq * dim), 256, 0, sa_stream(stream)>>>(dx, (const long long*)tokens, sp_idx,
-                                                                                 n_axes, batch, seq, dim, d_tok_w, sp,
-                                                                                 d_pos_w);
+  if (sa_deterministic() && dim <= 1024) {
+    // positional table: one thread per element already adds in batch order; the token / spatial tables as ordered gathers
+    embed_bwd_kernel<<<ew_grid((long long)seq * dim), 256, 0, st>>>(dx, (const long long*)tokens, sp_idx, 0, batch, seq, dim,
+                                                                    nullptr, sp, d_pos_w);
+    SA_LAUNCH_CHECK();
+    embed_bwd_ordered_kernel<0><<<(unsigned)num_tokens, 256, 0, st>>>(dx, (const long long*)tokens, nullptr, batch, seq, dim,
+                                                                     d_tok_w);
+    SA_LAUNCH_CHECK();
+    for (int a = 0; a < n_axes; ++a) {
+      embed_bwd_ordered_kernel<1><<<(unsigned)sp_rows[a], 256, 0, st>>>(dx, nullptr, sp_idx + (size_t)a * seq, batch, seq, dim,
+                                                                       d_sp_w[a]);
+      SA_LAUNCH_CHECK();
+    }
+    return SA_OK;
+  }
+  embed_bwd_kernel<<<ew_grid((long long)seq * dim), 256, 0, st>>>(dx, (const long long*)tokens, sp_idx, n_axes, batch, seq,
+                                                                  dim, d_tok_w, sp, d_pos_w);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -310,8 +387,11 @@ extern "C" int sa_layernorm_bwd(const float* dy, const float* x, const float* w,
   if (blocks > 148 * 4) blocks = 148 * 4;
   const long long rpb = sa_cdiv(rows, blocks);
   blocks = sa_cdiv(rows, rpb);
-  layernorm_bwd_kernel<<<(unsigned)blocks, 256, 2 * dim * sizeof(float), sa_stream(stream)>>>(dy, x, w, mean, rstd, rows,
-                                                                                              dim, dx, dw, db, rpb);
+  const size_t smem = (size_t)8 * 2 * dim * sizeof(float);
+  if (smem > 48 * 1024)
+    SA_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  layernorm_bwd_kernel<<<(unsigned)blocks, 256, smem, sa_stream(stream)>>>(dy, x, w, mean, rstd, rows, dim, dx, dw, db, rpb,
+                                                                           sa_turn_slot(1, sa_stream(stream)));
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -319,9 +399,12 @@ extern "C" int sa_layernorm_bwd(const float* dy, const float* x, const float* w,
 extern "C" int sa_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int vocab,
                              float grad_scale, const float* grad_scale_dev, float* loss_sum, float* dlogits, void* stream) {
   SA_CHECK_ARG(logits && target && rows > 0 && vocab > 0 && ld >= vocab, "bad arguments");
-  ce_kernel<<<(unsigned)sa_cdiv(rows, 8), 256, 0, sa_stream(stream)>>>(logits, ld, (const long long*)target, rows, vocab,
-                                                                       grad_scale, grad_scale_dev, loss_sum, dlogits);
+  const int64_t blocks = sa_cdiv(rows, 8);
+  float* partials = loss_sum && blocks <= (1 << 19) ? sa_partial_slot((int)blocks, sa_stream(stream)) : nullptr;
+  ce_kernel<<<(unsigned)blocks, 256, 0, sa_stream(stream)>>>(logits, ld, (const long long*)target, rows, vocab, grad_scale,
+                                                             grad_scale_dev, loss_sum, dlogits, partials);
   SA_LAUNCH_CHECK();
+  if (partials) return sa_ordered_sum(partials, (int)blocks, loss_sum, sa_stream(stream));
   return SA_OK;
 }
 
@@ -349,8 +432,10 @@ extern "C" int sa_gate_wgrad(float* t, const float* w, int64_t n, const float* g
   if (n == 0) return SA_OK;
   long long blocks = sa_cdiv(n, 256 * 4);
   if (blocks > 148 * 4) blocks = 148 * 4;
-  gate_wgrad_kernel<<<(unsigned)blocks, 256, 0, sa_stream(stream)>>>(t, w, n, g, dot);
+  float* partials = sa_partial_slot((int)blocks, sa_stream(stream));
+  gate_wgrad_kernel<<<(unsigned)blocks, 256, 0, sa_stream(stream)>>>(t, w, n, g, dot, partials);
   SA_LAUNCH_CHECK();
+  if (partials) return sa_ordered_sum(partials, (int)blocks, dot, sa_stream(stream));
   return SA_OK;
 }
 

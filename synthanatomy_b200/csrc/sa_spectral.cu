@@ -41,7 +41,8 @@ swap_outer_inner_kernel(const float* __restrict__ src, float* __restrict__ dst, 
 //   grad     = coef * coef_dev[0] * (amp_p - amp_t) * (re_p, im_p) / amp_p  (backward w.r.t. the prediction's spectrum)
 __global__ void __launch_bounds__(256)
 spectral_amp_kernel(const float* __restrict__ p, const float* __restrict__ t, long long rows, int L, float coef,
-                    const float* __restrict__ coef_dev, float* __restrict__ sse, float* __restrict__ grad) {
+                    const float* __restrict__ coef_dev, float* __restrict__ sse, float* __restrict__ grad,
+                    float* __restrict__ partials) {
   const long long total = rows * L;
   const float cf = coef * (coef_dev ? __ldg(coef_dev) : 1.0f);
   float acc = 0.f;
@@ -67,7 +68,8 @@ spectral_amp_kernel(const float* __restrict__ p, const float* __restrict__ t, lo
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int w = 0; w < 8; ++w) s += part[w];
-      atomicAdd(sse, s);
+      if (partials) partials[blockIdx.x] = s;       // deterministic mode: summed in block order afterwards
+      else atomicAdd(sse, s);
     }
   }
 }
@@ -91,7 +93,10 @@ extern "C" int sa_spectral_amp_loss(const float* pred_spec, const float* target_
   if (rows == 0) return SA_OK;
   long long blocks = sa_cdiv(rows * (long long)L, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  spectral_amp_kernel<<<(unsigned)blocks, 256, 0, sa_stream(stream)>>>(pred_spec, target_spec, rows, L, coef, coef_dev, sse, grad);
+  float* partials = sse ? sa_partial_slot((int)blocks, sa_stream(stream)) : nullptr;
+  spectral_amp_kernel<<<(unsigned)blocks, 256, 0, sa_stream(stream)>>>(pred_spec, target_spec, rows, L, coef, coef_dev, sse, grad,
+                                                                       partials);
   SA_LAUNCH_CHECK();
+  if (partials) return sa_ordered_sum(partials, (int)blocks, sse, sa_stream(stream));
   return SA_OK;
 }

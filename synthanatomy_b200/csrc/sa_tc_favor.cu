@@ -173,6 +173,7 @@ struct FvParams {
   const __nv_bfloat16* dfeat;
   int* argmax;
   float* gsum;
+  float* gpart;          // deterministic mode: one partial of gsum per (CTA, lane quadrant), summed in order afterwards
   int is_query;
   const __nv_bfloat16* out;
   const __nv_bfloat16* dout;
@@ -1169,7 +1170,10 @@ tc_featmap_bwd_kernel(const __grid_constant__ FvParams P) {
     }
     if (!P.is_query && hf == 0) {
       const float w = sa_warp_sum(gacc);
-      if (lane == 0) atomicAdd(P.gsum, w);
+      if (lane == 0) {
+        if (P.gpart) P.gpart[blockIdx.x * 4 + q] = w;
+        else atomicAdd(P.gsum, w);
+      }
     }
   }
   FV_EPILOGUE();
@@ -1229,7 +1233,7 @@ void fill_common(FvParams& P, const sa_favor_desc* d, int out_ld, float eps) {
   P.r = powf((float)d->m, -0.5f);
   P.eps = eps;
   P.proj = nullptr; P.kmax_in = nullptr; P.kmax_out = nullptr; P.x = nullptr; P.feat = nullptr; P.dfeat = nullptr;
-  P.argmax = nullptr; P.gsum = nullptr; P.is_query = 0; P.out = nullptr; P.dout = nullptr; P.den_in = nullptr;
+  P.argmax = nullptr; P.gsum = nullptr; P.gpart = nullptr; P.is_query = 0; P.out = nullptr; P.dout = nullptr; P.den_in = nullptr;
   P.den_out = nullptr; P.o_out = nullptr; P.df_out = nullptr; P.sums = nullptr; P.st_vec = nullptr; P.dinv = nullptr;
   P.st_out = nullptr;
 }
@@ -1371,8 +1375,11 @@ int sa_tc_favor_featmap_bwd(const sa_favor_desc* d, const void* x, const float* 
   if ((rc = feat_map(&P.map_b, dfeat, d)) != SA_OK) return rc;
   P.tmem_cols = 128;
   const int total = P.nchunks * d->batch * d->heads;
-  tc_featmap_bwd_kernel<<<dim3((unsigned)(total < sa_sm_count() ? total : sa_sm_count())), F_THREADS, smem_fbwd(d->mp), st>>>(P);
+  const int ctas = total < sa_sm_count() ? total : sa_sm_count();
+  P.gpart = (gsum && !is_query) ? sa_partial_slot(ctas * 4, st) : nullptr;
+  tc_featmap_bwd_kernel<<<dim3((unsigned)ctas), F_THREADS, smem_fbwd(d->mp), st>>>(P);
   SA_LAUNCH_CHECK();
+  if (P.gpart) return sa_ordered_sum(P.gpart, ctas * 4, gsum, st);
   return SA_OK;
 }
 

@@ -511,6 +511,7 @@ struct TnParams {
   float scale;
   float* d;
   float* colsum;               // optional: colsum[i] += sum_r A[r][i] (unscaled) -- the bias gradient that goes with D
+  unsigned* turn;              // deterministic mode: one counter per output tile, the row splits add in split order
 };
 
 __global__ void __launch_bounds__(W_THREADS, 1)
@@ -610,6 +611,8 @@ tc_gemm_tn_kernel(const __grid_constant__ TnParams P) {
     const float st = P.scale * (P.scale_dev ? __ldg(P.scale_dev) : 1.0f);
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    unsigned* turn = P.turn ? P.turn + tile : nullptr;
+    sa_turn_wait(turn, (unsigned)split);
     for (int c0 = 0; c0 < P.BN; c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
@@ -629,6 +632,7 @@ tc_gemm_tn_kernel(const __grid_constant__ TnParams P) {
       tmem_ld_wait();
       if (i < P.na) atomicAdd(P.colsum + i, __uint_as_float(v[0]));
     }
+    sa_group_turn_end(turn, (unsigned)split, 1, 128, threadIdx.x == 64);
   }
 
   tc_fence_before();
@@ -801,6 +805,7 @@ int sa_tc_gemm_tn_colsum(int64_t m, int na, int nb, const void* a, int64_t lda, 
   rc = make_2d(&P.bmap, b, (uint64_t)nb, (uint64_t)m, (uint64_t)ldb, 64, W_KP);
   if (rc != SA_OK) return rc;
   const size_t smem = (size_t)W_STAGES * (2 * W_BLOCK + (size_t)P.bblocks * W_BLOCK) + W_BLOCK + 1024;
+  P.turn = sa_turn_slot((int)tiles, st);
   tc_gemm_tn_kernel<<<(unsigned)(tiles * splits), W_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;

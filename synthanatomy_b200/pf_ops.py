@@ -115,8 +115,9 @@ def embed_fwd(tokens, sp_idx, tok_w, sp_ws, pos_w, x_f32, x_act) -> None:
 def embed_bwd(dx, tokens, sp_idx, d_tok_w, d_sp_ws, d_pos_w) -> None:
     B, N = tokens.shape
     dim = d_tok_w.shape[1]
-    _lib.check(lib().sa_embed_bwd(_p(dx), _p(tokens), _p(sp_idx), len(d_sp_ws), B, N, dim, _p(d_tok_w),
-                                  _ptr_array(d_sp_ws), _p(d_pos_w), _stream()), "sa_embed_bwd")
+    sp_rows = (C.c_int32 * max(1, len(d_sp_ws)))(*[int(w.shape[0]) for w in d_sp_ws])
+    _lib.check(lib().sa_embed_bwd(_p(dx), _p(tokens), _p(sp_idx), len(d_sp_ws), B, N, dim, int(d_tok_w.shape[0]), sp_rows,
+                                  _p(d_tok_w), _ptr_array(d_sp_ws), _p(d_pos_w), _stream()), "sa_embed_bwd")
 
 
 def layernorm_fwd(x, w, b, eps, y_f32, y_act, mean, rstd) -> None:

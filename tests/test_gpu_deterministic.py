@@ -76,3 +76,40 @@ def test_switch_follows_torch_flag():
     finally:
         torch.backends.cudnn.deterministic = old
         ops.sync_deterministic()
+
+
+def _pf_grads(dt, seed=0):
+    import numpy as np
+    from synthanatomy_b200.losses import CELoss
+    from synthanatomy_b200.networks.transformers import Ordering, Performer
+    from synthanatomy_b200.utils.transformer import prepare_batch
+    grid = (10, 14, 10)
+    n = int(np.prod(grid))
+    torch.manual_seed(seed)
+    order = Ordering("raster_scan", 3, (1, *grid), (False,) * 3, ((2, 0, 1),), ((0, 1),), ("rotate_90", "transpose"))
+    net = Performer(num_tokens=2049, dim=512, heads=16, dim_head=64, local_attn_heads=8, local_window_size=420,
+                    max_seq_len=n + 1, depth=2, ordering=order, causal=True, feature_redraw_interval=1000,
+                    generalized_attention=False, use_rezero=True, spatial_position_emb="absolute", spatial_shape=grid,
+                    compute_dtype=dt).cuda().train()
+    with torch.no_grad():                      # open the ReZero gates so that every gradient is a real sum
+        for layer in net.performer.net.layers:
+            layer[0].g.fill_(0.5); layer[1].g.fill_(0.5)
+    quant = torch.randint(0, 2048, (3, *grid), generator=torch.Generator().manual_seed(seed + 2))
+    (x, _), y = prepare_batch({"quantization": quant}, order.get_sequence_ordering(), 2048)
+    logits = net(x.cuda())
+    loss = CELoss()(logits.transpose(1, 2), y.cuda())
+    loss.backward()
+    named = [(k, p.grad.clone()) for k, p in net.named_parameters() if p.grad is not None]
+    assert len(named) > 20
+    return loss.detach().clone(), named
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_performer_training_step_is_bit_reproducible(dt, deterministic):
+    """dim 512, 2 layers, 16 heads (8 local), 1400 tokens, batch 3: split-K weight-gradient GEMMs with their bias column
+    sums, gate gradients, the FAVOR+ stabiliser gradient, LayerNorm / embedding-table gradients and the loss sum"""
+    a = _pf_grads(dt)
+    b = _pf_grads(dt)
+    assert torch.equal(a[0], b[0])
+    for (k, ga), (_, gb) in zip(a[1], b[1]):
+        assert torch.equal(ga, gb), f"gradient {k} differs by {float((ga - gb).abs().max())}"
