@@ -102,6 +102,8 @@ def parse():
     ap.add_argument("--no-vendor", action="store_true", help="skip the cuDNN / cuBLAS comparator legs")
     ap.add_argument("--no-parity", action="store_true", help="skip the bf16x3 (fp32-class tensor-core) arms")
     ap.add_argument("--no-extra", action="store_true", help="skip the VQ-kernel (config 3) and N = 1400 Performer arms")
+    ap.add_argument("--deterministic", action="store_true",
+                    help="the reference's `deterministic=True`: ordered split-K / column / loss sums (bit-reproducible steps)")
     return ap.parse_args()
 
 
@@ -898,6 +900,8 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     ops.lib()   # fail loudly here if the CUDA library is missing
+    if args.deterministic:
+        ops.set_deterministic(True)
     out = vqvae_b200(args, world, rank, local, dev) if args.workload in ("vqvae", "both") else None
     if args.workload in ("performer", "both"):
         pf = performer_b200(args, world, rank, local, dev)
@@ -908,6 +912,8 @@ def main():
                 out["performer"] = pf
                 out["gpu_launches"] = int(out["gpu_launches"]) + int(pf["gpu_launches"])
     if rank == 0:
+        if args.deterministic:
+            out["deterministic"] = True
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -78,6 +78,40 @@ __global__ void __launch_bounds__(1024) ordered_sum_kernel(const float* __restri
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) parts_reduce_kernel(const float* __restrict__ parts, long long nparts, long long stride,
+                                                            long long width, float* __restrict__ out) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < width; j += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (long long p = 0; p < nparts; ++p) acc += parts[p * stride + j];
+    out[j] += acc;
+  }
+}
+}  // namespace
+
+float* sa_parts_alloc(int64_t nparts, int64_t stride, cudaStream_t st) {
+  if (!g_deterministic || nparts <= 0 || stride <= 0) return nullptr;
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, (size_t)nparts * (size_t)stride * sizeof(float), st) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return (float*)p;
+}
+
+int sa_parts_reduce(const float* parts, int64_t nparts, int64_t stride, int64_t width, float* out, cudaStream_t st) {
+  int64_t blocks = sa_cdiv(width, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  parts_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(parts, nparts, stride, width, out);
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
+int sa_parts_free(float* parts, cudaStream_t st) {
+  if (parts) SA_CUDA(cudaFreeAsync(parts, st));
+  return SA_OK;
+}
+
 int sa_ordered_sum(const float* partials, int n, float* out, cudaStream_t st) {
   ordered_sum_kernel<<<1, 1024, 0, st>>>(partials, n, out);
   SA_LAUNCH_CHECK();

@@ -27,6 +27,12 @@ unsigned* sa_turn_slot(int n, cudaStream_t st);
 // index order (one CTA, fixed tree)
 float* sa_partial_slot(int n, cudaStream_t st);
 int sa_ordered_sum(const float* partials, int n, float* out, cudaStream_t st);
+// tensor-valued sums (split-K weight gradients, column sums) in deterministic mode: contributor p stores its partial --
+// same layout as the output -- at parts + p * stride (stream-ordered allocation, nullptr when the mode is off), and
+// sa_parts_reduce adds out[j] += sum_p parts[p * stride + j] (ascending p) for j < width; sa_parts_free releases it.
+float* sa_parts_alloc(int64_t nparts, int64_t stride, cudaStream_t st);
+int sa_parts_reduce(const float* parts, int64_t nparts, int64_t stride, int64_t width, float* out, cudaStream_t st);
+int sa_parts_free(float* parts, cudaStream_t st);
 
 #define SA_CHECK_ARG(cond, msg)                                   \
   do {                                                            \

@@ -48,7 +48,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int A, int B,
 template <typename T>
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restrict__ db, int64_t rows_per_block,
-                 unsigned* turn) {
+                 float* __restrict__ parts) {
   __shared__ float s_acc[256];
   const int cl = min(C, 256);          // threads along c
   const int rl = 256 / cl;             // row lanes (>= 1)
@@ -62,14 +62,12 @@ bias_grad_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restric
       for (int64_t r = r0 + tr; r < r1; r += rl) acc += sa_ld(dy, r * C + c);
     s_acc[threadIdx.x] = acc;
     __syncthreads();
-    const unsigned my = (unsigned)(c0 / cl) * gridDim.x + blockIdx.x;     // deterministic mode: blocks add in order
-    sa_block_turn_begin(turn, my);
     if (tr == 0 && c < C) {
       float s = 0.f;
       for (int j = 0; j < rl; ++j) s += s_acc[j * cl + tc];
-      atomicAdd(db + c, s);
+      if (parts) parts[(int64_t)blockIdx.x * C + c] = s;     // deterministic mode: summed in block order afterwards
+      else atomicAdd(db + c, s);
     }
-    sa_block_turn_end(turn, my);
     __syncthreads();
   }
 }
@@ -78,7 +76,7 @@ bias_grad_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restric
 template <typename T>
 __global__ void __launch_bounds__(256)
 bias_grad_vec_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __restrict__ db, int64_t rows_per_block,
-                     unsigned* turn) {
+                     float* __restrict__ parts) {
   constexpr int VEC = 16 / sizeof(T);
   __shared__ float s_acc[256 * VEC];
   const int cv = C / VEC;
@@ -132,17 +130,15 @@ bias_grad_vec_kernel(const T* __restrict__ dy, int64_t rows, int C, float* __res
 #pragma unroll
     for (int i = 0; i < VEC; ++i) s_acc[i * 256 + threadIdx.x] = acc[i];
     __syncthreads();
-    const unsigned my = (unsigned)(v0 / cl) * gridDim.x + blockIdx.x;
-    sa_block_turn_begin(turn, my);
     if (tr == 0 && v < cv) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         float t = 0.f;
         for (int j = 0; j < rl; ++j) t += s_acc[i * 256 + j * cl + tc];
-        atomicAdd(db + v * VEC + i, t);
+        if (parts) parts[(int64_t)blockIdx.x * C + v * VEC + i] = t;
+        else atomicAdd(db + v * VEC + i, t);
       }
     }
-    sa_block_turn_end(turn, my);
     __syncthreads();
   }
 }
@@ -344,22 +340,26 @@ extern "C" int sa_bias_grad(const void* dy, int64_t rows, int c, int dtype, floa
   if (!accumulate) SA_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * c, st));
   if (rows == 0) return SA_OK;
   int64_t blocks = sa_cdiv(rows, 256);
-  const int64_t max_blocks = sa_deterministic() ? 148 * 2 : 148 * 8;      // ordered adds serialise the blocks' tails
-  if (blocks > max_blocks) blocks = max_blocks;
-  unsigned* turn = sa_turn_slot(1, st);
+  if (blocks > 148 * 8) blocks = 148 * 8;
   const int64_t rpb = sa_cdiv(rows, blocks);
   blocks = sa_cdiv(rows, rpb);
   const int vec = dtype == SA_BF16 ? 8 : 4;
   const bool vec_ok = (c % vec == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+  float* parts = sa_parts_alloc(blocks, c, st);      // deterministic mode: per-block partials, summed in block order
   if (vec_ok && dtype == SA_BF16)
-    bias_grad_vec_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, c, db, rpb, turn);
+    bias_grad_vec_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, c, db, rpb, parts);
   else if (vec_ok)
-    bias_grad_vec_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, rows, c, db, rpb, turn);
+    bias_grad_vec_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, rows, c, db, rpb, parts);
   else if (dtype == SA_BF16)
-    bias_grad_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, c, db, rpb, turn);
+    bias_grad_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, rows, c, db, rpb, parts);
   else
-    bias_grad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, rows, c, db, rpb, turn);
+    bias_grad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, rows, c, db, rpb, parts);
   SA_LAUNCH_CHECK();
+  if (parts) {
+    const int rc = sa_parts_reduce(parts, blocks, c, c, db, st);
+    if (rc != SA_OK) return rc;
+    return sa_parts_free(parts, st);
+  }
   return SA_OK;
 }
 

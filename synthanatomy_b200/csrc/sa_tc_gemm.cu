@@ -511,7 +511,8 @@ struct TnParams {
   float scale;
   float* d;
   float* colsum;               // optional: colsum[i] += sum_r A[r][i] (unscaled) -- the bias gradient that goes with D
-  unsigned* turn;              // deterministic mode: one counter per output tile, the row splits add in split order
+  float* parts;                // deterministic mode: split s stores its partial [na x nb | na column sums] at
+  long long part_stride;       //   parts + s * part_stride (summed in split order afterwards)
 };
 
 __global__ void __launch_bounds__(W_THREADS, 1)
@@ -611,28 +612,35 @@ tc_gemm_tn_kernel(const __grid_constant__ TnParams P) {
     const float st = P.scale * (P.scale_dev ? __ldg(P.scale_dev) : 1.0f);
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
-    unsigned* turn = P.turn ? P.turn + tile : nullptr;
-    sa_turn_wait(turn, (unsigned)split);
+    float* const out = P.parts ? P.parts + (long long)split * P.part_stride : P.d;
     for (int c0 = 0; c0 < P.BN; c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
       const int col = bt * P.BN + c0;
       if (i < P.na) {
-        float* dst = P.d + (long long)i * P.nb + col;
+        float* dst = out + (long long)i * P.nb + col;
         const int nc = min(32, P.nb - col);
+        if (P.parts) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nc) atomicAdd(dst + j, st * __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j)
+            if (j < nc) dst[j] = st * __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nc) atomicAdd(dst + j, st * __uint_as_float(v[j]));
+        }
       }
     }
     if (do_colsum) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)P.BN, v);   // columns 0..15 all hold the sum
       tmem_ld_wait();
-      if (i < P.na) atomicAdd(P.colsum + i, __uint_as_float(v[0]));
+      if (i < P.na) {
+        if (P.parts) out[(long long)P.na * P.nb + i] = __uint_as_float(v[0]);
+        else atomicAdd(P.colsum + i, __uint_as_float(v[0]));
+      }
     }
-    sa_group_turn_end(turn, (unsigned)split, 1, 128, threadIdx.x == 64);
   }
 
   tc_fence_before();
@@ -805,8 +813,14 @@ int sa_tc_gemm_tn_colsum(int64_t m, int na, int nb, const void* a, int64_t lda, 
   rc = make_2d(&P.bmap, b, (uint64_t)nb, (uint64_t)m, (uint64_t)ldb, 64, W_KP);
   if (rc != SA_OK) return rc;
   const size_t smem = (size_t)W_STAGES * (2 * W_BLOCK + (size_t)P.bblocks * W_BLOCK) + W_BLOCK + 1024;
-  P.turn = sa_turn_slot((int)tiles, st);
+  P.part_stride = (long long)na * nb + (colsum ? na : 0);
+  P.parts = sa_parts_alloc(splits, P.part_stride, st);
   tc_gemm_tn_kernel<<<(unsigned)(tiles * splits), W_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
+  if (P.parts) {
+    if ((rc = sa_parts_reduce(P.parts, splits, P.part_stride, (long long)na * nb, d, st)) != SA_OK) return rc;
+    if (colsum && (rc = sa_parts_reduce(P.parts + (long long)na * nb, splits, P.part_stride, na, colsum, st)) != SA_OK) return rc;
+    return sa_parts_free(P.parts, st);
+  }
   return SA_OK;
 }

@@ -27,6 +27,7 @@ constexpr int PW_THREADS = 320;
 constexpr int PW_M = 128;                     // positions per tile
 constexpr uint32_t PW_BLK = PW_M * 128;       // [128 x 64] bf16 block
 constexpr int PW_STAGES = 2;
+constexpr int PW_PART = 128 * 128 + 128 + 128;   // floats per CTA partial in deterministic mode
 
 struct PwParams {
   CUtensorMap gmap, hmap, wmap, omap;
@@ -35,7 +36,7 @@ struct PwParams {
   float* dwp;
   float* dbias;
   float* dbias_h;        // MODE 0, optional: column sums of dh (the bias gradient of the conv that produced h)
-  unsigned* turn;        // deterministic mode (MODE 0): one counter, the CTAs add their partials in CTA order
+  float* parts;          // deterministic mode (MODE 0): CTA b stores [dW 128 x 128 | db 128 | dbh 128] at parts + b * PW_PART
   const float* bias;     // forward mode
   int relu;
 };
@@ -227,11 +228,10 @@ tc_pw_kernel(const __grid_constant__ PwParams P) {
       if (++stage == PW_STAGES) stage = 0;
     }
     if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    // deterministic mode: the CTAs add their dW / db / column-sum partials in CTA order
-    if (my_tiles > 0) sa_turn_wait(P.turn, blockIdx.x);
+    float* const part = P.parts ? P.parts + (long long)blockIdx.x * PW_PART : nullptr;   // summed in CTA order afterwards
     if (want_dbh) {
       // the four lane quadrants of a column half meet in shared memory and leave as ONE addition per column (a fixed
-      // order inside the CTA; across CTAs the turnstile above orders them)
+      // order inside the CTA; across CTAs the per-CTA partials are summed in CTA order)
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         float v = colsum[j];
@@ -241,31 +241,39 @@ tc_pw_kernel(const __grid_constant__ PwParams P) {
       }
       pw_bar_epi();
       const int c = threadIdx.x - 64;
-      if (c < 128 && my_tiles > 0)
-        atomicAdd(P.dbias_h + c, (s_colsum[0][c] + s_colsum[1][c]) + (s_colsum[2][c] + s_colsum[3][c]));
+      if (c < 128 && my_tiles > 0) {
+        const float v = (s_colsum[0][c] + s_colsum[1][c]) + (s_colsum[2][c] + s_colsum[3][c]);
+        if (part) part[128 * 128 + 128 + c] = v;
+        else atomicAdd(P.dbias_h + c, v);
+      }
     }
     if (MODE == 0 && my_tiles > 0) {
       // dW1 / db1 partials of this CTA: lane = n
       mbar_wait(&final_full, 0);
       tc_fence_after();
       const int n = quad * 32 + lane;
-      float* dst = P.dwp + (long long)n * 128 + half * 64;
+      float* dst = (part ? part : P.dwp) + (long long)n * 128 + half * 64;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t v[32];
         tmem_ld_32x32(tDw + tlane + (uint32_t)(half * 64 + hh * 32), v);
         tmem_ld_wait();
+        if (part) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + hh * 32 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) dst[hh * 32 + j] = __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + hh * 32 + j, __uint_as_float(v[j]));
+        }
       }
       if (half == 0) {
         uint32_t v[32];
         tmem_ld_32x32(tDb + tlane, v);       // columns 0..15 hold the sum, the rest of the 32 are never written
         tmem_ld_wait();
-        atomicAdd(P.dbias + n, __uint_as_float(v[0]));
+        if (part) part[128 * 128 + n] = __uint_as_float(v[0]);
+        else atomicAdd(P.dbias + n, __uint_as_float(v[0]));
       }
     }
-    if (my_tiles > 0) sa_group_turn_end(P.turn, blockIdx.x, 1, 256, threadIdx.x == 64);
   }
   tc_fence_before();
   __syncthreads();
@@ -323,9 +331,16 @@ extern "C" int sa_conv1x1_bwd_fused_dbh(int64_t m, int c_out, int c_in, const vo
   const size_t smem = (size_t)(2 + 1 + 2 + PW_STAGES * 4) * PW_BLK + 1024;
   const unsigned grid = (unsigned)(P.tiles < g_pw_sms ? P.tiles : g_pw_sms);
   P.bias = nullptr; P.relu = 0;
-  P.turn = sa_turn_slot(1, sa_stream(stream));
-  tc_pw_kernel<0><<<grid, PW_THREADS, smem, sa_stream(stream)>>>(P);
+  cudaStream_t st = sa_stream(stream);
+  P.parts = sa_parts_alloc(grid, PW_PART, st);
+  tc_pw_kernel<0><<<grid, PW_THREADS, smem, st>>>(P);
   SA_LAUNCH_CHECK();
+  if (P.parts) {
+    if ((rc = sa_parts_reduce(P.parts, grid, PW_PART, 128 * 128, dwp, st)) != SA_OK) return rc;
+    if ((rc = sa_parts_reduce(P.parts + 128 * 128, grid, PW_PART, 128, dbias, st)) != SA_OK) return rc;
+    if (dbias_h && (rc = sa_parts_reduce(P.parts + 128 * 128 + 128, grid, PW_PART, 128, dbias_h, st)) != SA_OK) return rc;
+    return sa_parts_free(P.parts, st);
+  }
   return SA_OK;
 }
 
@@ -350,7 +365,7 @@ extern "C" int sa_conv1x1_fwd_fused(int64_t m, int c_out, int c_in, const void* 
   static thread_local PwParams P;
   P.m = m;
   P.tiles = (int)sa_cdiv(m, PW_M);
-  P.dwp = nullptr; P.dbias = nullptr; P.dbias_h = nullptr; P.bias = bias; P.relu = relu; P.turn = nullptr;
+  P.dwp = nullptr; P.dbias = nullptr; P.dbias_h = nullptr; P.bias = bias; P.relu = relu; P.parts = nullptr;
   int rc;
   if ((rc = pw_map(&P.gmap, x, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;
   if ((rc = pw_map(&P.hmap, addend, 128, (uint64_t)m, PW_M)) != SA_OK) return rc;

@@ -41,7 +41,8 @@ struct WgParams {
   int td, th, tw, ntd, nth, ntw;
   int64_t tiles_total, tiles_per_split;
   float* dwp;
-  unsigned* turn;      // deterministic mode: one counter per (group, half); the splits add in split order
+  float* parts;        // deterministic mode: split s stores its partial dWp at parts + s * out_size (summed in order afterwards)
+  int64_t out_size;
 };
 
 __global__ void __launch_bounds__(WG_THREADS)
@@ -139,19 +140,24 @@ tc_wgrad_kernel(const __grid_constant__ WgParams P) {
     const int n = half * 128 + quad * 32 + lane;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
-    unsigned* turn = P.turn ? P.turn + half * P.ngroups + group : nullptr;
-    sa_turn_wait(turn, (unsigned)split);
+    float* const out = P.parts ? P.parts + (int64_t)split * P.out_size : P.dwp;
     for (int t = 0; t < T; ++t) {
-      float* dst = P.dwp + ((int64_t)(tap0 + t) * P.Cn + n) * P.Cc;
+      float* dst = out + ((int64_t)(tap0 + t) * P.Cn + n) * P.Cc;
       for (int c0 = 0; c0 < P.Cc; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * P.Cc + c0), v);
         tmem_ld_wait();
+        if (P.parts) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+        }
       }
     }
-    sa_group_turn_end(turn, (unsigned)split, 1, 128, threadIdx.x == 64);
   }
 
   tc_fence_before();
@@ -275,8 +281,13 @@ int sa_tc_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void* q, floa
   P.tiles_per_split = sa_cdiv(P.tiles_total, splits);
   splits = sa_cdiv(P.tiles_total, P.tiles_per_split);
   const unsigned grid = (unsigned)(base_ctas * splits);
-  P.turn = sa_turn_slot((int)base_ctas, st);
+  P.out_size = (int64_t)P.ntaps * P.Cn * P.Cc;
+  P.parts = sa_parts_alloc(splits, P.out_size, st);
   tc_wgrad_kernel<<<grid, WG_THREADS, stages * stage_bytes + 1024, st>>>(P);
   SA_LAUNCH_CHECK();
+  if (P.parts) {
+    if ((rc = sa_parts_reduce(P.parts, splits, P.out_size, P.out_size, dwp, st)) != SA_OK) return rc;
+    return sa_parts_free(P.parts, st);
+  }
   return SA_OK;
 }

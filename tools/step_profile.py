@@ -24,8 +24,11 @@ def main():
     ap.add_argument("--depth", type=int, default=24)
     ap.add_argument("--grid", type=int, nargs=3, default=[20, 28, 25])
     ap.add_argument("--warm", type=int, default=2)
+    ap.add_argument("--deterministic", action="store_true")
     a = ap.parse_args()
     from synthanatomy_b200 import ops
+    if a.deterministic:
+        ops.set_deterministic(True)
     dt = {"bf16": torch.bfloat16, "bf16x3": ops.BF16X3, "fp32": torch.float32}[a.dtype]
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
