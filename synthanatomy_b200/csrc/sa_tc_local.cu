@@ -48,8 +48,23 @@ struct LcParams {
 __device__ __forceinline__ int lc_lo(int p, int W) { const int w = p / W - 1; return (w > 0 ? w : 0) * W; }
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// bit c of (lo | hi << 32) = column c of a 64-column score tile is visible, for the visible interval [c_lo, c_hi] of a row
+// (causal + window masks are one interval per row): boundary tiles overwrite their hidden scores with -inf through one
+// bit test + select per score and then run the same arithmetic as interior tiles (exp2(-inf) = 0 exactly)
+__device__ __forceinline__ void lc_colmask(int c_lo, int c_hi, uint32_t& lo, uint32_t& hi) {
+  c_lo = max(c_lo, 0);
+  c_hi = min(c_hi, 63);
+  unsigned long long m = 0ull;
+  if (c_hi >= c_lo) m = (~0ull >> (63 - c_hi)) & (~0ull << c_lo);
+  lo = (uint32_t)m;
+  hi = (uint32_t)(m >> 32);
+}
+__device__ __forceinline__ void lc_apply_mask(uint32_t (&v)[32], uint32_t bits) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) v[c] = (bits >> c) & 1u ? v[c] : 0xff800000u;      // -inf
 }
 __device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -106,6 +121,193 @@ __device__ __forceinline__ float row_delta(const __nv_bfloat16* o, const __nv_bf
     acc = fmaf(bf16lo(x.w), bf16lo(y.w), acc); acc = fmaf(bf16hi(x.w), bf16hi(y.w), acc);
   }
   return acc;
+}
+
+// ------------------------------------------------------------------------------------------------ forward (v2)
+// O accumulates in TMEM (P V with accumulate) instead of in registers, so the softmax warps of tile t + 1 no longer wait
+// for the P V product of tile t: they read the S row once (64 registers), keep a running maximum that is only RAISED
+// when a tile's maximum exceeds it by more than 2^8 (the probabilities stay exact: the final O / l division uses the same
+// reference maximum; P <= 256 is harmless in bf16), and in that rare case rescale their O lanes in TMEM
+// (tcgen05.ld / st, warp-uniform).  P is double-buffered in shared memory; the tensor pipe runs one tile behind.
+constexpr float L_RESCALE_THRESHOLD = 8.0f;       // log2 units
+
+__global__ void __launch_bounds__(L_THREADS, 2)
+tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t q_full, s_full[2], p_full[2], o_done, o_final;
+  __shared__ uint64_t kv_full[L_STAGES_FWD], kv_empty[L_STAGES_FWD];
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Qs = smem;                       // 16 KB
+  uint8_t* Ps = Qs + 16384;                 // 2 x 16 KB: P of tile t in buffer t & 1
+  uint8_t* KV = Ps + 2 * 16384;             // stages x (K 8 KB | V 8 KB)
+  const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
+  const int i0 = blockIdx.x * 128;
+  const int j_beg = (lc_lo(i0, P.W) / 64) * 64;
+  const int j_last = min(P.N - 1, i0 + 127);
+  const int ntiles = (j_last - j_beg) / 64 + 1;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&q_full, 1); mbar_init(&o_done, 1); mbar_init(&o_final, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
+    for (int i = 0; i < L_STAGES_FWD; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 4) { tmem_alloc(&tmem_base_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 128;     // S buffers at columns 0 / 64, O at 128
+
+  if (warp == 5) {
+    if (lane == 0) {
+      prefetch_tmap(&P.qmap); prefetch_tmap(&P.kmap); prefetch_tmap(&P.vmap);
+      mbar_expect_tx(&q_full, 16384);
+      tma_load_2d(Qs, &P.qmap, &q_full, h * 64, b * P.N + i0);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&kv_full[stage], 16384);
+        uint8_t* ks = KV + stage * 16384;
+        tma_load_2d(ks, &P.kmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
+        tma_load_2d(ks + 8192, &P.vmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
+        if (++stage == L_STAGES_FWD) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t qa = smem_u32(Qs), pa = smem_u32(Ps), kva = smem_u32(KV);
+      mbar_wait(&q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      mma_kk(tS0, qa, kva, idesc_s, false);
+      umma_commit(&s_full[0]);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        int nstage = stage + 1; uint32_t nphase = phase;
+        if (nstage == L_STAGES_FWD) { nstage = 0; nphase ^= 1; }
+        if (t + 1 < ntiles) {
+          // S of the next tile.  Its buffer was last read for tile t - 1 (p_full waited below, one iteration ago); its
+          // commit also covers P V of tile t - 1, which is what frees P buffer (t + 1) & 1 for the softmax warps.
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          mma_kk(tS0 + (uint32_t)(((t + 1) & 1) * 64), qa, kva + nstage * 16384, idesc_s, false);
+          umma_commit(&s_full[(t + 1) & 1]);
+        }
+        mbar_wait(&p_full[t & 1], (uint32_t)((t >> 1) & 1));    // P_t is in shared memory, O lanes rescaled if needed
+        tc_fence_after();
+        mma_km(tO, pa + (uint32_t)((t & 1) * 16384), kva + stage * 16384 + 8192, idesc_o, t > 0);
+        umma_commit(&o_done);
+        umma_commit(&kv_empty[stage]);
+        if (t == ntiles - 1) umma_commit(&o_final);
+        stage = nstage; phase = nphase;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warps: thread = query row
+    const int r = warp * 32 + lane;
+    const int p = i0 + r;
+    const int lo = lc_lo(p, P.W);
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const float c2 = P.scale * LOG2E;
+    const int w_p0 = i0 + warp * 32;                      // first row of this warp; lo() is non-decreasing in the row
+    const int w_lo_max = lc_lo(w_p0 + 31, P.W);
+    float m = -INFINITY, l = 0.f;                         // m: the reference maximum the stored probabilities use
+    for (int t = 0; t < ntiles; ++t) {
+      const int j0 = j_beg + t * 64;
+      mbar_wait(&s_full[t & 1], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const uint32_t ts = tS0 + lane_addr + (uint32_t)((t & 1) * 64);
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(ts, va);
+      tmem_ld_32x32(ts + 32, vb);
+      tmem_ld_wait();
+      // interior tiles (every key of the tile visible to every row of this warp: a warp-uniform test, so no divergence)
+      // skip the per-score mask arithmetic
+      const bool full = P.fast && (j0 + 63 <= w_p0) && (j0 >= w_lo_max) && (w_p0 + 31 < P.N);
+      if (!full) {                                   // boundary tile: hide the masked scores, then the same arithmetic
+        uint32_t mlo, mhi;
+        lc_colmask(lo - j0, (p < P.N) ? p - j0 : -1, mlo, mhi);
+        lc_apply_mask(va, mlo);
+        lc_apply_mask(vb, mhi);
+      }
+      float mt;
+      {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};        // independent chains: the warp is latency-bound
+#pragma unroll
+        for (int c = 0; c < 32; ++c) m4[c & 3] = fmaxf(m4[c & 3], fmaxf(__uint_as_float(va[c]), __uint_as_float(vb[c])));
+        mt = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * c2;
+      }
+      // raise the reference maximum only when it pays (warp-uniform: tcgen05.ld / st are warp-collective)
+      if (__any_sync(0xffffffffu, mt > m + L_RESCALE_THRESHOLD)) {
+        const float m_new = fmaxf(m, mt);
+        const float alpha = (m == -INFINITY) ? 1.0f : ex2(m - m_new);     // m = -inf: nothing accumulated yet (O lane is 0)
+        if (t > 0) {
+          mbar_wait(&o_done, (uint32_t)((t - 1) & 1));                   // P V of tile t - 1 has landed in O
+          tc_fence_after();
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t v[16];
+            tmem_ld_32x16(tO + lane_addr + (uint32_t)(q4 * 16), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st_32x16(tO + lane_addr + (uint32_t)(q4 * 16), v);
+          }
+          tmem_st_wait();
+        }
+        l *= alpha;
+        m = m_new;
+      }
+      const float m_use = (m == -INFINITY) ? 0.f : m;
+      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint8_t* pbuf = Ps + (t & 1) * 16384;
+      {
+        float f[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { f[c] = ex2(fmaf(__uint_as_float(va[c]), c2, -m_use)); ps4[c & 3] += f[c]; }
+        st_sw128_32(pbuf, r, 0, f);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { f[c] = ex2(fmaf(__uint_as_float(vb[c]), c2, -m_use)); ps4[c & 3] += f[c]; }
+        st_sw128_32(pbuf, r, 32, f);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&p_full[t & 1]);
+      l += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+    }
+    // (a parity wait names a phase only relative to the current one, and the softmax warps may be two P V products ahead
+    //  of the tensor pipe here: the last product has its own barrier)
+    mbar_wait(&o_final, 0);
+    tc_fence_after();
+    float o[64];
+    {
+      uint32_t v[32];
+      tmem_ld_32x32(tO + lane_addr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[e] = __uint_as_float(v[e]);
+      tmem_ld_32x32(tO + lane_addr + 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[32 + e] = __uint_as_float(v[e]);
+    }
+    if (p < P.N) {
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int e = 0; e < 64; ++e) o[e] *= inv;
+      store_row64_bf16(P.o_out + ((long long)b * P.N + p) * P.out_ld + h * 64, o);
+      P.lse[(long long)bh * P.N + p] = (m + log2f(l)) * 0.6931471805599453f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 256);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -389,6 +591,8 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
       tc_fence_after();
       // interior tile for the whole warp (uniform): no mask arithmetic
       const bool full = P.fast && (j0 + 63 <= w_p0) && (j0 >= w_lo_max) && (w_p0 + 31 < P.N);
+      uint32_t mlo = 0xffffffffu, mhi = 0xffffffffu;
+      if (!full) lc_colmask(lo - j0, row_ok ? p - j0 : -1, mlo, mhi);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t vs[32], vd[32];
@@ -396,19 +600,10 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
         tmem_ld_32x32(tdP + lane_addr + (uint32_t)(hh * 32), vd);
         tmem_ld_wait();
         float f[32];
-        if (full) {
+        if (!full) lc_apply_mask(vs, hh ? mhi : mlo);       // boundary tile: hidden scores -> -inf -> probability 0
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            f[c] = ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) * (__uint_as_float(vd[c]) - delta) * P.scale;
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int j = j0 + hh * 32 + c;
-            const bool ok = row_ok && (j <= p) && (j >= lo);
-            const float pr = ok ? ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) : 0.f;
-            f[c] = pr * (__uint_as_float(vd[c]) - delta) * P.scale;
-          }
-        }
+        for (int c = 0; c < 32; ++c)
+          f[c] = ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) * (__uint_as_float(vd[c]) - delta) * P.scale;
         st_sw128_32(dSs, r, hh * 32, f);
       }
       fence_proxy_async();
@@ -546,6 +741,8 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
       tc_fence_after();
       // every (key of this warp, query of this tile) pair visible (warp-uniform): no mask arithmetic
       const bool full = P.fast && (w_j0 + 31 <= q0) && (q0 + 63 <= w_p_hi_min) && (w_j0 + 31 < P.N);
+      uint32_t mlo = 0xffffffffu, mhi = 0xffffffffu;
+      if (!full) lc_colmask(j - q0, p_hi - q0, mlo, mhi);          // queries p = q0 + c with j <= p <= p_hi
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t vs[32], vd[32];
@@ -553,22 +750,12 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
         tmem_ld_32x32(tdPT + lane_addr + (uint32_t)(hh * 32), vd);
         tmem_ld_wait();
         float fp[32], fd[32];
-        if (full) {
+        if (!full) lc_apply_mask(vs, hh ? mhi : mlo);       // boundary tile: hidden scores -> -inf -> probability 0
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float pr = ex2(fmaf(__uint_as_float(vs[c]), c2, -s_lse2[buf][hh * 32 + c]));
-            fp[c] = pr;
-            fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int p = q0 + hh * 32 + c;
-            const bool ok = (j <= p) && (p <= p_hi);
-            const float pr = ok ? ex2(fmaf(__uint_as_float(vs[c]), c2, -s_lse2[buf][hh * 32 + c])) : 0.f;
-            fp[c] = pr;
-            fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
-          }
+        for (int c = 0; c < 32; ++c) {
+          const float pr = ex2(fmaf(__uint_as_float(vs[c]), c2, -s_lse2[buf][hh * 32 + c]));
+          fp[c] = pr;
+          fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
         }
         st_sw128_32(PTs, r, hh * 32, fp);
         st_sw128_32(dSTs, r, hh * 32, fd);
@@ -691,12 +878,14 @@ std::once_flag g_once;
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 constexpr size_t SMEM_FWD = 16384 * 2 + L_STAGES_FWD * 16384 + 1024;
+constexpr size_t SMEM_FWD2 = 16384 * 3 + L_STAGES_FWD * 16384 + 1024;
 constexpr size_t SMEM_DQ = 16384 * 3 + L_STAGES_FWD * 16384 + 1024;
 constexpr size_t SMEM_DKV = 16384 * 4 + L_STAGES_BWD * 16384 + 1024;
 
 void init_once() {
   std::call_once(g_once, [] {
     cudaFuncSetAttribute(tc_local_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD);
+    cudaFuncSetAttribute(tc_local_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2);
     cudaFuncSetAttribute(tc_local_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQ);
     cudaFuncSetAttribute(tc_local_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DKV);
   });
@@ -739,7 +928,9 @@ int sa_tc_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, c
   if ((rc = make_map(&P.vmap, v, d, d->ld, 64)) != SA_OK) return rc;
   P.o_out = (__nv_bfloat16*)out; P.lse = lse;
   dim3 grid((unsigned)sa_cdiv(d->seq, 128), (unsigned)(d->batch * d->heads));
-  tc_local_fwd_kernel<<<grid, L_THREADS, SMEM_FWD, st>>>(P);
+  const char* env = getenv("SA_LOCAL_FWD");                 // A/B switch: 1 = the older kernel (O folded in registers)
+  if (env && env[0] == '1') tc_local_fwd_kernel<<<grid, L_THREADS, SMEM_FWD, st>>>(P);
+  else tc_local_fwd2_kernel<<<grid, L_THREADS, SMEM_FWD2, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }

@@ -620,3 +620,31 @@ def test_gemm_gelu_derivative_epilogues(dtype, m, n, k):
     want = v * 0.74 * d.float().cpu()
     torch.testing.assert_close(o.float().cpu(), want, rtol=tol, atol=tol * float(want.abs().max()))
     assert abs(float(dot) - float((v * w).sum())) <= 1e-3 * float((v * w).abs().sum()) ** 0.5 * 30 + 1e-3
+
+
+def test_tcgen05_local_attention_rescale_path():
+    """the forward kernel keeps O in TMEM and raises its reference maximum only when a tile's maximum exceeds it by 2^8:
+    keys whose magnitude grows along the sequence force that rescale (tcgen05.ld / st of the O lanes) many times"""
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(5)
+    B, H, N, W, d = 1, 2, 1000, 420, 64
+    q = _bf(torch.randn(B, H, N, d, generator=g))
+    ramp = (1.0 + 24.0 * torch.arange(N) / N).view(1, 1, N, 1)
+    k = _bf(torch.randn(B, H, N, d, generator=g) * ramp)
+    v = _bf(torch.randn(B, H, N, d, generator=g))
+    out = po.local_attention(q, k, v, W, "none")
+    inner = H * d
+    buf = torch.cat([_heads_to_rows(t) for t in (q, k, v)], dim=1).cuda().bfloat16()
+    ldsc = pf.local_desc(B, N, H, d, W, 3 * inner, inner, torch.bfloat16)
+    O = torch.zeros(B * N, inner, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device="cuda")
+    pf.local_attn_fwd(ldsc, buf, 0, inner, 2 * inner, None, O, 0, lse)
+    assert ops.last_path() == 2
+    _close(_rows_to_heads(O.float().cpu(), B, H), out, 2e-2, "tc local out (rescale path)")
+    ops.set_force_simt(True)
+    try:
+        O2 = torch.zeros_like(O); lse2 = torch.empty_like(lse)
+        pf.local_attn_fwd(ldsc, buf, 0, inner, 2 * inner, None, O2, 0, lse2)
+    finally:
+        ops.set_force_simt(False)
+    _close(lse, lse2, 1e-3, "lse tc vs simt (rescale path)")
