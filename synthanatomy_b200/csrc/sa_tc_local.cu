@@ -27,6 +27,7 @@ namespace {
 constexpr int L_THREADS = 192;
 constexpr int L_STAGES_FWD = 3;
 constexpr int L_STAGES_BWD = 2;
+constexpr int L_STAGES_DQ = 2;            // dq kernel: the second dS buffer takes the third K/V stage's shared memory
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct LcParams {
@@ -504,15 +505,15 @@ tc_local_fwd_kernel(const __grid_constant__ LcParams P) {
 __global__ void __launch_bounds__(L_THREADS, 2)
 tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t q_full, sdp_full, ds_full, dq_full;
-  __shared__ uint64_t kv_full[L_STAGES_FWD], kv_empty[L_STAGES_FWD];
+  __shared__ uint64_t q_full, sdp_full, sdp_free, ds_full[2], dq_full;
+  __shared__ uint64_t kv_full[L_STAGES_DQ], kv_empty[L_STAGES_DQ];
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Qs = smem;                       // 16 KB
   uint8_t* dOs = Qs + 16384;                // 16 KB
-  uint8_t* dSs = dOs + 16384;               // 16 KB  [128 q x 64 keys]
-  uint8_t* KV = dSs + 16384;                // stages x (K 8 KB | V 8 KB)
+  uint8_t* dSs = dOs + 16384;               // 2 x 16 KB  [128 q x 64 keys], tile t in buffer t & 1
+  uint8_t* KV = dSs + 2 * 16384;            // stages x (K 8 KB | V 8 KB)
   const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
   const int i0 = blockIdx.x * 128;
   const int j_beg = (lc_lo(i0, P.W) / 64) * 64;
@@ -520,8 +521,8 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
   const int ntiles = (j_last - j_beg) / 64 + 1;
 
   if (threadIdx.x == 0) {
-    mbar_init(&q_full, 1); mbar_init(&sdp_full, 1); mbar_init(&ds_full, 128); mbar_init(&dq_full, 1);
-    for (int i = 0; i < L_STAGES_FWD; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(&q_full, 1); mbar_init(&sdp_full, 1); mbar_init(&sdp_free, 128); mbar_init(&ds_full[0], 128); mbar_init(&ds_full[1], 128); mbar_init(&dq_full, 1);
+    for (int i = 0; i < L_STAGES_DQ; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -545,7 +546,7 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
         uint8_t* ks = KV + stage * 16384;
         tma_load_2d(ks, &P.kmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
         tma_load_2d(ks + 8192, &P.vmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
-        if (++stage == L_STAGES_FWD) { stage = 0; phase ^= 1; }
+        if (++stage == L_STAGES_DQ) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 4) {
@@ -554,18 +555,29 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
       const uint32_t idesc_km = make_idesc_bf16(128, 64, 0, 1);
       const uint32_t qa = smem_u32(Qs), doa = smem_u32(dOs), dsa = smem_u32(dSs), kva = smem_u32(KV);
       mbar_wait(&q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      mma_kk(tS, qa, kva, idesc_kk, false);                                // S = Q K^T
+      mma_kk(tdP, doa, kva + 8192, idesc_kk, false);                       // dP = dO V^T
+      umma_commit(&sdp_full);
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(&kv_full[stage], phase);
+        int nstage = stage + 1; uint32_t nphase = phase;
+        if (nstage == L_STAGES_DQ) { nstage = 0; nphase ^= 1; }
+        if (t + 1 < ntiles) {
+          // S / dP of the next tile as soon as the softmax warps have READ this tile's (they still compute on registers)
+          mbar_wait(&kv_full[nstage], nphase);
+          mbar_wait(&sdp_free, (uint32_t)(t & 1));
+          tc_fence_after();
+          mma_kk(tS, qa, kva + nstage * 16384, idesc_kk, false);
+          mma_kk(tdP, doa, kva + nstage * 16384 + 8192, idesc_kk, false);
+          umma_commit(&sdp_full);
+        }
+        mbar_wait(&ds_full[t & 1], (uint32_t)((t >> 1) & 1));
         tc_fence_after();
-        mma_kk(tS, qa, kva + stage * 16384, idesc_kk, false);              // S = Q K^T
-        mma_kk(tdP, doa, kva + stage * 16384 + 8192, idesc_kk, false);     // dP = dO V^T
-        umma_commit(&sdp_full);
-        mbar_wait(&ds_full, (uint32_t)(t & 1));
-        tc_fence_after();
-        mma_km(tdQ, dsa, kva + stage * 16384, idesc_km, t > 0);            // dQ += dS K
+        mma_km(tdQ, dsa + (uint32_t)((t & 1) * 16384), kva + stage * 16384, idesc_km, t > 0);   // dQ += dS K
         umma_commit(&kv_empty[stage]);
-        if (++stage == L_STAGES_FWD) { stage = 0; phase ^= 1; }
+        stage = nstage; phase = nphase;
       }
       umma_commit(&dq_full);
     }
@@ -599,16 +611,20 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
         tmem_ld_32x32(tS + lane_addr + (uint32_t)(hh * 32), vs);
         tmem_ld_32x32(tdP + lane_addr + (uint32_t)(hh * 32), vd);
         tmem_ld_wait();
+        if (hh == 1) {                                      // S and dP of this tile are in registers: the next tile's may land
+          tc_fence_before();
+          mbar_arrive(&sdp_free);
+        }
         float f[32];
         if (!full) lc_apply_mask(vs, hh ? mhi : mlo);       // boundary tile: hidden scores -> -inf -> probability 0
 #pragma unroll
         for (int c = 0; c < 32; ++c)
           f[c] = ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) * (__uint_as_float(vd[c]) - delta) * P.scale;
-        st_sw128_32(dSs, r, hh * 32, f);
+        st_sw128_32(dSs + (t & 1) * 16384, r, hh * 32, f);
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&ds_full);
+      mbar_arrive(&ds_full[t & 1]);
     }
     mbar_wait(&dq_full, 0);
     tc_fence_after();
@@ -879,7 +895,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 constexpr size_t SMEM_FWD = 16384 * 2 + L_STAGES_FWD * 16384 + 1024;
 constexpr size_t SMEM_FWD2 = 16384 * 3 + L_STAGES_FWD * 16384 + 1024;
-constexpr size_t SMEM_DQ = 16384 * 3 + L_STAGES_FWD * 16384 + 1024;
+constexpr size_t SMEM_DQ = 16384 * 4 + L_STAGES_DQ * 16384 + 1024;
 constexpr size_t SMEM_DKV = 16384 * 4 + L_STAGES_BWD * 16384 + 1024;
 
 void init_once() {
