@@ -132,6 +132,9 @@ __device__ __forceinline__ float row_delta(const __nv_bfloat16* o, const __nv_bf
 // (tcgen05.ld / st, warp-uniform).  P is double-buffered in shared memory; the tensor pipe runs one tile behind.
 constexpr float L_RESCALE_THRESHOLD = 8.0f;       // log2 units
 
+// TS: the probabilities / score gradients reach the second product as TMEM-resident A operands (tcgen05.st) instead of
+// through 128B-swizzled shared memory
+template <bool TS>
 __global__ void __launch_bounds__(L_THREADS, 2)
 tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -202,7 +205,17 @@ tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
         }
         mbar_wait(&p_full[t & 1], (uint32_t)((t >> 1) & 1));    // P_t is in shared memory, O lanes rescaled if needed
         tc_fence_after();
-        mma_km(tO, pa + (uint32_t)((t & 1) * 16384), kva + stage * 16384 + 8192, idesc_o, t > 0);
+        if (TS) {
+          // P as the TMEM-resident A operand (TS form): 64 keys = 32 columns of packed bf16 pairs, 8 columns per K step
+          const uint32_t tp = tmem_base + 192 + (uint32_t)((t & 1) * 32);
+          const uint32_t vb_addr = kva + stage * 16384 + 8192;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tO, tp + (uint32_t)(kk * 8), make_smem_desc(vb_addr + kk * 2048, 8192, 1024, 2), idesc_o,
+                         (t > 0 || kk != 0) ? 1u : 0u);
+        } else {
+          mma_km(tO, pa + (uint32_t)((t & 1) * 16384), kva + stage * 16384 + 8192, idesc_o, t > 0);
+        }
         umma_commit(&o_done);
         umma_commit(&kv_empty[stage]);
         if (t == ntiles - 1) umma_commit(&o_final);
@@ -268,7 +281,25 @@ tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
       const float m_use = (m == -INFINITY) ? 0.f : m;
       float ps4[4] = {0.f, 0.f, 0.f, 0.f};
       uint8_t* pbuf = Ps + (t & 1) * 16384;
-      {
+      if (TS) {
+        const uint32_t tp = tmem_base + 192 + (uint32_t)((t & 1) * 32) + lane_addr;
+        uint32_t u[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float f0 = ex2(fmaf(__uint_as_float(va[c]), c2, -m_use)), f1 = ex2(fmaf(__uint_as_float(va[c + 1]), c2, -m_use));
+          ps4[c & 3] += f0; ps4[(c + 1) & 3] += f1;
+          u[c >> 1] = pack_bf16x2(f0, f1);
+        }
+        tmem_st_32x16(tp, u);
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float f0 = ex2(fmaf(__uint_as_float(vb[c]), c2, -m_use)), f1 = ex2(fmaf(__uint_as_float(vb[c + 1]), c2, -m_use));
+          ps4[c & 3] += f0; ps4[(c + 1) & 3] += f1;
+          u[c >> 1] = pack_bf16x2(f0, f1);
+        }
+        tmem_st_32x16(tp + 16, u);
+        tmem_st_wait();
+      } else {
         float f[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) { f[c] = ex2(fmaf(__uint_as_float(va[c]), c2, -m_use)); ps4[c & 3] += f[c]; }
@@ -276,8 +307,8 @@ tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) { f[c] = ex2(fmaf(__uint_as_float(vb[c]), c2, -m_use)); ps4[c & 3] += f[c]; }
         st_sw128_32(pbuf, r, 32, f);
+        fence_proxy_async();
       }
-      fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&p_full[t & 1]);
       l += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
@@ -502,6 +533,9 @@ tc_local_fwd_kernel(const __grid_constant__ LcParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dq
+// TS: the probabilities / score gradients reach the second product as TMEM-resident A operands (tcgen05.st) instead of
+// through 128B-swizzled shared memory
+template <bool TS>
 __global__ void __launch_bounds__(L_THREADS, 2)
 tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -575,7 +609,15 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
         }
         mbar_wait(&ds_full[t & 1], (uint32_t)((t >> 1) & 1));
         tc_fence_after();
-        mma_km(tdQ, dsa + (uint32_t)((t & 1) * 16384), kva + stage * 16384, idesc_km, t > 0);   // dQ += dS K
+        if (TS) {                                                          // dQ += dS K, dS the TMEM-resident A operand
+          const uint32_t tds = tmem_base + 192 + (uint32_t)((t & 1) * 32);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tdQ, tds + (uint32_t)(kk * 8), make_smem_desc(kva + stage * 16384 + kk * 2048, 8192, 1024, 2),
+                         idesc_km, (t > 0 || kk != 0) ? 1u : 0u);
+        } else {
+          mma_km(tdQ, dsa + (uint32_t)((t & 1) * 16384), kva + stage * 16384, idesc_km, t > 0);   // dQ += dS K
+        }
         umma_commit(&kv_empty[stage]);
         stage = nstage; phase = nphase;
       }
@@ -620,9 +662,17 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
 #pragma unroll
         for (int c = 0; c < 32; ++c)
           f[c] = ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) * (__uint_as_float(vd[c]) - delta) * P.scale;
-        st_sw128_32(dSs + (t & 1) * 16384, r, hh * 32, f);
+        if (TS) {
+          uint32_t u[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) u[c >> 1] = pack_bf16x2(f[c], f[c + 1]);
+          tmem_st_32x16(tmem_base + 192 + (uint32_t)((t & 1) * 32 + hh * 16) + lane_addr, u);
+        } else {
+          st_sw128_32(dSs + (t & 1) * 16384, r, hh * 32, f);
+        }
       }
-      fence_proxy_async();
+      if (TS) tmem_st_wait();
+      else fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&ds_full[t & 1]);
     }
@@ -648,6 +698,9 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dk, dv
+// TS: the probabilities / score gradients reach the second product as TMEM-resident A operands (tcgen05.st) instead of
+// through 128B-swizzled shared memory
+template <bool TS>
 __global__ void __launch_bounds__(L_THREADS, 2)
 tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -712,8 +765,20 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
         umma_commit(&sdp_full);
         mbar_wait(&ds_full, (uint32_t)(t & 1));
         tc_fence_after();
-        mma_km(tdV, pta, qda + stage * 16384 + 8192, idesc_km, t > 0);     // dV += P^T dO
-        mma_km(tdK, dsta, qda + stage * 16384, idesc_km, t > 0);           // dK += dS^T Q
+        if (TS) {
+          // P^T / dS^T as TMEM-resident A operands, written in place over the first 32 columns of S^T / dP^T
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tdV, tST + (uint32_t)(kk * 8), make_smem_desc(qda + stage * 16384 + 8192 + kk * 2048, 8192, 1024, 2),
+                         idesc_km, (t > 0 || kk != 0) ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tdK, tdPT + (uint32_t)(kk * 8), make_smem_desc(qda + stage * 16384 + kk * 2048, 8192, 1024, 2),
+                         idesc_km, (t > 0 || kk != 0) ? 1u : 0u);
+        } else {
+          mma_km(tdV, pta, qda + stage * 16384 + 8192, idesc_km, t > 0);     // dV += P^T dO
+          mma_km(tdK, dsta, qda + stage * 16384, idesc_km, t > 0);           // dK += dS^T Q
+        }
         umma_commit(&qd_empty[stage]);
         if (++stage == L_STAGES_BWD) { stage = 0; phase ^= 1; }
       }
@@ -773,10 +838,21 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
           fp[c] = pr;
           fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
         }
-        st_sw128_32(PTs, r, hh * 32, fp);
-        st_sw128_32(dSTs, r, hh * 32, fd);
+        if (TS) {
+          uint32_t u[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) u[c >> 1] = pack_bf16x2(fp[c], fp[c + 1]);
+          tmem_st_32x16(tST + lane_addr + (uint32_t)(hh * 16), u);
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) u[c >> 1] = pack_bf16x2(fd[c], fd[c + 1]);
+          tmem_st_32x16(tdPT + lane_addr + (uint32_t)(hh * 16), u);
+        } else {
+          st_sw128_32(PTs, r, hh * 32, fp);
+          st_sw128_32(dSTs, r, hh * 32, fd);
+        }
       }
-      fence_proxy_async();
+      if (TS) tmem_st_wait();
+      else fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&ds_full);
       if (!P.delta_ws) load_stats(t + 1, nl2, ndl);
@@ -901,11 +977,17 @@ constexpr size_t SMEM_DKV = 16384 * 4 + L_STAGES_BWD * 16384 + 1024;
 void init_once() {
   std::call_once(g_once, [] {
     cudaFuncSetAttribute(tc_local_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD);
-    cudaFuncSetAttribute(tc_local_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2);
-    cudaFuncSetAttribute(tc_local_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQ);
-    cudaFuncSetAttribute(tc_local_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DKV);
+    cudaFuncSetAttribute(tc_local_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2);
+    cudaFuncSetAttribute(tc_local_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2);
+    cudaFuncSetAttribute(tc_local_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQ);
+    cudaFuncSetAttribute(tc_local_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQ);
+    cudaFuncSetAttribute(tc_local_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DKV);
+    cudaFuncSetAttribute(tc_local_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DKV);
   });
 }
+
+// A/B switch: SA_LOCAL_TS=0 stages P / dS through shared memory (the older SS form)
+bool local_ts() { const char* env = getenv("SA_LOCAL_TS"); return !(env && env[0] == '0'); }
 
 int make_map(CUtensorMap* m, const void* base, const sa_local_desc* d, int ld, uint32_t box_rows) {
   const uint64_t dims[2] = {(uint64_t)d->heads * 64, (uint64_t)d->batch * d->seq};
@@ -946,7 +1028,8 @@ int sa_tc_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, c
   dim3 grid((unsigned)sa_cdiv(d->seq, 128), (unsigned)(d->batch * d->heads));
   const char* env = getenv("SA_LOCAL_FWD");                 // A/B switch: 1 = the older kernel (O folded in registers)
   if (env && env[0] == '1') tc_local_fwd_kernel<<<grid, L_THREADS, SMEM_FWD, st>>>(P);
-  else tc_local_fwd2_kernel<<<grid, L_THREADS, SMEM_FWD2, st>>>(P);
+  else if (local_ts()) tc_local_fwd2_kernel<true><<<grid, L_THREADS, SMEM_FWD2, st>>>(P);
+  else tc_local_fwd2_kernel<false><<<grid, L_THREADS, SMEM_FWD2, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
@@ -972,14 +1055,16 @@ int sa_tc_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, c
   if ((rc = make_map(&P.kmap, k, d, d->ld, 64)) != SA_OK) return rc;
   if ((rc = make_map(&P.vmap, v, d, d->ld, 64)) != SA_OK) return rc;
   dim3 grid((unsigned)sa_cdiv(d->seq, 128), (unsigned)(d->batch * d->heads));
-  tc_local_bwd_dq_kernel<<<grid, L_THREADS, SMEM_DQ, st>>>(P);
+  if (local_ts()) tc_local_bwd_dq_kernel<true><<<grid, L_THREADS, SMEM_DQ, st>>>(P);
+  else tc_local_bwd_dq_kernel<false><<<grid, L_THREADS, SMEM_DQ, st>>>(P);
   SA_LAUNCH_CHECK();
   // dkv kernel: 128-row K / V boxes, 64-row Q / dO boxes
   if ((rc = make_map(&P.qmap, q, d, d->ld, 64)) != SA_OK) return rc;
   if ((rc = make_map(&P.domap, dout, d, d->out_ld, 64)) != SA_OK) return rc;
   if ((rc = make_map(&P.kmap, k, d, d->ld, 128)) != SA_OK) return rc;
   if ((rc = make_map(&P.vmap, v, d, d->ld, 128)) != SA_OK) return rc;
-  tc_local_bwd_dkv_kernel<<<grid, L_THREADS, SMEM_DKV, st>>>(P);
+  if (local_ts()) tc_local_bwd_dkv_kernel<true><<<grid, L_THREADS, SMEM_DKV, st>>>(P);
+  else tc_local_bwd_dkv_kernel<false><<<grid, L_THREADS, SMEM_DKV, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
 }
