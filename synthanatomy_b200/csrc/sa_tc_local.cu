@@ -4,12 +4,18 @@
 //   query p attends keys j with lo(p) <= j <= p,  lo(p) = max(0, floor(p / w) - 1) * w      (window w, look-back 1)
 //   S = q k^T * d^-1/2   P = softmax(S)   O = P v          (q, k already carry the rotary position term: sa_rotary)
 //
-// forward   one CTA per (batch, head, 128-query tile); key tiles of 64.  S = Q K^T and O_part = P V on tcgen05
-//           (accumulators in TMEM), online softmax out of TMEM by 4 warps (thread = query row), P re-staged as bf16
-//           into 128B-swizzled shared memory (the K-major A operand of the second MMA), O accumulated in registers.
-// backward  dq kernel: per 128-query tile, loop key tiles:  S, dP = dO V^T  ->  dS = P (dP - delta) / sqrt(d)  ->  dQ += dS K
+// forward   one CTA per (batch, head, 128-query tile); key tiles of 64.  S = Q K^T (double-buffered in TMEM) and
+//           O += P V on tcgen05 with O resident in TMEM: the softmax warps (thread = query row) read an S row once, keep
+//           a reference maximum that is raised only when a tile exceeds it by 2^8 (then they rescale their O lanes with
+//           tcgen05.ld / st), and hand P over as the TMEM-resident A operand of the second product (TS form) -- they
+//           never wait for a P V product, so the tensor pipe simply runs one tile behind.
+// backward  dq kernel: per 128-query tile, loop key tiles:  S, dP = dO V^T  ->  dS = P (dP - delta) / sqrt(d)  ->  dQ += dS K;
+//                      S / dP of tile t + 1 are issued as soon as the softmax warps have read tile t's out of TMEM
 //           dkv kernel: per 128-key tile, loop 64-query tiles, transposed roles (TMEM lane = key):
-//                       S^T = K Q^T, dP^T = V dO^T  ->  P^T, dS^T  ->  dV += P^T dO,  dK += dS^T Q
+//                       S^T = K Q^T, dP^T = V dO^T  ->  P^T, dS^T (written in place over S^T / dP^T)  ->  dV += P^T dO,
+//                       dK += dS^T Q
+//           Causal + window masks are one visible interval per row: boundary tiles overwrite hidden scores with -inf
+//           through a 64-bit column mask and then run the interior-tile arithmetic.
 // Warp roles: warps 0-3 softmax / epilogue (TMEM lane quadrants 0-3), warp 4 MMA issuer, warp 5 TMA producer.
 //
 // Replaces local_attention.LocalAttention.forward (+ autograd) called by performer-pytorch SelfAttention for the local
@@ -124,7 +130,7 @@ __device__ __forceinline__ float row_delta(const __nv_bfloat16* o, const __nv_bf
   return acc;
 }
 
-// ------------------------------------------------------------------------------------------------ forward (v2)
+// ------------------------------------------------------------------------------------------------ forward
 // O accumulates in TMEM (P V with accumulate) instead of in registers, so the softmax warps of tile t + 1 no longer wait
 // for the P V product of tile t: they read the S row once (64 registers), keep a running maximum that is only RAISED
 // when a tile's maximum exceeds it by more than 2^8 (the probabilities stay exact: the final O / l division uses the same
@@ -139,13 +145,14 @@ __global__ void __launch_bounds__(L_THREADS, 2)
 tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t q_full, s_full[2], p_full[2], o_done, o_final;
-  __shared__ uint64_t kv_full[L_STAGES_FWD], kv_empty[L_STAGES_FWD];
+  constexpr int NST = TS ? L_STAGES_FWD + 2 : L_STAGES_FWD;    // TS: the two P buffers' shared memory holds K/V stages
+  __shared__ uint64_t kv_full[NST], kv_empty[NST];
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Qs = smem;                       // 16 KB
   uint8_t* Ps = Qs + 16384;                 // 2 x 16 KB: P of tile t in buffer t & 1
-  uint8_t* KV = Ps + 2 * 16384;             // stages x (K 8 KB | V 8 KB)
+  uint8_t* KV = TS ? Ps : Ps + 2 * 16384;   // stages x (K 8 KB | V 8 KB)
   const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
   const int i0 = blockIdx.x * 128;
   const int j_beg = (lc_lo(i0, P.W) / 64) * 64;
@@ -155,7 +162,7 @@ tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1); mbar_init(&o_done, 1); mbar_init(&o_final, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
-    for (int i = 0; i < L_STAGES_FWD; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -178,7 +185,7 @@ tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
         uint8_t* ks = KV + stage * 16384;
         tma_load_2d(ks, &P.kmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
         tma_load_2d(ks + 8192, &P.vmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
-        if (++stage == L_STAGES_FWD) { stage = 0; phase ^= 1; }
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 4) {
@@ -194,7 +201,7 @@ tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         int nstage = stage + 1; uint32_t nphase = phase;
-        if (nstage == L_STAGES_FWD) { nstage = 0; nphase ^= 1; }
+        if (nstage == NST) { nstage = 0; nphase ^= 1; }
         if (t + 1 < ntiles) {
           // S of the next tile.  Its buffer was last read for tile t - 1 (p_full waited below, one iteration ago); its
           // commit also covers P V of tile t - 1, which is what frees P buffer (t + 1) & 1 for the softmax warps.
@@ -342,196 +349,6 @@ tc_local_fwd2_kernel(const __grid_constant__ LcParams P) {
   if (warp == 4) tmem_dealloc(tmem_base, 256);
 }
 
-// ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(L_THREADS, 2)
-tc_local_fwd_kernel(const __grid_constant__ LcParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t q_full, s_full[2], p_full, o_full;
-  __shared__ uint64_t kv_full[L_STAGES_FWD], kv_empty[L_STAGES_FWD];
-  __shared__ uint32_t tmem_base_slot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Qs = smem;                       // 16 KB
-  uint8_t* Ps = Qs + 16384;                 // 8 KB used as [128 x 64] -> 16 KB
-  uint8_t* KV = Ps + 16384;                 // stages x (K 8 KB | V 8 KB)
-  const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
-  const int i0 = blockIdx.x * 128;
-  const int j_beg = (lc_lo(i0, P.W) / 64) * 64;
-  const int j_last = min(P.N - 1, i0 + 127);
-  const int ntiles = (j_last - j_beg) / 64 + 1;
-
-  if (threadIdx.x == 0) {
-    mbar_init(&q_full, 1); mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
-    for (int i = 0; i < L_STAGES_FWD; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    fence_mbar_init();
-    fence_proxy_async();
-  }
-  if (warp == 4) { tmem_alloc(&tmem_base_slot, 256); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
-  const uint32_t tS0 = tmem_base, tO = tmem_base + 128;     // S buffers at columns 0 / 64, O_part at 128
-
-  if (warp == 5) {
-    if (lane == 0) {
-      prefetch_tmap(&P.qmap); prefetch_tmap(&P.kmap); prefetch_tmap(&P.vmap);
-      mbar_expect_tx(&q_full, 16384);
-      tma_load_2d(Qs, &P.qmap, &q_full, h * 64, b * P.N + i0);
-      int stage = 0; uint32_t phase = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_expect_tx(&kv_full[stage], 16384);
-        uint8_t* ks = KV + stage * 16384;
-        tma_load_2d(ks, &P.kmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
-        tma_load_2d(ks + 8192, &P.vmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
-        if (++stage == L_STAGES_FWD) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 4) {
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
-      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-      const uint32_t qa = smem_u32(Qs), pa = smem_u32(Ps), kva = smem_u32(KV);
-      mbar_wait(&q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      mma_kk(tS0, qa, kva, idesc_s, false);
-      umma_commit(&s_full[0]);
-      int stage = 0; uint32_t phase = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        int nstage = stage + 1; uint32_t nphase = phase;
-        if (nstage == L_STAGES_FWD) { nstage = 0; nphase ^= 1; }
-        if (t + 1 < ntiles) {                                   // S of the next tile, while the softmax warps work on this one
-          mbar_wait(&kv_full[nstage], nphase);
-          tc_fence_after();
-          mma_kk(tS0 + (uint32_t)(((t + 1) & 1) * 64), qa, kva + nstage * 16384, idesc_s, false);
-          umma_commit(&s_full[(t + 1) & 1]);
-        }
-        mbar_wait(&p_full, (uint32_t)(t & 1));                  // P_t is in shared memory (and S_t, O_{t-1} were read)
-        tc_fence_after();
-        mma_km(tO, pa, kva + stage * 16384 + 8192, idesc_o, false);
-        umma_commit(&o_full);
-        umma_commit(&kv_empty[stage]);
-        stage = nstage; phase = nphase;
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- softmax warps: thread = query row
-    const int r = warp * 32 + lane;
-    const int p = i0 + r;
-    const int lo = lc_lo(p, P.W);
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const float c2 = P.scale * LOG2E;
-    const int w_p0 = i0 + warp * 32;                      // first row of this warp; lo() is non-decreasing in the row
-    const int w_lo_max = lc_lo(w_p0 + 31, P.W);
-    float o[64];
-#pragma unroll
-    for (int e = 0; e < 64; ++e) o[e] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    for (int t = 0; t < ntiles; ++t) {
-      const int j0 = j_beg + t * 64;
-      mbar_wait(&s_full[t & 1], (uint32_t)((t >> 1) & 1));
-      tc_fence_after();
-      const uint32_t ts = tS0 + lane_addr + (uint32_t)((t & 1) * 64);
-      // interior tiles (every key of the tile visible to every row of this warp: a warp-uniform test, so no divergence)
-      // skip the per-score mask arithmetic
-      const bool full = P.fast && (j0 + 63 <= w_p0) && (j0 >= w_lo_max) && (w_p0 + 31 < P.N);
-      // pass 1 over the S row: running maximum (TMEM reads are cheap; keeps the register footprint at 2 CTAs / SM)
-      float mt = -INFINITY;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[32];
-        tmem_ld_32x32(ts + (uint32_t)(hh * 32), v);
-        tmem_ld_wait();
-        if (full) {
-          float mr = __uint_as_float(v[0]);
-#pragma unroll
-          for (int c = 1; c < 32; ++c) mr = fmaxf(mr, __uint_as_float(v[c]));
-          mt = fmaxf(mt, mr * c2);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int j = j0 + hh * 32 + c;
-            const bool ok = (j <= p) && (j >= lo) && (p < P.N);
-            mt = fmaxf(mt, ok ? __uint_as_float(v[c]) * c2 : -INFINITY);
-          }
-        }
-      }
-      const float m_new = fmaxf(m, mt);
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2(m - m_safe);
-      if (t > 0) {                                              // fold in O_part of the previous tile (scale m_old)
-        mbar_wait(&o_full, (uint32_t)((t - 1) & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[32];
-          tmem_ld_32x32(tO + lane_addr + (uint32_t)(hh * 32), v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[hh * 32 + e] += __uint_as_float(v[e]);
-        }
-      }
-      // pass 2: probabilities -> bf16 -> swizzled shared memory (A operand of P V)
-      float ps = 0.f;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[32];
-        tmem_ld_32x32(ts + (uint32_t)(hh * 32), v);
-        tmem_ld_wait();
-        float f[32];
-        if (full) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            f[c] = ex2(fmaf(__uint_as_float(v[c]), c2, -m_safe));
-            ps += f[c];
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int j = j0 + hh * 32 + c;
-            const bool ok = (j <= p) && (j >= lo) && (p < P.N);
-            f[c] = ok ? ex2(fmaf(__uint_as_float(v[c]), c2, -m_safe)) : 0.f;
-            ps += f[c];
-          }
-        }
-        st_sw128_32(Ps, r, hh * 32, f);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&p_full);
-#pragma unroll
-      for (int e = 0; e < 64; ++e) o[e] *= alpha;
-      l = l * alpha + ps;
-      m = m_new;
-    }
-    mbar_wait(&o_full, (uint32_t)((ntiles - 1) & 1));
-    tc_fence_after();
-    {
-      uint32_t v[32];
-      tmem_ld_32x32(tO + lane_addr, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) o[e] += __uint_as_float(v[e]);
-      tmem_ld_32x32(tO + lane_addr + 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) o[32 + e] += __uint_as_float(v[e]);
-    }
-    if (p < P.N) {
-      const float inv = 1.0f / l;
-#pragma unroll
-      for (int e = 0; e < 64; ++e) o[e] *= inv;
-      store_row64_bf16(P.o_out + ((long long)b * P.N + p) * P.out_ld + h * 64, o);
-      P.lse[(long long)bh * P.N + p] = (m + log2f(l)) * 0.6931471805599453f;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
-}
-
 // ------------------------------------------------------------------------------------------------ backward: dq
 // TS: the probabilities / score gradients reach the second product as TMEM-resident A operands (tcgen05.st) instead of
 // through 128B-swizzled shared memory
@@ -540,14 +357,15 @@ __global__ void __launch_bounds__(L_THREADS, 2)
 tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t q_full, sdp_full, sdp_free, ds_full[2], dq_full;
-  __shared__ uint64_t kv_full[L_STAGES_DQ], kv_empty[L_STAGES_DQ];
+  constexpr int NST = TS ? L_STAGES_DQ + 2 : L_STAGES_DQ;      // TS: the two dS buffers' shared memory holds K/V stages
+  __shared__ uint64_t kv_full[NST], kv_empty[NST];
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Qs = smem;                       // 16 KB
   uint8_t* dOs = Qs + 16384;                // 16 KB
   uint8_t* dSs = dOs + 16384;               // 2 x 16 KB  [128 q x 64 keys], tile t in buffer t & 1
-  uint8_t* KV = dSs + 2 * 16384;            // stages x (K 8 KB | V 8 KB)
+  uint8_t* KV = TS ? dSs : dSs + 2 * 16384; // stages x (K 8 KB | V 8 KB)
   const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
   const int i0 = blockIdx.x * 128;
   const int j_beg = (lc_lo(i0, P.W) / 64) * 64;
@@ -556,7 +374,7 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
 
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1); mbar_init(&sdp_full, 1); mbar_init(&sdp_free, 128); mbar_init(&ds_full[0], 128); mbar_init(&ds_full[1], 128); mbar_init(&dq_full, 1);
-    for (int i = 0; i < L_STAGES_DQ; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -580,7 +398,7 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
         uint8_t* ks = KV + stage * 16384;
         tma_load_2d(ks, &P.kmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
         tma_load_2d(ks + 8192, &P.vmap, &kv_full[stage], h * 64, b * P.N + j_beg + t * 64);
-        if (++stage == L_STAGES_DQ) { stage = 0; phase ^= 1; }
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 4) {
@@ -597,7 +415,7 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         int nstage = stage + 1; uint32_t nphase = phase;
-        if (nstage == L_STAGES_DQ) { nstage = 0; nphase ^= 1; }
+        if (nstage == NST) { nstage = 0; nphase ^= 1; }
         if (t + 1 < ntiles) {
           // S / dP of the next tile as soon as the softmax warps have READ this tile's (they still compute on registers)
           mbar_wait(&kv_full[nstage], nphase);
@@ -705,7 +523,8 @@ __global__ void __launch_bounds__(L_THREADS, 2)
 tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t kv_full, sdp_full, ds_full, acc_full;
-  __shared__ uint64_t qd_full[L_STAGES_BWD], qd_empty[L_STAGES_BWD];
+  constexpr int NST = TS ? L_STAGES_BWD + 2 : L_STAGES_BWD;    // TS: the P^T / dS^T buffers' shared memory holds Q/dO stages
+  __shared__ uint64_t qd_full[NST], qd_empty[NST];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_lse2[2][64], s_delta[2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -714,7 +533,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
   uint8_t* Vs = Ks + 16384;                 // 16 KB
   uint8_t* PTs = Vs + 16384;                // 16 KB [128 keys x 64 queries]
   uint8_t* dSTs = PTs + 16384;              // 16 KB
-  uint8_t* QD = dSTs + 16384;               // stages x (Q 8 KB | dO 8 KB)
+  uint8_t* QD = TS ? PTs : dSTs + 16384;    // stages x (Q 8 KB | dO 8 KB)
   const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H;
   const int j0 = blockIdx.x * 128;
   const int j_hi = min(P.N - 1, j0 + 127);
@@ -723,7 +542,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
 
   if (threadIdx.x == 0) {
     mbar_init(&kv_full, 1); mbar_init(&sdp_full, 1); mbar_init(&ds_full, 128); mbar_init(&acc_full, 1);
-    for (int i = 0; i < L_STAGES_BWD; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -747,7 +566,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
         uint8_t* qs = QD + stage * 16384;
         tma_load_2d(qs, &P.qmap, &qd_full[stage], h * 64, b * P.N + j0 + t * 64);
         tma_load_2d(qs + 8192, &P.domap, &qd_full[stage], h * 64, b * P.N + j0 + t * 64);
-        if (++stage == L_STAGES_BWD) { stage = 0; phase ^= 1; }
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 4) {
@@ -780,7 +599,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
           mma_km(tdK, dsta, qda + stage * 16384, idesc_km, t > 0);           // dK += dS^T Q
         }
         umma_commit(&qd_empty[stage]);
-        if (++stage == L_STAGES_BWD) { stage = 0; phase ^= 1; }
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
       umma_commit(&acc_full);
     }
@@ -969,14 +788,12 @@ rotary_qk_vec_kernel(__nv_bfloat16* __restrict__ buf, long long ld, long long k_
 std::once_flag g_once;
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-constexpr size_t SMEM_FWD = 16384 * 2 + L_STAGES_FWD * 16384 + 1024;
 constexpr size_t SMEM_FWD2 = 16384 * 3 + L_STAGES_FWD * 16384 + 1024;
 constexpr size_t SMEM_DQ = 16384 * 4 + L_STAGES_DQ * 16384 + 1024;
 constexpr size_t SMEM_DKV = 16384 * 4 + L_STAGES_BWD * 16384 + 1024;
 
 void init_once() {
   std::call_once(g_once, [] {
-    cudaFuncSetAttribute(tc_local_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD);
     cudaFuncSetAttribute(tc_local_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2);
     cudaFuncSetAttribute(tc_local_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD2);
     cudaFuncSetAttribute(tc_local_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQ);
@@ -1026,9 +843,7 @@ int sa_tc_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, c
   if ((rc = make_map(&P.vmap, v, d, d->ld, 64)) != SA_OK) return rc;
   P.o_out = (__nv_bfloat16*)out; P.lse = lse;
   dim3 grid((unsigned)sa_cdiv(d->seq, 128), (unsigned)(d->batch * d->heads));
-  const char* env = getenv("SA_LOCAL_FWD");                 // A/B switch: 1 = the older kernel (O folded in registers)
-  if (env && env[0] == '1') tc_local_fwd_kernel<<<grid, L_THREADS, SMEM_FWD, st>>>(P);
-  else if (local_ts()) tc_local_fwd2_kernel<true><<<grid, L_THREADS, SMEM_FWD2, st>>>(P);
+  if (local_ts()) tc_local_fwd2_kernel<true><<<grid, L_THREADS, SMEM_FWD2, st>>>(P);
   else tc_local_fwd2_kernel<false><<<grid, L_THREADS, SMEM_FWD2, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
