@@ -479,7 +479,7 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
         if (!full) lc_apply_mask(vs, hh ? mhi : mlo);       // boundary tile: hidden scores -> -inf -> probability 0
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          f[c] = ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) * (__uint_as_float(vd[c]) - delta) * P.scale;
+          f[c] = ex2(fmaf(__uint_as_float(vs[c]), c2, -lse2)) * (__uint_as_float(vd[c]) - delta);   // d^-1/2: applied to dQ
         if (TS) {
           uint32_t u[16];
 #pragma unroll
@@ -508,7 +508,11 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
 #pragma unroll
       for (int e = 0; e < 32; ++e) g[32 + e] = __uint_as_float(v[e]);
     }
-    if (row_ok) store_row64_bf16(P.dq + ((long long)b * P.N + p) * P.ld + h * 64, g);
+    if (row_ok) {
+#pragma unroll
+      for (int e = 0; e < 64; ++e) g[e] *= P.scale;       // dS = P (dP - delta) d^-1/2: the factor commutes with the product
+      store_row64_bf16(P.dq + ((long long)b * P.N + p) * P.ld + h * 64, g);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -655,7 +659,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
         for (int c = 0; c < 32; ++c) {
           const float pr = ex2(fmaf(__uint_as_float(vs[c]), c2, -s_lse2[buf][hh * 32 + c]));
           fp[c] = pr;
-          fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]) * P.scale;
+          fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]);                    // d^-1/2: applied to dK
         }
         if (TS) {
           uint32_t u[16];
@@ -691,6 +695,10 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 32; ++e) g[32 + e] = __uint_as_float(v[e]);
+      if (which) {
+#pragma unroll
+        for (int e = 0; e < 64; ++e) g[e] *= P.scale;
+      }
       if (j < P.N) store_row64_bf16((which ? P.dk : P.dv) + ((long long)b * P.N + j) * P.ld + h * 64, g);
     }
   }
