@@ -34,6 +34,8 @@ struct NtParams {
   CUtensorMap imap_a, imap_b;     // TMA-load maps of epilogue inputs: `pre` and `dot_with` (bf16 blocks) or `resid` (fp32 chunks)
   int stages, tma_out;            // pipeline stages; 1 = outputs leave through shared-memory staging + TMA stores
   int tma_in;                     // 1: GELU' epilogue reads pre / dot_with blocks through TMA; 2: residual chunks through TMA
+  int row_out;                    // 1: fp32 output with an unaligned leading dimension (the logits, n = 2049): 32 x 32 chunks are
+                                  //    transposed through shared memory so that a warp stores whole row segments
   long long m;
   int n, k;
   int BN, m_tiles, n_tiles, kblocks;
@@ -292,7 +294,7 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
         tmem_ld_wait();
         const int nc = min(min(32, half_cols - cc), P.n - col);
         if (nc <= 0) continue;                             // warp-uniform
-        if (!P.tma_out && !row_ok) continue;               // (the staging path needs every lane)
+        if (!P.tma_out && !P.row_out && !row_ok) continue;  // (the staging paths need every lane)
         const long long o = row * e.ldo + col;
         if (P.tma_out) {
           // Outputs leave through 128B-swizzled shared-memory staging blocks and TMA stores: the per-thread stores
@@ -462,6 +464,22 @@ tc_gemm_nt_kernel(const __grid_constant__ NtParams P) {
           }
           if (e.out_f32) st32_f32(e.out_f32 + o, f);
           if (e.out_act) st32_bf16(reinterpret_cast<T*>(e.out_act) + o, f);
+        } else if (P.row_out) {
+          // (acc + bias) * scale -> fp32, no other epilogue tensor: thread = row would store 4 bytes to 32 different
+          // lines per instruction; through the staging block a warp writes 128 contiguous bytes of ONE row at a time
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = (__uint_as_float(v[j]) + ((e.bias && j < nc) ? __ldg(e.bias + col + j) : 0.f)) * st;
+          stage_f32_32(stgB, lane, f);
+          __syncwarp();
+          const int rows_here = (int)min(32LL, P.m - (long long)row0);
+          if (lane < nc) {
+            float* dst = e.out_f32 + (long long)row0 * e.ldo + col + lane;
+            for (int i = 0; i < rows_here; ++i)
+              dst[(long long)i * e.ldo] =
+                  *reinterpret_cast<const float*>(stgB + i * 128 + ((((lane >> 2) ^ (i & 7))) << 4) + (lane & 3) * 4);
+          }
+          __syncwarp();
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -712,7 +730,9 @@ int sa_tc_gemm_nt(int64_t m, int n, int k, const void* a, int64_t lda, const voi
   if (const char* env = getenv("SA_GEMM_TMA_OUT")) { if (env[0] == '0') P.tma_out = 0; }
   const size_t stage_bytes = G_BM * 128 + (size_t)(P.BN / cg) * 128;
   P.stages = pair ? G_STAGES_MAX : G_STAGES;
-  const size_t stg_bytes = P.tma_out ? 8 * 8192 : 0;
+  P.row_out = (!P.tma_out && !vec && e.out_f32 && !e.out_act && !e.pre && !e.dot_with && !e.resid && e.act == SA_ACT_NONE) ? 1 : 0;
+  if (const char* env = getenv("SA_GEMM_ROW_OUT")) { if (env[0] == '0') P.row_out = 0; }
+  const size_t stg_bytes = (P.tma_out || P.row_out) ? 8 * 8192 : 0;
   while (P.stages > 2 && (size_t)P.stages * stage_bytes + stg_bytes + 1024 > (size_t)g_max_smem - 2048) --P.stages;
   if (P.tma_out) {
     const uint64_t dims[2] = {(uint64_t)n, (uint64_t)m};
