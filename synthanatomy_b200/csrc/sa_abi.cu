@@ -214,7 +214,8 @@ extern "C" int sa_conv3d_wgrad(const sa_conv_desc* d, const void* p, const void*
     const size_t n = (size_t)d->ksize * d->ksize * d->ksize * d->c_out * d->c_in;
     SA_CUDA(cudaMemsetAsync(dwp, 0, n * sizeof(float), st));
   }
-  if (!sa_force_simt() && sa_tc_wgrad3_supported(d)) return sa_tc_conv3d_wgrad3(d, p, q, dwp, st);
-  if (!sa_force_simt() && sa_tc_wgrad_supported(d)) return sa_tc_conv3d_wgrad(d, p, q, dwp, st);
+  const bool dw_aligned = (reinterpret_cast<uintptr_t>(dwp) & 15) == 0;      // the tcgen05 epilogues add 16-byte vectors
+  if (!sa_force_simt() && dw_aligned && sa_tc_wgrad3_supported(d)) return sa_tc_conv3d_wgrad3(d, p, q, dwp, st);
+  if (!sa_force_simt() && dw_aligned && sa_tc_wgrad_supported(d)) return sa_tc_conv3d_wgrad(d, p, q, dwp, st);
   return sa_simt_conv3d_wgrad(d, p, q, dwp, st);
 }

@@ -95,13 +95,6 @@ __device__ __forceinline__ void sa_turn_wait(const unsigned* ctr, unsigned my) {
     __nanosleep(40);
   }
 }
-// a group of `nthreads` threads (named barrier `bar_id`) has finished its ordered additions: pass the turn on
-__device__ __forceinline__ void sa_group_turn_end(unsigned* ctr, unsigned my, int bar_id, int nthreads, bool leader) {
-  if (ctr == nullptr) return;
-  __threadfence();
-  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
-  if (leader) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctr), "r"(my + 1u) : "memory");
-}
 // the caller has made the partial's additions visible (__threadfence) and joined its threads (barrier) before this
 __device__ __forceinline__ void sa_turn_pass(unsigned* ctr, unsigned my) {
   if (ctr == nullptr) return;
@@ -118,6 +111,12 @@ __device__ __forceinline__ void sa_block_turn_end(unsigned* ctr, unsigned my) {
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) sa_turn_pass(ctr, my);
+}
+
+// fp32 reduction of four consecutive, 16-byte-aligned words in one instruction (REDG.ADD.F32x4): a quarter of the
+// instructions and L2 transactions of four scalar atomicAdds in the split-K epilogues (thread = row, 32+ columns each)
+__device__ __forceinline__ void sa_red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 __device__ __forceinline__ float sa_warp_sum(float v) {

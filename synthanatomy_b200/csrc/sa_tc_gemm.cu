@@ -529,6 +529,7 @@ struct TnParams {
   float scale;
   float* d;
   float* colsum;               // optional: colsum[i] += sum_r A[r][i] (unscaled) -- the bias gradient that goes with D
+  int red4;                    // D rows are 16-byte aligned: vector reductions
   float* parts;                // deterministic mode: split s stores its partial [na x nb | na column sums] at
   long long part_stride;       //   parts + s * part_stride (summed in split order afterwards)
 };
@@ -643,6 +644,11 @@ tc_gemm_tn_kernel(const __grid_constant__ TnParams P) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < nc) dst[j] = st * __uint_as_float(v[j]);
+        } else if (P.red4 && nc == 32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            sa_red_add_v4(dst + j, st * __uint_as_float(v[j]), st * __uint_as_float(v[j + 1]), st * __uint_as_float(v[j + 2]),
+                          st * __uint_as_float(v[j + 3]));
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -833,6 +839,7 @@ int sa_tc_gemm_tn_colsum(int64_t m, int na, int nb, const void* a, int64_t lda, 
   rc = make_2d(&P.bmap, b, (uint64_t)nb, (uint64_t)m, (uint64_t)ldb, 64, W_KP);
   if (rc != SA_OK) return rc;
   const size_t smem = (size_t)W_STAGES * (2 * W_BLOCK + (size_t)P.bblocks * W_BLOCK) + W_BLOCK + 1024;
+  P.red4 = ((nb & 3) == 0 && aligned16(d)) ? 1 : 0;
   P.part_stride = (long long)na * nb + (colsum ? na : 0);
   P.parts = sa_parts_alloc(splits, P.part_stride, st);
   tc_gemm_tn_kernel<<<(unsigned)(tiles * splits), W_THREADS, smem, st>>>(P);

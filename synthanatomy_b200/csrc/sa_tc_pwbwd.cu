@@ -263,7 +263,9 @@ tc_pw_kernel(const __grid_constant__ PwParams P) {
           for (int j = 0; j < 32; ++j) dst[hh * 32 + j] = __uint_as_float(v[j]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + hh * 32 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            sa_red_add_v4(dst + hh * 32 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
         }
       }
       if (half == 0) {
@@ -308,6 +310,7 @@ extern "C" int sa_conv1x1_bwd_fused_dbh(int64_t m, int c_out, int c_in, const vo
                                         void* dh, float* dwp, float* dbias, float* dbias_h, void* stream) {
   SA_CHECK_ARG(g && h && wp_t && dh && dwp && dbias, "null pointer");
   SA_CHECK_ARG(m > 0, "bad sizes");
+  SA_CHECK_ARG((reinterpret_cast<uintptr_t>(dwp) & 15) == 0, "dwp must be 16-byte aligned");
   SA_UNSUPPORTED(c_out != 128 || c_in != 128, "the fused pointwise backward is built for 128 -> 128 channels");
   SA_UNSUPPORTED(m >= (1LL << 31) - 256, "too many positions");
   if (!sa_get_tmap_encode()) { sa_set_error("cuTensorMapEncodeTiled unavailable"); return SA_ERR_CUDA; }

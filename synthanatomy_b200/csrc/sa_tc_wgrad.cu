@@ -152,9 +152,11 @@ tc_wgrad_kernel(const __grid_constant__ WgParams P) {
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        } else {
+        } else {                                   // rows of dWp are Cc floats: 16-byte aligned vector reductions
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            sa_red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
         }
       }
     }
