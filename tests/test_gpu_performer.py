@@ -648,3 +648,27 @@ def test_tcgen05_local_attention_rescale_path():
     finally:
         ops.set_force_simt(False)
     _close(lse, lse2, 1e-3, "lse tc vs simt (rescale path)")
+
+
+@pytest.mark.parametrize("m,n,k", [(1000, 2049, 512), (333, 77, 64), (4100, 1001, 128)])
+def test_tcgen05_gemm_nt_unaligned_fp32_rows(m, n, k):
+    """fp32 output whose rows start at odd 4-byte offsets (the logits, n = 2049): the epilogue transposes 32 x 32 chunks
+    through its staging blocks and stores row segments; same numbers as the per-thread epilogue (SA_GEMM_ROW_OUT=0)."""
+    import os
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(m + n)
+    a, b = _bf(torch.randn(m, k, generator=g)), _bf(torch.randn(n, k, generator=g) * 0.1)
+    bias = torch.randn(n, generator=g)
+    A, Bm = a.cuda().bfloat16(), b.cuda().bfloat16()
+    out = torch.full((m, n), 7.0, device="cuda")
+    pf.gemm_nt(A, Bm, bias=bias.cuda(), out_f32=out)
+    assert ops.last_path() == 2
+    want = a @ b.t() + bias
+    _close(out, want, 2e-5 * max(1.0, k / 256), "row-segment epilogue")
+    os.environ["SA_GEMM_ROW_OUT"] = "0"
+    try:
+        out2 = torch.empty_like(out)
+        pf.gemm_nt(A, Bm, bias=bias.cuda(), out_f32=out2)
+    finally:
+        del os.environ["SA_GEMM_ROW_OUT"]
+    assert torch.equal(out, out2)
