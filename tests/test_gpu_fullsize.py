@@ -157,3 +157,34 @@ def test_performer_config4_batch_permutation_equivariance():
         b = net(x[perm])
     assert tuple(a.shape) == (6, n, 2049) and torch.isfinite(a).all()
     assert torch.equal(a[perm], b)
+
+
+def test_local_attention_tc_matches_cuda_core_path_at_14000_tokens():
+    """window 420, look-back one window, 14 000 tokens (110 query tiles, ~15 key tiles each): the tcgen05 kernels (O, P, dS
+    resident in TMEM, lazily rescaled reference maximum) against the CUDA-core kernels on the same bf16 buffers"""
+    from synthanatomy_b200 import ops, pf_ops as pf
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, H, N, d, W = 1, 2, 14000, 64, 420
+    inner = H * d
+    buf = (torch.randn(B * N, 3 * inner, device="cuda", generator=g) * 0.7).bfloat16()
+    dout = torch.randn(B * N, inner, device="cuda", generator=g).bfloat16()
+    desc = pf.local_desc(B, N, H, d, W, 3 * inner, inner, torch.bfloat16)
+    res = []
+    for simt in (False, True):
+        ops.set_force_simt(simt)
+        try:
+            out = torch.zeros(B * N, inner, device="cuda", dtype=torch.bfloat16)
+            lse = torch.empty(B * H, N, device="cuda")
+            dbuf = torch.zeros_like(buf)
+            pf.local_attn_fwd(desc, buf, 0, inner, 2 * inner, None, out, 0, lse)
+            assert ops.last_path() == (1 if simt else 2)
+            pf.local_attn_bwd(desc, buf, 0, inner, 2 * inner, None, out, dout, 0, lse, dbuf)
+            res.append((out.float(), lse.clone(), dbuf.float()))
+        finally:
+            ops.set_force_simt(False)
+    (o_tc, l_tc, d_tc), (o_ref, l_ref, d_ref) = res
+    torch.testing.assert_close(l_tc, l_ref, rtol=0, atol=2e-3)
+    assert float((o_tc - o_ref).abs().max()) <= 2e-2 * float(o_ref.abs().max())
+    for i, name in enumerate(("dq", "dk", "dv")):
+        a, b = d_tc[:, i * inner:(i + 1) * inner], d_ref[:, i * inner:(i + 1) * inner]
+        assert float((a - b).abs().max()) <= 2e-2 * float(b.abs().max()), name
