@@ -36,7 +36,14 @@ constexpr size_t kTurnRing = 1u << 20;          // counters (4 MB)
 struct TurnPool { unsigned* base = nullptr; size_t next = 0; };
 TurnPool g_turn[64];
 std::mutex g_turn_mu;
+thread_local bool g_det_failed = false;
 }  // namespace
+
+bool sa_det_alloc_failed() {
+  const bool f = g_det_failed;
+  g_det_failed = false;
+  return f;
+}
 
 bool sa_deterministic() { return g_deterministic != 0; }
 extern "C" void sa_set_deterministic(int on) { g_deterministic = on; }
@@ -45,19 +52,24 @@ extern "C" int sa_get_deterministic(void) { return g_deterministic; }
 unsigned* sa_turn_slot(int n, cudaStream_t st) {
   if (!g_deterministic || n <= 0) return nullptr;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { g_det_failed = true; return nullptr; }
   const size_t want = ((size_t)n + 31) & ~(size_t)31;
-  if (want > kTurnRing) return nullptr;
+  if (want > kTurnRing) { g_det_failed = true; return nullptr; }
   std::lock_guard<std::mutex> lock(g_turn_mu);
   TurnPool& pool = g_turn[dev];
   if (!pool.base) {
-    if (cudaMalloc(&pool.base, kTurnRing * sizeof(unsigned)) != cudaSuccess) { pool.base = nullptr; return nullptr; }
+    if (cudaMalloc(&pool.base, kTurnRing * sizeof(unsigned)) != cudaSuccess) {
+      pool.base = nullptr;
+      cudaGetLastError();
+      g_det_failed = true;
+      return nullptr;
+    }
   }
   if (pool.next + want > kTurnRing) pool.next = 0;
   unsigned* slot = pool.base + pool.next;
   pool.next += want;
   // zeroed on the launch's own stream: a slot comes round again only after 2^20 counters' worth of later launches
-  if (cudaMemsetAsync(slot, 0, want * sizeof(unsigned), st) != cudaSuccess) return nullptr;
+  if (cudaMemsetAsync(slot, 0, want * sizeof(unsigned), st) != cudaSuccess) { g_det_failed = true; return nullptr; }
   return slot;
 }
 
@@ -94,6 +106,7 @@ float* sa_parts_alloc(int64_t nparts, int64_t stride, cudaStream_t st) {
   void* p = nullptr;
   if (cudaMallocAsync(&p, (size_t)nparts * (size_t)stride * sizeof(float), st) != cudaSuccess) {
     cudaGetLastError();
+    g_det_failed = true;
     return nullptr;
   }
   return (float*)p;

@@ -22,6 +22,9 @@ bool sa_force_simt();
 // arrival order with plain atomics), else `n` zeroed counters valid for ONE launch on `st`.
 bool sa_deterministic();
 unsigned* sa_turn_slot(int n, cudaStream_t st);
+// true (once) when a deterministic-mode buffer could not be provided since the last call on this thread: the launch that
+// asked for it would have fallen back to arrival-order atomics, so SA_LAUNCH_CHECK turns it into an error instead
+bool sa_det_alloc_failed();
 // scalar sums (losses, gate / stabiliser gradients) in deterministic mode: every contributor writes its partial into its
 // own word of a zeroed slot (sa_partial_slot; nullptr when the mode is off) and sa_ordered_sum adds them to out[0] in
 // index order (one CTA, fixed tree)
@@ -69,6 +72,10 @@ int sa_parts_free(float* parts, cudaStream_t st);
       return SA_ERR_CUDA;                                                               \
     }                                                                                   \
     sa_note_launch();                                                                   \
+    if (sa_det_alloc_failed()) {                                                        \
+      sa_set_error("%s: deterministic mode: could not allocate the ordered-sum buffers", __func__); \
+      return SA_ERR_CUDA;                                                               \
+    }                                                                                   \
   } while (0)
 
 static inline cudaStream_t sa_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -400,7 +400,7 @@ extern "C" int sa_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* tar
                              float grad_scale, const float* grad_scale_dev, float* loss_sum, float* dlogits, void* stream) {
   SA_CHECK_ARG(logits && target && rows > 0 && vocab > 0 && ld >= vocab, "bad arguments");
   const int64_t blocks = sa_cdiv(rows, 8);
-  float* partials = loss_sum && blocks <= (1 << 19) ? sa_partial_slot((int)blocks, sa_stream(stream)) : nullptr;
+  float* partials = loss_sum ? sa_partial_slot((int)blocks, sa_stream(stream)) : nullptr;
   ce_kernel<<<(unsigned)blocks, 256, 0, sa_stream(stream)>>>(logits, ld, (const long long*)target, rows, vocab, grad_scale,
                                                              grad_scale_dev, loss_sum, dlogits, partials);
   SA_LAUNCH_CHECK();
