@@ -530,7 +530,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
   constexpr int NST = TS ? L_STAGES_BWD + 2 : L_STAGES_BWD;    // TS: the P^T / dS^T buffers' shared memory holds Q/dO stages
   __shared__ uint64_t qd_full[NST], qd_empty[NST];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_lse2[2][64], s_delta[2][64];
+  __shared__ __align__(16) float s_lse2[2][64], s_delta[2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Ks = smem;                       // 16 KB [128 keys x 64]
@@ -655,11 +655,21 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
         tmem_ld_wait();
         float fp[32], fd[32];
         if (!full) lc_apply_mask(vs, hh ? mhi : mlo);       // boundary tile: hidden scores -> -inf -> probability 0
+        // the tile's per-query statistics as 16-byte broadcast reads (one LDS.128 per four scores instead of two LDS.32
+        // per score: the shared-memory pipe was 25 % busy with them)
+        const float4* l4 = reinterpret_cast<const float4*>(&s_lse2[buf][hh * 32]);
+        const float4* d4 = reinterpret_cast<const float4*>(&s_delta[buf][hh * 32]);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float pr = ex2(fmaf(__uint_as_float(vs[c]), c2, -s_lse2[buf][hh * 32 + c]));
-          fp[c] = pr;
-          fd[c] = pr * (__uint_as_float(vd[c]) - s_delta[buf][hh * 32 + c]);                    // d^-1/2: applied to dK
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 lq = l4[c4], dq4 = d4[c4];
+          const float lv[4] = {lq.x, lq.y, lq.z, lq.w}, dv[4] = {dq4.x, dq4.y, dq4.z, dq4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            const float pr = ex2(fmaf(__uint_as_float(vs[c]), c2, -lv[e]));
+            fp[c] = pr;
+            fd[c] = pr * (__uint_as_float(vd[c]) - dv[e]);                                       // d^-1/2: applied to dK
+          }
         }
         if (TS) {
           uint32_t u[16];
