@@ -22,7 +22,7 @@ template <int DIM>
 __global__ void __launch_bounds__(VQ_THREADS)
 vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ cb, int64_t rows, int n_embed,
                   int64_t* __restrict__ idx_out, float* __restrict__ q_out, int straight_through,
-                  float* __restrict__ counts, float* __restrict__ dw, float* __restrict__ sse, unsigned* turn) {
+                  float* __restrict__ counts, float* __restrict__ dw, float* __restrict__ sse) {
   extern __shared__ float smem[];
   float* s_cb = smem;                          // [VQ_CODE_CHUNK][DIM + 1]  (+1: conflict-free row reads)
   float* s_w2 = smem + VQ_CODE_CHUNK * (DIM + 1);  // [VQ_CODE_CHUNK]
@@ -105,13 +105,11 @@ vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ cb, int
     local_sse = sa_warp_sum(local_sse);
     if ((t & 31) == 0) s_red[t >> 5] = local_sse;
     __syncthreads();
-    sa_block_turn_begin(turn, blockIdx.x);      // deterministic mode: the blocks add in block order
     if (t == 0) {
       float s = 0.f;
       for (int i = 0; i < VQ_THREADS / 32; ++i) s += s_red[i];
       atomicAdd(sse, s);
     }
-    sa_block_turn_end(turn, blockIdx.x);
   }
 }
 
@@ -133,6 +131,33 @@ vq_dw_ordered_kernel(const float* __restrict__ z, const int64_t* __restrict__ id
     float s = 0.f;
     for (int j = 0; j < LANES; ++j) s += s_part[j * DIM + c];
     dw[(int64_t)k * DIM + c] += s;
+  }
+}
+
+// deterministic mode: the loss numerator sum (codebook[idx] - z)^2 as one partial per block (fixed tree inside the block),
+// added in block order by sa_ordered_sum.  A separate kernel on purpose: any ordered-sum code inside vq_forward_kernel --
+// a turnstile, a second store target, even an index computation for the atomic -- moved it from 127 to 155-170 us per launch
+// at config 3 with the mode switched OFF (the kernel is a latency-bound 32-FMA chain per code; its code layout matters).
+template <int DIM>
+__global__ void __launch_bounds__(256)
+vq_sse_ordered_kernel(const float* __restrict__ z, const float* __restrict__ cb, const int64_t* __restrict__ idx,
+                      int64_t rows, float* __restrict__ partials) {
+  constexpr int RPB = 256 / DIM;
+  __shared__ float s_w[8];
+  const int c = threadIdx.x % DIM;
+  const int64_t row = (int64_t)blockIdx.x * RPB + threadIdx.x / DIM;
+  float v = 0.f;
+  if (row < rows) {
+    const float df = __fsub_rn(cb[idx[row] * DIM + c], z[row * DIM + c]);
+    v = df * df;
+  }
+  v = sa_warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += s_w[i];
+    partials[blockIdx.x] = s;
   }
 }
 
@@ -225,17 +250,21 @@ extern "C" int sa_vq_forward(const float* z, const float* codebook, int64_t rows
   cudaStream_t st = sa_stream(stream);
   const unsigned grid = (unsigned)sa_cdiv(rows, VQ_ROWS_PER_BLOCK);
   const size_t smem = (size_t)(VQ_CODE_CHUNK * (dim + 1) + VQ_CODE_CHUNK) * sizeof(float);
-  // deterministic mode: the loss sum goes through the turnstile and the per-code sums of z come from a second, ordered
-  // kernel (the counts are sums of ones: exact in fp32 below 2^24 rows per code, hence order-free)
-  unsigned* turn = sse ? sa_turn_slot(1, st) : nullptr;
-  float* dw_ordered = sa_deterministic() ? dw : nullptr;
-  if (dw_ordered) dw = nullptr;
+  // deterministic mode: the forward kernel only counts (sums of ones: exact in fp32 below 2^24 rows per code, hence
+  // order-free); the per-code sums of z and the loss sum come from two ordered kernels after it
+  const bool det = sa_deterministic();
+  float* dw_ordered = det ? dw : nullptr;
+  float* sse_ordered = det ? sse : nullptr;
+  if (det) { dw = nullptr; sse = nullptr; }
+  const int sse_blocks = (int)sa_cdiv(rows, 256 / dim);
+  float* sse_parts = sse_ordered ? sa_partial_slot(sse_blocks, st) : nullptr;
 #define SA_VQ_LAUNCH(D)                                                                                            \
   do {                                                                                                             \
     SA_CUDA(cudaFuncSetAttribute(vq_forward_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     vq_forward_kernel<D><<<grid, VQ_THREADS, smem, st>>>(z, codebook, rows, n_embed, idx, q, straight_through, counts, \
-                                                         dw, sse, turn);                                          \
+                                                         dw, sse);                                                     \
     if (dw_ordered) vq_dw_ordered_kernel<D><<<(unsigned)n_embed, 256, 0, st>>>(z, idx, rows, dw_ordered);          \
+    if (sse_parts) vq_sse_ordered_kernel<D><<<(unsigned)sse_blocks, 256, 0, st>>>(z, codebook, idx, rows, sse_parts); \
   } while (0)
   switch (dim) {
     case 8: SA_VQ_LAUNCH(8); break;
@@ -245,6 +274,7 @@ extern "C" int sa_vq_forward(const float* z, const float* codebook, int64_t rows
   }
 #undef SA_VQ_LAUNCH
   SA_LAUNCH_CHECK();
+  if (sse_parts) return sa_ordered_sum(sse_parts, sse_blocks, sse_ordered, st);
   return SA_OK;
 }
 
