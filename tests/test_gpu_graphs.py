@@ -100,3 +100,51 @@ def test_graphed_performer_step_equals_eager_and_redraws_outside_the_graph():
         assert torch.isfinite(loss)
         seen.append(proj.detach().clone())
     assert any(not torch.equal(seen[0], s) for s in seen[1:]), "no projection redraw happened between replays"
+
+
+def test_graphed_step_in_deterministic_mode_replays_bit_identically():
+    """the deterministic mode's ordered-sum buffers (stream-ordered cudaMallocAsync / cudaFreeAsync partials, zeroed counter
+    slots) are captured with the step: two replays on the same batch at lr = 0 give bit-identical losses and gradients, and
+    they equal a second, independently captured graph (Performer with fixed projections: no state changes under replay)"""
+    from synthanatomy_b200 import ops
+    from synthanatomy_b200.losses import CELoss
+    from synthanatomy_b200.networks.transformers import Ordering, Performer
+    from synthanatomy_b200.optim import Adam
+    from synthanatomy_b200.utils.graphs import GraphedTrainStep
+    grid = (6, 7, 8)
+    n = int(np.prod(grid))
+    order = Ordering("raster_scan", 3, (1, *grid), (False,) * 3, ((2, 0, 1),), ((0, 1),), ("rotate_90", "transpose"))
+    kw = dict(num_tokens=65, dim=128, depth=2, heads=4, dim_head=64, local_attn_heads=2, local_window_size=20,
+              max_seq_len=n + 1, ordering=order, causal=True, feature_redraw_interval=1, use_rezero=True,
+              spatial_position_emb="absolute", spatial_shape=grid, compute_dtype=torch.bfloat16)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randint(0, 64, (3, n), device="cuda", generator=g)
+    y = torch.randint(0, 64, (3, n), device="cuda", generator=g)
+    fwd = lambda m, t: m(t).transpose(1, 2)          # TransformerTrainingInferer
+    ops.set_deterministic(True)
+    try:
+        results = []
+        for _ in range(2):
+            torch.manual_seed(0)
+            net = Performer(**kw).cuda().train()
+            net.fix_projection_matrices_()
+            with torch.no_grad():
+                for layer in net.performer.net.layers:
+                    layer[0].g.fill_(0.5); layer[1].g.fill_(0.5)
+            opt = Adam(net.parameters(), lr=0.0)
+            step = GraphedTrainStep(net, CELoss(), opt, (x,), y, warmup=2, forward=fwd)
+            runs = []
+            for _ in range(2):
+                loss = step(x, target=y).detach().clone()
+                runs.append((loss, [p.grad.clone() for p in net.parameters() if p.grad is not None]))
+            assert torch.isfinite(runs[0][0])
+            assert torch.equal(runs[0][0], runs[1][0])
+            for a, b in zip(runs[0][1], runs[1][1]):
+                assert torch.equal(a, b)
+            results.append(runs[0])
+            step.release()
+        assert torch.equal(results[0][0], results[1][0])
+        for a, b in zip(results[0][1], results[1][1]):
+            assert torch.equal(a, b)
+    finally:
+        ops.set_deterministic(None)
