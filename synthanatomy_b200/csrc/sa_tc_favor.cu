@@ -135,9 +135,12 @@ __device__ __forceinline__ void stage_proj(uint8_t* Ps, const float* __restrict_
   }
 }
 
-// delta[bh][n] = dout[n] . out[n] and 1 / den[bh][n], once per backward pass (four kernels need them per row)
+// delta[bh][n] = dout[n] . out[n] and 1 / den[bh][n], once per backward pass (four kernels need them per row); optionally
+// also dout_s = dout / den (bf16, dense [B * N][H * 64]): the W operand of the backward state scan, which then arrives by
+// TMA like v does in the forward scan instead of being rebuilt per chunk by that kernel's running-state warps
 __global__ void fv_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                                const float* __restrict__ den, float2* __restrict__ dinv, int B, int N, int H, int out_ld) {
+                                const float* __restrict__ den, float2* __restrict__ dinv, int B, int N, int H, int out_ld,
+                                __nv_bfloat16* __restrict__ dout_s) {
   const long long total = (long long)B * N * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int h = (int)(i % H);
@@ -145,7 +148,20 @@ __global__ void fv_delta_kernel(const __nv_bfloat16* __restrict__ out, const __n
     const int n = (int)(row % N), b = (int)(row / N);
     const long long ro = row * out_ld + h * 64;
     const long long o = ((long long)b * H + h) * N + n;
-    dinv[o] = make_float2(row_dot64(out + ro, dout + ro), 1.0f / den[o]);
+    const float inv = 1.0f / den[o];
+    dinv[o] = make_float2(row_dot64(out + ro, dout + ro), inv);
+    if (dout_s) {
+      const uint4* src = reinterpret_cast<const uint4*>(dout + ro);
+      uint4* dst = reinterpret_cast<uint4*>(dout_s + row * (long long)(H * 64) + h * 64);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float f[8];
+        unpack8(__ldg(src + q), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= inv;
+        dst[q] = pack8(f);
+      }
+    }
   }
 }
 
@@ -174,6 +190,7 @@ struct FvParams {
   const __nv_bfloat16* st_vec;       // dqk: the bf16 states (their row 64 is read directly)
   __nv_bfloat16* st_out;             // state_scan: the bf16 prefix / suffix states it writes
   const float2* dinv;                // backward: per (batch, head, position) {delta = dout . out, 1 / den}
+  int w_tma;                         // state_scan<1>: the W operand (dout / den, prepared by fv_delta_kernel) arrives by TMA (map_b)
 };
 
 #define FV_PROLOGUE(NBAR_INIT)                                                              \
@@ -565,16 +582,17 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
   if (warp == 9) {
     // ------------------------------------------------------------ TMA producer (the last chunk in walking order is never added)
     if (lane == 0) {
+      const bool w_tma = MODE == 0 || P.w_tma;
       prefetch_tmap(&P.map_a);
-      if (MODE == 0) prefetch_tmap(&P.map_b);
+      if (w_tma) prefetch_tmap(&P.map_b);
       for (int it = 0; it + 1 < nch; ++it) {
         const int s = it % SS_STAGES;
         const int chunk = MODE ? nch - 1 - it : it;
         mbar_wait(&f_empty[s], (uint32_t)(((it / SS_STAGES) & 1) ^ 1));
-        mbar_expect_tx(&f_full[s], (uint32_t)nb * BLK + (MODE == 0 ? BLK : 0u));
+        mbar_expect_tx(&f_full[s], (uint32_t)nb * BLK + (w_tma ? BLK : 0u));
         uint8_t* st = smem + s * stage_bytes;
         for (int cb = 0; cb < nb; ++cb) tma_load_3d(st + (2 + cb) * BLK, &P.map_a, &f_full[s], (cb_beg + cb) * 64, chunk * FC, bh);
-        if (MODE == 0) tma_load_3d(st, &P.map_b, &f_full[s], h * 64, chunk * FC, b);
+        if (w_tma) tma_load_3d(st, &P.map_b, &f_full[s], h * 64, chunk * FC, b);
       }
     }
   } else if (warp == 8) {
@@ -610,6 +628,20 @@ tc_state_scan_kernel(const __grid_constant__ FvParams P) {
       const int chunk = nch - 1 - it;
       const int n = chunk * FC + r;
       uint8_t* Ws = smem + s * stage_bytes;
+      if (P.w_tma) {               // W arrives by TMA: only the aug column is written here (one thread per row)
+        if (hf == 0) {
+          float aug = 0.f;
+          if (n < P.N) {
+            const float2 di = __ldg(P.dinv + (long long)bh * P.N + n);
+            aug = -di.x * di.y;
+          }
+          __nv_bfloat16* p0 = reinterpret_cast<__nv_bfloat16*>(sw_row(Ws + BLK, r) + ((0 ^ (r & 7)) << 4));
+          *p0 = __float2bfloat16_rn(aug);
+        }
+        fence_proxy_async();
+        mbar_arrive(&w_ready[s]);
+        return;
+      }
       float f[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = 0.f;
@@ -1261,12 +1293,17 @@ dim3 fv_grid(const sa_favor_desc* d) { return dim3((unsigned)sa_cdiv(d->seq, FC)
 // chunk sums + prefix:  mode 0: (kf, v) forward prefix;  mode 1: (qf, dout / den) suffix
 int launch_states(const sa_favor_desc* d, int mode, const void* feat, const void* w, const void* out, const void* dout,
                   int out_ld, const float* den, float eps, float* sums, void* states, cudaStream_t st,
-                  const float2* dinv = nullptr) {
+                  const float2* dinv = nullptr, const void* dout_s = nullptr) {
   static thread_local FvParams P;
   fill_common(P, d, out_ld, eps);
   int rc;
   if ((rc = feat_map(&P.map_a, feat, d)) != SA_OK) return rc;
   if (mode == 0 && (rc = head_map(&P.map_b, w, d, d->ld)) != SA_OK) return rc;
+  P.w_tma = 0;
+  if (mode == 1 && dout_s) {
+    if ((rc = head_map(&P.map_b, dout_s, d, d->heads * 64)) != SA_OK) return rc;
+    P.w_tma = 1;
+  }
   P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.den_in = den; P.sums = sums; P.dinv = dinv;
   bool serial = true;                                  // SA_FAVOR_STATE_SCAN=0: the two-kernel form (chunk sums, then prefix)
   if (const char* e = getenv("SA_FAVOR_STATE_SCAN")) serial = e[0] != '0';
@@ -1423,15 +1460,24 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
     return rc;
   }
   float2* dinv = reinterpret_cast<float2*>(stR + states_bytes(d));
+  // dout / den for the backward state scan lives in the chunk-sum region of the workspace (unused by the state-scan form)
+  __nv_bfloat16* dout_s = nullptr;
+  {
+    bool serial = true;
+    if (const char* e = getenv("SA_FAVOR_STATE_SCAN")) serial = e[0] != '0';
+    if (const char* e = getenv("SA_FAVOR_W_TMA")) { if (e[0] == '0') serial = false; }       // A/B switch
+    const size_t need = (size_t)d->batch * d->seq * d->heads * 64 * sizeof(__nv_bfloat16);
+    if (serial && need <= sums_bytes(d)) dout_s = reinterpret_cast<__nv_bfloat16*>(sums);
+  }
   {
     const long long total = (long long)d->batch * d->seq * d->heads;
     long long blocks = sa_cdiv(total, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     fv_delta_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, den, dinv, d->batch,
-                                                      d->seq, d->heads, out_ld);
+                                                      d->seq, d->heads, out_ld, dout_s);
     SA_LAUNCH_CHECK();
   }
-  if ((rc = launch_states(d, 1, qf, nullptr, out, dout, out_ld, den, eps, sums, stR, st, dinv)) != SA_OK) return rc;
+  if ((rc = launch_states(d, 1, qf, nullptr, out, dout, out_ld, den, eps, sums, stR, st, dinv, dout_s)) != SA_OK) return rc;
   static thread_local FvParams P;
   const size_t smem = SMEM_DQK;
   // dq'
