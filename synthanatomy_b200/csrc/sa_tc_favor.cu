@@ -106,20 +106,6 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
   return u;
 }
-// dot product of two 64-element bf16 rows in global memory
-__device__ __forceinline__ float row_dot64(const __nv_bfloat16* a, const __nv_bfloat16* b) {
-  const uint4* pa = reinterpret_cast<const uint4*>(a);
-  const uint4* pb = reinterpret_cast<const uint4*>(b);
-  float acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float x[8], y[8];
-    unpack8(__ldg(pa + i), x); unpack8(__ldg(pb + i), y);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc = fmaf(x[j], y[j], acc);
-  }
-  return acc;
-}
 
 // P [m][64] fp32 (global) -> bf16 128B-swizzled [mp rows][64] block image (rows >= m are zero)
 __device__ __forceinline__ void stage_proj(uint8_t* Ps, const float* __restrict__ proj, int m, int mp, int tid) {
@@ -138,29 +124,38 @@ __device__ __forceinline__ void stage_proj(uint8_t* Ps, const float* __restrict_
 // delta[bh][n] = dout[n] . out[n] and 1 / den[bh][n], once per backward pass (four kernels need them per row); optionally
 // also dout_s = dout / den (bf16, dense [B * N][H * 64]): the W operand of the backward state scan, which then arrives by
 // TMA like v does in the forward scan instead of being rebuilt per chunk by that kernel's running-state warps
-__global__ void fv_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                                const float* __restrict__ den, float2* __restrict__ dinv, int B, int N, int H, int out_ld,
-                                __nv_bfloat16* __restrict__ dout_s) {
-  const long long total = (long long)B * N * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int h = (int)(i % H);
-    const long long row = i / H;                  // b * N + n
+__global__ void __launch_bounds__(256)
+fv_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                const float* __restrict__ den, float2* __restrict__ dinv, int B, int N, int H, int out_ld,
+                __nv_bfloat16* __restrict__ dout_s) {
+  // eight lanes per (row, head): one 16-byte piece of the 64 columns each (coalesced), the dot product through shuffles
+  const long long total = (long long)B * N * H * 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;          // a multiple of 32: a warp stays together
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 - (threadIdx.x & 31) < total; i0 += stride) {
+    const bool live = i0 < total;
+    const long long i = live ? i0 : total - 1;
+    const int q = (int)(i & 7);
+    const long long rh = i >> 3;
+    const int h = (int)(rh % H);
+    const long long row = rh / H;                 // b * N + n
     const int n = (int)(row % N), b = (int)(row / N);
-    const long long ro = row * out_ld + h * 64;
+    const long long ro = row * out_ld + h * 64 + q * 8;
     const long long o = ((long long)b * H + h) * N + n;
+    float fo[8], fd[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(out + ro)), fo);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dout + ro)), fd);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(fo[j], fd[j], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     const float inv = 1.0f / den[o];
-    dinv[o] = make_float2(row_dot64(out + ro, dout + ro), inv);
-    if (dout_s) {
-      const uint4* src = reinterpret_cast<const uint4*>(dout + ro);
-      uint4* dst = reinterpret_cast<uint4*>(dout_s + row * (long long)(H * 64) + h * 64);
+    if (live && q == 0) dinv[o] = make_float2(acc, inv);
+    if (live && dout_s) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float f[8];
-        unpack8(__ldg(src + q), f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] *= inv;
-        dst[q] = pack8(f);
-      }
+      for (int j = 0; j < 8; ++j) fd[j] *= inv;
+      *reinterpret_cast<uint4*>(dout_s + row * (long long)(H * 64) + h * 64 + q * 8) = pack8(fd);
     }
   }
 }
@@ -1470,9 +1465,9 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
     if (serial && need <= sums_bytes(d)) dout_s = reinterpret_cast<__nv_bfloat16*>(sums);
   }
   {
-    const long long total = (long long)d->batch * d->seq * d->heads;
+    const long long total = (long long)d->batch * d->seq * d->heads * 8;
     long long blocks = sa_cdiv(total, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > 148 * 32) blocks = 148 * 32;
     fv_delta_kernel<<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, den, dinv, d->batch,
                                                       d->seq, d->heads, out_ld, dout_s);
     SA_LAUNCH_CHECK();
