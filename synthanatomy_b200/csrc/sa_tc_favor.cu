@@ -771,15 +771,28 @@ tc_scan_kernel(const __grid_constant__ FvParams P) {
   uint8_t* Ws = smem + SC_STAGES * SC_STAGE;
   uint8_t* Am = smem;                    // 2 blocks, re-using stage 0 after the feature loop
   constexpr int NST = MODE == 0 ? ST_ROWS : 64;
+  // the first loads go out BEFORE the TMEM allocation (which waits for a finishing CTA of this SM to release its columns):
+  // the ring stages are free at this point, so the chunk's first blocks arrive while the allocation is pending
+  auto issue_stage = [&](int cb, int stage) {
+    mbar_expect_tx(&full[stage], SC_STAGE);
+    uint8_t* s = Ring + stage * SC_STAGE;
+    tma_load_3d(s, &P.map_a, &full[stage], cb * 64, n0, bh);
+    tma_load_3d(s + BLK, &P.map_b, &full[stage], cb * 64, n0, bh);
+    tma_load_2d(s + 2 * BLK, &P.map_c, &full[stage], cb * 64, (bh * P.nchunks + chunk) * ST_ROWS);
+  };
+  const int npre = P.nblk < SC_STAGES ? P.nblk : SC_STAGES;
+  if (warp == 9 && lane == 0) {
+    prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b); prefetch_tmap(&P.map_c); prefetch_tmap(&P.map_d);
+    mbar_expect_tx(&w_full, BLK);
+    tma_load_3d(Ws, &P.map_d, &w_full, h * 64, n0, b);
+    for (int cb = 0; cb < npre; ++cb) issue_stage(cb, cb);
+  }
   FV_ALLOC();
   const uint32_t tA = tmem_base, tO = tmem_base + 128;
   if (warp == 9) {
     if (lane == 0) {
-      prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b); prefetch_tmap(&P.map_c); prefetch_tmap(&P.map_d);
-      mbar_expect_tx(&w_full, BLK);
-      tma_load_3d(Ws, &P.map_d, &w_full, h * 64, n0, b);
-      int stage = 0; uint32_t phase = 0;
-      for (int cb = 0; cb < P.nblk; ++cb) {
+      int stage = npre % SC_STAGES; uint32_t phase = npre == SC_STAGES ? 1u : 0u;
+      for (int cb = npre; cb < P.nblk; ++cb) {
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], SC_STAGE);
         uint8_t* s = Ring + stage * SC_STAGE;
@@ -908,18 +921,25 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
   uint8_t* Bm = smem + BLK;              // 2 blocks; the first one holds Y until B' = X Y^T has been formed
   uint8_t* Ys = Bm;
   uint8_t* Ring = smem + 3 * BLK;
+  const int npre = P.nblk < DQ_STAGES ? P.nblk : DQ_STAGES;
   if (warp == 9 && lane == 0) {
     prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b); prefetch_tmap(&P.map_c); prefetch_tmap(&P.map_d);
     mbar_expect_tx(&xy_full, 2 * BLK);
     tma_load_3d(Xs, &P.map_a, &xy_full, h * 64, n0, b);
     tma_load_3d(Ys, &P.map_b, &xy_full, h * 64, n0, b);
+    for (int cb = 0; cb < npre; ++cb) {      // the free ring stages too: they arrive while the TMEM allocation is pending
+      mbar_expect_tx(&ring_full[cb], DQ_STAGE);
+      uint8_t* sp = Ring + cb * DQ_STAGE;
+      tma_load_3d(sp, &P.map_c, &ring_full[cb], cb * 64, n0, bh);
+      tma_load_2d(sp + BLK, &P.map_d, &ring_full[cb], cb * 64, (bh * P.nchunks + chunk) * ST_ROWS);
+    }
   }
   FV_ALLOC();
   const uint32_t tB = tmem_base, tD = tmem_base + 128;
   if (warp == 9) {
     if (lane == 0) {       // (after the CTA-wide barrier of the TMEM allocation: this loop waits on the MMA warp)
-      int stage = 0; uint32_t phase = 0;
-      for (int cb = 0; cb < P.nblk; ++cb) {
+      int stage = npre % DQ_STAGES; uint32_t phase = npre == DQ_STAGES ? 1u : 0u;
+      for (int cb = npre; cb < P.nblk; ++cb) {
         mbar_wait(&ring_empty[stage], phase ^ 1);
         mbar_expect_tx(&ring_full[stage], DQ_STAGE);
         uint8_t* sp = Ring + stage * DQ_STAGE;
