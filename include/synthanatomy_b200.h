@@ -228,6 +228,19 @@ int sa_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, in
                     int64_t spatial, void* stream);
 /* dst = (dst_dtype) src, n elements */
 int sa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+/* Per-step preparation of dense-layer weights, many tensors per launch: for each item dst[r][c] = bf16(src[r][c])
+ * (leading dimension dst_ld; NULL: skipped) and dst_t[c][r] = bf16(src[r][c]) (leading dimension dst_t_ld; NULL: skipped);
+ * src fp32 dense [rows][cols].  `items` is host memory.  Pointer + leading-dimension pairs let several sources land in
+ * one destination (q | k | v weights -> one [3 inner x dim] operand and its transpose). */
+typedef struct sa_wprep_item {
+  const float* src;
+  void* dst;
+  void* dst_t;
+  int rows, cols;
+  int dst_ld, dst_t_ld;
+} sa_wprep_item;
+int sa_weight_prep(const sa_wprep_item* items, int n, void* stream);
 /* sse[0] += sum (a-b)^2 ; grad = scale * scale_dev[0] * (a - b)  (F.mse_loss fwd+bwd,
  * src/losses/vqvae/vqvae.py:56).  a: prediction (a_dtype), b: target fp32; sse, grad (a_dtype) and the DEVICE
  * scalar scale_dev (the incoming loss gradient) may each be NULL. */

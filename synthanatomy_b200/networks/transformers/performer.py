@@ -17,6 +17,7 @@ statistics, softmax / feature-map statistics, logits and all gradients of parame
 from __future__ import annotations
 
 import math
+import weakref
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -357,6 +358,72 @@ def _t(w: torch.Tensor) -> torch.Tensor:
     return ops.ncdhw_to_ndhwc(w.contiguous().view(1, n, k), w.dtype).view(k, n)
 
 
+class _WeightPrep:
+    """bf16 copies of every layer's dense weights (q | k | v concatenated) and their transposes, refreshed once per forward
+    pass by ONE multi-tensor launch (`sa_weight_prep`) into buffers that live as long as the module's parameters stay where
+    they are.  Before: a concat, four casts and four transposes per layer and step (218 launches at depth 24)."""
+
+    def __init__(self, net: "Performer", D: "_Dims", dev):
+        layers = net.performer.net.layers
+        self.key = self._key(net)
+        inner, dim, ff = D.inner, D.dim, D.ff
+        per = 2 * (3 * inner * dim + inner * dim + 2 * ff * dim)
+        self.buf = torch.empty((len(layers) * per,), device=dev, dtype=torch.bfloat16)
+        self.fwd, self.bwd = [], []
+        items = []
+        off = 0
+
+        def take(rows, cols):
+            nonlocal off
+            t = self.buf[off:off + rows * cols].view(rows, cols)
+            off += rows * cols
+            return t
+
+        for layer in layers:
+            att, ffn = layer[0].fn, layer[1].fn.fn
+            Wq, Wk, Wv, Wo = att.to_q.weight, att.to_k.weight, att.to_v.weight, att.to_out.weight
+            W1, W2 = ffn.w1.weight, ffn.w2.weight
+            qkv, qkv_t = take(3 * inner, dim), take(dim, 3 * inner)
+            o, o_t = take(dim, inner), take(inner, dim)
+            w1, w1_t = take(ff, dim), take(dim, ff)
+            w2, w2_t = take(dim, ff), take(ff, dim)
+            for i, W in enumerate((Wq, Wk, Wv)):
+                items.append((W, qkv[i * inner:], qkv_t[:, i * inner:], inner, dim, dim, 3 * inner))
+            items.append((Wo, o, o_t, dim, inner, inner, dim))
+            items.append((W1, w1, w1_t, ff, dim, dim, ff))
+            items.append((W2, w2, w2_t, dim, ff, ff, dim))
+            self.fwd.append((qkv, o, w1, w2))
+            self.bwd.append((qkv_t, o_t, w1_t, w2_t))
+        arr = (ops._lib.WPrepItem * len(items))()
+        for a, (W, d, dt_, rows, cols, ld, ldt) in zip(arr, items):
+            assert tuple(W.shape) == (rows, cols) and W.dtype == torch.float32 and W.is_contiguous()
+            a.src, a.dst, a.dst_t = W.data_ptr(), d.data_ptr(), dt_.data_ptr()
+            a.rows, a.cols, a.dst_ld, a.dst_t_ld = rows, cols, ld, ldt
+        self.items, self.n = arr, len(items)
+
+    @staticmethod
+    def _key(net):
+        return tuple(p.data_ptr() for p in net.performer.net.layers.parameters())
+
+    def refresh(self):
+        ops._lib.check(ops.lib().sa_weight_prep(self.items, self.n, ops._stream()), "sa_weight_prep")
+
+
+_WPREP: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _weight_prep(net: "Performer", D: "_Dims", dev) -> Optional[_WeightPrep]:
+    """the module's prepared bf16 weights for this pass, or None where the per-layer path applies (fp32 / bf16x3 arithmetic)"""
+    if D.dt != torch.bfloat16:
+        return None
+    wp = _WPREP.get(net)
+    if wp is None or wp.buf.device != dev or wp.key != _WeightPrep._key(net):
+        wp = _WeightPrep(net, D, dev)
+        _WPREP[net] = wp               # (not a module attribute: the ctypes table must not travel with deepcopy / pickle)
+    wp.refresh()
+    return wp
+
+
 class _Ctx:
     """what every piece of the programme shares for one forward / backward pass"""
 
@@ -364,6 +431,7 @@ class _Ctx:
         self.net, self.x3, self.dev = net, x3, dev
         self.lead = 0
         self.D = D = _Dims(net, B, N, dt)
+        self.wp = None if x3 else _weight_prep(net, D, dev)
         self.fd = pf_ops.favor_desc(B, N, D.gh, D.dh, D.m, D.mp, 3 * D.inner, dt) if D.gh > 0 else None
         self.ld = pf_ops.local_desc(B, N, D.lh, D.dh, D.W, 3 * D.inner, D.inner, dt) if D.lh > 0 else None
 
@@ -436,8 +504,11 @@ class _LayerFn(torch.autograd.Function):
         x32 = x32.detach()
         xa = x32 if (is32 or xa is None) else xa.detach()
         attn_mod = net.performer.net.layers[li][0].fn
-        Wqkv = _as(torch.cat((Wq, Wk, Wv), dim=0), dt)
-        Wo_, W1_, W2_ = _as(Wo, dt), _as(W1, dt), _as(W2, dt)
+        if C.wp is not None:                   # prepared for all layers by one launch at the top of the pass
+            Wqkv, Wo_, W1_, W2_ = C.wp.fwd[li]
+        else:
+            Wqkv = _as(torch.cat((Wq, Wk, Wv), dim=0), dt)
+            Wo_, W1_, W2_ = _as(Wo, dt), _as(W1, dt), _as(W2, dt)
         # ---- attention sub-layer
         xa_attn = xa
         qkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
@@ -481,6 +552,7 @@ class _LayerFn(torch.autograd.Function):
             ctx.C = C
             ctx.saved = (xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_mid, u, h, proj, inv_freq, states)
             ctx.weights = (Wqkv, Wo_, W1_, W2_)
+            ctx.weights_t = C.wp.bwd[li] if C.wp is not None else None
             ctx.scalars = (g_a, g_f, b1, b2)
             ctx.masters = (Wo, W2)
         if is32:
@@ -504,6 +576,10 @@ class _LayerFn(torch.autograd.Function):
             raise RuntimeError("Performer: second backward through a layer whose activations were released")
         xa_attn, qkv, qf, kf, argq, kmax, den, lse, attn, xa_ffn, u, h, proj, inv_freq, states = ctx.saved
         Wqkv, Wo_, W1_, W2_ = ctx.weights
+        if ctx.weights_t is not None:
+            Wqkv_t, Wo_t, W1_t, W2_t = ctx.weights_t
+        else:
+            Wqkv_t, Wo_t, W1_t, W2_t = _t(Wqkv), _t(Wo_), _t(W1_), _t(W2_)
         g_a, g_f, b1, b2 = ctx.scalars
         Wo, W2 = ctx.masters
         ctx.saved = ctx.weights = ctx.masters = None
@@ -514,7 +590,7 @@ class _LayerFn(torch.autograd.Function):
         #  GEMM's epilogue does not have to stream h again)
         dot = torch.zeros((1,), device=dev, dtype=f32)
         du = torch.empty((M, D.ff), device=dev, dtype=dt)
-        pf_ops.gemm_nt(dxa, _t(W2_), scale_dev=g_f, act=SA_ACT_MUL_PRE, pre=u, out_act=du)
+        pf_ops.gemm_nt(dxa, W2_t, scale_dev=g_f, act=SA_ACT_MUL_PRE, pre=u, out_act=du)
         colsum = torch.empty((D.dim,), device=dev, dtype=f32)
         dW2 = torch.empty((D.dim, D.ff), device=dev, dtype=f32)
         pf_ops.gemm_tn(dxa, h, dW2, colsum=colsum)         # + the column sums of dx (bias gradient) from the same tiles
@@ -527,12 +603,12 @@ class _LayerFn(torch.autograd.Function):
         pf_ops.gemm_tn(du, xa_ffn, dW1, colsum=db1)
         d_mid = torch.empty((M, D.dim), device=dev, dtype=f32)
         dxa_mid = d_mid if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
-        pf_ops.gemm_nt(du, _t(W1_), resid=g32, out_f32=d_mid, out_act=None if is32 else dxa_mid)
+        pf_ops.gemm_nt(du, W1_t, resid=g32, out_f32=d_mid, out_act=None if is32 else dxa_mid)
         del du, u, h
         # ---- attention sub-layer: x_mid = x + g_a * (attn Wo^T)
         dot = torch.zeros((1,), device=dev, dtype=f32)
         dattn = torch.empty((M, D.inner), device=dev, dtype=dt)
-        pf_ops.gemm_nt(dxa_mid, _t(Wo_), scale_dev=g_a, out_act=dattn)
+        pf_ops.gemm_nt(dxa_mid, Wo_t, scale_dev=g_a, out_act=dattn)
         dWo = torch.empty((D.dim, D.inner), device=dev, dtype=f32)
         pf_ops.gemm_tn(dxa_mid, attn, dWo)
         pf_ops.gate_wgrad(dWo, Wo, g_a, dot)               # dg_a = sum (dx^T attn) . Wo;  dWo *= g_a
@@ -559,7 +635,7 @@ class _LayerFn(torch.autograd.Function):
         pf_ops.gemm_tn(dqkv, xa_attn, dWqkv)
         dx = torch.empty((M, D.dim), device=dev, dtype=f32)
         dxa_in = None if is32 else torch.empty((M, D.dim), device=dev, dtype=dt)
-        pf_ops.gemm_nt(dqkv, _t(Wqkv), resid=d_mid, out_f32=dx, out_act=dxa_in)
+        pf_ops.gemm_nt(dqkv, Wqkv_t, resid=d_mid, out_f32=dx, out_act=dxa_in)
         if dxa_in is not None:
             _GRAD_COPY["last"] = (dx.data_ptr(), dxa_in)
         return (dx, None, None, None, dot.view(()), dWqkv[:D.inner], dWqkv[D.inner:2 * D.inner], dWqkv[2 * D.inner:], dWo,
