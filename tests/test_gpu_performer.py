@@ -672,3 +672,30 @@ def test_tcgen05_gemm_nt_unaligned_fp32_rows(m, n, k):
     finally:
         del os.environ["SA_GEMM_ROW_OUT"]
     assert torch.equal(out, out2)
+
+
+def test_weight_prep_multi_tensor():
+    """sa_weight_prep: bf16 copies and transposes of many fp32 matrices in one launch, several sources into one destination"""
+    import ctypes as C
+    from synthanatomy_b200 import _lib
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(9)
+    shapes = [(70, 33), (128, 512), (5, 1000), (257, 64)] * 15          # 60 items: more than one launch
+    srcs = [torch.randn(r, c, generator=g).cuda() for r, c in shapes]
+    dsts = [torch.zeros(r, c, device="cuda", dtype=torch.bfloat16) for r, c in shapes]
+    dts = [torch.zeros(c, r, device="cuda", dtype=torch.bfloat16) for r, c in shapes]
+    # two more sources stacked into one [6 x 40] destination and its [40 x 6] transpose
+    a, b = torch.randn(2, 40, generator=g).cuda(), torch.randn(4, 40, generator=g).cuda()
+    cat, cat_t = torch.zeros(6, 40, device="cuda", dtype=torch.bfloat16), torch.zeros(40, 6, device="cuda", dtype=torch.bfloat16)
+    items = (_lib.WPrepItem * (len(shapes) + 2))()
+    for it, s, d, t in zip(items, srcs, dsts, dts):
+        it.src, it.dst, it.dst_t = s.data_ptr(), d.data_ptr(), t.data_ptr()
+        it.rows, it.cols, it.dst_ld, it.dst_t_ld = s.shape[0], s.shape[1], s.shape[1], s.shape[0]
+    for it, s, r0 in ((items[len(shapes)], a, 0), (items[len(shapes) + 1], b, 2)):
+        it.src, it.dst, it.dst_t = s.data_ptr(), cat[r0:].data_ptr(), cat_t[:, r0:].data_ptr()
+        it.rows, it.cols, it.dst_ld, it.dst_t_ld = s.shape[0], 40, 40, 6
+    _lib.check(ops.lib().sa_weight_prep(items, len(items), torch.cuda.current_stream().cuda_stream), "sa_weight_prep")
+    for s, d, t in zip(srcs, dsts, dts):
+        assert torch.equal(d, s.bfloat16()) and torch.equal(t, s.bfloat16().t())
+    want = torch.cat((a, b)).bfloat16()
+    assert torch.equal(cat, want) and torch.equal(cat_t, want.t())
