@@ -133,6 +133,15 @@ int sa_conv1x1_fwd_fused(int64_t m, int c_out, int c_in, const void* x, const vo
  * back into the torch-layout .grad. */
 int sa_pack_weight(const float* src, int A, int B, int taps, int transpose, int flip, void* dst,
                    int dst_dtype, void* stream);
+
+/* sa_pack_weight for many weights in a few launches (`items` is host memory; one destination dtype per call) */
+typedef struct sa_wpack_item {
+  const float* src;
+  void* dst;
+  int A, B, taps;
+  int transpose, flip;
+} sa_wpack_item;
+int sa_pack_weight_multi(const sa_wpack_item* items, int n, int dst_dtype, void* stream);
 int sa_unpack_wgrad(const float* src, int A, int B, int taps, int transpose, int flip, float* dst,
                     int accumulate, void* stream);
 

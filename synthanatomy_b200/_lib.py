@@ -66,6 +66,12 @@ class LocalDesc(C.Structure):
 SA_ACT_NONE, SA_ACT_GELU_FWD, SA_ACT_GELU_BWD, SA_ACT_GELU_FWD_D, SA_ACT_MUL_PRE = 0, 1, 2, 3, 4
 
 # name -> (restype, argtypes); the single source of truth for tests/test_abi.py as well
+class WPackItem(C.Structure):
+    """sa_wpack_item (include/synthanatomy_b200.h)"""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("A", C.c_int), ("B", C.c_int), ("taps", C.c_int),
+                ("transpose", C.c_int), ("flip", C.c_int)]
+
+
 class WPrepItem(C.Structure):
     """sa_wprep_item (include/synthanatomy_b200.h)"""
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_t", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int),
@@ -102,6 +108,7 @@ SIGNATURES = {
     "sa_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p]),
     "sa_cast": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
     "sa_weight_prep": (c_int, [c_void_p, c_int, c_void_p]),
+    "sa_pack_weight_multi": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "sa_bn_workspace": (C.c_size_t, [c_int]),
     "sa_bn_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p]),

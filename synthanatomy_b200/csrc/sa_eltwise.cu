@@ -322,6 +322,62 @@ extern "C" int sa_pack_weight(const float* src, int A, int B, int taps, int tran
   return SA_OK;
 }
 
+// many weights per launch (blockIdx.y = weight): the per-pass packing of a whole network's conv weights, forward and
+// transposed (data-gradient) forms, in a few launches instead of two per conv and step
+namespace {
+constexpr int WPACK_BATCH = 48;
+struct WPackBatch {
+  const float* src[WPACK_BATCH];
+  void* dst[WPACK_BATCH];
+  int A[WPACK_BATCH], B[WPACK_BATCH], taps[WPACK_BATCH];
+  unsigned char transpose[WPACK_BATCH], flip[WPACK_BATCH];
+};
+
+template <typename TO>
+__global__ void pack_weight_multi_kernel(const __grid_constant__ WPackBatch b) {
+  const int w = blockIdx.y;
+  const int A = b.A[w], B = b.B[w], taps = b.taps[w];
+  const int transpose = b.transpose[w], flip = b.flip[w];
+  const float* __restrict__ src = b.src[w];
+  TO* __restrict__ dst = reinterpret_cast<TO*>(b.dst[w]);
+  const int64_t n = (int64_t)A * B * taps;
+  const int R = transpose ? B : A, C = transpose ? A : B;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int r = (int)((i / C) % R);
+    const int tp = (int)(i / ((int64_t)C * R));
+    const int t = flip ? taps - 1 - tp : tp;
+    const int a = transpose ? c : r, bb = transpose ? r : c;
+    sa_st(dst, i, src[((int64_t)a * B + bb) * taps + t]);
+  }
+}
+}  // namespace
+
+extern "C" int sa_pack_weight_multi(const sa_wpack_item* items, int n, int dst_dtype, void* stream) {
+  SA_CHECK_ARG(items != nullptr && n >= 0, "bad arguments");
+  SA_CHECK_ARG(dst_dtype == SA_F32 || dst_dtype == SA_BF16, "bad dtype");
+  cudaStream_t st = sa_stream(stream);
+  for (int base = 0; base < n; base += WPACK_BATCH) {
+    WPackBatch b = {};
+    const int cnt = n - base < WPACK_BATCH ? n - base : WPACK_BATCH;
+    int64_t nmax = 1;
+    for (int i = 0; i < cnt; ++i) {
+      const sa_wpack_item& it = items[base + i];
+      SA_CHECK_ARG(it.src && it.dst && it.A > 0 && it.B > 0 && it.taps > 0, "bad item");
+      b.src[i] = it.src; b.dst[i] = it.dst; b.A[i] = it.A; b.B[i] = it.B; b.taps[i] = it.taps;
+      b.transpose[i] = (unsigned char)(it.transpose != 0); b.flip[i] = (unsigned char)(it.flip != 0);
+      const int64_t ni = (int64_t)it.A * it.B * it.taps;
+      if (ni > nmax) nmax = ni;
+    }
+    unsigned gx = ew_grid(nmax, 4);
+    if (gx > 148 * 2) gx = 148 * 2;
+    if (dst_dtype == SA_BF16) pack_weight_multi_kernel<__nv_bfloat16><<<dim3(gx, (unsigned)cnt), EW_THREADS, 0, st>>>(b);
+    else pack_weight_multi_kernel<float><<<dim3(gx, (unsigned)cnt), EW_THREADS, 0, st>>>(b);
+    SA_LAUNCH_CHECK();
+  }
+  return SA_OK;
+}
+
 extern "C" int sa_unpack_wgrad(const float* src, int A, int B, int taps, int transpose, int flip, float* dst,
                                int accumulate, void* stream) {
   SA_CHECK_ARG(src && dst, "null pointer");

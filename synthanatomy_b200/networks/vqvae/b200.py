@@ -16,6 +16,7 @@ is always fp32 (baseline.py:38,43).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -216,6 +217,7 @@ def _stack_backward(ops_list, saved, params, g, in_is_relu: bool, need_dx: bool,
 # weight, /root/reference/src/engines/trainer.py:264-289: two autograd.grad(..., retain_graph=True) before backward() --
 # wraps the iteration in `retain_activations()`.
 _RETAIN_ACTIVATIONS = [False]
+_PACK_PLANS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()    # module -> {id(programme): ops.PackPlan}
 
 
 class retain_activations:
@@ -270,6 +272,7 @@ class _OpFn(torch.autograd.Function):
             y, saved = _stack_forward([op], x.detach(), pdet, need_grad)
         if need_grad:
             ctx.op, ctx.saved, ctx.pdet, ctx.relu_in, ctx.x3 = op, saved, pdet, relu_in, x3
+            ctx.plan = ops.current_pack_plan()       # the transposed packs of the backward pass come from the same plan
         return y
 
     @staticmethod
@@ -277,7 +280,7 @@ class _OpFn(torch.autograd.Function):
         if ctx.saved is None:
             raise RuntimeError("B200VQVAE: second backward through a layer whose activations were released; wrap the "
                                "iteration in synthanatomy_b200.networks.vqvae.b200.retain_activations()")
-        with ops.x3_mode(ctx.x3):
+        with ops.x3_mode(ctx.x3), ops.pack_plan(ctx.plan, begin=False):
             dx, grads = _stack_backward([ctx.op], ctx.saved, ctx.pdet, g.contiguous(), ctx.relu_in,
                                         ctx.needs_input_grad[0], allow_relu_tail=True)
         if not _RETAIN_ACTIVATIONS[0]:
@@ -504,9 +507,13 @@ class B200VQVAE(VQVAEBase, nn.Module):
         dt, x3 = ops.resolve_dtype(self._dtype())     # BF16X3: fp32 tensors, split-bf16 tensor-core products
         h = _InFn.apply(x, dt)
         relu_in = False                               # is the op's input a post-ReLU tensor?  (mask fused into its dgrad)
-        for op in prog:
-            h = _OpFn.apply(h, op, relu_in, x3, *op.params())
-            relu_in = True if isinstance(op, _ResOp) else op.relu
+        # every conv weight of the stack (forward and transposed forms) is packed by a few multi-tensor launches here
+        plans = _PACK_PLANS.setdefault(self, {})
+        plan = plans.setdefault(id(prog), ops.PackPlan())
+        with ops.pack_plan(plan):
+            for op in prog:
+                h = _OpFn.apply(h, op, relu_in, x3, *op.params())
+                relu_in = True if isinstance(op, _ResOp) else op.relu
         return _OutFn.apply(h, dt)
 
     # ---- VQVAEBase API (baseline.py:301-362) ----

@@ -165,14 +165,93 @@ def _desc(batch, in_dhw, out_dhw, c_in, c_out, k, s, p, transposed, dtype) -> Co
     return d
 
 
+class PackPlan:
+    """The packed forms (forward and transposed, per dtype) of one stack's conv weights, refreshed by a few multi-tensor
+    launches at the top of a pass instead of two `sa_pack_weight` launches per conv and step.  The first pass through a
+    stack records what it packs; `begin()` of every later pass re-packs all of it into the same buffers and stamps the
+    entries with the pass number, and `pack_weight` hands out an entry only while its stamp is the current one -- anything
+    not (or no longer) covered is packed the old way and recorded."""
+
+    def __init__(self):
+        self.entries = {}            # key -> [w, out, A, B, taps, transpose, flip, stamp]
+        self.epoch = 0
+        self._tables = None          # dtype -> (ctypes item array, n), rebuilt when the entries change
+
+    def begin(self) -> None:
+        self.epoch += 1
+        if not self.entries:
+            return
+        if self._tables is None:
+            by_dtype = {}
+            for e in self.entries.values():
+                by_dtype.setdefault(e[1].dtype, []).append(e)
+            self._tables = {}
+            for dt, es in by_dtype.items():
+                arr = (_lib.WPackItem * len(es))()
+                for a, (w, out, A, B, taps, tr, fl, _) in zip(arr, es):
+                    a.src, a.dst, a.A, a.B, a.taps, a.transpose, a.flip = w.data_ptr(), out.data_ptr(), A, B, taps, int(tr), int(fl)
+                self._tables[dt] = (arr, len(es))
+        for dt, (arr, n) in self._tables.items():
+            _lib.check(lib().sa_pack_weight_multi(arr, n, _dt(dt), _stream()), "sa_pack_weight_multi")
+        for e in self.entries.values():
+            e[7] = self.epoch
+
+    def lookup(self, key):
+        e = self.entries.get(key)
+        return e[1] if e is not None and e[7] == self.epoch else None
+
+    def record(self, key, w, out, A, B, taps, transpose, flip) -> None:
+        if len(self.entries) >= 1024:        # weights that move every pass (a dtype-converted copy) must not pile up here
+            self.entries.clear()
+        self.entries[key] = [w, out, A, B, taps, transpose, flip, self.epoch]
+        self._tables = None
+
+
+_PACK_PLAN: Optional[PackPlan] = None
+
+
+class pack_plan:
+    """`with pack_plan(plan):` -- pack_weight calls inside consult / feed `plan`; begin=True refreshes it first (top of a
+    forward pass), begin=False only makes it current (the backward pass of ops recorded under it)."""
+
+    def __init__(self, plan: Optional[PackPlan], begin: bool = True):
+        self.plan, self.begin = plan, begin
+
+    def __enter__(self):
+        global _PACK_PLAN
+        self.prev = _PACK_PLAN
+        _PACK_PLAN = self.plan
+        if self.plan is not None and self.begin:
+            self.plan.begin()
+        return self.plan
+
+    def __exit__(self, *exc):
+        global _PACK_PLAN
+        _PACK_PLAN = self.prev
+        return False
+
+
+def current_pack_plan() -> Optional[PackPlan]:
+    return _PACK_PLAN
+
+
 def pack_weight(w: torch.Tensor, transpose: bool, dtype: torch.dtype, flip: bool = False) -> torch.Tensor:
     """torch layout [A][B][k,k,k] fp32 -> packed [taps][A][B] (or [taps][B][A] if transpose) in `dtype`."""
     A, B = w.shape[0], w.shape[1]
     taps = w[0, 0].numel()
+    plan = _PACK_PLAN
+    key = None
+    if plan is not None:
+        key = (w.data_ptr(), tuple(w.shape), bool(transpose), dtype, bool(flip))
+        hit = plan.lookup(key)
+        if hit is not None:
+            return hit
     R, Cc = (B, A) if transpose else (A, B)
     out = torch.empty((taps, R, Cc), device=w.device, dtype=dtype)
     _lib.check(lib().sa_pack_weight(_p(w), A, B, taps, int(transpose), int(flip), _p(out), _dt(dtype), _stream()),
                "sa_pack_weight")
+    if plan is not None:
+        plan.record(key, w, out, A, B, taps, bool(transpose), bool(flip))
     return out
 
 
