@@ -192,6 +192,14 @@ int sa_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, cons
 int sa_local_attn_bwd_ws(const sa_local_desc* d, const void* q, const void* k, const void* v, const float* inv_freq,
                          const void* out, const void* dout, const float* lse, void* dq, void* dk, void* dv,
                          float* delta_ws, void* stream);
+/* q and k already carry the rotary term (sa_rotary / sa_rotary_qk applied in place before sa_local_attn_fwd, inv_freq ==
+ * NULL there): dq and dk leave through the transpose of the rotation, applied to the fp32 gradient rows inside the
+ * kernels' epilogues instead of a separate in-place pass over the stored gradients.  rot_table: [seq][dim_head / 2]
+ * (cos, sin) pairs of n * inv_freq, fp32, 16-byte aligned, written by sa_rotary_table (same sincosf as sa_rotary). */
+int sa_rotary_table(const float* inv_freq, int seq, int dim_head, float* table, void* stream);
+int sa_local_attn_bwd_rot(const sa_local_desc* d, const void* q, const void* k, const void* v, const float* inv_freq,
+                          const float* rot_table, const void* out, const void* dout, const float* lse, void* dq, void* dk,
+                          void* dv, float* delta_ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Autoregressive sampling with recurrent state.  The reference re-runs the whole network

@@ -47,7 +47,8 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc*, const void*, const void*, const v
 bool sa_tc_local_supported(const sa_local_desc*, const void*, const void*, const void*, const float*);
 int sa_tc_local_attn_fwd(const sa_local_desc*, const void*, const void*, const void*, void*, float*, cudaStream_t);
 int sa_tc_local_attn_bwd(const sa_local_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
-                         void*, void*, void*, float*, cudaStream_t);
+                         void*, void*, void*, float*, const float*, cudaStream_t);
+int sa_rotary_table_launch(const float*, int, int, float*, cudaStream_t);
 int sa_rotary_launch(void*, int, int64_t, int, int, int, int, const float*, int, cudaStream_t);
 int sa_rotary_qk_launch(void*, int, int64_t, int64_t, int, int, int, int, const float*, int, cudaStream_t);
 
@@ -196,8 +197,29 @@ extern "C" int sa_local_attn_bwd_ws(const sa_local_desc* d, const void* q, const
                                     void* dk, void* dv, float* delta_ws, void* stream) {
   SA_CHECK_ARG(d && q && k && v && out && dout && lse && dq && dk && dv, "null pointer");
   if (!sa_force_simt() && sa_tc_local_supported(d, q, k, v, inv_freq))
-    return sa_tc_local_attn_bwd(d, q, k, v, out, dout, lse, dq, dk, dv, delta_ws, sa_stream(stream));
+    return sa_tc_local_attn_bwd(d, q, k, v, out, dout, lse, dq, dk, dv, delta_ws, nullptr, sa_stream(stream));
   return sa_simt_local_attn_bwd(d, q, k, v, inv_freq, out, dout, lse, dq, dk, dv, sa_stream(stream));
+}
+
+extern "C" int sa_rotary_table(const float* inv_freq, int seq, int dim_head, float* table, void* stream) {
+  SA_CHECK_ARG(inv_freq && table, "null pointer");
+  SA_CHECK_ARG(seq > 0 && dim_head > 0 && (dim_head & 1) == 0, "bad sizes");
+  return sa_rotary_table_launch(inv_freq, seq, dim_head / 2, table, sa_stream(stream));
+}
+
+extern "C" int sa_local_attn_bwd_rot(const sa_local_desc* d, const void* q, const void* k, const void* v,
+                                     const float* inv_freq, const float* rot_table, const void* out, const void* dout,
+                                     const float* lse, void* dq, void* dk, void* dv, float* delta_ws, void* stream) {
+  SA_CHECK_ARG(d && q && k && v && inv_freq && rot_table && out && dout && lse && dq && dk && dv, "null pointer");
+  SA_CHECK_ARG((reinterpret_cast<uintptr_t>(rot_table) & 15) == 0, "rot_table must be 16-byte aligned");
+  cudaStream_t st = sa_stream(stream);
+  if (!sa_force_simt() && sa_tc_local_supported(d, q, k, v, nullptr))
+    return sa_tc_local_attn_bwd(d, q, k, v, out, dout, lse, dq, dk, dv, delta_ws, rot_table, st);
+  // CUDA-core kernels: the gradients of the rotated q / k, then the transpose of the rotation as its own in-place pass
+  int rc = sa_simt_local_attn_bwd(d, q, k, v, nullptr, out, dout, lse, dq, dk, dv, st);
+  if (rc != SA_OK) return rc;
+  if ((rc = sa_rotary_launch(dq, d->act_dtype, d->ld, d->batch, d->seq, d->heads, d->dim_head, inv_freq, 1, st)) != SA_OK) return rc;
+  return sa_rotary_launch(dk, d->act_dtype, d->ld, d->batch, d->seq, d->heads, d->dim_head, inv_freq, 1, st);
 }
 
 extern "C" int sa_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, const void* v,

@@ -50,6 +50,7 @@ struct LcParams {
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
   float* delta_ws;           // optional [batch * heads][seq]: delta = dO . O per query, written by the dq kernel for the dk/dv kernel
+  const float2* rot;         // optional [seq][32] (cos, sin): q / k carry the rotary term, dq / dk leave through its transpose
 };
 
 __device__ __forceinline__ int lc_lo(int p, int W) { const int w = p / W - 1; return (w > 0 ? w : 0) * W; }
@@ -111,6 +112,20 @@ __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const float
     u.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]); u.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
     u.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]); u.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
     q[i] = u;
+  }
+}
+
+// transpose of the rotary map on one 64-wide gradient row (pairs (e, e + 32); table row = 32 x (cos, sin) of the position):
+// the forward pass rotated q / k in place, so their gradients leave the attention kernels through the inverse rotation
+// -- in registers, on the fp32 values, instead of a separate in-place pass over the stored bf16 gradients
+__device__ __forceinline__ void lc_unrotate64(float (&g)[64], const float2* __restrict__ tb) {
+#pragma unroll
+  for (int e4 = 0; e4 < 16; ++e4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(tb) + e4);      // (cos, sin) of frequencies 2 e4, 2 e4 + 1
+    const int e = 2 * e4;
+    const float a0 = g[e], b0 = g[e + 32], a1 = g[e + 1], b1 = g[e + 33];
+    g[e] = a0 * t.x + b0 * t.y;      g[e + 32] = b0 * t.x - a0 * t.y;
+    g[e + 1] = a1 * t.z + b1 * t.w;  g[e + 33] = b1 * t.z - a1 * t.w;
   }
 }
 
@@ -511,6 +526,7 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
     if (row_ok) {
 #pragma unroll
       for (int e = 0; e < 64; ++e) g[e] *= P.scale;       // dS = P (dP - delta) d^-1/2: the factor commutes with the product
+      if (P.rot) lc_unrotate64(g, P.rot + (long long)p * 32);
       store_row64_bf16(P.dq + ((long long)b * P.N + p) * P.ld + h * 64, g);
     }
   }
@@ -708,6 +724,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
       if (which) {
 #pragma unroll
         for (int e = 0; e < 64; ++e) g[e] *= P.scale;
+        if (P.rot && j < P.N) lc_unrotate64(g, P.rot + (long long)j * 32);
       }
       if (j < P.N) store_row64_bf16((which ? P.dk : P.dv) + ((long long)b * P.N + j) * P.ld + h * 64, g);
     }
@@ -803,6 +820,18 @@ rotary_qk_vec_kernel(__nv_bfloat16* __restrict__ buf, long long ld, long long k_
   }
 }
 
+// (cos, sin)(n * inv_freq[dd]) with the same sincosf the rotary kernels evaluate
+__global__ void rotary_table_kernel(const float* __restrict__ inv_freq, int N, int half, float2* __restrict__ table) {
+  const long long total = (long long)N * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int dd = (int)(i % half);
+    const int n = (int)(i / half);
+    float sn, cs;
+    sincosf((float)n * inv_freq[dd], &sn, &cs);
+    table[i] = make_float2(cs, sn);
+  }
+}
+
 std::once_flag g_once;
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -836,7 +865,7 @@ void fill_common(LcParams& P, const sa_local_desc* d) {
   P.scale = 1.0f / sqrtf((float)d->dim_head);
   { const char* env = getenv("SA_LOCAL_FASTMASK"); P.fast = (env && env[0] == '0') ? 0 : 1; }
   P.out = nullptr; P.dout = nullptr; P.o_out = nullptr; P.lse = nullptr; P.dq = P.dk = P.dv = nullptr;
-  P.delta_ws = nullptr;
+  P.delta_ws = nullptr; P.rot = nullptr;
 }
 
 }  // namespace
@@ -867,9 +896,17 @@ int sa_tc_local_attn_fwd(const sa_local_desc* d, const void* q, const void* k, c
   return SA_OK;
 }
 
+int sa_rotary_table_launch(const float* inv_freq, int seq, int half, float* table, cudaStream_t st) {
+  long long blocks = sa_cdiv((long long)seq * half, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rotary_table_kernel<<<(unsigned)blocks, 256, 0, st>>>(inv_freq, seq, half, reinterpret_cast<float2*>(table));
+  SA_LAUNCH_CHECK();
+  return SA_OK;
+}
+
 int sa_tc_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, const void* v, const void* out,
                          const void* dout, const float* lse, void* dq, void* dk, void* dv, float* delta_ws,
-                         cudaStream_t st) {
+                         const float* rot_table, cudaStream_t st) {
   init_once();
   sa_note_path(SA_PATH_TCGEN05);
   if (!aligned16(out) || !aligned16(dout) || !aligned16(dq) || !aligned16(dk) || !aligned16(dv)) {
@@ -881,6 +918,7 @@ int sa_tc_local_attn_bwd(const sa_local_desc* d, const void* q, const void* k, c
   P.out = (const __nv_bfloat16*)out; P.dout = (const __nv_bfloat16*)dout; P.lse = const_cast<float*>(lse);
   P.dq = (__nv_bfloat16*)dq; P.dk = (__nv_bfloat16*)dk; P.dv = (__nv_bfloat16*)dv;
   P.delta_ws = delta_ws;
+  P.rot = reinterpret_cast<const float2*>(rot_table);
   int rc;
   // dq kernel: 128-row Q / dO boxes, 64-row K / V boxes
   if ((rc = make_map(&P.qmap, q, d, d->ld, 128)) != SA_OK) return rc;

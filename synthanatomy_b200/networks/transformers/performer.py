@@ -17,6 +17,7 @@ statistics, softmax / feature-map statistics, logits and all gradients of parame
 from __future__ import annotations
 
 import math
+import os
 import weakref
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -424,6 +425,23 @@ def _weight_prep(net: "Performer", D: "_Dims", dev) -> Optional[_WeightPrep]:
     return wp
 
 
+# (cos, sin) tables of the local heads' rotary term, read by the local-attention backward kernels' epilogues.  One entry
+# per frequency buffer (every layer owns one); the entry keeps the buffer alive, so its address cannot be reused, and a
+# load_state_dict / in-place write moves _version.
+_ROT_TABLES = {}
+
+
+def _rot_table(inv_freq: torch.Tensor, N: int, dh: int) -> torch.Tensor:
+    key = (inv_freq.data_ptr(), inv_freq._version, N, dh)
+    hit = _ROT_TABLES.get(key)
+    if hit is None:
+        if len(_ROT_TABLES) >= 256:
+            _ROT_TABLES.clear()
+        hit = (inv_freq, pf_ops.rotary_table(inv_freq, N, dh))
+        _ROT_TABLES[key] = hit
+    return hit[1]
+
+
 class _Ctx:
     """what every piece of the programme shares for one forward / backward pass"""
 
@@ -615,9 +633,14 @@ class _LayerFn(torch.autograd.Function):
         dqkv = torch.empty((M, 3 * D.inner), device=dev, dtype=dt)
         if D.lh > 0:
             c0 = D.gh * D.dh
-            pf_ops.local_attn_bwd(C.ld, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, dattn, c0, lse, dqkv)
-            if inv_freq is not None:       # transpose of the rotary map on the gradients of the rotated q / k
+            if inv_freq is not None and os.environ.get("SA_LOCAL_ROT_FUSED", "1") == "0":      # A/B: the two-pass form
+                pf_ops.local_attn_bwd(C.ld, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, dattn, c0, lse, dqkv)
                 pf_ops.rotary_qk(dqkv, c0, D.inner + c0, B, N, D.lh, D.dh, inv_freq, True)
+            elif inv_freq is not None:     # the gradients of the rotated q / k leave through the transpose of the rotary map
+                pf_ops.local_attn_bwd_rot(C.ld, qkv, c0, D.inner + c0, 2 * D.inner + c0, inv_freq,
+                                          _rot_table(inv_freq, N, D.dh), attn, dattn, c0, lse, dqkv)
+            else:
+                pf_ops.local_attn_bwd(C.ld, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, dattn, c0, lse, dqkv)
         if D.gh > 0:
             fd = C.fd
             dqf = torch.empty_like(qf)

@@ -267,6 +267,22 @@ def local_attn_bwd(d, buf, qcol, kcol, vcol, inv_freq, out, dout, ocol, lse, dbu
                                           _ptr(dbuf, vcol), _p(delta_ws), _stream()), "sa_local_attn_bwd")
 
 
+def rotary_table(inv_freq: torch.Tensor, seq: int, dim_head: int) -> torch.Tensor:
+    """[seq, dim_head / 2, 2] fp32 (cos, sin) of n * inv_freq, evaluated as the rotary kernels evaluate them"""
+    table = torch.empty((seq, dim_head // 2, 2), device=inv_freq.device, dtype=torch.float32)
+    _lib.check(lib().sa_rotary_table(_p(inv_freq), seq, dim_head, _p(table), _stream()), "sa_rotary_table")
+    return table
+
+
+def local_attn_bwd_rot(d, buf, qcol, kcol, vcol, inv_freq, rot_table, out, dout, ocol, lse, dbuf) -> None:
+    """local_attn_bwd for q / k rotated in place before the forward call: dq / dk leave through the rotation's transpose"""
+    delta_ws = torch.empty_like(lse)
+    _lib.check(lib().sa_local_attn_bwd_rot(C.byref(d), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol), _p(inv_freq),
+                                           _p(rot_table), _ptr(out, ocol), _ptr(dout, ocol), _p(lse), _ptr(dbuf, qcol),
+                                           _ptr(dbuf, kcol), _ptr(dbuf, vcol), _p(delta_ws), _stream()),
+               "sa_local_attn_bwd_rot")
+
+
 # ------------------------------------------------------------------------------------------------
 # token plumbing between the two models
 # ------------------------------------------------------------------------------------------------
@@ -380,6 +396,6 @@ def _instrument(name, fn):
 
 
 for _n in ("gemm_nt", "gemm_tn", "embed_fwd", "embed_bwd", "layernorm_fwd", "layernorm_bwd", "ce_fwd_bwd", "cast2d",
-           "rotary", "rotary_qk", "favor_kmax", "favor_featmap_fwd", "favor_featmap_bwd", "favor_scan_fwd", "favor_scan_bwd", "local_attn_fwd",
+           "rotary", "rotary_qk", "favor_kmax", "favor_featmap_fwd", "favor_featmap_bwd", "favor_scan_fwd", "favor_scan_bwd", "local_attn_fwd", "rotary_table", "local_attn_bwd_rot",
            "local_attn_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])

@@ -312,6 +312,54 @@ def test_tcgen05_local_attention_bf16(B, H, N, W):
     _close(lse, lse2, 1e-3, "lse tc vs simt")
 
 
+@pytest.mark.parametrize("B,H,N,W,simt", [(2, 2, 300, 40, False), (1, 2, 1400, 420, False), (1, 1, 150, 64, False),
+                                          (2, 1, 130, 7, False), (1, 2, 300, 40, True)])
+def test_local_attention_rotary_transpose_in_the_backward_epilogue(B, H, N, W, simt):
+    """q / k rotated in place, forward on the rotated buffers, sa_local_attn_bwd_rot: dq / dk leave the tcgen05 kernels
+    through the transpose of the rotation (registers, fp32).  Against the oracle's rotary local attention on the same
+    bf16-rounded inputs; and the CUDA-core branch of the same entry point (rotation as its own pass)."""
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(N + W + 1)
+    d = 64
+    q, k, v = (_bf(torch.randn(B, H, N, d, generator=g)).requires_grad_(True) for _ in range(3))
+    w = _bf(torch.randn(B, H, N, d, generator=g))
+    out = po.local_attention(q, k, v, W, "rotary")
+    (out * w).sum().backward()
+    inner = H * d
+    buf = torch.cat([_heads_to_rows(t.detach()) for t in (q, k, v)], dim=1).cuda().bfloat16()
+    inv_freq = (1.0 / (10000 ** (torch.arange(0, d, 2).float() / d))).cuda()
+    table = pf.rotary_table(inv_freq, N, d)
+    ang = torch.arange(N, dtype=torch.float32)[:, None] * inv_freq.cpu()[None, :]
+    _close(table[..., 0].cpu(), torch.cos(ang), 1e-5, "cos table"); _close(table[..., 1].cpu(), torch.sin(ang), 1e-5, "sin table")
+    ldsc = pf.local_desc(B, N, H, d, W, 3 * inner, inner, torch.bfloat16)
+    O = torch.zeros(B * N, inner, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device="cuda")
+    ops.set_force_simt(simt)
+    try:
+        pf.rotary_qk(buf, 0, inner, B, N, H, d, inv_freq, False)
+        pf.local_attn_fwd(ldsc, buf, 0, inner, 2 * inner, None, O, 0, lse)
+        _close(_rows_to_heads(O.float().cpu(), B, H), out, 3e-2, "rotary local out")
+        dbuf = torch.zeros_like(buf)
+        dO = _heads_to_rows(w).cuda().bfloat16()
+        pf.local_attn_bwd_rot(ldsc, buf, 0, inner, 2 * inner, inv_freq, table, O, dO, 0, lse, dbuf)
+        assert ops.last_path() == (1 if simt else 2)
+        # the two-pass form on the same buffers: gradients of the rotated q / k, then the in-place transpose
+        dref = torch.zeros_like(buf)
+        pf.local_attn_bwd(ldsc, buf, 0, inner, 2 * inner, None, O, dO, 0, lse, dref)
+        pf.rotary_qk(dref, 0, inner, B, N, H, d, inv_freq, True)
+    finally:
+        ops.set_force_simt(False)
+    for i, (name, t) in enumerate((("dq", q), ("dk", k), ("dv", v))):
+        got = _rows_to_heads(dbuf[:, i * inner:(i + 1) * inner].float().cpu(), B, H)
+        two = _rows_to_heads(dref[:, i * inner:(i + 1) * inner].float().cpu(), B, H)
+        scale = float(t.grad.abs().max())
+        err = float((got - t.grad).abs().max())
+        assert err <= 3e-2 * scale, f"rot local {name}: {err:.3e} vs max {scale:.3e}"
+        # one bf16 rounding instead of two: the fused form differs from the two-pass form by bf16 ulps only
+        assert float((got - two).abs().max()) <= 2.0 ** -6 * scale, name
+    assert torch.equal(dbuf[:, 2 * inner:], dref[:, 2 * inner:]), "dv does not depend on where the rotation is undone"
+
+
 def test_rotary_inplace_matches_oracle():
     ops, pf = _mods()
     g = torch.Generator().manual_seed(2)
