@@ -117,15 +117,22 @@ __device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const float
 
 // transpose of the rotary map on one 64-wide gradient row (pairs (e, e + 32); table row = 32 x (cos, sin) of the position):
 // the forward pass rotated q / k in place, so their gradients leave the attention kernels through the inverse rotation
-// -- in registers, on the fp32 values, instead of a separate in-place pass over the stored bf16 gradients
-__device__ __forceinline__ void lc_unrotate64(float (&g)[64], const float2* __restrict__ tb) {
+// -- in registers, on the fp32 values, instead of a separate in-place pass over the stored bf16 gradients.  The table row
+// is requested BEFORE the wait for the last accumulator (one CTA per SM: an L2 round trip in the CTA's tail is exposed).
+__device__ __forceinline__ void lc_rot_fetch(float4 (&t)[16], const float2* __restrict__ tb) {
+#pragma unroll
+  for (int e4 = 0; e4 < 16; ++e4)        // (cos, sin) of frequencies 2 e4, 2 e4 + 1; volatile: stays above the mbarrier wait
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(t[e4].x), "=f"(t[e4].y), "=f"(t[e4].z), "=f"(t[e4].w)
+                 : "l"(reinterpret_cast<const float4*>(tb) + e4));
+}
+__device__ __forceinline__ void lc_unrotate64(float (&g)[64], const float4 (&t)[16]) {
 #pragma unroll
   for (int e4 = 0; e4 < 16; ++e4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(tb) + e4);      // (cos, sin) of frequencies 2 e4, 2 e4 + 1
     const int e = 2 * e4;
     const float a0 = g[e], b0 = g[e + 32], a1 = g[e + 1], b1 = g[e + 33];
-    g[e] = a0 * t.x + b0 * t.y;      g[e + 32] = b0 * t.x - a0 * t.y;
-    g[e + 1] = a1 * t.z + b1 * t.w;  g[e + 33] = b1 * t.z - a1 * t.w;
+    g[e] = a0 * t[e4].x + b0 * t[e4].y;      g[e + 32] = b0 * t[e4].x - a0 * t[e4].y;
+    g[e + 1] = a1 * t[e4].z + b1 * t[e4].w;  g[e + 33] = b1 * t[e4].z - a1 * t[e4].w;
   }
 }
 
@@ -509,6 +516,8 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
       tc_fence_before();
       mbar_arrive(&ds_full[t & 1]);
     }
+    float4 rt[16];
+    if (P.rot && row_ok) lc_rot_fetch(rt, P.rot + (long long)p * 32);
     mbar_wait(&dq_full, 0);
     tc_fence_after();
     float g[64];
@@ -526,7 +535,7 @@ tc_local_bwd_dq_kernel(const __grid_constant__ LcParams P) {
     if (row_ok) {
 #pragma unroll
       for (int e = 0; e < 64; ++e) g[e] *= P.scale;       // dS = P (dP - delta) d^-1/2: the factor commutes with the product
-      if (P.rot) lc_unrotate64(g, P.rot + (long long)p * 32);
+      if (P.rot) lc_unrotate64(g, rt);
       store_row64_bf16(P.dq + ((long long)b * P.N + p) * P.ld + h * 64, g);
     }
   }
@@ -706,6 +715,8 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
       mbar_arrive(&ds_full);
       if (!P.delta_ws) load_stats(t + 1, nl2, ndl);
     }
+    float4 rt[16];
+    if (P.rot && j < P.N) lc_rot_fetch(rt, P.rot + (long long)j * 32);
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     float g[64];
@@ -724,7 +735,7 @@ tc_local_bwd_dkv_kernel(const __grid_constant__ LcParams P) {
       if (which) {
 #pragma unroll
         for (int e = 0; e < 64; ++e) g[e] *= P.scale;
-        if (P.rot && j < P.N) lc_unrotate64(g, P.rot + (long long)j * 32);
+        if (P.rot && j < P.N) lc_unrotate64(g, rt);
       }
       if (j < P.N) store_row64_bf16((which ? P.dk : P.dv) + ((long long)b * P.N + j) * P.ld + h * 64, g);
     }
