@@ -157,6 +157,19 @@ int sa_favor_scan_bwd_saved(const sa_favor_desc* d, const void* qf, const void* 
                             void* dv, void* workspace, size_t ws_bytes, const void* states, size_t states_bytes,
                             void* stream);
 
+/* sa_favor_scan_bwd_saved + sa_favor_featmap_bwd of the queries and of the keys in one call: the gradients of the
+ * feature tensors (dq', dk') are consumed block by block inside the dq' / dk' kernels and never stored.
+ *   x_q, x_k : the q / k head columns the features were computed from (leading dimension d->ld);  dx_q, dx_k likewise
+ *   argq     : arg-max feature per query row, as saved by sa_favor_featmap_fwd;  *gsum += sum over all key rows of dD
+ *              (what sa_favor_kmax_fixup needs afterwards);  states may be NULL (recomputed).
+ * Only the tcgen05 path has this form: ask sa_favor_scan_bwd_fused_supported() first (else SA_ERR_UNSUPPORTED). */
+int sa_favor_scan_bwd_fused_supported(const sa_favor_desc* d);
+int sa_favor_scan_bwd_fused(const sa_favor_desc* d, const void* qf, const void* kf, const void* x_q, const void* x_k,
+                            const void* v, const float* proj, float eps_cumsum, float eps_feature, const void* out,
+                            const void* dout, int out_ld, const float* den, const int32_t* argq, void* dx_q, void* dx_k,
+                            void* dv, float* gsum, void* workspace, size_t ws_bytes, const void* states, size_t states_bytes,
+                            void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Local-window heads.  Replaces local_attention.LocalAttention.forward (window w, causal, look_backward = 1,
  * autopad, scale d^-1/2, optional rotary position term with frequencies inv_freq[d/2]):

@@ -177,6 +177,10 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "sa_local_attn_bwd_ws": (c_int, [C.POINTER(LocalDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sa_favor_scan_bwd_fused_supported": (c_int, [C.POINTER(FavorDesc)]),
+    "sa_favor_scan_bwd_fused": (c_int, [C.POINTER(FavorDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, C.c_size_t, c_void_p, C.c_size_t, c_void_p]),
     "sa_rotary_table": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sa_local_attn_bwd_rot": (c_int, [C.POINTER(LocalDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -44,6 +44,10 @@ int sa_tc_favor_scan_fwd(const sa_favor_desc*, const void*, const void*, const v
 int sa_tc_favor_scan_bwd(const sa_favor_desc*, const void*, const void*, const void*, float, const void*, const void*,
                          int, const float*, void*, void*, void*, void*, size_t, const void*, cudaStream_t);
 
+int sa_tc_favor_scan_bwd_fused(const sa_favor_desc*, const void*, const void*, const void*, const void*, const void*,
+                               const float*, float, float, const void*, const void*, int, const float*, const int32_t*, void*,
+                               void*, void*, float*, void*, size_t, const void*, cudaStream_t);
+
 bool sa_tc_local_supported(const sa_local_desc*, const void*, const void*, const void*, const float*);
 int sa_tc_local_attn_fwd(const sa_local_desc*, const void*, const void*, const void*, void*, float*, cudaStream_t);
 int sa_tc_local_attn_bwd(const sa_local_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
@@ -175,6 +179,26 @@ extern "C" int sa_favor_scan_bwd_saved(const sa_favor_desc* d, const void* qf, c
   }
   return sa_simt_favor_scan_bwd(d, qf, kf, v, eps_cumsum, out, dout, out_ld, den, dqf, dkf, dv, workspace, ws_bytes,
                                 sa_stream(stream));
+}
+
+extern "C" int sa_favor_scan_bwd_fused_supported(const sa_favor_desc* d) {
+  return d && !sa_force_simt() && sa_tc_favor_supported(d) ? 1 : 0;
+}
+
+extern "C" int sa_favor_scan_bwd_fused(const sa_favor_desc* d, const void* qf, const void* kf, const void* x_q,
+                                       const void* x_k, const void* v, const float* proj, float eps_cumsum,
+                                       float eps_feature, const void* out, const void* dout, int out_ld, const float* den,
+                                       const int32_t* argq, void* dx_q, void* dx_k, void* dv, float* gsum, void* workspace,
+                                       size_t ws_bytes, const void* states, size_t states_bytes, void* stream) {
+  SA_CHECK_ARG(d && qf && kf && x_q && x_k && v && proj && out && dout && den && argq && dx_q && dx_k && dv && gsum && workspace,
+               "null pointer");
+  if (!sa_favor_scan_bwd_fused_supported(d)) {
+    sa_set_error("sa_favor_scan_bwd_fused: only the tcgen05 path has this form (sa_favor_scan_bwd_fused_supported)");
+    return SA_ERR_UNSUPPORTED;
+  }
+  SA_CHECK_ARG(!states || states_bytes >= sa_tc_favor_states_bytes(d), "states buffer too small");
+  return sa_tc_favor_scan_bwd_fused(d, qf, kf, v, x_q, x_k, proj, eps_cumsum, eps_feature, out, dout, out_ld, den, argq, dx_q,
+                                    dx_k, dv, gsum, workspace, ws_bytes, states, sa_stream(stream));
 }
 
 extern "C" int sa_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps_cumsum,

@@ -1052,6 +1052,263 @@ tc_dqk_kernel(const __grid_constant__ FvParams P) {
   FV_EPILOGUE();
 }
 
+// ------------------------------------------------------------------------------------------------ dq' / dk' + feature map, backward
+// tc_dqk_kernel with the feature-map backward as its epilogue: dq' / dk' never reach HBM.  Per feature block c the
+// epilogue warps turn the finished [128 x 64] block of dq' (dk') -- still fp32, in registers -- into
+//   dD = df (feat - r eps)          feat = the chunk's OWN features (q' for dq', k' for dk'), a third box of the ring stage
+// write it as bf16 over that box (own row, conflict-free swizzled 16-byte accesses) and hand it to the MMA warp, which
+// accumulates dD P over the blocks in its own 64 TMEM columns.  The last epilogue of a tile is tc_featmap_bwd_kernel's:
+//   dx = c (dD P - s P[argmax]) - c^2 s x,   s = the row sum of dD.
+// Against the two-kernel form this drops the write of df and the reads of df + feat by the second kernel (2 x 366 MB per
+// tensor and layer at the benchmark size).  ~210 KB of shared memory, so ONE CTA per SM -- and therefore persistent: P
+// is staged once, the three-stage ring runs across tile boundaries, X / Y of the next tile are requested as soon as the
+// last df block of this tile has been issued, and B' = X Y^T of the next tile runs under this tile's last epilogue.
+constexpr int DF_STAGES = 3;
+constexpr uint32_t DF_STAGE = 2 * BLK + ST_BLK;  // F block | state block | own-feature block (-> dD): 42 KB
+
+template <int MODE>
+__global__ void __launch_bounds__(F_THREADS, 1)
+tc_dqk_fb_kernel(const __grid_constant__ FvParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ uint64_t xy_full, xy_empty, b_full, bm_ready, x_full, ring_full[DF_STAGES], ring_empty[DF_STAGES],
+      dd_ready[DF_STAGES], acc_full[2], acc_empty[2];
+  __shared__ float s_delta[FC], s_inv[FC], s_red[2][FC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Xs = smem;
+  uint8_t* Bm = smem + BLK;              // 2 blocks; the first one holds Y until B' = X Y^T has been formed
+  uint8_t* Ys = Bm;
+  uint8_t* Ring = smem + 3 * BLK;
+  uint8_t* Ps = Ring + DF_STAGES * DF_STAGE;     // mp x 128 B
+  const int total = P.nchunks * P.B * P.H;
+  if (threadIdx.x == 0) {
+    mbar_init(&xy_full, 1); mbar_init(&xy_empty, 1); mbar_init(&b_full, 1); mbar_init(&bm_ready, 256); mbar_init(&x_full, 1);
+    for (int i = 0; i < DF_STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); mbar_init(&dd_ready[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (warp < 8) { stage_proj(Ps, P.proj, P.m, P.mp, threadIdx.x); fence_proxy_async(); }
+  FV_ALLOC();
+  const uint32_t tB = tmem_base, tD = tmem_base + 128, tX = tmem_base + 256;
+  if (warp == 9) {
+    if (lane == 0) {
+      prefetch_tmap(&P.map_a); prefetch_tmap(&P.map_b); prefetch_tmap(&P.map_c); prefetch_tmap(&P.map_d); prefetch_tmap(&P.map_e);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int bh = tile / P.nchunks, chunk = tile % P.nchunks;
+        const int b = bh / P.H, h = bh % P.H, n0 = chunk * FC;
+        mbar_wait(&xy_empty, (uint32_t)((it & 1) ^ 1));     // the df MMAs of the previous tile no longer read Xs / Bm
+        mbar_expect_tx(&xy_full, 2 * BLK);
+        tma_load_3d(Xs, &P.map_a, &xy_full, h * 64, n0, b);
+        tma_load_3d(Ys, &P.map_b, &xy_full, h * 64, n0, b);
+        for (int cb = 0; cb < P.nblk; ++cb) {
+          mbar_wait(&ring_empty[stage], phase ^ 1);
+          mbar_expect_tx(&ring_full[stage], DF_STAGE);
+          uint8_t* sp = Ring + stage * DF_STAGE;
+          tma_load_3d(sp, &P.map_c, &ring_full[stage], cb * 64, n0, bh);
+          tma_load_2d(sp + BLK, &P.map_d, &ring_full[stage], cb * 64, (bh * P.nchunks + chunk) * ST_ROWS);
+          tma_load_3d(sp + BLK + ST_BLK, &P.map_e, &ring_full[stage], cb * 64, n0, bh);
+          if (++stage == DF_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t xa = smem_u32(Xs), ya = smem_u32(Ys), bma = smem_u32(Bm), pa = smem_u32(Ps);
+      const uint32_t idesc_x = make_idesc_bf16(128, 64, 0, 1);
+      int s1 = 0, s2 = 0; uint32_t ph1 = 0, ph2 = 0;
+      int it = 0, gb = 0;            // gb: running count of df blocks (the two df accumulators alternate across tiles)
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it, gb += P.nblk) {
+        mbar_wait(&xy_full, (uint32_t)(it & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tB, make_smem_desc(xa + k * 32, 16, 1024, 2), make_smem_desc(ya + k * 32, 16, 1024, 2),
+                    make_idesc_bf16(128, 128, 0, 0), k > 0);
+        umma_commit(&b_full);
+        for (int cb = 0; cb <= P.nblk; ++cb) {
+          if (cb < P.nblk) {       // df block cb:  X . St_c + Bm . F_c
+            const int g = gb + cb, ab = g & 1;
+            const int ncols = (cb == P.nblk - 1) ? P.tail : 64;
+            const uint32_t idesc = make_idesc_bf16(128, ncols, 0, 1);
+            const uint32_t td = tD + (uint32_t)(ab * 64);
+            mbar_wait(&ring_full[s1], ph1);
+            mbar_wait(&acc_empty[ab], (uint32_t)(((g >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t fa = smem_u32(Ring + s1 * DF_STAGE), sa = fa + BLK;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(td, make_smem_desc(xa + k * 32, 16, 1024, 2), make_smem_desc(sa + k * 2048, ST_BLK, 1024, 2), idesc, k > 0);
+            if (cb == 0) { mbar_wait(&bm_ready, (uint32_t)(it & 1)); tc_fence_after(); }
+#pragma unroll
+            for (int k = 0; k < FC / 16; ++k)
+              umma_bf16(td, make_smem_desc(bma + (k >> 2) * BLK + (k & 3) * 32, 16, 1024, 2),
+                        make_smem_desc(fa + k * 2048, BLK, 1024, 2), idesc, 1u);
+            umma_commit(&acc_full[ab]);
+            if (cb == P.nblk - 1) umma_commit(&xy_empty);
+            if (++s1 == DF_STAGES) { s1 = 0; ph1 ^= 1; }
+          }
+          if (cb >= 1) {           // dx += dD_{cb-1} P_{cb-1}: issued after the MMAs of block cb, so it waits under them
+            const int pb = cb - 1;
+            mbar_wait(&dd_ready[s2], ph2);
+            tc_fence_after();
+            const uint32_t da = smem_u32(Ring + s2 * DF_STAGE + BLK + ST_BLK);
+            const int ksteps = (pb == P.nblk - 1) ? (P.tail >> 4) : 4;
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(tX, make_smem_desc(da + k * 32, 16, 1024, 2), make_smem_desc(pa + (pb * 4 + k) * 2048, 8192, 1024, 2),
+                        idesc_x, (pb | k) != 0);
+            umma_commit(&ring_empty[s2]);
+            if (++s2 == DF_STAGES) { s2 = 0; ph2 ^= 1; }
+          }
+        }
+        umma_commit(&x_full);
+      }
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3, hf = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    const float re = P.r * P.eps;
+    float gacc = 0.f;
+    int se = 0; uint32_t phe = 0;
+    int it = 0, gb = 0;
+    float2 di = make_float2(0.f, 0.f);       // {delta, 1 / den} of this thread's row: requested one tile ahead
+    if (hf == 0 && (int)blockIdx.x < total) {
+      const int bh0 = blockIdx.x / P.nchunks, nn = (blockIdx.x % P.nchunks) * FC + r;
+      if (nn < P.N) di = __ldg(P.dinv + (long long)bh0 * P.N + nn);
+    }
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it, gb += P.nblk) {
+      const int bh = tile / P.nchunks, chunk = tile % P.nchunks;
+      const int b = bh / P.H, h = bh % P.H;
+      const int n = chunk * FC + r;
+      const bool row_ok = n < P.N;
+      if (hf == 0) {
+        s_delta[r] = di.x; s_inv[r] = di.y;
+        di = make_float2(0.f, 0.f);
+        const int nt = tile + gridDim.x;
+        if (nt < total) {
+          const int nn = (nt % P.nchunks) * FC + r;
+          if (nn < P.N) di = __ldg(P.dinv + (long long)(nt / P.nchunks) * P.N + nn);
+        }
+      }
+      // what the tile's last epilogue needs is requested now: the arg-max feature of the row (queries) and the x row
+      int am = -1;
+      if (MODE == 0 && row_ok) am = P.argmax[(long long)bh * P.N + n];
+      const long long xo = ((long long)b * P.N + n) * P.ld + h * 64 + hf * 32;
+      uint4 xr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xr[i] = row_ok ? __ldg(reinterpret_cast<const uint4*>(P.x + xo) + i) : make_uint4(0, 0, 0, 0);
+      bar_epi();
+      const float my_delta = s_delta[r], my_inv = s_inv[r];
+      mbar_wait(&b_full, (uint32_t)(it & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld_32x32(tB + tlane + (uint32_t)(hf * 64 + hh * 32), v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int cix = 0; cix < 32; ++cix) {
+          const int cc = hf * 64 + hh * 32 + cix;
+          if (MODE == 0) f[cix] = (cc <= r) ? __uint_as_float(v[cix]) - my_delta : 0.f;
+          else f[cix] = (cc >= r) ? (__uint_as_float(v[cix]) - s_delta[cc]) * s_inv[cc] : 0.f;
+        }
+        st_sw_32(Bm + hf * BLK, r, hh * 32, f);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bm_ready);
+      const __nv_bfloat16* vecrow = P.st_vec + ((long long)(bh * P.nchunks + chunk) * ST_ROWS + 64) * P.mp;
+      float part = 0.f;
+      for (int cb = 0; cb < P.nblk; ++cb) {
+        const int g = gb + cb, ab = g & 1;
+        const int ncols = (cb == P.nblk - 1) ? P.tail : 64;
+        const int c0 = cb * 64 + hf * 32;
+        const int nv = hf * 32 < ncols ? (min(32, ncols - hf * 32) >> 3) : 0;      // 16-byte vectors (8 columns each)
+        uint4 vr[4];                           // the "1" row of this block: fetched before the accumulator is waited for
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vr[i] = i < nv ? __ldg(reinterpret_cast<const uint4*>(vecrow + c0) + i) : make_uint4(0, 0, 0, 0);
+        mbar_wait(&ring_full[se], phe);        // the own-feature box of this stage (TMA writes become visible to this thread)
+        mbar_wait(&acc_full[ab], (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        uint32_t v[32];
+        if (nv > 0) {                          // warp-uniform
+          tmem_ld_32x32(tD + tlane + (uint32_t)(ab * 64 + hf * 32), v);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[ab]);
+        if (nv > 0) {
+          uint8_t* rowd = sw_row(Ring + se * DF_STAGE + BLK + ST_BLK, r);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < nv) {
+              float sv[8], a[8], gg[8];
+              unpack8(vr[i], sv);
+              uint4* pd = reinterpret_cast<uint4*>(rowd + (((hf * 4 + i) ^ (r & 7)) << 4));
+              unpack8(*pd, a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float acc = __uint_as_float(v[i * 8 + j]);
+                const float df = MODE == 0 ? my_inv * (acc - my_delta * sv[j]) : acc + sv[j];
+                gg[j] = (row_ok && c0 + i * 8 + j < P.m) ? df * (a[j] - re) : 0.f;
+                part += gg[j];
+              }
+              *pd = pack8(gg);
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&dd_ready[se]);
+        if (++se == DF_STAGES) { se = 0; phe ^= 1; }
+      }
+      bar_epi();                                // readers of s_red of the previous tile are done
+      s_red[hf][r] = part;
+      bar_epi();
+      const float ssum = row_ok ? s_red[0][r] + s_red[1][r] : 0.f;
+      if (MODE == 1 && hf == 0) gacc += ssum;   // keys: the sum over all rows feeds the global stabiliser's gradient
+      mbar_wait(&x_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tX + tlane + (uint32_t)(hf * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();                        // (the next tile's dD P overwrites these columns after dd_ready)
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(P.o_out + xo);
+        const float c2s = P.c * P.c * ssum;
+        const uint8_t* prow = am >= 0 ? sw_row(Ps, am) : nullptr;     // bf16 P row of the arg-max feature (64 columns)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float xv[8], f[8], pv[8];
+          unpack8(xr[i], xv);
+          if (prow) {
+            unpack8(*reinterpret_cast<const uint4*>(prow + (((hf * 4 + i) ^ (am & 7)) << 4)), pv);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pv[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = P.c * (__uint_as_float(v[i * 8 + j]) - ssum * pv[j]) - c2s * xv[j];
+          dst[i] = pack8(f);
+        }
+      }
+    }
+    if (MODE == 1 && hf == 0 && (P.gsum || P.gpart)) {
+      const float w = sa_warp_sum(gacc);
+      if (lane == 0) {
+        if (P.gpart) P.gpart[blockIdx.x * 4 + q] = w;
+        else atomicAdd(P.gsum, w);
+      }
+    }
+  }
+  FV_EPILOGUE();
+}
+
 // ------------------------------------------------------------------------------------------------ feature map, backward
 // Persistent (one CTA per SM, P staged once), pipelined over the feature blocks: the producer warp streams (feat, dfeat)
 // blocks of 64 features through a four-stage TMA ring; the epilogue warps turn each dfeat block IN PLACE into
@@ -1234,6 +1491,7 @@ size_t smem_featmap(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + round_up(
 size_t smem_state(int mp) { return (size_t)(2 + nblk_of(mp)) * BLK + 1024; }
 constexpr size_t SMEM_SCAN = SC_STAGES * SC_STAGE + BLK + 1024;
 size_t smem_dqk(int mp) { return (size_t)4 * BLK + (size_t)nblk_of(mp) * (BLK + ST_BLK) + 1024; }
+size_t smem_dqk_fb(int mp) { return (size_t)3 * BLK + (size_t)DF_STAGES * DF_STAGE + round_up((size_t)mp * 128, 1024) + 1024; }
 size_t smem_fbwd(int mp) { return (size_t)FB_STAGES * FB_STAGE + round_up((size_t)mp * 128, 1024) + 1024; }
 constexpr size_t SMEM_MAX = 227 * 1024 - 4096;   // opt-in ceiling minus the static shared memory of the kernels
 
@@ -1252,6 +1510,8 @@ void init_once() {
     cudaFuncSetAttribute(tc_dqk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQK);
     cudaFuncSetAttribute(tc_dqk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DQK);
     cudaFuncSetAttribute(tc_featmap_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_dqk_fb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(tc_dqk_fb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   });
 }
 
@@ -1303,6 +1563,11 @@ size_t states_bytes(const sa_favor_desc* d) {
   return round_up((size_t)d->batch * d->heads * sa_cdiv(d->seq, FC) * ST_ROWS * d->mp * sizeof(__nv_bfloat16), 1024);
 }
 
+// persistent kernels: one CTA per SM walks the (batch, head, chunk) tiles
+dim3 fb_grid(const sa_favor_desc* d) {
+  const long long total = sa_cdiv(d->seq, FC) * (long long)d->batch * d->heads;
+  return dim3((unsigned)(total < sa_sm_count() ? total : sa_sm_count()));
+}
 dim3 fv_grid(const sa_favor_desc* d) { return dim3((unsigned)sa_cdiv(d->seq, FC), (unsigned)(d->batch * d->heads)); }
 
 // chunk sums + prefix:  mode 0: (kf, v) forward prefix;  mode 1: (qf, dout / den) suffix
@@ -1453,15 +1718,30 @@ int sa_tc_favor_scan_fwd(const sa_favor_desc* d, const void* qf, const void* kf,
   return SA_OK;
 }
 
-int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps, const void* out,
-                         const void* dout, int out_ld, const float* den, void* dqf, void* dkf, void* dv, void* ws,
-                         size_t ws_bytes, const void* states_in, cudaStream_t st) {
+namespace {
+// the feature-map backward folded into the dq' / dk' kernels (tc_dqk_fb_kernel): what tc_featmap_bwd_kernel would be given
+struct FbArgs {
+  const void* x_q; const void* x_k;      // q / k head columns the features were computed from (leading dimension d->ld)
+  const float* proj; float eps_feature;
+  const int32_t* argq;                   // arg-max feature per query row (the non-detached row stabiliser)
+  void* dx_q; void* dx_k;                // gradients of the q / k head columns (leading dimension d->ld)
+  float* gsum;                           // += sum of dD over all key rows (the global key stabiliser's gradient)
+};
+
+int scan_bwd_impl(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps, const void* out,
+                  const void* dout, int out_ld, const float* den, void* dqf, void* dkf, void* dv, void* ws,
+                  size_t ws_bytes, const void* states_in, const FbArgs* fb, cudaStream_t st) {
   init_once();
   sa_note_path(SA_PATH_TCGEN05);
   if (ws_bytes < sa_tc_favor_scan_workspace(d, 1)) { sa_set_error("tc_favor_scan_bwd: workspace too small"); return SA_ERR_WORKSPACE; }
-  if (!aligned16(qf) || !aligned16(kf) || !aligned16(v) || !aligned16(out) || !aligned16(dout) || !aligned16(dqf) ||
-      !aligned16(dkf) || !aligned16(dv) || !aligned16(ws) || (out_ld & 7)) {
+  if (!aligned16(qf) || !aligned16(kf) || !aligned16(v) || !aligned16(out) || !aligned16(dout) || !aligned16(dv) ||
+      !aligned16(ws) || (out_ld & 7)) {
     sa_set_error("tc_favor_scan_bwd: pointers / leading dimensions not 16-byte aligned");
+    return SA_ERR_INVALID;
+  }
+  if (fb ? (!aligned16(fb->x_q) || !aligned16(fb->x_k) || !aligned16(fb->dx_q) || !aligned16(fb->dx_k) || !aligned16(fb->proj))
+         : (!aligned16(dqf) || !aligned16(dkf))) {
+    sa_set_error("tc_favor_scan_bwd: pointers not 16-byte aligned");
     return SA_ERR_INVALID;
   }
   float* sums = (float*)ws;
@@ -1505,7 +1785,16 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   P.st_vec = (const __nv_bfloat16*)stS;
   P.dinv = dinv;
   P.tmem_cols = 256;
-  tc_dqk_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  if (fb) {
+    if ((rc = feat_map(&P.map_e, qf, d)) != SA_OK) return rc;
+    P.proj = fb->proj; P.eps = fb->eps_feature; P.is_query = 1; P.argmax = const_cast<int32_t*>(fb->argq);
+    P.x = (const __nv_bfloat16*)fb->x_q; P.o_out = (__nv_bfloat16*)fb->dx_q;
+    P.tmem_cols = 512;                   // B' (128) | two df accumulators (2 x 64) | dx (64): one CTA per SM
+    tc_dqk_fb_kernel<0><<<fb_grid(d), F_THREADS, smem_dqk_fb(d->mp), st>>>(P);
+    P.tmem_cols = 256;
+  } else {
+    tc_dqk_kernel<0><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+  }
   SA_LAUNCH_CHECK();
   // dk'
   if ((rc = head_map(&P.map_a, v, d, d->ld)) != SA_OK) return rc;
@@ -1514,8 +1803,22 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   if ((rc = state_map(&P.map_d, stR, d, P.nchunks)) != SA_OK) return rc;
   P.df_out = (__nv_bfloat16*)dkf;
   P.st_vec = (const __nv_bfloat16*)stR;
-  tc_dqk_kernel<1><<<fv_grid(d), F_THREADS, smem, st>>>(P);
-  SA_LAUNCH_CHECK();
+  if (fb) {
+    if ((rc = feat_map(&P.map_e, kf, d)) != SA_OK) return rc;
+    const dim3 g = fb_grid(d);
+    const int nparts = (int)g.x * 4;
+    P.tmem_cols = 512;
+    P.is_query = 0; P.argmax = nullptr; P.gsum = fb->gsum;
+    P.gpart = fb->gsum ? sa_partial_slot(nparts, st) : nullptr;
+    P.x = (const __nv_bfloat16*)fb->x_k; P.o_out = (__nv_bfloat16*)fb->dx_k;
+    tc_dqk_fb_kernel<1><<<g, F_THREADS, smem_dqk_fb(d->mp), st>>>(P);
+    SA_LAUNCH_CHECK();
+    P.tmem_cols = 256;
+    if (P.gpart && (rc = sa_ordered_sum(P.gpart, nparts, fb->gsum, st)) != SA_OK) return rc;
+  } else {
+    tc_dqk_kernel<1><<<fv_grid(d), F_THREADS, smem, st>>>(P);
+    SA_LAUNCH_CHECK();
+  }
   // dv
   fill_common(P, d, out_ld, eps);
   if ((rc = feat_map(&P.map_a, kf, d)) != SA_OK) return rc;
@@ -1527,4 +1830,20 @@ int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf,
   tc_scan_kernel<1><<<fv_grid(d), F_THREADS, SMEM_SCAN, st>>>(P);
   SA_LAUNCH_CHECK();
   return SA_OK;
+}
+}  // namespace
+
+int sa_tc_favor_scan_bwd(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, float eps, const void* out,
+                         const void* dout, int out_ld, const float* den, void* dqf, void* dkf, void* dv, void* ws,
+                         size_t ws_bytes, const void* states_in, cudaStream_t st) {
+  return scan_bwd_impl(d, qf, kf, v, eps, out, dout, out_ld, den, dqf, dkf, dv, ws, ws_bytes, states_in, nullptr, st);
+}
+
+// backward scan + feature-map backward of both tensors: dq' / dk' stay on chip
+int sa_tc_favor_scan_bwd_fused(const sa_favor_desc* d, const void* qf, const void* kf, const void* v, const void* x_q,
+                               const void* x_k, const float* proj, float eps, float eps_feature, const void* out,
+                               const void* dout, int out_ld, const float* den, const int32_t* argq, void* dx_q, void* dx_k,
+                               void* dv, float* gsum, void* ws, size_t ws_bytes, const void* states_in, cudaStream_t st) {
+  const FbArgs fb{x_q, x_k, proj, eps_feature, argq, dx_q, dx_k, gsum};
+  return scan_bwd_impl(d, qf, kf, v, eps, out, dout, out_ld, den, nullptr, nullptr, dv, ws, ws_bytes, states_in, &fb, st);
 }

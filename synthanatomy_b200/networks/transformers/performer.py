@@ -442,6 +442,11 @@ def _rot_table(inv_freq: torch.Tensor, N: int, dh: int) -> torch.Tensor:
     return hit[1]
 
 
+def _FAVOR_FUSED_BWD() -> bool:
+    """A/B switch (0: scan_bwd + two featmap_bwd launches): the feature-map backward as the epilogue of the dq' / dk' kernels"""
+    return os.environ.get("SA_FAVOR_FUSED_BWD", "1") != "0"
+
+
 class _Ctx:
     """what every piece of the programme shares for one forward / backward pass"""
 
@@ -643,17 +648,22 @@ class _LayerFn(torch.autograd.Function):
                 pf_ops.local_attn_bwd(C.ld, qkv, c0, D.inner + c0, 2 * D.inner + c0, None, attn, dattn, c0, lse, dqkv)
         if D.gh > 0:
             fd = C.fd
-            dqf = torch.empty_like(qf)
-            dkf = torch.empty_like(kf)
             if states is not None and pf_ops.favor_scan_states_bytes(fd) == 0:
                 states = None          # the dispatch changed since the forward pass: recompute
-            pf_ops.favor_scan_bwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, dattn, 0, den, dqf, dkf, dqkv,
-                                  2 * D.inner, C.ws(True), states)
             gsum = torch.zeros((1,), device=dev, dtype=f32)
-            pf_ops.favor_featmap_bwd(fd, qkv, 0, proj, True, net.eps_feature, qf, dqf, argq, dqkv, 0, None)
-            pf_ops.favor_featmap_bwd(fd, qkv, D.inner, proj, False, net.eps_feature, kf, dkf, None, dqkv, D.inner, gsum)
+            if _FAVOR_FUSED_BWD() and pf_ops.favor_scan_bwd_fused_supported(fd):
+                # dq' / dk' are turned into dq / dk block by block inside the kernels that produce them
+                pf_ops.favor_scan_bwd_fused(fd, qf, kf, qkv, 0, D.inner, 2 * D.inner, proj, net.eps_cumsum, net.eps_feature,
+                                            attn, dattn, 0, den, argq, dqkv, gsum, C.ws(True), states)
+            else:
+                dqf = torch.empty_like(qf)
+                dkf = torch.empty_like(kf)
+                pf_ops.favor_scan_bwd(fd, qf, kf, qkv, 2 * D.inner, net.eps_cumsum, attn, dattn, 0, den, dqf, dkf, dqkv,
+                                      2 * D.inner, C.ws(True), states)
+                pf_ops.favor_featmap_bwd(fd, qkv, 0, proj, True, net.eps_feature, qf, dqf, argq, dqkv, 0, None)
+                pf_ops.favor_featmap_bwd(fd, qkv, D.inner, proj, False, net.eps_feature, kf, dkf, None, dqkv, D.inner, gsum)
+                del dqf, dkf
             pf_ops.favor_kmax_fixup(fd, proj, kmax, gsum, dqkv, D.inner)
-            del dqf, dkf
         dWqkv = torch.empty((3 * D.inner, D.dim), device=dev, dtype=f32)
         pf_ops.gemm_tn(dqkv, xa_attn, dWqkv)
         dx = torch.empty((M, D.dim), device=dev, dtype=f32)

@@ -218,6 +218,22 @@ def favor_scan_bwd(d, qf, kf, vbuf, vcol, eps, out, dout, ocol, den, dqf, dkf, d
                "sa_favor_scan_bwd")
 
 
+def favor_scan_bwd_fused_supported(d) -> bool:
+    return bool(lib().sa_favor_scan_bwd_fused_supported(C.byref(d)))
+
+
+def favor_scan_bwd_fused(d, qf, kf, buf, qcol, kcol, vcol, proj, eps, eps_feature, out, dout, ocol, den, argq, dbuf, gsum, ws,
+                         states=None) -> None:
+    """favor_scan_bwd + favor_featmap_bwd of the queries and the keys: dq' / dk' are never stored; dbuf gets dq, dk, dv"""
+    assert _rowmajor(out) == _rowmajor(dout) and _rowmajor(buf) == _rowmajor(dbuf)
+    _lib.check(lib().sa_favor_scan_bwd_fused(C.byref(d), _p(qf), _p(kf), _ptr(buf, qcol), _ptr(buf, kcol), _ptr(buf, vcol),
+                                             _p(proj), float(eps), float(eps_feature), _ptr(out, ocol), _ptr(dout, ocol),
+                                             _rowmajor(out), _p(den), _p(argq), _ptr(dbuf, qcol), _ptr(dbuf, kcol),
+                                             _ptr(dbuf, vcol), _p(gsum), _p(ws), ws.numel() * ws.element_size(), _p(states),
+                                             0 if states is None else states.numel() * states.element_size(), _stream()),
+               "sa_favor_scan_bwd_fused")
+
+
 def rotary(buf, col, batch, seq, heads, dim_head, inv_freq, inverse: bool) -> None:
     """in-place rotary position term on `heads` head blocks of the row-major buffer starting at column `col`"""
     _lib.check(lib().sa_rotary(_ptr(buf, col), _dt(buf.dtype), _rowmajor(buf), batch, seq, heads, dim_head, _p(inv_freq),
@@ -396,6 +412,6 @@ def _instrument(name, fn):
 
 
 for _n in ("gemm_nt", "gemm_tn", "embed_fwd", "embed_bwd", "layernorm_fwd", "layernorm_bwd", "ce_fwd_bwd", "cast2d",
-           "rotary", "rotary_qk", "favor_kmax", "favor_featmap_fwd", "favor_featmap_bwd", "favor_scan_fwd", "favor_scan_bwd", "local_attn_fwd", "rotary_table", "local_attn_bwd_rot",
+           "rotary", "rotary_qk", "favor_kmax", "favor_featmap_fwd", "favor_featmap_bwd", "favor_scan_fwd", "favor_scan_bwd", "favor_scan_bwd_fused", "local_attn_fwd", "rotary_table", "local_attn_bwd_rot",
            "local_attn_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n])

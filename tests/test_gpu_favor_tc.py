@@ -151,3 +151,74 @@ def test_tcgen05_favor_scan_bf16(B, H, N, m):
     finally:
         ops.set_force_simt(False)
     _rel(den, den2, 1e-2, "den tc vs simt")
+
+
+@pytest.mark.parametrize("B,H,N,m", [(2, 2, 300, 266), (1, 3, 1000, 266), (1, 1, 128, 266), (1, 2, 77, 40), (1, 1, 513, 100),
+                                     (1, 2, 1400, 266), (2, 4, 2600, 266), (3, 7, 1100, 40)])
+def test_tcgen05_favor_backward_with_the_feature_map_folded_in(B, H, N, m):
+    """sa_favor_scan_bwd_fused (dq' / dk' consumed inside the kernels that produce them) against (a) the oracle's gradients
+    of the whole FAVOR+ head (feature maps + causal linear attention) on the same bf16-rounded inputs and (b) the
+    three-call form (scan_bwd + two featmap_bwd) on the same device buffers, which rounds dq' / dk' to bf16 in between.
+    The last two cases have more (batch, head, chunk) tiles than the GPU has SMs: the persistent CTAs walk several."""
+    ops, pf = _mods()
+    g = torch.Generator().manual_seed(N + m + 7)
+    d, mp = 64, ((m + 15) // 16) * 16
+    q = _bf(torch.randn(B, H, N, d, generator=g)).requires_grad_(True)
+    k = _bf(torch.randn(B, H, N, d, generator=g)).requires_grad_(True)
+    v = _bf(torch.randn(B, H, N, d, generator=g)).requires_grad_(True)
+    w = _bf(torch.randn(B, H, N, d, generator=g))
+    P = _bf(po.gaussian_orthogonal_random_matrix(m, d, generator=g))
+    out = po.causal_linear_attention(po.softmax_kernel(q, P, True), po.softmax_kernel(k, P, False), v)
+    (out * w).sum().backward()
+
+    inner = H * d
+    ld = 3 * inner
+    buf = torch.cat([_heads_to_rows(t.detach()) for t in (q, k, v)], dim=1).cuda().bfloat16()
+    Pd = P.cuda()
+    fd = pf.favor_desc(B, N, H, d, m, mp, ld, torch.bfloat16)
+    assert pf.favor_scan_bwd_fused_supported(fd)
+    kmax = torch.zeros(1, dtype=torch.int64, device="cuda")
+    pf.favor_kmax(fd, buf, inner, Pd, kmax)
+    QF = torch.empty(B, H, N, mp, device="cuda", dtype=torch.bfloat16)
+    KF = torch.empty_like(QF)
+    argq = torch.empty(B, H, N, dtype=torch.int32, device="cuda")
+    pf.favor_featmap_fwd(fd, buf, 0, Pd, True, None, 1e-4, QF, argq)
+    pf.favor_featmap_fwd(fd, buf, inner, Pd, False, kmax, 1e-4, KF, None)
+    ws = torch.empty(pf.favor_scan_workspace(fd, True), dtype=torch.uint8, device="cuda")
+    O = torch.zeros(B * N, inner, device="cuda", dtype=torch.bfloat16)
+    den = torch.empty(B, H, N, device="cuda")
+    states = torch.empty(pf.favor_scan_states_bytes(fd), dtype=torch.uint8, device="cuda")
+    pf.favor_scan_fwd(fd, QF, KF, buf, 2 * inner, 1e-6, O, 0, den, ws, states)
+    dO = _heads_to_rows(w).cuda().bfloat16()
+
+    # three calls
+    dref = torch.zeros_like(buf)
+    dQF, dKF = torch.empty_like(QF), torch.empty_like(KF)
+    gs_ref = torch.zeros(1, device="cuda")
+    pf.favor_scan_bwd(fd, QF, KF, buf, 2 * inner, 1e-6, O, dO, 0, den, dQF, dKF, dref, 2 * inner, ws, states)
+    pf.favor_featmap_bwd(fd, buf, 0, Pd, True, 1e-4, QF, dQF, argq, dref, 0, None)
+    pf.favor_featmap_bwd(fd, buf, inner, Pd, False, 1e-4, KF, dKF, None, dref, inner, gs_ref)
+    # one call (with the saved states, and recomputing them)
+    for st in (states, None):
+        dbuf = torch.full_like(buf, 7.0)
+        gs = torch.zeros(1, device="cuda")
+        pf.favor_scan_bwd_fused(fd, QF, KF, buf, 0, inner, 2 * inner, Pd, 1e-6, 1e-4, O, dO, 0, den, argq, dbuf, gs, ws, st)
+        assert ops.last_path() == 2
+        torch.cuda.synchronize()
+        assert torch.equal(dbuf[:, 2 * inner:], dref[:, 2 * inner:]), "dv comes from the same kernel in both forms"
+        for i, name in enumerate(("dq", "dk")):
+            got = dbuf[:, i * inner:(i + 1) * inner].float().cpu()
+            two = dref[:, i * inner:(i + 1) * inner].float().cpu()
+            _rel(got, two, 2e-2, f"{name} fused vs three calls")
+        assert abs(float(gs) - float(gs_ref)) <= 2e-2 * max(1.0, float(dKF.float().abs().sum()) * 1e-3), (float(gs), float(gs_ref))
+    # against the oracle, end to end (key-stabiliser term included): the bf16 re-staging error grows with the sequence
+    # length in either form, so the bound is 4e-2 or 1.2 x what the three-call form shows on the same inputs
+    pf.favor_kmax_fixup(fd, Pd, kmax, gs, dbuf, inner)
+    pf.favor_kmax_fixup(fd, Pd, kmax, gs_ref, dref, inner)
+    for i, (name, t) in enumerate((("dq", q), ("dk", k), ("dv", v))):
+        want = t.grad
+        got = _rows_to_heads(dbuf[:, i * inner:(i + 1) * inner].float().cpu(), B, H)
+        two = _rows_to_heads(dref[:, i * inner:(i + 1) * inner].float().cpu(), B, H)
+        scale = float(want.abs().max())
+        err, err_two = float((got - want).abs().max()), float((two - want).abs().max())
+        assert err <= max(4e-2 * scale, 1.2 * err_two), f"{name} vs oracle: {err:.3e} (three calls: {err_two:.3e}, max |ref| {scale:.3e})"
