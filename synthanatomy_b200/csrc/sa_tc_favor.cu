@@ -17,6 +17,7 @@
 //   dqk<0>        B = dout v^T - delta -> tril;  dq' = (dout S - delta ksum + B k') / den
 //   dqk<1>        B^T = (v dout^T - delta) / den -> triu;  dk' = v R + Rden + B^T q'
 //   featmap_bwd   dD = dfeat (feat - r eps) (- row sum at the arg-max for queries);  dx = c dD P - c^2 s x
+//   dqk_fb<0/1>   dqk<0/1> with featmap_bwd as its epilogue (dq' / dk' stay on chip): the training path's backward
 //
 // Warp roles (320 threads): warps 0-7 epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2),
 // warp 8 MMA issuer, warp 9 TMA producer.
