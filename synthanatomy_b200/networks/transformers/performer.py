@@ -432,7 +432,7 @@ _ROT_TABLES = {}
 
 
 def _rot_table(inv_freq: torch.Tensor, N: int, dh: int) -> torch.Tensor:
-    key = (inv_freq.data_ptr(), inv_freq._version, N, dh)
+    key = (str(inv_freq.device), inv_freq.data_ptr(), inv_freq._version, N, dh)       # (addresses are per device)
     hit = _ROT_TABLES.get(key)
     if hit is None:
         if len(_ROT_TABLES) >= 256:

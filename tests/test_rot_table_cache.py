@@ -44,7 +44,7 @@ def test_entries_keep_their_buffer_alive_and_the_cache_is_bounded(monkeypatch):
     ptr = f.data_ptr()
     pm._rot_table(f, 10, 64)
     del f                                                                # the address cannot be handed to another tensor
-    assert any(k[0] == ptr for k in pm._ROT_TABLES)
+    assert any(k[1] == ptr for k in pm._ROT_TABLES)
     for n in range(400):
         pm._rot_table(torch.rand(32), 10 + n, 64)
     assert len(pm._ROT_TABLES) <= 256 and len(calls) == 401
